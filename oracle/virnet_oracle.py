@@ -1,0 +1,308 @@
+"""CPU oracle for the VIRNet hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product path (virnet_b200/) never does.
+
+What it is: a functional restatement, in plain fp32 torch CPU ops, of the reference's
+forward path and losses.  The reference (zsyOAOA/VIRNet) is pure PyTorch: its arithmetic
+lives in the third-party dependency `torch` (README.md:23 pins pytorch==1.13.0;
+environment.yml:52 pins 1.12.0; this image has torch 2.11.0) through the call sites
+cited on each function below.  Everything here works on a flat `state_dict` with the
+reference's parameter names, so the same weights can be fed to the reference, to this
+oracle and to the CUDA path.
+
+Parity pinning: the reference ships no tests, golden vectors or checkpoints
+(SURVEY.md §8c), so the oracle is pinned against outputs of the reference itself, run
+in the build container by tools/gen_golden.py (which imports /root/reference) and
+committed under tests/golden/.  tests/test_oracle_golden.py replays them.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+# networks/VIRNet.py:15-16 and networks/KNet.py:5-6
+SNET_LOG_MAX, SNET_LOG_MIN = math.log(1e2), math.log(1e-10)
+KNET_LOG_MAX, KNET_LOG_MIN = math.log(1e2), math.log(1e-4)
+
+
+@dataclass
+class NetCfg:
+    """Constructor arguments of VIRAttResUNet / VIRAttResUNetSR (networks/VIRNet.py:22-29, 52-62)."""
+    im_chn: int = 3
+    sigma_chn: int = 1
+    kernel_chn: int = 3
+    n_feat: Sequence[int] = (96, 192, 288)
+    dep_S: int = 5
+    dep_K: int = 8
+    n_resblocks: int = 3
+    noise_cond: bool = True
+    kernel_cond: bool = True
+    extra_mode: str = "Input"
+    noise_avg: bool = False
+    sisr: bool = False
+
+    @property
+    def extra_chn(self) -> int:
+        c = self.sigma_chn if self.noise_cond else 0
+        if self.sisr and self.kernel_cond:
+            c += self.kernel_chn
+        return c
+
+
+# --------------------------------------------------------------------------------------
+# parameter construction in the reference's creation order (drives the RNG stream)
+# --------------------------------------------------------------------------------------
+def _conv_params(sd: SD, name: str, cin: int, cout: int, k: int, bias: bool = True, transposed: bool = False):
+    """Default nn.Conv2d / nn.ConvTranspose2d init (kaiming_uniform(a=sqrt(5)) + uniform bias)."""
+    m = (torch.nn.ConvTranspose2d(cin, cout, k, stride=k) if transposed
+         else torch.nn.Conv2d(cin, cout, k, bias=bias))
+    sd[name + ".weight"] = m.weight.detach()
+    if m.bias is not None:
+        sd[name + ".bias"] = m.bias.detach()
+
+
+def _att_layer_params(sd: SD, name: str, out_chn: int, extra_chn: int):
+    nf1, nf2 = out_chn // 8, out_chn // 4                       # networks/AttResUNet.py:15-16
+    _conv_params(sd, name + ".conv1", extra_chn, nf1, 1)
+    _conv_params(sd, name + ".conv2", nf1, nf2, 1)
+    _conv_params(sd, name + ".mul_conv", nf2, out_chn, 1)
+    _conv_params(sd, name + ".add_conv", nf2, out_chn, 1)
+
+
+def build_state_dict(cfg: NetCfg) -> SD:
+    """Create parameters exactly as the reference constructors do, consuming the global torch
+    RNG in the same order: SNet -> (KNet) -> RNet (networks/VIRNet.py:31-40, 66-78)."""
+    sd: SD = {}
+    # --- SNet: DnCNN (networks/DnCNN.py:22-29), orthogonal init + zero bias (:46-52)
+    names = []
+    _conv_params(sd, "SNet.conv1", cfg.im_chn, 64, 3); names.append("SNet.conv1")
+    for ii in range(1, cfg.dep_S - 1):
+        nm = f"SNet.mid_layer.{2 * (ii - 1)}"
+        _conv_params(sd, nm, 64, 64, 3); names.append(nm)
+    _conv_params(sd, "SNet.conv_last", 64, cfg.sigma_chn, 3); names.append("SNet.conv_last")
+    gain = torch.nn.init.calculate_gain("leaky_relu", 0.25)
+    for nm in names:                                             # module order == creation order
+        torch.nn.init.orthogonal_(sd[nm + ".weight"], gain=gain)
+        sd[nm + ".bias"].zero_()
+    # --- KNet (networks/KNet.py:41-50)
+    if cfg.sisr:
+        _conv_params(sd, "KNet.head", cfg.im_chn, 64, 9, bias=False)
+        for b in range(cfg.dep_K):
+            _conv_params(sd, f"KNet.body.{b}.body.0", 64, 64, 3)
+            _conv_params(sd, f"KNet.body.{b}.body.2", 64, 64, 3)
+            _conv_params(sd, f"KNet.body.{b}.body.3.body.0", 64, 64 // 16, 1)
+            _conv_params(sd, f"KNet.body.{b}.body.3.body.2", 64 // 16, 64, 1)
+        _conv_params(sd, "KNet.tail.0", 64, cfg.kernel_chn, 3)
+    # --- RNet: AttResUNet (networks/AttResUNet.py:109-139)
+    mode = cfg.extra_mode.lower()
+    assert mode in ("null", "input", "down", "both")
+    nf = list(cfg.n_feat)
+    depth = len(nf)
+    extra = cfg.extra_chn
+    head_in = cfg.im_chn if mode in ("down", "null") else cfg.im_chn + extra
+    _conv_params(sd, "RNet.head", head_in, nf[0], 3)
+    extra_down = extra if mode in ("down", "both") else 0
+    for ii in range(depth):
+        for b in range(cfg.n_resblocks):
+            p = f"RNet.down_path.{ii}.body.{b}"
+            if extra_down > 0:
+                _att_layer_params(sd, p + ".sft1", nf[ii], extra_down)
+                _att_layer_params(sd, p + ".sft2", nf[ii], extra_down)
+            _conv_params(sd, p + ".conv1", nf[ii], nf[ii], 3)
+            _conv_params(sd, p + ".conv2", nf[ii], nf[ii], 3)
+        if ii + 1 < depth:
+            _conv_params(sd, f"RNet.down_path.{ii}.downsampler", nf[ii], nf[ii + 1], 3)
+    for k, jj in enumerate(reversed(range(depth - 1))):
+        _conv_params(sd, f"RNet.up_path.{k}.upsampler", nf[jj + 1], nf[jj], 2, transposed=True)
+        for b in range(cfg.n_resblocks):
+            p = f"RNet.up_path.{k}.body.{b}"
+            _conv_params(sd, p + ".conv1", nf[jj], nf[jj], 3)
+            _conv_params(sd, p + ".conv2", nf[jj], nf[jj], 3)
+    _conv_params(sd, "RNet.tail", nf[0], cfg.im_chn, 3)
+    return sd
+
+
+# --------------------------------------------------------------------------------------
+# forward restatement
+# --------------------------------------------------------------------------------------
+def _conv(sd: SD, name: str, x: Tensor, stride: int = 1, padding: int = 1) -> Tensor:
+    return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=padding)
+
+
+def pad_input(x: Tensor, mod: int) -> Tensor:
+    """utils/util_net.py:20-25 — reflect pad bottom/right up to a multiple of `mod`."""
+    h, w = x.shape[-2:]
+    bottom = int(math.ceil(h / mod) * mod - h)
+    right = int(math.ceil(w / mod) * mod - w)
+    return F.pad(x, pad=(0, right, 0, bottom), mode="reflect")
+
+
+def dncnn(sd: SD, x: Tensor, cfg: NetCfg) -> Tensor:
+    """networks/DnCNN.py:37-44 — conv+LReLU(0.25) x (dep-1), conv; optional global average."""
+    h = F.leaky_relu(_conv(sd, "SNet.conv1", x), 0.25)
+    for ii in range(1, cfg.dep_S - 1):
+        h = F.leaky_relu(_conv(sd, f"SNet.mid_layer.{2 * (ii - 1)}", h), 0.25)
+    out = _conv(sd, "SNet.conv_last", h)
+    if cfg.noise_avg:
+        out = out.mean(dim=(2, 3), keepdim=True)                # nn.AdaptiveAvgPool2d((1,1)) DnCNN.py:30-33
+    return out
+
+
+def att_layer(sd: SD, p: str, extra: Tensor) -> Tuple[Tensor, Tensor]:
+    """networks/AttResUNet.py:27-32 — SFT-style (mul, add) from the conditioning maps."""
+    f1 = F.leaky_relu(_conv(sd, p + ".conv1", extra, padding=0), 0.2)
+    f2 = F.leaky_relu(_conv(sd, p + ".conv2", f1, padding=0), 0.2)
+    mul = torch.sigmoid(_conv(sd, p + ".mul_conv", f2, padding=0))
+    add = _conv(sd, p + ".add_conv", f2, padding=0)
+    return mul, add
+
+
+def att_res_block(sd: SD, p: str, x: Tensor, extra: Optional[Tensor]) -> Tensor:
+    """networks/AttResUNet.py:48-60 — pre-activation residual block with optional modulation."""
+    if extra is not None:
+        mul1, add1 = att_layer(sd, p + ".sft1", extra)
+        f1 = _conv(sd, p + ".conv1", F.leaky_relu(x * mul1 + add1, 0.2))
+        mul2, add2 = att_layer(sd, p + ".sft2", extra)
+        f2 = _conv(sd, p + ".conv2", F.leaky_relu(f1 * mul2 + add2, 0.2))
+    else:
+        f1 = _conv(sd, p + ".conv1", F.leaky_relu(x, 0.2))
+        f2 = _conv(sd, p + ".conv2", F.leaky_relu(f1, 0.2))
+    return x + f2
+
+
+def att_res_unet(sd: SD, x_in: Tensor, extra_in: Optional[Tensor], cfg: NetCfg) -> Tensor:
+    """networks/AttResUNet.py:141-175."""
+    mode = cfg.extra_mode.lower()
+    depth = len(cfg.n_feat)
+    h, w = x_in.shape[-2:]
+    x = pad_input(x_in, 2 ** (depth - 1))
+    extra = pad_input(extra_in, 2 ** (depth - 1)) if mode != "null" else None
+    if mode in ("input", "both"):
+        x = _conv(sd, "RNet.head", torch.cat([x, extra], 1))
+    else:
+        x = _conv(sd, "RNet.head", x)
+    blocks: List[Tensor] = []
+    extra_down = [extra] if mode in ("down", "both") else None
+    for ii in range(depth):
+        e = extra_down[ii] if extra_down is not None else None
+        for b in range(cfg.n_resblocks):
+            x = att_res_block(sd, f"RNet.down_path.{ii}.body.{b}", x, e)
+        if ii != depth - 1:
+            blocks.append(x)
+            x = _conv(sd, f"RNet.down_path.{ii}.downsampler", x, stride=2)
+            if extra_down is not None:
+                extra_down.append(F.interpolate(extra, x.shape[-2:], mode="nearest"))
+    for k in range(depth - 1):
+        up = f"RNet.up_path.{k}"
+        x = F.conv_transpose2d(x, sd[up + ".upsampler.weight"], sd[up + ".upsampler.bias"], stride=2)
+        x = x + blocks[-k - 1]
+        for b in range(cfg.n_resblocks):
+            x = att_res_block(sd, f"{up}.body.{b}", x, None)
+    return _conv(sd, "RNet.tail", x)[..., :h, :w] + x_in
+
+
+def kernel_net(sd: SD, x: Tensor, cfg: NetCfg) -> Tensor:
+    """networks/KNet.py:52-59 (+ RB_Layer :37-39, CALayer :23-26)."""
+    h = F.conv2d(x, sd["KNet.head.weight"], None, stride=4, padding=4)
+    for b in range(cfg.dep_K):
+        p = f"KNet.body.{b}.body"
+        f = F.leaky_relu(_conv(sd, p + ".0", h), 0.2)
+        f = _conv(sd, p + ".2", f)
+        y = f.mean(dim=(2, 3), keepdim=True)
+        y = F.leaky_relu(_conv(sd, p + ".3.body.0", y, padding=0), 0.2)
+        y = torch.sigmoid(_conv(sd, p + ".3.body.2", y, padding=0))
+        h = f * y + h
+    out = _conv(sd, "KNet.tail.0", h).mean(dim=(2, 3), keepdim=True)
+    lam12 = torch.exp(torch.clamp(out[:, :2], min=KNET_LOG_MIN, max=KNET_LOG_MAX))
+    rho = torch.tanh(out[:, -1]).unsqueeze(1)
+    return torch.cat((lam12, rho), dim=1)
+
+
+def vir_denoise_forward(sd: SD, x: Tensor, cfg: NetCfg) -> Tuple[Tensor, Tensor]:
+    """networks/VIRNet.py:42-46."""
+    sigma = torch.exp(torch.clamp(dncnn(sd, x, cfg), min=SNET_LOG_MIN, max=SNET_LOG_MAX))
+    extra = sigma.sqrt() if cfg.noise_cond else None
+    mu = att_res_unet(sd, x, extra, cfg)
+    return mu, sigma
+
+
+def vir_sisr_forward(sd: SD, x: Tensor, sf: int, cfg: NetCfg) -> Tuple[Tensor, Tensor, Tensor]:
+    """networks/VIRNet.py:80-97."""
+    sigma = torch.exp(torch.clamp(dncnn(sd, x, cfg), min=SNET_LOG_MIN, max=SNET_LOG_MAX))
+    kinfo = kernel_net(sd, x, cfg)
+    x_up = F.interpolate(x, scale_factor=sf, mode="nearest")
+    h_up, w_up = x_up.shape[-2:]
+    extra = None
+    if cfg.noise_cond or cfg.kernel_cond:
+        parts = []
+        if cfg.kernel_cond:
+            parts.append(kinfo.repeat(1, 1, h_up, w_up))
+        if cfg.noise_cond:
+            if cfg.noise_avg:
+                parts.append(sigma.sqrt().repeat(1, 1, h_up, w_up))
+            else:
+                parts.append(F.interpolate(sigma.sqrt(), scale_factor=sf, mode="nearest"))
+        extra = torch.cat(parts, 1)
+    mu = att_res_unet(sd, x_up, extra, cfg)
+    return mu, kinfo.squeeze(-1).squeeze(-1), sigma
+
+
+# --------------------------------------------------------------------------------------
+# loss restatement (loss/ELBO_simple.py)
+# --------------------------------------------------------------------------------------
+def kl_inverse_gamma_simple(beta_q: Tensor, alpha_p, beta_p: Tensor) -> Tensor:
+    """loss/ELBO_simple.py:12-14."""
+    return (alpha_p * (beta_p / beta_q - 1) + alpha_p * (beta_q.log() - beta_p.log())).mean()
+
+
+def kl_gauss_simple(mu_q: Tensor, mu_p: Tensor, var_p) -> Tensor:
+    """loss/ELBO_simple.py:16."""
+    return 0.5 * ((mu_q - mu_p) ** 2 / var_p).mean()
+
+
+def likelihood(x: Tensor, mu_q: Tensor, var_q, alpha_q, beta_q: Tensor) -> Tensor:
+    """loss/ELBO_simple.py:18-21."""
+    alpha_q = torch.as_tensor(alpha_q, dtype=torch.float32)
+    t = 0.5 * (beta_q.log() - torch.digamma(alpha_q) + alpha_q / beta_q * ((x - mu_q) ** 2 + var_q))
+    return (t + 0.5 * math.log(2 * math.pi)).mean()
+
+
+def elbo_denoising_simple(mu, sigma_est, im_noisy, im_gt, eps2, alpha0, beta0):
+    """loss/ELBO_simple.py:23-53 (single-output form; the list form is unused by the shipped nets)."""
+    kl_gauss = kl_gauss_simple(mu, im_gt, eps2)
+    beta = sigma_est * alpha0
+    kl_ig = kl_inverse_gamma_simple(beta, alpha0 - 1, beta0)
+    lh = likelihood(im_noisy, mu, eps2, alpha0 - 1, beta)
+    return lh + kl_gauss + kl_ig, lh, kl_gauss, kl_ig
+
+
+# --------------------------------------------------------------------------------------
+# one reference training step (train_denoising_syn.py:175-184), used as the CPU baseline
+# --------------------------------------------------------------------------------------
+def clip_grad_norm_(params: List[Tensor], max_norm: float) -> Tensor:
+    """torch.nn.utils.clip_grad_norm_ semantics (L2, eps 1e-6, coefficient clamped to 1)."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(p.grad) for p in params]))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for p in params:
+        p.grad.mul_(coef)
+    return total
+
+
+def denoise_loss_and_grads(sd: SD, cfg: NetCfg, im_noisy, im_gt, sigma_gt, alpha0=24.5, eps2=1e-6):
+    """Forward + ELBO + backward through autograd on the restated graph; returns
+    (loss tuple, mu, sigma, grads dict)."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    mu, sigma = vir_denoise_forward(leaf, im_noisy, cfg)
+    beta0 = alpha0 * sigma_gt
+    loss, lh, klg, klig = elbo_denoising_simple(mu, sigma, im_noisy, im_gt, eps2, alpha0, beta0)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaf.items()}
+    return (loss.detach(), lh.detach(), klg.detach(), klig.detach()), mu.detach(), sigma.detach(), grads

@@ -1,0 +1,90 @@
+"""ctypes binding of libvirnet_sm100.so (the C ABI declared in include/virnet_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
+virnet_b200/csrc``).  There is no fallback: if the library is missing, or a call
+returns an error, we raise — the product path never drops to a CPU / eager
+implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libvirnet_sm100.so"
+
+VK_BF16, VK_TF32 = 0, 1
+VK_CONV3X3_S1, VK_CONV3X3_S2, VK_CONVT2X2_S2, VK_CONV1X1 = 0, 1, 2, 3
+VK_EPI_STD, VK_EPI_NCHW_F32 = 0, 1
+
+
+class VkError(RuntimeError):
+    pass
+
+
+class vk_conv_args(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("kind", C.c_int32),
+        ("x", C.c_void_p),
+        ("n", C.c_int32), ("ih", C.c_int32), ("iw", C.c_int32), ("ldx", C.c_int32),
+        ("w", C.c_void_p),
+        ("wrows", C.c_int32),
+        ("bias", C.c_void_p),
+        ("cout", C.c_int32), ("ldo", C.c_int32), ("epi", C.c_int32),
+        ("resid", C.c_void_p), ("mask", C.c_void_p), ("out1", C.c_void_p), ("out2", C.c_void_p),
+        ("alpha", C.c_float),
+        ("round_out2", C.c_int32), ("act_expclamp", C.c_int32),
+        ("clamp_lo", C.c_float), ("clamp_hi", C.c_float),
+        ("crop_h", C.c_int32), ("crop_w", C.c_int32),
+        ("force_tiles_per_cta", C.c_int32), ("force_chunk_bytes", C.c_int32),
+        ("force_stages", C.c_int32), ("force_tw", C.c_int32),
+    ]
+
+
+_lib = None
+
+# every symbol include/virnet_b200.h declares: (name, restype, argtypes)
+_SIGNATURES = {
+    "vk_conv_igemm": (C.c_int, [C.POINTER(vk_conv_args), C.c_void_p]),
+    "vk_sizeof_conv_args": (C.c_uint32, []),
+    "vk_version": (C.c_char_p, []),
+    "vk_launch_count": (C.c_uint64, []),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (once).  Raises VkError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VkError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C virnet_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vk_sizeof_conv_args() != C.sizeof(vk_conv_args):
+        raise VkError("vk_conv_args layout mismatch between lib.py and the built library; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code == 0:
+        return
+    if code < 0:
+        names = {-1: "VK_E_BADARG", -2: "VK_E_UNSUPPORTED", -3: "VK_E_NODRIVER"}
+        raise VkError(f"{what}: {names.get(code, code)}")
+    raise VkError(f"{what}: cudaError {code}")
+
+
+def launch_count() -> int:
+    return int(load().vk_launch_count())
