@@ -41,6 +41,9 @@ extern "C" {
 #define VK_CONV3X3_S2 1 /* nn.Conv2d(k=3,s=2,p=1)   AttResUNet.py:67 (DownBlock.downsampler) */
 #define VK_CONVT2X2_S2 2 /* nn.ConvTranspose2d(k=2,s=2) AttResUNet.py:80 (UpBlock.upsampler): 1x1 GEMM + depth-to-space */
 #define VK_CONV1X1 3    /* nn.Conv2d(k=1)          AttResUNet.py:18-25 (AttLayer), KNet.py:17-19 (CALayer) */
+#define VK_CONV2X2_S2 4 /* input gradient of VK_CONVT2X2_S2: a 2x2 stride-2 conv over the upsampled grid */
+#define VK_CONV3X3_S2_DGRAD 5 /* input gradient of VK_CONV3X3_S2: x = coarse-grid dY, output on the fine
+                                 grid (out_h x out_w), computed as 4 output-parity phases (4 launches) */
 
 /* epilogues */
 #define VK_EPI_STD 0      /* NHWC: v=acc+bias; v*=lrelu'(mask); v+=resid; out1=v; out2=lrelu(v) */
@@ -55,7 +58,7 @@ typedef struct vk_conv_args {
   /* packed weights [taps][wrows][ldx] (K-major), wrows multiple of 16 */
   const void* w;
   int32_t wrows;
-  const float* bias; /* [wrows] or NULL */
+  const float* bias; /* [cout] fp32 (for CONVT: shared by the 4 quadrants) or NULL */
   /* output: EPI_STD NHWC [n][oh][ow][ldo] (oh,ow follow from kind);
    *         EPI_NCHW_F32 [n][cout][crop_h][crop_w] fp32 */
   int32_t cout; /* valid output channels (per quadrant for CONVT) */
@@ -70,6 +73,7 @@ typedef struct vk_conv_args {
   int32_t act_expclamp;
   float clamp_lo, clamp_hi;
   int32_t crop_h, crop_w;
+  int32_t out_h, out_w; /* VK_CONV3X3_S2_DGRAD only: fine-grid size (the forward conv's input size) */
   /* tuning overrides, 0 = automatic */
   int32_t force_tiles_per_cta;
   int32_t force_chunk_bytes;
@@ -81,6 +85,104 @@ typedef struct vk_conv_args {
  * Replaces F.conv2d / F.conv_transpose2d and their input-gradient (dgrad is
  * the same kernel over rotated, transposed packed weights). */
 int vk_conv_igemm(const vk_conv_args* args, void* stream);
+
+typedef struct vk_wgrad_args {
+  int32_t dtype; /* VK_BF16 | VK_TF32 */
+  int32_t kind;  /* geometry of the FORWARD op whose weight gradient is taken */
+  /* M operand: NHWC [n][gh][gw][lda], un-shifted; its pixel grid is the GEMM K dimension.
+   *   conv  : dY (gradient w.r.t. the conv output), m_valid = Cout
+   *   convT : X  (forward input),                  m_valid = Cin           */
+  const void* a;
+  int32_t n, gh, gw, lda, m_valid;
+  /* N operand: NHWC [n][bh][bw][ldb], loaded shifted / strided per tap.
+   *   conv  : X (forward input),  n_valid = Cin
+   *   convT : dY (upsampled grid), n_valid = Cout                          */
+  const void* b;
+  int32_t bh, bw, ldb, n_valid;
+  float* dw;    /* fp32 [taps][m_valid][n_valid], ACCUMULATED into (zero it first) */
+  float* dbias; /* fp32 [m_valid] accumulated column sums of the M operand, or NULL */
+  int32_t force_ksplit;
+  int32_t force_k_rows;
+  int32_t force_stages;
+} vk_wgrad_args;
+
+/* Weight (and bias) gradient: autograd of F.conv2d / F.conv_transpose2d w.r.t.
+ * weight and bias (train_denoising_syn.py:179 loss.backward()). */
+int vk_conv_wgrad(const vk_wgrad_args* args, void* stream);
+
+/* dW workspace [taps][M][N] -> parameter layout [M][N][taps] (OIHW for Conv2d,
+ * [Cin][Cout][kh][kw] for ConvTranspose2d); accumulate != 0 adds into `out`. */
+int vk_wgrad_unpack(const float* ws, float* out, int32_t taps, int32_t m, int32_t n, int32_t accumulate,
+                    void* stream);
+
+uint32_t vk_sizeof_wgrad_args(void);
+
+/* ---- HBM-bound kernels ------------------------------------------------- */
+
+/* NCHW fp32 image (+ conditioning channels) -> NHWC `dtype`, reflect-padded bottom/right
+ * to (hp, wp), nearest-upsampled by sf, channel-padded with zeros to ld.
+ * Replaces util_net.pad_input (utils/util_net.py:20-25), torch.cat([x, extra]) (AttResUNet.py:152-153),
+ * sigma.sqrt() (VIRNet.py:44,92-94), F.interpolate(nearest) and .repeat (VIRNet.py:83-95).
+ * extra: NCHW fp32 map [n][e][eh][ew] (extra_is_map=1, sampled at (y/esf, x/esf)) or per-sample
+ * constants [n][e]; bit i of extra_sqrt_mask applies sqrt to extra channel i. */
+int vk_pack_input(int32_t dtype, const float* img, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
+                  const float* extra, int32_t e, int32_t extra_is_map, int32_t extra_sqrt_mask, int32_t eh,
+                  int32_t ew, int32_t esf, void* out, int32_t hp, int32_t wp, int32_t ld, void* stream);
+
+/* NCHW fp32 gradient [n][c][h][w] -> NHWC `dtype` [n][hp][wp][ld], zero outside the crop
+ * (autograd of `tail(x)[..., :h, :w]`, AttResUNet.py:173). */
+int vk_pack_grad(int32_t dtype, const float* g, int32_t n, int32_t c, int32_t h, int32_t w, void* out, int32_t hp,
+                 int32_t wp, int32_t ld, void* stream);
+
+/* Chain rule through sigma = exp(clamp(l, log_lo, log_hi)), s = sqrt(sigma) and the reflect
+ * padding of s (VIRNet.py:43-44, util_net.py:20-25):
+ *   g_l = [in range] * sigma * (g_sigma + fold(g_in[..., chan]) / (2 sqrt(sigma)))
+ * sigma, g_sigma: NCHW fp32 [n][sc][h][w] (g_sigma may be NULL); g_in: NHWC `dtype`
+ * [n][hp][wp][ld_in] or NULL; out: NHWC `dtype` [n][h][w][ld]. */
+int vk_sigma_head_bwd(int32_t dtype, const float* sigma, const float* g_sigma, const void* g_in, int32_t ld_in,
+                      int32_t chan, int32_t hp, int32_t wp, void* out, int32_t ld, int32_t n, int32_t sc,
+                      int32_t h, int32_t w, float log_lo, float log_hi, void* stream);
+
+/* elbo_denoising_simple (loss/ELBO_simple.py:23-53), forward and gradient in one pass.
+ * All tensors NCHW fp32; sigma / beta0 have sc (1 or c) channels; the prior parameter used is
+ * beta0[i] * beta0_scale (pass sigma_gt and alpha0 to fuse train_denoising_syn.py:172).  out4 = {loss, lh, kl_gauss,
+ * kl_Igamma}; d_mu / d_sigma (may be NULL) receive grad_scale * dloss/d(.).  acc3: 3 doubles of
+ * scratch.  digamma_alpha0_m1 = digamma(alpha0 - 1), computed by the caller. */
+int vk_elbo_denoise(const float* mu, const float* sigma, const float* noisy, const float* gt, const float* beta0,
+                    float beta0_scale, int32_t n, int32_t c, int32_t sc, int32_t h, int32_t w, float eps2, float alpha0,
+                    float digamma_alpha0_m1, float grad_scale, float* d_mu, float* d_sigma, double* acc3,
+                    float* out4, void* stream);
+
+/* One launch packs every layer's fp32 parameters into the K-major GEMM operands.
+ * descs_dev: device array of vk_pack_desc; max_elems = largest dst element count. */
+typedef struct vk_pack_desc {
+  const float* src; /* parameter [dim0][dim1][taps] fp32 */
+  void* dst;        /* [dst_taps][rows][ld] `dtype` */
+  int32_t dim0, dim1, taps;
+  int32_t rows, ld;
+  int32_t dst_taps;
+  int32_t mode; /* 0 conv fprop, 1 conv dgrad (rotated, transposed), 2 convT fprop, 3 convT dgrad,
+                   4 stride-2 conv dgrad (transposed, not rotated) */
+  int32_t pad_;
+} vk_pack_desc;
+int vk_pack_weights(int32_t dtype, const void* descs_dev, int32_t ndesc, int64_t max_elems, int32_t round_tf32,
+                    void* stream);
+
+/* out[c] += sum over pixels of x[p][c] (NHWC `dtype`, pitch ld): ConvTranspose2d bias gradient. */
+int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_t ld, int32_t c, float* out, void* stream);
+
+/* Per-sub-network gradient L2 norm -> clip coefficient -> Adam update over flat fp32 buffers, no
+ * host synchronisation (train_denoising_syn.py:182-184).  groups_dev: device array of
+ * vk_adam_group; sq_ws: ngroups doubles of scratch; grads are first multiplied by grad_scale
+ * (1/world_size after a sum all-reduce); norms_out (may be NULL) receives the pre-clip norms. */
+typedef struct vk_adam_group {
+  int64_t begin, end; /* element range in the flat buffers */
+  float max_norm;
+  int32_t pad_;
+} vk_adam_group;
+int vk_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const void* groups_dev,
+                      int32_t ngroups, int64_t max_group_elems, double* sq_ws, float grad_scale, float lr,
+                      float beta1, float beta2, float eps, int32_t step, float* norms_out, void* stream);
 
 /* sizeof(vk_conv_args) as compiled into the library (binding self-check). */
 uint32_t vk_sizeof_conv_args(void);

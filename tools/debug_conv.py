@@ -34,6 +34,10 @@ CASES = [
     dict(name="conv3s2_bf16_ragged", dt="bf16", kind="3x3s2", cin=96, cout=192, n=1, h=38, w=50),
     dict(name="convT_bf16_192_96", dt="bf16", kind="convT", cin=192, cout=96, n=2, h=16, w=16, epi="resid"),
     dict(name="convT_tf32_288_192", dt="tf32", kind="convT", cin=288, cout=192, n=1, h=9, w=11),
+    dict(name="conv2x2s2_bf16_96_192", dt="bf16", kind="2x2s2", cin=96, cout=192, n=2, h=32, w=32),
+    dict(name="conv2x2s2_tf32_192_288", dt="tf32", kind="2x2s2", cin=192, cout=288, n=1, h=20, w=24),
+    dict(name="s2dgrad_bf16_192_96", dt="bf16", kind="3x3s2dgrad", cin=192, cout=96, n=2, h=32, w=32, epi="resid"),
+    dict(name="s2dgrad_tf32_odd", dt="tf32", kind="3x3s2dgrad", cin=192, cout=96, n=1, h=37, w=51),
     dict(name="conv3_bf16_c96_128x128_b4", dt="bf16", kind="3x3", cin=96, cout=96, n=4, h=128, w=128, bench=True),
     dict(name="conv3_bf16_c192_64x64_b4", dt="bf16", kind="3x3", cin=192, cout=192, n=4, h=64, w=64, bench=True),
     dict(name="conv3_bf16_c288_32x32_b4", dt="bf16", kind="3x3", cin=288, cout=288, n=4, h=32, w=32, bench=True),
@@ -75,17 +79,33 @@ def run_case(idx: int) -> int:
         wp = ops.pack_conv_weight(wt, dtype, ldx)
         vk_kind = {"3x3": ops.VK_CONV3X3_S1, "3x3s2": ops.VK_CONV3X3_S2, "1x1": ops.VK_CONV1X1}[kind]
         wrows = wp.shape[1]
+    elif kind == "2x2s2":
+        wt = q(torch.randn(cout, cin, 2, 2, device=dev, generator=g) / (cin * 4) ** 0.5)
+        ref = F.conv2d(x, wt, bias, stride=2)
+        wp = ops.pack_conv_weight(wt, dtype, ldx)
+        vk_kind = ops.VK_CONV2X2_S2
+        wrows = wp.shape[1]
+    elif kind == "3x3s2dgrad":
+        # x plays dY of a stride-2 conv (cout_fwd = cin here) whose input had `cout` channels and size (h, w)
+        wt = q(torch.randn(cin, cout, 3, 3, device=dev, generator=g) / (cin * 9) ** 0.5)   # [Co_f, Ci_f, 3, 3]
+        fine = torch.zeros(n, cout, h, w, device=dev, requires_grad=True)
+        yf = F.conv2d(fine, wt, None, stride=2, padding=1)
+        x = q(torch.randn(yf.shape, device=dev, generator=g))
+        yf.backward(x)
+        ref = fine.grad + bias.view(1, -1, 1, 1)
+        x_nhwc = ops.to_nhwc(x, dtype)
+        ldx = x_nhwc.shape[-1]
+        # packed [t][ci_f][co_f] = W[co_f][ci_f][t]  (transposed, not rotated)
+        wp = ops.pack_conv_weight(wt.permute(1, 0, 2, 3).contiguous(), dtype, ldx)
+        vk_kind = ops.VK_CONV3X3_S2_DGRAD
+        wrows = wp.shape[1]
     else:
         wt = q(torch.randn(cin, cout, 2, 2, device=dev, generator=g) / (cin) ** 0.5)
         ref = F.conv_transpose2d(x, wt, bias, stride=2)
         wp = ops.pack_convT_weight(wt, dtype, ldx)
         vk_kind = ops.VK_CONVT2X2_S2
         wrows = wp.shape[1]
-    bias_p = torch.zeros(wrows, device=dev)
-    if kind == "convT":
-        bias_p[:] = bias.repeat(4)
-    else:
-        bias_p[:cout] = bias
+    bias_p = bias.clone()
     oh, ow = ref.shape[-2:]
     ldo = ops.chan_pad(cout, dtype)
     tdt = ops.TORCH_DTYPE[dtype]
@@ -109,7 +129,7 @@ def run_case(idx: int) -> int:
         use_mask = epi == "full"
         ops.conv_igemm(x_nhwc, wp, dtype=dtype, kind=vk_kind, cout=cout, bias=bias_p, ldo=ldo,
                        resid=ops.to_nhwc(resid, dtype, ldo), mask=ops.to_nhwc(maskt, dtype, ldo) if use_mask else None,
-                       out1=o1, out2=o2, alpha=0.2, tune=tune)
+                       out1=o1, out2=o2, alpha=0.2, tune=tune, out_hw=(oh, ow))
         v = ref
         if use_mask:
             v = v * torch.where(maskt > 0, 1.0, 0.2)
@@ -118,7 +138,7 @@ def run_case(idx: int) -> int:
         results["out2"] = (ops.from_nhwc(o2, cout), F.leaky_relu(v, 0.2))
     else:
         o1 = torch.full((n, oh, ow, ldo), float("nan"), device=dev, dtype=tdt)
-        ops.conv_igemm(x_nhwc, wp, dtype=dtype, kind=vk_kind, cout=cout, bias=bias_p, ldo=ldo, out1=o1, tune=tune)
+        ops.conv_igemm(x_nhwc, wp, dtype=dtype, kind=vk_kind, cout=cout, bias=bias_p, ldo=ldo, out1=o1, tune=tune, out_hw=(oh, ow))
         results["out1"] = (ops.from_nhwc(o1, cout), ref)
     torch.cuda.synchronize()
 

@@ -72,7 +72,8 @@ int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* ptr, cons
   }
   EncodeFn enc = get_encode_fn();
   if (enc == nullptr) return VK_E_NODRIVER;
-  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+  CUtensorMapSwizzle sw = swizzle_bytes == 129  ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                          : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
@@ -146,8 +147,21 @@ constexpr int kSmemBudget = 200 * 1024;   // dynamic smem we allow one CTA (<= 2
 
 using namespace vk;
 
+static int conv_igemm_impl(const vk_conv_args* a, void* stream, int phase);
+
 extern "C" int vk_conv_igemm(const vk_conv_args* a, void* stream) {
   if (a == nullptr || a->x == nullptr || a->w == nullptr) return VK_E_BADARG;
+  if (a->kind == VK_CONV3X3_S2_DGRAD) {
+    for (int phase = 0; phase < 4; ++phase) {
+      int r = conv_igemm_impl(a, stream, phase);
+      if (r) return r;
+    }
+    return 0;
+  }
+  return conv_igemm_impl(a, stream, 0);
+}
+
+static int conv_igemm_impl(const vk_conv_args* a, void* stream, int phase) {
   if (a->dtype != VK_BF16 && a->dtype != VK_TF32) return VK_E_BADARG;
   const int esize = a->dtype == VK_BF16 ? 2 : 4;
   const int chan_align = 32 / esize;                       // one UMMA K step = 32 bytes
@@ -163,19 +177,36 @@ extern "C" int vk_conv_igemm(const vk_conv_args* a, void* stream) {
     case VK_CONV3X3_S2: prm.oh = (a->ih + 1) / 2, prm.ow = (a->iw + 1) / 2, prm.a_stride = 2; break;
     case VK_CONVT2X2_S2: prm.oh = a->ih, prm.ow = a->iw, prm.a_stride = 1, taps = 1, us = 2; break;
     case VK_CONV1X1: prm.oh = a->ih, prm.ow = a->iw, prm.a_stride = 1, taps = 1; break;
+    case VK_CONV2X2_S2: prm.oh = a->ih / 2, prm.ow = a->iw / 2, prm.a_stride = 2, taps = 4; break;
+    case VK_CONV3X3_S2_DGRAD: {
+      // phase (py, px): fine pixels y = 2u + py, x = 2v + px; the M tiles walk (u, v)
+      if (a->out_h <= 0 || a->out_w <= 0 || (a->out_h + 1) / 2 != a->ih || (a->out_w + 1) / 2 != a->iw)
+        return VK_E_BADARG;
+      const int py = phase >> 1, px = phase & 1;
+      prm.oh = (a->out_h - py + 1) / 2, prm.ow = (a->out_w - px + 1) / 2;
+      prm.a_stride = 1, us = 2;
+      if (prm.oh <= 0 || prm.ow <= 0) return 0;   // empty phase (1-pixel-wide images)
+      break;
+    }
     default: return VK_E_BADARG;
   }
   prm.n_img = a->n;
   prm.us = us;
   prm.cout = a->cout;
-  prm.cq = (us == 2) ? a->wrows / 4 : a->wrows;
-  if (us == 2 && (a->wrows % 64 || prm.cq < a->cout)) return VK_E_BADARG;
-  if (us == 1 && a->wrows < a->cout) return VK_E_BADARG;
+  const bool is_convT = a->kind == VK_CONVT2X2_S2;
+  prm.cq = is_convT ? a->wrows / 4 : a->wrows;
+  prm.quad_base = a->kind == VK_CONV3X3_S2_DGRAD ? phase : 0;
+  prm.out_h = a->kind == VK_CONV3X3_S2_DGRAD ? a->out_h : prm.oh * us;
+  prm.out_w = a->kind == VK_CONV3X3_S2_DGRAD ? a->out_w : prm.ow * us;
+  if (is_convT && (a->wrows % 64 || prm.cq < a->cout)) return VK_E_BADARG;
+  if (!is_convT && a->wrows < a->cout) return VK_E_BADARG;
+  if (a->kind == VK_CONV3X3_S2_DGRAD || a->kind == VK_CONV2X2_S2) taps = a->kind == VK_CONV2X2_S2 ? 4 : 9;
   if (a->epi == VK_EPI_STD) {
     if (a->ldo <= 0 || a->ldo % (16 / esize)) return VK_E_BADARG;   // 16-byte vector stores
     if (a->ldo < a->cout) return VK_E_BADARG;
   } else if (a->epi == VK_EPI_NCHW_F32) {
     if (us != 1 || a->out1 == nullptr) return VK_E_BADARG;
+    prm.out_h = prm.oh, prm.out_w = prm.ow;
   } else {
     return VK_E_BADARG;
   }
@@ -187,7 +218,7 @@ extern "C" int vk_conv_igemm(const vk_conv_args* a, void* stream) {
   for (int i = 0; i < 5; ++i) {
     const int tw = cand_tw[i], th = 128 / tw;
     if (a->force_tw && a->force_tw != tw) continue;
-    if (a->kind == VK_CONV3X3_S2 && tw * 2 > 256) continue;         // TMA box limit with elementStrides
+    if (prm.a_stride == 2 && tw * 2 > 256) continue;                // TMA box limit with elementStrides
     const long long tiles = (long long)((prm.ow + tw - 1) / tw) * ((prm.oh + th - 1) / th);
     // halo overhead of the slab loads: (th+2)/th rows fetched per tile row
     const long long cost = tiles * (a->kind == VK_CONV3X3_S1 ? (th + 2) * tw : th * tw);
@@ -219,6 +250,26 @@ extern "C" int vk_conv_igemm(const vk_conv_args* a, void* stream) {
         ConvLoad& l = prm.loads[r * 3 + s];
         l.dx = s - 1, l.dy = r - 1, l.ntaps = 1, l.tap[0] = r * 3 + s, l.rowoff[0] = 0;
       }
+  } else if (a->kind == VK_CONV2X2_S2) {
+    prm.n_loads = 4;
+    prm.b_taps = 1;
+    for (int t = 0; t < 4; ++t) {
+      ConvLoad& l = prm.loads[t];
+      l.dx = t & 1, l.dy = t >> 1, l.ntaps = 1, l.tap[0] = t, l.rowoff[0] = 0;
+    }
+  } else if (a->kind == VK_CONV3X3_S2_DGRAD) {
+    // fine row y = 2*oy - 1 + r: even rows see r = 1 (oy = u); odd rows r = 0 (oy = u + 1) and r = 2 (oy = u)
+    const int py = phase >> 1, px = phase & 1;
+    const int nr = py ? 2 : 1, ns = px ? 2 : 1;
+    const int rr[2] = {py ? 0 : 1, 2}, dyv[2] = {py ? 1 : 0, 0};
+    const int ss[2] = {px ? 0 : 1, 2}, dxv[2] = {px ? 1 : 0, 0};
+    prm.n_loads = 0;
+    prm.b_taps = 1;
+    for (int i = 0; i < nr; ++i)
+      for (int j = 0; j < ns; ++j) {
+        ConvLoad& l = prm.loads[prm.n_loads++];
+        l.dx = dxv[j], l.dy = dyv[i], l.ntaps = 1, l.tap[0] = rr[i] * 3 + ss[j], l.rowoff[0] = 0;
+      }
   } else {
     prm.n_loads = 1;
     prm.b_taps = 1;
@@ -229,7 +280,7 @@ extern "C" int vk_conv_igemm(const vk_conv_args* a, void* stream) {
 
   // ---- N split ----
   int n_cta;
-  if (us == 2) {
+  if (is_convT) {
     n_cta = prm.cq <= 256 ? prm.cq : 0;
     if (n_cta == 0) return VK_E_UNSUPPORTED;
   } else {

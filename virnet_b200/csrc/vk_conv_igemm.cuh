@@ -55,13 +55,15 @@ struct ConvIgemmParams {
   int stages;
   // epilogue
   int epi;
-  int us;                     // depth-to-space factor (1, or 2 for ConvT)
+  int us;                     // depth-to-space factor (1, or 2 for ConvT / stride-2 dgrad phases)
+  int quad_base;              // sub-pixel index added to the column-derived quadrant
+  int out_h, out_w;           // spatial dims of the EPI_STD output tensors
   int cq;                     // channels per sub-pixel quadrant (== cout when us == 1)
   int cout;                   // valid output channels (per quadrant)
   int ldo;                    // channel pitch of out1/out2/resid/mask (elements)
   float alpha;                // LeakyReLU slope for out2 and for the mask
   int round_out2;             // tf32 mode: round out2 to tf32 (RN) when storing
-  const float* bias;          // [n total] fp32 or null
+  const float* bias;          // [cout] fp32 (the parameter itself) or null
   const void* resid;          // DT NHWC (EPI_STD) / fp32 NCHW (EPI_NCHW_F32) or null
   const void* mask;           // DT NHWC: multiply by (mask>0 ? 1 : alpha), or null
   void* out1;                 // or null
@@ -178,7 +180,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tmem_relinquish();
   }
   if (warp >= 2 && prm.bias != nullptr) {
-    for (int i = threadIdx.x - 64; i < prm.n_cta; i += 128) bias_s[i] = __ldg(prm.bias + n0 + i);
+    // bias is the raw parameter [cout]; ConvT repeats it for each of the 4 sub-pixel quadrants
+    for (int i = threadIdx.x - 64; i < prm.n_cta; i += 128) {
+      const int c = (n0 + i) % prm.cq;
+      bias_s[i] = c < prm.cout ? __ldg(prm.bias + c) : 0.f;
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -276,15 +282,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int i = 0; i < 16; ++i) v[i] += bias_s[jc + i];
         }
         const int cg = n0 + jc;                 // global GEMM column of v[0]
-        const int quad = cg / prm.cq;
-        const int co = cg - quad * prm.cq;      // channel within the quadrant
-        const int nch = (pix_ok && co < prm.cout) ? min(16, prm.cout - co) : 0;
+        const int quad_c = cg / prm.cq;
+        const int co = cg - quad_c * prm.cq;    // channel within the quadrant
+        const int quad = quad_c + prm.quad_base;
+        const bool out_ok = pix_ok && (prm.epi != EPI_STD ||
+                                       ((oy * us + quad / us) < prm.out_h && (ox * us + quad % us) < prm.out_w));
+        const int nch = (out_ok && co < prm.cout) ? min(16, prm.cout - co) : 0;
         if (nch == 0) {
           // nothing to store for this thread (ragged tile edge / channel padding)
         } else if (prm.epi == EPI_STD) {
           const int qy = quad / us, qx = quad - qy * us;
-          const long long opix =
-              (static_cast<long long>(img) * (prm.oh * us) + (oy * us + qy)) * (prm.ow * us) + (ox * us + qx);
+          const int yy = oy * us + qy, xx = ox * us + qx;
+          const long long opix = (static_cast<long long>(img) * prm.out_h + yy) * prm.out_w + xx;
           const long long off = opix * prm.ldo + co;
           DT* o1 = reinterpret_cast<DT*>(prm.out1);
           DT* o2 = reinterpret_cast<DT*>(prm.out2);

@@ -1,0 +1,476 @@
+// vk_elementwise.cu — the HBM-bound kernels of the VIRNet hot path (sm_100a):
+// layout packing at the NCHW-fp32 boundary, the fused ELBO loss (forward + gradient in
+// one pass), the variance-head chain rule, weight packing, gradient-norm + clip + Adam.
+// All are pure streaming kernels: coalesced, vectorised where the layout allows, grids
+// sized in multiples of the SM count.
+#include <algorithm>
+#include <cstdio>
+
+#include "../../include/virnet_b200.h"
+#include "vk_common.cuh"
+#include "vk_host.h"
+
+namespace vk {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {   // F.pad(mode='reflect') on the far side only
+  return i < n ? i : 2 * (n - 1) - i;
+}
+template <typename DT>
+__device__ __forceinline__ DT cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------
+// pack_input: NCHW fp32 image (+ conditioning maps) -> NHWC DT, reflect-padded
+//   out[n][y][x][c] = c <  C      : img[n][c][ry/sf][rx/sf]
+//                     c <  C + E  : f(extra)          (map, or per-sample constant)
+//                     else        : 0
+// (utils/util_net.py:20-25 pad_input, networks/AttResUNet.py:147-153 cat,
+//  networks/VIRNet.py:44 sqrt, :83-95 nearest upsample / repeat)
+// ---------------------------------------------------------------------------
+template <typename DT>
+__global__ void pack_input_kernel(const float* __restrict__ img, int C, int h, int w, int sf,
+                                  const float* __restrict__ extra, int E, int extra_is_map, int extra_sqrt,
+                                  int eh, int ew, int esf, DT* __restrict__ out, int N, int Hp, int Wp, int ld) {
+  const long long total = static_cast<long long>(N) * Hp * Wp;
+  const int H = h * sf, W = w * sf;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = int(p % Wp);
+    const int y = int((p / Wp) % Hp);
+    const int n = int(p / (static_cast<long long>(Wp) * Hp));
+    const int ry = reflect_idx(y, H), rx = reflect_idx(x, W);
+    DT* o = out + p * ld;
+    int c = 0;
+    for (; c < C; ++c) o[c] = cvt_out<DT>(__ldg(img + ((static_cast<long long>(n) * C + c) * h + ry / sf) * w + rx / sf));
+    for (int e = 0; e < E; ++e, ++c) {
+      float v;
+      if (extra_is_map)
+        v = __ldg(extra + ((static_cast<long long>(n) * E + e) * eh + ry / esf) * ew + rx / esf);
+      else
+        v = __ldg(extra + static_cast<long long>(n) * E + e);
+      if (extra_sqrt & (1 << e)) v = sqrtf(v);
+      o[c] = cvt_out<DT>(v);
+    }
+    for (; c < ld; ++c) o[c] = cvt_out<DT>(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pack_grad: NCHW fp32 [N][C][h][w] -> NHWC DT [N][Hp][Wp][ld], zero outside (crop backward)
+// ---------------------------------------------------------------------------
+template <typename DT>
+__global__ void pack_grad_kernel(const float* __restrict__ g, int C, int h, int w, DT* __restrict__ out, int N,
+                                 int Hp, int Wp, int ld) {
+  const long long total = static_cast<long long>(N) * Hp * Wp;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = int(p % Wp);
+    const int y = int((p / Wp) % Hp);
+    const int n = int(p / (static_cast<long long>(Wp) * Hp));
+    const bool in = (y < h) && (x < w);
+    DT* o = out + p * ld;
+    for (int c = 0; c < ld; ++c) {
+      float v = 0.f;
+      if (in && c < C) v = __ldg(g + ((static_cast<long long>(n) * C + c) * h + y) * w + x);
+      o[c] = cvt_out<DT>(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// sigma_head_bwd: chain rule through  sigma = exp(clamp(l)),  s = sqrt(sigma)
+//   g_l = [lo <= l <= hi] * sigma * (g_sigma + g_s / (2 sqrt(sigma)))
+// g_s arrives as channel `chan` of the head-conv input gradient (NHWC DT, padded grid);
+// the reflect padding folds the mirrored rows/cols back onto their source pixel.
+// Output: NHWC DT [N][h][w][ld], channels [0, SC) hold g_l, the rest zero.
+// (networks/VIRNet.py:43-44; autograd of torch.exp/clamp/sqrt/F.pad)
+// ---------------------------------------------------------------------------
+template <typename DT>
+__global__ void sigma_head_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ g_sigma,
+                                      const DT* __restrict__ g_in, int ld_in, int chan, int Hp, int Wp,
+                                      DT* __restrict__ out, int ld, int N, int SC, int h, int w, float sig_lo,
+                                      float sig_hi) {
+  const long long total = static_cast<long long>(N) * h * w;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = int(p % w);
+    const int y = int((p / w) % h);
+    const int n = int(p / (static_cast<long long>(w) * h));
+    // mirrored partners of (y, x) inside the padded grid
+    const int y2 = 2 * (h - 1) - y, x2 = 2 * (w - 1) - x;
+    const bool my = (y2 >= h) && (y2 < Hp), mx = (x2 >= w) && (x2 < Wp);
+    DT* o = out + p * ld;
+    for (int c = 0; c < ld; ++c) {
+      float v = 0.f;
+      if (c < SC) {
+        const long long si = ((static_cast<long long>(n) * SC + c) * h + y) * w + x;
+        const float sg = __ldg(sigma + si);
+        float gs = 0.f;
+        if (g_in != nullptr) {
+          const DT* gi = g_in + static_cast<long long>(n) * Hp * Wp * ld_in + chan + c;
+          gs = float(gi[(static_cast<long long>(y) * Wp + x) * ld_in]);
+          if (my) gs += float(gi[(static_cast<long long>(y2) * Wp + x) * ld_in]);
+          if (mx) gs += float(gi[(static_cast<long long>(y) * Wp + x2) * ld_in]);
+          if (my && mx) gs += float(gi[(static_cast<long long>(y2) * Wp + x2) * ld_in]);
+        }
+        const float gsig = g_sigma != nullptr ? __ldg(g_sigma + si) : 0.f;
+        const bool in_range = (sg > sig_lo) && (sg < sig_hi);
+        v = in_range ? sg * (gsig + gs * 0.5f * rsqrtf(sg)) : 0.f;
+      }
+      o[c] = cvt_out<DT>(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fused ELBO (loss/ELBO_simple.py:12-53): one pass computes the three means and
+// the gradients w.r.t. mu and sigma.  acc[0..2] (double) += lh, kl_gauss, kl_ig sums.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void elbo_denoise_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
+                                    const float* __restrict__ noisy, const float* __restrict__ gt,
+                                    const float* __restrict__ beta0, float beta0_scale, int N, int C, int SC,
+                                    long long HW, float eps2, float alpha0, float digamma_am1, float gscale,
+                                    float* __restrict__ d_mu, float* __restrict__ d_sigma,
+                                    double* __restrict__ acc) {
+  // one thread per (n, pixel); loops over the C image channels so the 1-channel sigma
+  // gradient is produced without atomics
+  const long long total = static_cast<long long>(N) * HW;
+  const float am1 = alpha0 - 1.f;
+  const float inv_m3 = 1.f / (static_cast<float>(N) * C * HW);
+  const float inv_ms = 1.f / (static_cast<float>(N) * SC * HW);
+  const float half_log2pi = 0.9189385332046727f;
+  float s_lh = 0.f, s_kg = 0.f, s_ig = 0.f;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / HW, px = p - n * HW;
+    float dsig_acc = 0.f, d_ig = 0.f;
+    float inv_beta = 0.f, lbeta = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const long long i3 = (n * C + c) * HW + px;
+      const long long i1 = (n * SC + (SC == 1 ? 0 : c)) * HW + px;
+      if (SC != 1 || c == 0) {
+        const float sg = __ldg(sigma + i1);
+        const float b0 = __ldg(beta0 + i1) * beta0_scale;
+        const float beta = sg * alpha0;
+        inv_beta = 1.f / beta;
+        lbeta = logf(beta);
+        s_ig += am1 * (b0 * inv_beta - 1.f) + am1 * (lbeta - logf(b0));
+        d_ig = inv_ms * am1 * (inv_beta - b0 * inv_beta * inv_beta) * alpha0;
+        dsig_acc = d_ig;
+      }
+      const float m = __ldg(mu + i3), y = __ldg(noisy + i3), g = __ldg(gt + i3);
+      const float e = m - g, r = y - m;
+      s_kg += 0.5f * e * e / eps2;
+      const float q = r * r + eps2;
+      s_lh += 0.5f * (lbeta - digamma_am1 + am1 * inv_beta * q) + half_log2pi;
+      if (d_mu != nullptr) d_mu[i3] = gscale * inv_m3 * (e / eps2 - am1 * inv_beta * r);
+      const float dl = inv_m3 * 0.5f * (inv_beta - am1 * inv_beta * inv_beta * q) * alpha0;
+      if (SC == 1) {
+        dsig_acc += dl;
+      } else if (d_sigma != nullptr) {
+        d_sigma[i1] = gscale * (d_ig + dl);
+      }
+    }
+    if (SC == 1 && d_sigma != nullptr) d_sigma[n * HW + px] = gscale * dsig_acc;
+  }
+  __shared__ float red[3][32];
+  s_lh = warp_sum(s_lh), s_kg = warp_sum(s_kg), s_ig = warp_sum(s_ig);
+  const int wid = threadIdx.x >> 5, lid = threadIdx.x & 31;
+  if (lid == 0) red[0][wid] = s_lh, red[1][wid] = s_kg, red[2][wid] = s_ig;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    float a = lid < nw ? red[0][lid] : 0.f, b = lid < nw ? red[1][lid] : 0.f, c = lid < nw ? red[2][lid] : 0.f;
+    a = warp_sum(a), b = warp_sum(b), c = warp_sum(c);
+    if (lid == 0) {
+      atomicAdd(acc + 0, static_cast<double>(a));
+      atomicAdd(acc + 1, static_cast<double>(b));
+      atomicAdd(acc + 2, static_cast<double>(c));
+    }
+  }
+}
+
+__global__ void elbo_finalize_kernel(const double* __restrict__ acc, double m3, double ms, float* __restrict__ out) {
+  const double lh = acc[0] / m3, kg = acc[1] / m3, ig = acc[2] / ms;
+  out[0] = static_cast<float>(lh + kg + ig);
+  out[1] = static_cast<float>(lh);
+  out[2] = static_cast<float>(kg);
+  out[3] = static_cast<float>(ig);
+}
+
+// ---------------------------------------------------------------------------
+// Weight packing: parameter layout (fp32) -> K-major GEMM operand [taps][rows][ld] (DT)
+//   mode 0  conv fprop    : src [Co][Ci][T]      dst[t][co][ci]
+//   mode 1  conv dgrad    : src [Co][Ci][T]      dst[T-1-t][ci][co]     (180-degree rotation, Ci/Co swapped)
+//   mode 2  convT fprop   : src [Ci][Co][4]      dst[0][t*Co+co][ci]
+//   mode 3  convT dgrad   : src [Ci][Co][4]      dst[t][ci][co]         (a 2x2 stride-2 conv)
+//   mode 4  s2-conv dgrad : src [Co][Ci][T]      dst[t][ci][co]         (transposed, NOT rotated)
+// ---------------------------------------------------------------------------
+struct PackDesc {
+  const float* src;
+  void* dst;
+  int dim0, dim1, taps;   // src dims [dim0][dim1][taps]
+  int rows, ld;           // dst rows per tap, dst row pitch
+  int dst_taps;
+  int mode;
+  int pad;
+};
+
+template <typename DT>
+__global__ void pack_weights_kernel(const PackDesc* __restrict__ descs, int round_tf32_flag) {
+  const PackDesc d = descs[blockIdx.y];
+  const long long total = static_cast<long long>(d.dst_taps) * d.rows * d.ld;
+  DT* dst = reinterpret_cast<DT*>(d.dst);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = int(i % d.ld);
+    const int r = int((i / d.ld) % d.rows);
+    const int t = int(i / (static_cast<long long>(d.ld) * d.rows));
+    float v = 0.f;
+    int i0 = -1, i1 = -1, it = 0;
+    switch (d.mode) {
+      case 0: i0 = r, i1 = k, it = t; break;
+      case 1: i0 = k, i1 = r, it = d.taps - 1 - t; break;
+      case 2: i0 = k, i1 = r % d.dim1, it = r / d.dim1; break;
+      case 3: i0 = r, i1 = k, it = t; break;
+      default: i0 = k, i1 = r, it = t; break;   // mode 4: transpose Ci/Co without rotation
+    }
+    if (i0 >= 0 && i0 < d.dim0 && i1 >= 0 && i1 < d.dim1 && it < d.taps)
+      v = __ldg(d.src + (static_cast<long long>(i0) * d.dim1 + i1) * d.taps + it);
+    if (round_tf32_flag) v = round_tf32(v);
+    dst[i] = cvt_out<DT>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// channel_sum: out[c] += sum over pixels of x[p][c]  (ConvTranspose2d bias gradient)
+// ---------------------------------------------------------------------------
+template <typename DT>
+__global__ void channel_sum_kernel(const DT* __restrict__ x, long long npix, int ld, int C, float* __restrict__ out) {
+  // block = 256 threads = 8 pixel lanes x 32 channel lanes
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  __shared__ float part[8][33];
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + cl;
+    float s = 0.f;
+    if (c < C)
+      for (long long p = blockIdx.x * 8ll + pl; p < npix; p += gridDim.x * 8ll) s += float(x[p * ld + c]);
+    part[pl][cl] = s;
+    __syncthreads();
+    if (pl == 0 && c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += part[j][cl];
+      atomicAdd(out + c, t);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Gradient norm -> clip -> Adam over flat fp32 buffers, grouped by sub-network
+// (train_denoising_syn.py:182-184: clip_grad_norm_ per sub-net, optim.Adam.step)
+// ---------------------------------------------------------------------------
+struct AdamGroup {
+  long long begin, end;   // element range in the flat buffers
+  float max_norm;
+  int pad;
+};
+
+__global__ void grad_sqnorm_kernel(const float* __restrict__ g, const AdamGroup* __restrict__ groups, int ngroups,
+                                   float gscale, double* __restrict__ sq) {
+  const int gi = blockIdx.y;
+  const AdamGroup gr = groups[gi];
+  float s = 0.f;
+  for (long long i = gr.begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < gr.end;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = g[i] * gscale;
+    s += v * v;
+  }
+  __shared__ float red[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float a = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    a = warp_sum(a);
+    if (threadIdx.x == 0) atomicAdd(sq + gi, static_cast<double>(a));
+  }
+}
+
+__global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, const AdamGroup* __restrict__ groups, int ngroups,
+                                 const double* __restrict__ sq, float gscale, float lr, float beta1, float beta2,
+                                 float eps, float bc1, float bc2_sqrt, float* __restrict__ norms_out) {
+  const int gi = blockIdx.y;
+  const AdamGroup gr = groups[gi];
+  const float total = static_cast<float>(sqrt(sq[gi]));
+  const float coef = fminf(gr.max_norm / (total + 1e-6f), 1.f) * gscale;   // clip_grad_norm_ semantics
+  if (norms_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) norms_out[gi] = total;
+  const float step = lr / bc1;
+  for (long long i = gr.begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < gr.end;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gg = g[i] * coef;
+    const float mm = beta1 * m[i] + (1.f - beta1) * gg;
+    const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+    m[i] = mm;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    p[i] -= step * mm / denom;
+  }
+}
+
+static inline int grid_for(long long total, int threads, int max_waves = 8) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(kSMs) * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return int(b);
+}
+
+}  // namespace vk
+
+using namespace vk;
+#define VK_ST(s) reinterpret_cast<cudaStream_t>(s)
+#define VK_LAUNCHED()                                        \
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);    \
+  return int(cudaGetLastError())
+
+extern "C" int vk_pack_input(int32_t dtype, const float* img, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
+                             const float* extra, int32_t e, int32_t extra_is_map, int32_t extra_sqrt_mask,
+                             int32_t eh, int32_t ew, int32_t esf, void* out, int32_t hp, int32_t wp, int32_t ld,
+                             void* stream) {
+  if (img == nullptr || out == nullptr || n <= 0 || c <= 0 || c + e > ld || sf <= 0) return VK_E_BADARG;
+  if (e > 0 && extra == nullptr) return VK_E_BADARG;
+  if (hp < h * sf || wp < w * sf || hp > 2 * h * sf - 1 || wp > 2 * w * sf - 1) return VK_E_BADARG;
+  if (esf <= 0) esf = 1;
+  const long long total = static_cast<long long>(n) * hp * wp;
+  const int grid = grid_for(total, 256);
+  if (dtype == VK_BF16)
+    pack_input_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(
+        img, c, h, w, sf, extra, e, extra_is_map, extra_sqrt_mask, eh, ew, esf,
+        reinterpret_cast<__nv_bfloat16*>(out), n, hp, wp, ld);
+  else if (dtype == VK_TF32)
+    pack_input_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(img, c, h, w, sf, extra, e, extra_is_map,
+                                                             extra_sqrt_mask, eh, ew, esf,
+                                                             reinterpret_cast<float*>(out), n, hp, wp, ld);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_pack_grad(int32_t dtype, const float* g, int32_t n, int32_t c, int32_t h, int32_t w, void* out,
+                            int32_t hp, int32_t wp, int32_t ld, void* stream) {
+  if (g == nullptr || out == nullptr || n <= 0 || c <= 0 || c > ld || hp < h || wp < w) return VK_E_BADARG;
+  const long long total = static_cast<long long>(n) * hp * wp;
+  const int grid = grid_for(total, 256);
+  if (dtype == VK_BF16)
+    pack_grad_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(g, c, h, w, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                    n, hp, wp, ld);
+  else if (dtype == VK_TF32)
+    pack_grad_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(g, c, h, w, reinterpret_cast<float*>(out), n, hp, wp, ld);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_sigma_head_bwd(int32_t dtype, const float* sigma, const float* g_sigma, const void* g_in,
+                                 int32_t ld_in, int32_t chan, int32_t hp, int32_t wp, void* out, int32_t ld,
+                                 int32_t n, int32_t sc, int32_t h, int32_t w, float log_lo, float log_hi,
+                                 void* stream) {
+  if (sigma == nullptr || out == nullptr || n <= 0 || sc <= 0 || sc > ld) return VK_E_BADARG;
+  if (g_in != nullptr && (chan < 0 || chan + sc > ld_in || hp < h || wp < w)) return VK_E_BADARG;
+  const long long total = static_cast<long long>(n) * h * w;
+  const int grid = grid_for(total, 256);
+  const float lo = expf(log_lo), hi = expf(log_hi);
+  if (dtype == VK_BF16)
+    sigma_head_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(
+        sigma, g_sigma, reinterpret_cast<const __nv_bfloat16*>(g_in), ld_in, chan, hp, wp,
+        reinterpret_cast<__nv_bfloat16*>(out), ld, n, sc, h, w, lo, hi);
+  else if (dtype == VK_TF32)
+    sigma_head_bwd_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(sigma, g_sigma,
+                                                                 reinterpret_cast<const float*>(g_in), ld_in, chan,
+                                                                 hp, wp, reinterpret_cast<float*>(out), ld, n, sc,
+                                                                 h, w, lo, hi);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_elbo_denoise(const float* mu, const float* sigma, const float* noisy, const float* gt,
+                               const float* beta0, float beta0_scale, int32_t n, int32_t c, int32_t sc, int32_t h,
+                               int32_t w, float eps2, float alpha0, float digamma_alpha0_m1, float grad_scale, float* d_mu,
+                               float* d_sigma, double* acc3, float* out4, void* stream) {
+  if (!mu || !sigma || !noisy || !gt || !beta0 || !acc3 || !out4) return VK_E_BADARG;
+  if (n <= 0 || c <= 0 || (sc != 1 && sc != c)) return VK_E_BADARG;
+  cudaStream_t st = VK_ST(stream);
+  cudaError_t e = cudaMemsetAsync(acc3, 0, 3 * sizeof(double), st);
+  if (e != cudaSuccess) return int(e);
+  const long long hw = static_cast<long long>(h) * w;
+  const int grid = grid_for(static_cast<long long>(n) * hw, 256, 4);
+  elbo_denoise_kernel<<<grid, 256, 0, st>>>(mu, sigma, noisy, gt, beta0, beta0_scale, n, c, sc, hw, eps2, alpha0,
+                                            digamma_alpha0_m1, grad_scale, d_mu, d_sigma, acc3);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  elbo_finalize_kernel<<<1, 1, 0, st>>>(acc3, double(n) * c * hw, double(n) * sc * hw, out4);
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_pack_weights(int32_t dtype, const void* descs_dev, int32_t ndesc, int64_t max_elems,
+                               int32_t round_tf32_flag, void* stream) {
+  if (descs_dev == nullptr || ndesc <= 0) return VK_E_BADARG;
+  dim3 grid(grid_for(max_elems, 256, 2), ndesc);
+  if (dtype == VK_BF16)
+    pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(
+        reinterpret_cast<const PackDesc*>(descs_dev), 0);
+  else if (dtype == VK_TF32)
+    pack_weights_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const PackDesc*>(descs_dev),
+                                                               round_tf32_flag);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_t ld, int32_t c, float* out,
+                              void* stream) {
+  if (x == nullptr || out == nullptr || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
+  const int grid = int(std::min<long long>((npix + 7) / 8, kSMs * 4));
+  if (dtype == VK_BF16)
+    channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                      npix, ld, c, out);
+  else if (dtype == VK_TF32)
+    channel_sum_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c, out);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                 const void* groups_dev, int32_t ngroups, int64_t max_group_elems, double* sq_ws,
+                                 float grad_scale, float lr, float beta1, float beta2, float eps, int32_t step,
+                                 float* norms_out, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !groups_dev || !sq_ws || ngroups <= 0 || step <= 0)
+    return VK_E_BADARG;
+  cudaStream_t st = VK_ST(stream);
+  cudaError_t e = cudaMemsetAsync(sq_ws, 0, ngroups * sizeof(double), st);
+  if (e != cudaSuccess) return int(e);
+  const AdamGroup* groups = reinterpret_cast<const AdamGroup*>(groups_dev);
+  dim3 grid(grid_for(max_group_elems, 256, 4), ngroups);
+  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(grads, groups, ngroups, grad_scale, sq_ws);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  const float bc1 = 1.f - powf(beta1, float(step));
+  const float bc2 = 1.f - powf(beta2, float(step));
+  adam_clip_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, groups, ngroups, sq_ws, grad_scale, lr,
+                                         beta1, beta2, eps, bc1, sqrtf(bc2), norms_out);
+  VK_LAUNCHED();
+}

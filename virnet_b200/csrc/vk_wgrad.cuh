@@ -1,0 +1,258 @@
+// vk_wgrad.cuh — weight-gradient of the convolutions as a tcgen05 GEMM whose K
+// dimension is the pixel index (sm_100a).
+//
+//   conv   : dW[tap][co][ci] = sum_pix dY[pix][co] * X[pix*stride + tap_offset][ci]
+//   convT  : dW[tap][ci][co] = sum_pix X[pix][ci]  * dYup[2*pix + tap_offset][co]
+//
+// i.e. D[m][n] (+)= sum_k A[k][m] * B[k][n] with BOTH operands "MN-major": a TMA box
+// of an NHWC tensor lands in shared memory as [pixel][channel] rows of 128 bytes
+// (SWIZZLE_128B), which is exactly the canonical MN-major SW128 UMMA layout
+// (K = pixel rows, 8-row groups 1024 B apart; 128-byte channel blocks LBO apart).
+// The M operand walks the un-shifted pixel grid; the N operand is loaded shifted
+// (and strided) per tap, re-using one row-slab for the three vertical taps of a
+// 3x3 stride-1 filter.  One CTA owns an (m-block of 128) x (n-block) x (tap group)
+// output and a strided subset of the pixel tiles (split-K); partial sums are added
+// to the fp32 gradient workspace with red.global.add.v4.f32.
+//
+// Bias gradient: one extra N=16 MMA per K step against a tile of ones.
+#pragma once
+#include "vk_common.cuh"
+#include "vk_conv_igemm.cuh"   // DTraits
+
+namespace vk {
+
+struct WgradTap {
+  int load;      // which N-operand buffer of the stage
+  int rowoff;    // first pixel row of this tap's K view inside that buffer
+  int tap;       // tap index in the output workspace
+};
+struct WgradLoad {
+  int dx, dy;    // N-operand box origin = tile origin * b_stride + (dx, dy)
+};
+
+struct WgradParams {
+  int n_img, gh, gw;            // pixel grid walked by the K tiles (conv: output grid; convT: input grid)
+  int tiles_x, tiles_y, n_tiles;
+  int tw_log2, th;              // K tile = (1<<tw_log2) x th pixels
+  int k_rows;                   // pixels per K tile
+  int box_rows;                 // pixel rows of one N-operand buffer
+  int b_stride;                 // tile origin -> N-operand coordinate multiplier
+  int n_a_blocks, n_b_blocks;   // 128-byte channel blocks per operand
+  int n_loads, n_taps;          // per tap group
+  int n_groups;                 // tap groups (blockIdx.z = group)
+  WgradLoad loads[3][3];        // [group][load]
+  WgradTap taps[3][3];          // [group][tap]
+  int n_cta;                    // GEMM N per CTA (multiple of 16)
+  int n_blocks_n;               // N blocks (blockIdx.y = m_block * n_blocks_n + n_block)
+  int acc_stride, tmem_cols;
+  int stages, ksplit;
+  int m_valid, n_valid;         // valid GEMM rows / cols overall
+  int total_taps;
+  float* dw;                    // [total_taps][m_valid][n_valid] fp32, accumulated
+  float* dbias;                 // [m_valid] fp32 accumulated, or null
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+constexpr int kWgradThreads = 192;
+
+template <typename DT>
+__global__ void __launch_bounds__(kWgradThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ WgradParams prm) {
+  constexpr bool kTF32 = DTraits<DT>::kTF32;
+  constexpr int kBlockElems = 128 / int(sizeof(DT));       // channels per 128-byte block
+  constexpr int kRowsPerMma = 32 / int(sizeof(DT));        // pixels (K) per UMMA
+  constexpr int kAdvance = kRowsPerMma * 128;              // bytes between consecutive K steps
+  // MN-major 32-bit operands only exist in the "128B swizzle, 32B atom" layout (K atom = 4 rows)
+  constexpr uint32_t kLayout = kTF32 ? 1u : 2u;            // SWIZZLE_128B_BASE32B : SWIZZLE_128B
+  constexpr uint32_t kSBO = kTF32 ? 512u : 1024u;          // pitch between K atoms (4 or 8 pixel rows)
+  constexpr int kMaxStages = 8;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int group = blockIdx.z;
+  const int m_block = blockIdx.y / prm.n_blocks_n;
+  const int n_block = blockIdx.y - m_block * prm.n_blocks_n;
+  const int m0 = m_block * 128;
+  const int n0 = n_block * prm.n_cta;
+  const bool do_bias = (prm.dbias != nullptr) && group == 0 && n_block == 0;
+
+  const int a_block_bytes = prm.k_rows * 128;
+  const int b_block_bytes = prm.box_rows * 128;
+  const int a_bytes = prm.n_a_blocks * a_block_bytes;
+  const int b_bytes = prm.n_b_blocks * b_block_bytes;
+  const int stage_bytes = a_bytes + prm.n_loads * b_bytes;
+  uint8_t* ones = smem + prm.stages * stage_bytes;         // 2 KB tile of ones (bias gradient)
+  const int tiles_per_img = prm.tiles_x * prm.tiles_y;
+  // K tiles of this CTA: blockIdx.x, blockIdx.x + ksplit, ...
+  const int my_tiles = (prm.n_tiles - int(blockIdx.x) + prm.ksplit - 1) / prm.ksplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < prm.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_slot, prm.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    // ones tile: the value 1.0 in the operand type; any layout of all-ones is all-ones
+    const uint32_t one = kTF32 ? 0x3F800000u : 0x3F803F80u;
+    uint32_t* o = reinterpret_cast<uint32_t*>(ones);
+    for (int i = threadIdx.x - 64; i < 512; i += 128) o[i] = one;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % prm.stages;
+        const uint32_t ph = (it / prm.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int t = blockIdx.x + it * prm.ksplit;
+        const int img = t / tiles_per_img;
+        const int r = t - img * tiles_per_img;
+        const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
+        const int x0 = tx << prm.tw_log2, y0 = ty * prm.th;
+        uint8_t* a_s = smem + s * stage_bytes;
+        uint8_t* b_s = a_s + a_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        for (int j = 0; j < prm.n_a_blocks; ++j)
+          tma_load_4d(a_s + j * a_block_bytes, &tmap_a, &full_bar[s], m0 + j * kBlockElems, x0, y0, img);
+        for (int l = 0; l < prm.n_loads; ++l) {
+          const WgradLoad& ld = prm.loads[group][l];
+          for (int j = 0; j < prm.n_b_blocks; ++j)
+            tma_load_4d(b_s + l * b_bytes + j * b_block_bytes, &tmap_b, &full_bar[s], n0 + j * kBlockElems,
+                        x0 * prm.b_stride + ld.dx, y0 * prm.b_stride + ld.dy, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(DTraits<DT>::kFmt, 128, prm.n_cta, 1, 1);
+      const uint32_t idesc_bias = make_idesc(DTraits<DT>::kFmt, 128, 16, 1, 1);
+      const uint32_t ones_addr = smem_u32(ones);
+      const int ksteps = prm.k_rows / kRowsPerMma;
+      uint32_t accum = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % prm.stages;
+        const uint32_t ph = (it / prm.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_s = smem_u32(smem + s * stage_bytes);
+        const uint32_t b_s = a_s + a_bytes;
+        for (int tp = 0; tp < prm.n_taps; ++tp) {
+          const WgradTap& tap = prm.taps[group][tp];
+          const uint32_t b_tap = b_s + tap.load * b_bytes + tap.rowoff * 128;
+          uint32_t acc = accum;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t ad = make_smem_desc(a_s + kk * kAdvance, a_block_bytes, kSBO, kLayout);
+            const uint64_t bd = make_smem_desc(b_tap + kk * kAdvance, b_block_bytes, kSBO, kLayout);
+            umma_ss<kTF32>(tmem_base + tp * prm.acc_stride, ad, bd, idesc, acc);
+            acc = 1;
+          }
+        }
+        if (do_bias) {
+          uint32_t acc = accum;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t ad = make_smem_desc(a_s + kk * kAdvance, a_block_bytes, kSBO, kLayout);
+            const uint64_t bd = make_smem_desc(ones_addr, 1024, kSBO, kLayout);
+            umma_ss<kTF32>(tmem_base + prm.n_taps * prm.acc_stride, ad, bd, idesc_bias, acc);
+            acc = 1;
+          }
+        }
+        accum = 1;
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ===================== epilogue: TMEM -> fp32 red.add =====================
+    const int q4 = warp & 3;
+    const int m = m0 + q4 * 32 + lane;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after_sync();
+    const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
+    const bool m_ok = (m < prm.m_valid) && (my_tiles > 0);
+    const bool vec_ok = (prm.n_valid % 4) == 0;
+    for (int tp = 0; tp < prm.n_taps; ++tp) {
+      const int tap = prm.taps[group][tp].tap;
+      float* row = prm.dw + (static_cast<long long>(tap) * prm.m_valid + m) * prm.n_valid;
+      for (int jc = 0; jc < prm.n_cta; jc += 16) {
+        uint32_t rr[16];
+        __syncwarp();
+        tmem_ld16(lane_addr + tp * prm.acc_stride + jc, rr);
+        tmem_ld_wait();
+        const int n = n0 + jc;
+        if (m_ok && n < prm.n_valid) {
+          if (vec_ok && n + 16 <= prm.n_valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              red_add_v4(row + n + i, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]),
+                         __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n + i < prm.n_valid) red_add(row + n + i, __uint_as_float(rr[i]));
+          }
+        }
+      }
+    }
+    if (do_bias) {
+      uint32_t rr[16];
+      __syncwarp();
+      tmem_ld16(lane_addr + prm.n_taps * prm.acc_stride, rr);
+      tmem_ld_wait();
+      if (m_ok) red_add(prm.dbias + m, __uint_as_float(rr[0]));
+    }
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, prm.tmem_cols);
+  }
+}
+
+// dW workspace [taps][M][N] -> parameter layout [M][N][taps] (OIHW for conv, [Cin][Cout][kh][kw] for ConvT)
+__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ out, int taps, int mn,
+                                    int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // index over M*N
+  if (i >= mn) return;
+  for (int t = 0; t < taps; ++t) {
+    const float v = ws[static_cast<long long>(t) * mn + i];
+    float* o = out + static_cast<long long>(i) * taps + t;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+}  // namespace vk

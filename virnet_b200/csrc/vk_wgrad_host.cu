@@ -1,0 +1,178 @@
+// vk_wgrad_host.cu — host side of vk_conv_wgrad (tiling, split-K, TMA maps, launch).
+#include <algorithm>
+#include <cstdio>
+
+#include "../../include/virnet_b200.h"
+#include "vk_host.h"
+#include "vk_wgrad.cuh"
+
+using namespace vk;
+
+namespace {
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int next_pow2_cols(int x) {
+  int c = 32;
+  while (c < x) c <<= 1;
+  return c;
+}
+constexpr int kWgradSmemBudget = 216 * 1024;
+
+template <typename DT>
+int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
+                 cudaStream_t st) {
+  static int cur = 0;
+  auto kern = wgrad_kernel<DT>;
+  if (smem_bytes > cur) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return int(e);
+    cur = smem_bytes;
+  }
+  kern<<<grid, kWgradThreads, smem_bytes, st>>>(ta, tb, prm);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+}  // namespace
+
+extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
+  if (a == nullptr || a->a == nullptr || a->b == nullptr || a->dw == nullptr) return VK_E_BADARG;
+  if (a->dtype != VK_BF16 && a->dtype != VK_TF32) return VK_E_BADARG;
+  const int esize = a->dtype == VK_BF16 ? 2 : 4;
+  const int block_elems = 128 / esize;
+  if (a->lda <= 0 || a->ldb <= 0 || (a->lda * esize) % 16 || (a->ldb * esize) % 16) return VK_E_BADARG;
+  if (a->m_valid <= 0 || a->n_valid <= 0 || a->m_valid > a->lda || a->n_valid > a->ldb) return VK_E_BADARG;
+  if (a->n <= 0 || a->gh <= 0 || a->gw <= 0 || a->bh <= 0 || a->bw <= 0) return VK_E_BADARG;
+
+  WgradParams prm{};
+  prm.n_img = a->n;
+  prm.gh = a->gh;
+  prm.gw = a->gw;
+  prm.m_valid = a->m_valid;
+  prm.n_valid = a->n_valid;
+  prm.dw = a->dw;
+  prm.dbias = a->dbias;
+
+  bool slab = false;
+  switch (a->kind) {
+    case VK_CONV3X3_S1:
+      slab = true;
+      prm.b_stride = 1, prm.n_groups = 3, prm.n_loads = 1, prm.n_taps = 3, prm.total_taps = 9;
+      break;
+    case VK_CONV3X3_S2:
+      prm.b_stride = 2, prm.n_groups = 3, prm.n_loads = 3, prm.n_taps = 3, prm.total_taps = 9;
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          prm.loads[r][s].dx = s - 1, prm.loads[r][s].dy = r - 1;
+          prm.taps[r][s].load = s, prm.taps[r][s].rowoff = 0, prm.taps[r][s].tap = r * 3 + s;
+        }
+      break;
+    case VK_CONVT2X2_S2:
+      prm.b_stride = 2, prm.n_groups = 2, prm.n_loads = 2, prm.n_taps = 2, prm.total_taps = 4;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          prm.loads[dy][dx].dx = dx, prm.loads[dy][dx].dy = dy;
+          prm.taps[dy][dx].load = dx, prm.taps[dy][dx].rowoff = 0, prm.taps[dy][dx].tap = dy * 2 + dx;
+        }
+      break;
+    case VK_CONV1X1:
+      prm.b_stride = 1, prm.n_groups = 1, prm.n_loads = 1, prm.n_taps = 1, prm.total_taps = 1;
+      prm.loads[0][0].dx = 0, prm.loads[0][0].dy = 0;
+      prm.taps[0][0].load = 0, prm.taps[0][0].rowoff = 0, prm.taps[0][0].tap = 0;
+      break;
+    default: return VK_E_BADARG;
+  }
+
+  // ---- N split under the TMEM budget: n_taps * round32(n_cta) + 32 (bias) <= 512 ----
+  const int n_pad = round_up(a->n_valid, 16);
+  const int max_n = std::min(256, ((512 - 32) / prm.n_taps) / 32 * 32);
+  const int parts = (n_pad + max_n - 1) / max_n;
+  const int n_cta = round_up((n_pad + parts - 1) / parts, 16);
+  prm.n_cta = n_cta;
+  prm.n_blocks_n = parts;
+  prm.acc_stride = round_up(n_cta, 32);
+  prm.tmem_cols = next_pow2_cols(prm.n_taps * prm.acc_stride + 32);
+  if (prm.tmem_cols > 512) return VK_E_UNSUPPORTED;
+  prm.n_a_blocks = 128 / block_elems;
+  prm.n_b_blocks = (n_cta + block_elems - 1) / block_elems;
+  const int m_blocks = (a->m_valid + 127) / 128;
+
+  // ---- K tile and stages under the smem budget ----
+  static const int cand[4][2] = {{16, 8}, {16, 4}, {8, 4}, {8, 2}};   // (tw, th): 128, 64, 32, 16 pixels
+  int tw = 0, th = 0, stages = 0;
+  for (int want = 3; want >= 1 && !stages; --want) {
+    for (int i = 0; i < 4 && !stages; ++i) {
+      const int k_rows = cand[i][0] * cand[i][1];
+      if (a->force_k_rows && a->force_k_rows != k_rows) continue;
+      if (k_rows * esize < 32 * 8 / 8 * 8) { /* at least one UMMA K step */ }
+      const int box_rows = slab ? (cand[i][1] + 2) * cand[i][0] : k_rows;
+      const int stage = prm.n_a_blocks * k_rows * 128 + prm.n_loads * prm.n_b_blocks * box_rows * 128;
+      int st = std::min(8, kWgradSmemBudget / stage);
+      if (a->force_stages) st = std::min(st, a->force_stages);
+      if (st >= want) tw = cand[i][0], th = cand[i][1], stages = st;
+    }
+  }
+  if (!stages) return VK_E_UNSUPPORTED;
+  prm.tw_log2 = 31 - __builtin_clz(tw);
+  prm.th = th;
+  prm.k_rows = tw * th;
+  prm.box_rows = slab ? (th + 2) * tw : tw * th;
+  prm.stages = stages;
+  if (slab) {
+    for (int s = 0; s < 3; ++s) {
+      prm.loads[s][0].dx = s - 1, prm.loads[s][0].dy = -1;
+      for (int r = 0; r < 3; ++r)
+        prm.taps[s][r].load = 0, prm.taps[s][r].rowoff = r * tw, prm.taps[s][r].tap = r * 3 + s;
+    }
+  }
+  prm.tiles_x = (a->gw + tw - 1) / tw;
+  prm.tiles_y = (a->gh + th - 1) / th;
+  prm.n_tiles = prm.tiles_x * prm.tiles_y * a->n;
+
+  const int base_ctas = m_blocks * parts * prm.n_groups;
+  int ksplit = std::max(1, (148 + base_ctas - 1) / base_ctas);
+  if (a->force_ksplit) ksplit = a->force_ksplit;
+  ksplit = std::min(ksplit, prm.n_tiles);
+  prm.ksplit = ksplit;
+
+  // ---- tensor maps: 128-byte channel blocks; SWIZZLE_128B (bf16) / 128B_ATOM_32B (fp32, code 129) ----
+  const int sw_code = a->dtype == VK_BF16 ? 128 : 129;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t rb = uint64_t(a->lda) * esize;
+    const uint64_t dims[4] = {uint64_t(a->lda), uint64_t(a->gw), uint64_t(a->gh), uint64_t(a->n)};
+    const uint64_t strides[3] = {rb, rb * a->gw, rb * a->gw * a->gh};
+    const uint32_t box[4] = {uint32_t(block_elems), uint32_t(tw), uint32_t(th), 1u};
+    const uint32_t es[4] = {1u, 1u, 1u, 1u};
+    int r = make_tensor_map(&ta, a->dtype, 4, a->a, dims, strides, box, es, sw_code);
+    if (r) return r;
+  }
+  {
+    const uint64_t rb = uint64_t(a->ldb) * esize;
+    const uint64_t dims[4] = {uint64_t(a->ldb), uint64_t(a->bw), uint64_t(a->bh), uint64_t(a->n)};
+    const uint64_t strides[3] = {rb, rb * a->bw, rb * a->bw * a->bh};
+    const uint32_t s = prm.b_stride;
+    const uint32_t box_h = slab ? th + 2 : th;
+    const uint32_t box[4] = {uint32_t(block_elems), uint32_t(tw) * s, box_h * s, 1u};
+    const uint32_t es[4] = {1u, s, s, 1u};
+    int r = make_tensor_map(&tb, a->dtype, 4, a->b, dims, strides, box, es, sw_code);
+    if (r) return r;
+  }
+
+  const int stage_bytes = prm.n_a_blocks * prm.k_rows * 128 + prm.n_loads * prm.n_b_blocks * prm.box_rows * 128;
+  const int smem_bytes = stages * stage_bytes + 2048 + 1024;
+  dim3 grid(ksplit, m_blocks * parts, prm.n_groups);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == VK_BF16) return launch_wgrad<__nv_bfloat16>(ta, tb, prm, grid, smem_bytes, st);
+  return launch_wgrad<float>(ta, tb, prm, grid, smem_bytes, st);
+}
+
+extern "C" int vk_wgrad_unpack(const float* ws, float* out, int32_t taps, int32_t m, int32_t n, int32_t accumulate,
+                               void* stream) {
+  if (ws == nullptr || out == nullptr || taps <= 0 || m <= 0 || n <= 0) return VK_E_BADARG;
+  const int mn = m * n;
+  wgrad_unpack_kernel<<<(mn + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ws, out, taps, mn,
+                                                                                            accumulate);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+extern "C" uint32_t vk_sizeof_wgrad_args(void) { return uint32_t(sizeof(vk_wgrad_args)); }

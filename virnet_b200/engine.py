@@ -1,0 +1,425 @@
+"""Execution engine of the denoising network (VIRAttResUNet): turns the parameter
+containers into one CUDA program over libvirnet_sm100.so.
+
+Forward dataflow (reference: networks/VIRNet.py:42-46, DnCNN.py:37-44, AttResUNet.py:141-175),
+all activations NHWC in the compute dtype (bf16, or fp32 storage with TF32 MMA):
+
+  pack_input(x) -> SNet convs (bias+LReLU(.25) fused) -> last conv with exp(clamp) epilogue -> sigma
+  pack_input(x, sqrt(sigma)) [reflect pad + concat fused] -> head conv (dual write: X, LReLU(X))
+  resblock: conv1 epilogue writes LReLU(conv1+b);  conv2 epilogue writes X' = X + conv2 + b and LReLU(X')
+  stride-2 conv via TMA element strides; ConvT as 1x1 GEMM + depth-to-space epilogue fused with `+ bridge`
+  tail conv epilogue: + bias, crop, + x_in, NCHW fp32 store
+
+Backward mirrors it: dgrad = the same implicit-GEMM kernel over rotated/transposed packed weights
+with the LeakyReLU' mask (taken from the sign of the saved activated tensor) and the residual
+gradient fused in the epilogue; wgrad = pixel-K GEMM with split-K fp32 reduction.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import lib as _l
+from . import ops
+from .ops import (VK_BF16, VK_TF32, VK_CONV3X3_S1, VK_CONV3X3_S2, VK_CONVT2X2_S2, VK_CONV2X2_S2,
+                  VK_CONV3X3_S2_DGRAD, VK_EPI_NCHW_F32)
+
+SNET_LOG_MAX, SNET_LOG_MIN = math.log(1e2), math.log(1e-10)     # networks/VIRNet.py:15-16
+
+PRECISIONS = {"bf16": VK_BF16, "tf32": VK_TF32}
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class _Layer:
+    """One Conv2d / ConvTranspose2d: parameters plus their packed GEMM operands."""
+
+    def __init__(self, name: str, mod: nn.Module, kind: str, need_dgrad: bool):
+        self.name, self.mod, self.kind, self.need_dgrad = name, mod, kind, need_dgrad
+        w = mod.weight
+        if kind == "convT":
+            self.cin, self.cout, self.taps = w.shape[0], w.shape[1], 4
+        else:
+            self.cout, self.cin, self.taps = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+        self.wf = self.wd = None        # packed forward / dgrad operands
+        self.ws = None                  # fp32 wgrad workspace view [taps][M][N]
+
+    @property
+    def weight(self):
+        return self.mod.weight
+
+    @property
+    def bias(self):
+        return self.mod.bias
+
+
+class DenoiseEngine:
+    def __init__(self, net: nn.Module, precision: str = "tf32"):
+        self.net = net
+        self.precision = precision
+        self.dtype = PRECISIONS[precision]
+        self.tdt = ops.TORCH_DTYPE[self.dtype]
+        snet, rnet = net.SNet, net.RNet
+        self.im_chn = rnet.in_chn
+        self.sigma_chn = snet.conv_last.out_channels
+        self.noise_cond = bool(net.noise_cond)
+        self.extra_mode = rnet.extra_mode
+        if self.extra_mode in ("down", "both"):
+            raise NotImplementedError("extra_mode 'Down'/'Both' (SFT modulation) belongs to the SISR engine")
+        if snet.noise_avg:
+            raise NotImplementedError("noise_avg=True belongs to the SISR engine")
+        self.head_extra = self.sigma_chn if (self.noise_cond and self.extra_mode == "input") else 0
+        self.depth, self.n_feat, self.n_res = rnet.depth, rnet.n_feat, rnet.n_resblocks
+
+        # ---- layer table (forward order) ----
+        L: List[_Layer] = []
+        s_convs = snet.conv_layers()
+        self.s_layers = []
+        for i, m in enumerate(s_convs):
+            nm = "SNet.conv1" if i == 0 else ("SNet.conv_last" if i == len(s_convs) - 1 else f"SNet.mid{i}")
+            self.s_layers.append(_Layer(nm, m, "conv", need_dgrad=i > 0))
+        L += self.s_layers
+        self.head = _Layer("RNet.head", rnet.head, "conv", need_dgrad=self.head_extra > 0)
+        L.append(self.head)
+        self.down = []
+        for ii, blk in enumerate(rnet.down_path):
+            res = [(_Layer(f"RNet.down{ii}.b{b}.conv1", rb.conv1, "conv", True),
+                    _Layer(f"RNet.down{ii}.b{b}.conv2", rb.conv2, "conv", True)) for b, rb in enumerate(blk.body)]
+            ds = _Layer(f"RNet.down{ii}.ds", blk.downsampler, "conv_s2", True) if ii + 1 < self.depth else None
+            self.down.append((res, ds))
+            for a, b in res:
+                L += [a, b]
+            if ds is not None:
+                L.append(ds)
+        self.up = []
+        for k, blk in enumerate(rnet.up_path):
+            us = _Layer(f"RNet.up{k}.us", blk.upsampler, "convT", True)
+            res = [(_Layer(f"RNet.up{k}.b{b}.conv1", rb.conv1, "conv", True),
+                    _Layer(f"RNet.up{k}.b{b}.conv2", rb.conv2, "conv", True)) for b, rb in enumerate(blk.body)]
+            self.up.append((us, res))
+            L.append(us)
+            for a, b in res:
+                L += [a, b]
+        self.tail = _Layer("RNet.tail", rnet.tail, "conv", True)
+        L.append(self.tail)
+        self.layers = L
+
+        self._flat_key = None
+        self._packed_version = None
+        self._bufs: Dict = {}
+        self.saved = None
+
+    # ------------------------------------------------------------------
+    # parameters: one flat fp32 buffer (params) + one for grads + wgrad workspace
+    # ------------------------------------------------------------------
+    def _params(self):
+        return list(self.net.parameters())
+
+    def _ensure_flat(self):
+        params = self._params()
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise _l.VkError("virnet_b200 runs on CUDA (sm_100a) only: move the module to the GPU first; "
+                             "there is no CPU fallback")
+        key = (dev, tuple(p.data_ptr() for p in params))
+        if key == self._flat_key:
+            return
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4            # keep every tensor 16-byte aligned
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(params, offs):
+            flat[o:o + p.numel()].view_as(p).copy_(p.data)
+            p.data = flat[o:o + p.numel()].view_as(p)
+        self.flat_params, self.flat_offsets, self.flat_total = flat, offs, total
+        self.flat_grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.param_index = {id(p): i for i, p in enumerate(params)}
+        self._flat_key = (dev, tuple(p.data_ptr() for p in params))
+        self._build_packing(dev)
+        self._packed_version = None
+        self._bufs = {}
+
+    def grad_view(self, p: torch.Tensor) -> torch.Tensor:
+        i = self.param_index[id(p)]
+        o = self.flat_offsets[i]
+        return self.flat_grads[o:o + p.numel()].view_as(p)
+
+    def _build_packing(self, dev):
+        dt, tdt = self.dtype, self.tdt
+        cp = lambda c: ops.chan_pad(c, dt)
+        descs = []
+        max_elems = 0
+        ws_total = 0
+
+        def add(src, dst, dim0, dim1, taps, rows, ld, dst_taps, mode):
+            nonlocal max_elems
+            d = _l.vk_pack_desc()
+            d.src, d.dst = src.data_ptr(), dst.data_ptr()
+            d.dim0, d.dim1, d.taps, d.rows, d.ld, d.dst_taps, d.mode = dim0, dim1, taps, rows, ld, dst_taps, mode
+            descs.append(d)
+            max_elems = max(max_elems, dst.numel())
+
+        for ly in self.layers:
+            w = ly.weight
+            if ly.kind == "convT":
+                ly.wf = torch.empty(1, 4 * ly.cout, cp(ly.cin), device=dev, dtype=tdt)
+                add(w, ly.wf, ly.cin, ly.cout, 4, 4 * ly.cout, cp(ly.cin), 1, 2)
+                ly.wd = torch.empty(4, _pad16(ly.cin), cp(ly.cout), device=dev, dtype=tdt)
+                add(w, ly.wd, ly.cin, ly.cout, 4, _pad16(ly.cin), cp(ly.cout), 4, 3)
+            else:
+                ly.wf = torch.empty(ly.taps, _pad16(ly.cout), cp(ly.cin), device=dev, dtype=tdt)
+                add(w, ly.wf, ly.cout, ly.cin, ly.taps, _pad16(ly.cout), cp(ly.cin), ly.taps, 0)
+                if ly.need_dgrad:
+                    ly.wd = torch.empty(ly.taps, _pad16(ly.cin), cp(ly.cout), device=dev, dtype=tdt)
+                    add(w, ly.wd, ly.cout, ly.cin, ly.taps, _pad16(ly.cin), cp(ly.cout), ly.taps,
+                        4 if ly.kind == "conv_s2" else 1)
+            ws_total += w.numel()
+        arr = (_l.vk_pack_desc * len(descs))(*descs)
+        raw = bytes(memoryview(arr))
+        self._pack_descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._pack_n, self._pack_max = len(descs), max_elems
+        # wgrad workspace: [taps][M][N] per layer, one flat buffer
+        self.flat_ws = torch.zeros(ws_total, device=dev, dtype=torch.float32)
+        o = 0
+        for ly in self.layers:
+            n = ly.weight.numel()
+            m_, n_ = (ly.cin, ly.cout) if ly.kind == "convT" else (ly.cout, ly.cin)
+            ly.ws = self.flat_ws[o:o + n].view(ly.taps, m_, n_)
+            o += n
+
+    def mark_params_dirty(self):
+        self._packed_version = None
+
+    def _ensure_packed(self):
+        ver = tuple(p._version for p in self._params())
+        if ver == self._packed_version:
+            return
+        ops.pack_weights(self._pack_descs, self._pack_n, self._pack_max, dtype=self.dtype, round_tf32=True)
+        self._packed_version = ver
+
+    # ------------------------------------------------------------------
+    # buffers
+    # ------------------------------------------------------------------
+    def _buf(self, name, shape, dtype=None):
+        key = (name, tuple(shape), dtype or self.tdt)
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.empty(shape, device=self.flat_params.device, dtype=dtype or self.tdt)
+            self._bufs[key] = b
+        return b
+
+    # ------------------------------------------------------------------
+    # conv helpers
+    # ------------------------------------------------------------------
+    def _conv(self, x, ly: _Layer, kind, *, w=None, cout=None, bias=True, **kw):
+        ops.conv_igemm(x, ly.wf if w is None else w, dtype=self.dtype, kind=kind, cout=ly.cout if cout is None else cout,
+                       bias=ly.bias if bias else None, round_out2=self.dtype == VK_TF32, **kw)
+
+    # ------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, save: bool):
+        self._ensure_flat()
+        self._ensure_packed()
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise _l.VkError("input must be a CUDA fp32 NCHW tensor")
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        assert C == self.im_chn
+        dt = self.dtype
+        cp = lambda c: ops.chan_pad(c, dt)
+        mod = 2 ** (self.depth - 1)
+        Hp, Wp = (H + mod - 1) // mod * mod, (W + mod - 1) // mod * mod
+        if Hp > 2 * H - 1 or Wp > 2 * W - 1:
+            raise _l.VkError("image too small for reflect padding")
+        A: Dict[str, torch.Tensor] = {}
+
+        # ---- SNet ----
+        xs = self._buf("xs", (N, H, W, cp(C)))
+        ops.pack_input(x, xs, dtype=dt)
+        A["xs"] = xs
+        cur = xs
+        for i, ly in enumerate(self.s_layers[:-1]):
+            o = self._buf(f"s{i}", (N, H, W, cp(ly.cout)))
+            self._conv(cur, ly, VK_CONV3X3_S1, ldo=cp(ly.cout), out2=o, alpha=0.25)
+            A[f"s{i}"] = o
+            cur = o
+        sigma = torch.empty(N, self.sigma_chn, H, W, device=x.device, dtype=torch.float32)
+        self._conv(cur, self.s_layers[-1], VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=sigma, act_expclamp=True,
+                   clamp=(SNET_LOG_MIN, SNET_LOG_MAX))
+
+        # ---- RNet ----
+        cin0 = C + self.head_extra
+        r0 = self._buf("r0", (N, Hp, Wp, cp(cin0)))
+        if self.head_extra:
+            ops.pack_input(x, r0, dtype=dt, extra=sigma, extra_is_map=True, extra_sqrt_mask=(1 << self.sigma_chn) - 1)
+        else:
+            ops.pack_input(x, r0, dtype=dt)
+        A["r0"] = r0
+        nf = self.n_feat
+        h, w = Hp, Wp
+        X = self._buf("X.head", (N, h, w, nf[0]))
+        Act = self._buf("A.head", (N, h, w, nf[0]))
+        self._conv(r0, self.head, VK_CONV3X3_S1, ldo=nf[0], out1=X, out2=Act, alpha=0.2)
+        bridges = []
+        dims = [(h, w)]
+        for ii, (res, ds) in enumerate(self.down):
+            c = nf[ii]
+            for b, (c1, c2) in enumerate(res):
+                A[f"d{ii}.{b}.a"] = Act
+                Bt = self._buf(f"d{ii}.{b}.B", (N, h, w, c))
+                self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out2=Bt, alpha=0.2)
+                A[f"d{ii}.{b}.b"] = Bt
+                Xn = self._buf(f"d{ii}.{b}.X", (N, h, w, c))
+                last = b == len(res) - 1
+                An = None if last else self._buf(f"d{ii}.{b}.A", (N, h, w, c))
+                self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2)
+                X, Act = Xn, An
+            if ds is not None:
+                bridges.append(X)
+                A[f"d{ii}.x"] = X
+                h2, w2 = (h + 1) // 2, (w + 1) // 2
+                Xd = self._buf(f"d{ii}.ds.X", (N, h2, w2, nf[ii + 1]))
+                Ad = self._buf(f"d{ii}.ds.A", (N, h2, w2, nf[ii + 1]))
+                self._conv(X, ds, VK_CONV3X3_S2, ldo=nf[ii + 1], out1=Xd, out2=Ad, alpha=0.2)
+                X, Act, h, w = Xd, Ad, h2, w2
+                dims.append((h, w))
+        for k, (us, res) in enumerate(self.up):
+            lvl = self.depth - 2 - k
+            c = nf[lvl]
+            A[f"u{k}.x"] = X
+            h, w = dims[lvl]
+            Xu = self._buf(f"u{k}.us.X", (N, h, w, c))
+            Au = self._buf(f"u{k}.us.A", (N, h, w, c))
+            self._conv(X, us, VK_CONVT2X2_S2, ldo=c, resid=bridges[lvl], out1=Xu, out2=Au, alpha=0.2)
+            X, Act = Xu, Au
+            for b, (c1, c2) in enumerate(res):
+                A[f"u{k}.{b}.a"] = Act
+                Bt = self._buf(f"u{k}.{b}.B", (N, h, w, c))
+                self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out2=Bt, alpha=0.2)
+                A[f"u{k}.{b}.b"] = Bt
+                Xn = self._buf(f"u{k}.{b}.X", (N, h, w, c))
+                last = b == len(res) - 1
+                An = None if last else self._buf(f"u{k}.{b}.A", (N, h, w, c))
+                self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2)
+                X, Act = Xn, An
+        A["tail.x"] = X
+        mu = torch.empty(N, C, H, W, device=x.device, dtype=torch.float32)
+        self._conv(X, self.tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, resid=x, out1=mu, crop=(H, W))
+        if save:
+            A["sigma"] = sigma
+            A["shape"] = (N, C, H, W, Hp, Wp, dims)
+            self.saved = A
+        return mu, sigma
+
+    # ------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------
+    def _wgrad(self, ly: _Layer, a, b, kind):
+        """a: M operand, b: N operand (see include/virnet_b200.h vk_wgrad_args)."""
+        m_valid, n_valid = (ly.cin, ly.cout) if ly.kind == "convT" else (ly.cout, ly.cin)
+        dbias = None
+        if ly.bias is not None and ly.kind != "convT":
+            dbias = self.grad_view(ly.bias)
+        ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias)
+
+    def _dgrad(self, g, ly: _Layer, kind, cout, **kw):
+        ops.conv_igemm(g, ly.wd, dtype=self.dtype, kind=kind, cout=cout, bias=None, **kw)
+
+    def _resblock_bwd(self, tag, c1, c2, gX, shape):
+        A = self.saved
+        N, h, w, c = shape
+        a, bt = A[tag + ".a"], A[tag + ".b"]
+        self._wgrad(c2, gX, bt, VK_CONV3X3_S1)
+        gF = self._buf("g." + tag + ".F", (N, h, w, c))
+        self._dgrad(gX, c2, VK_CONV3X3_S1, c, ldo=c, mask=bt, out1=gF, alpha=0.2)
+        self._wgrad(c1, gF, a, VK_CONV3X3_S1)
+        gXp = self._buf("g." + tag + ".X", (N, h, w, c))
+        self._dgrad(gF, c1, VK_CONV3X3_S1, c, ldo=c, mask=a, resid=gX, out1=gXp, alpha=0.2)
+        return gXp
+
+    def backward(self, g_mu: Optional[torch.Tensor], g_sigma: Optional[torch.Tensor]):
+        """Accumulates parameter gradients into self.flat_grads (zeroed here first)."""
+        A = self.saved
+        if A is None:
+            raise _l.VkError("backward called without a saved forward")
+        N, C, H, W, Hp, Wp, dims = A["shape"]
+        dt = self.dtype
+        cp = lambda c: ops.chan_pad(c, dt)
+        nf = self.n_feat
+        self.flat_grads.zero_()
+        self.flat_ws.zero_()
+        gR0 = None
+        if g_mu is not None:
+            g_mu = g_mu.contiguous().float()
+            G = self._buf("g.mu", (N, Hp, Wp, cp(C)))
+            ops.pack_grad(g_mu, G, dtype=dt)
+            # tail
+            self._wgrad(self.tail, G, A["tail.x"], VK_CONV3X3_S1)
+            h, w = dims[0]
+            gX = self._buf("g.tail.X", (N, h, w, nf[0]))
+            self._dgrad(G, self.tail, VK_CONV3X3_S1, nf[0], ldo=nf[0], out1=gX)
+            # up path, reversed
+            g_bridge = {}
+            for k in reversed(range(len(self.up))):
+                us, res = self.up[k]
+                lvl = self.depth - 2 - k
+                c = nf[lvl]
+                h, w = dims[lvl]
+                for b in reversed(range(len(res))):
+                    gX = self._resblock_bwd(f"u{k}.{b}", res[b][0], res[b][1], gX, (N, h, w, c))
+                g_bridge[lvl] = gX
+                xlow = A[f"u{k}.x"]
+                self._wgrad(us, xlow, gX, VK_CONVT2X2_S2)
+                ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt)
+                hl, wl = dims[lvl + 1]
+                gXl = self._buf(f"g.u{k}.low", (N, hl, wl, nf[lvl + 1]))
+                self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
+                gX = gXl
+            # down path, reversed
+            for ii in reversed(range(self.depth)):
+                res, ds = self.down[ii]
+                c = nf[ii]
+                h, w = dims[ii]
+                if ds is not None:
+                    # gX is the gradient w.r.t. the stride-2 conv output (coarse grid)
+                    self._wgrad(ds, gX, A[f"d{ii}.x"], VK_CONV3X3_S2)
+                    gXf = self._buf(f"g.d{ii}.ds", (N, h, w, c))
+                    self._dgrad(gX, ds, VK_CONV3X3_S2_DGRAD, c, ldo=c, resid=g_bridge[ii], out1=gXf, out_hw=(h, w))
+                    gX = gXf
+                for b in reversed(range(len(res))):
+                    gX = self._resblock_bwd(f"d{ii}.{b}", res[b][0], res[b][1], gX, (N, h, w, c))
+            # head
+            self._wgrad(self.head, gX, A["r0"], VK_CONV3X3_S1)
+            if self.head_extra:
+                cin0 = C + self.head_extra
+                gR0 = self._buf("g.r0", (N, Hp, Wp, cp(cin0)))
+                self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
+        # ---- SNet ----
+        if g_sigma is not None or gR0 is not None:
+            sc = self.sigma_chn
+            if g_sigma is not None:
+                g_sigma = g_sigma.contiguous().float()
+            GS = self._buf("g.sig", (N, H, W, cp(sc)))
+            ops.sigma_head_bwd(A["sigma"], g_sigma, gR0, C, GS, dtype=dt, log_lo=SNET_LOG_MIN, log_hi=SNET_LOG_MAX)
+            g = GS
+            nS = len(self.s_layers)
+            for i in reversed(range(nS)):
+                ly = self.s_layers[i]
+                inp = A["xs"] if i == 0 else A[f"s{i - 1}"]
+                self._wgrad(ly, g, inp, VK_CONV3X3_S1)
+                if i > 0:
+                    gn = self._buf(f"g.s{i - 1}", (N, H, W, cp(ly.cin)))
+                    self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
+                    g = gn
+        # ---- workspace -> parameter-layout gradients ----
+        for ly in self.layers:
+            ops.wgrad_unpack(ly.ws, self.grad_view(ly.weight), accumulate=False)
+        self.saved = None

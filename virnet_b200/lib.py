@@ -15,7 +15,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libvirnet_sm100.so"
 
 VK_BF16, VK_TF32 = 0, 1
-VK_CONV3X3_S1, VK_CONV3X3_S2, VK_CONVT2X2_S2, VK_CONV1X1 = 0, 1, 2, 3
+VK_CONV3X3_S1, VK_CONV3X3_S2, VK_CONVT2X2_S2, VK_CONV1X1, VK_CONV2X2_S2, VK_CONV3X3_S2_DGRAD = 0, 1, 2, 3, 4, 5
 VK_EPI_STD, VK_EPI_NCHW_F32 = 0, 1
 
 
@@ -37,9 +37,33 @@ class vk_conv_args(C.Structure):
         ("round_out2", C.c_int32), ("act_expclamp", C.c_int32),
         ("clamp_lo", C.c_float), ("clamp_hi", C.c_float),
         ("crop_h", C.c_int32), ("crop_w", C.c_int32),
+        ("out_h", C.c_int32), ("out_w", C.c_int32),
         ("force_tiles_per_cta", C.c_int32), ("force_chunk_bytes", C.c_int32),
         ("force_stages", C.c_int32), ("force_tw", C.c_int32),
     ]
+
+
+class vk_wgrad_args(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("kind", C.c_int32),
+        ("a", C.c_void_p),
+        ("n", C.c_int32), ("gh", C.c_int32), ("gw", C.c_int32), ("lda", C.c_int32), ("m_valid", C.c_int32),
+        ("b", C.c_void_p),
+        ("bh", C.c_int32), ("bw", C.c_int32), ("ldb", C.c_int32), ("n_valid", C.c_int32),
+        ("dw", C.c_void_p), ("dbias", C.c_void_p),
+        ("force_ksplit", C.c_int32), ("force_k_rows", C.c_int32), ("force_stages", C.c_int32),
+    ]
+
+
+class vk_pack_desc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
+                ("dim0", C.c_int32), ("dim1", C.c_int32), ("taps", C.c_int32),
+                ("rows", C.c_int32), ("ld", C.c_int32), ("dst_taps", C.c_int32),
+                ("mode", C.c_int32), ("pad_", C.c_int32)]
+
+
+class vk_adam_group(C.Structure):
+    _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("max_norm", C.c_float), ("pad_", C.c_int32)]
 
 
 _lib = None
@@ -47,6 +71,19 @@ _lib = None
 # every symbol include/virnet_b200.h declares: (name, restype, argtypes)
 _SIGNATURES = {
     "vk_conv_igemm": (C.c_int, [C.POINTER(vk_conv_args), C.c_void_p]),
+    "vk_conv_wgrad": (C.c_int, [C.POINTER(vk_wgrad_args), C.c_void_p]),
+    "vk_wgrad_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vk_sizeof_wgrad_args": (C.c_uint32, []),
+    "vk_pack_input": (C.c_int, [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] + [C.c_int32] * 6
+                      + [C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p]),
+    "vk_pack_grad": (C.c_int, [C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p]),
+    "vk_sigma_head_bwd": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]
+                          + [C.c_int32] * 5 + [C.c_float, C.c_float, C.c_void_p]),
+    "vk_elbo_denoise": (C.c_int, [C.c_void_p] * 5 + [C.c_float] + [C.c_int32] * 5 + [C.c_float] * 4 + [C.c_void_p] * 5),
+    "vk_pack_weights": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "vk_channel_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vk_adam_clip_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p] + [C.c_float] * 5
+                          + [C.c_int32, C.c_void_p, C.c_void_p]),
     "vk_sizeof_conv_args": (C.c_uint32, []),
     "vk_version": (C.c_char_p, []),
     "vk_launch_count": (C.c_uint64, []),
@@ -71,8 +108,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.vk_sizeof_conv_args() != C.sizeof(vk_conv_args):
-        raise VkError("vk_conv_args layout mismatch between lib.py and the built library; rebuild")
+    if (lib.vk_sizeof_conv_args() != C.sizeof(vk_conv_args)
+            or lib.vk_sizeof_wgrad_args() != C.sizeof(vk_wgrad_args)):
+        raise VkError("argument struct layout mismatch between lib.py and the built library; rebuild")
     _lib = lib
     return lib
 

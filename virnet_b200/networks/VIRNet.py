@@ -1,0 +1,96 @@
+"""Drop-in replacements for the reference's networks/VIRNet.py model classes.
+
+Same constructor arguments, `forward` signatures, sub-module attribute names and
+`state_dict` layout as the reference (networks/VIRNet.py:18-46 and :48-97), so
+train_denoising_syn.py / train_SISR.py / scripts/testing_demo.py can import these instead.
+The forward and backward passes run as one CUDA program over libvirnet_sm100.so
+(virnet_b200/engine.py); autograd sees the whole network as a single node, so DDP hooks,
+`loss.backward()`, `clip_grad_norm_` and torch optimizers keep working unchanged.
+
+Extra (non-reference) knob: `precision` — "tf32" (fp32 storage, TF32 tensor-core MMA; matches the
+reference's default GPU numerics and the 1e-3 parity bar) or "bf16" (training throughput mode).
+It can also be set with the VIRNET_B200_PRECISION environment variable.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from .containers import AttResUNet, DnCNN, KernelNet
+
+
+def _default_precision():
+    return os.environ.get("VIRNET_B200_PRECISION", "tf32").lower()
+
+
+class _WholeNetFn(torch.autograd.Function):
+    """One autograd node for SNet + RNet: forward saves activations inside the engine,
+    backward returns the parameter gradients computed by the dgrad / wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, x, engine, *params):
+        # grad mode is always off inside Function.forward; ask autograd which inputs need gradients
+        need_grad = any(ctx.needs_input_grad[2:])
+        mu, sigma = engine.forward(x, save=need_grad)
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        ctx.params = params
+        return mu, sigma
+
+    @staticmethod
+    def backward(ctx, g_mu, g_sigma):
+        eng = ctx.engine
+        eng.backward(g_mu, g_sigma)
+        grads = tuple(eng.grad_view(p).clone() if p.requires_grad else None for p in ctx.params)
+        return (None, None) + grads
+
+
+class VIRAttResUNet(nn.Module):
+    """Denoising: sigma = exp(clamp(SNet(x))), mu = RNet(x, sqrt(sigma)); returns (mu, sigma)."""
+
+    def __init__(self, im_chn, sigma_chn=3, n_feat=[64, 128, 192], dep_S=5, n_resblocks=2, noise_cond=True,
+                 extra_mode="Input", noise_avg=False, precision=None):
+        super().__init__()
+        self.SNet = DnCNN(im_chn, sigma_chn, dep=dep_S, noise_avg=noise_avg)
+        self.noise_cond = noise_cond
+        extra_chn = sigma_chn if noise_cond else 0
+        self.RNet = AttResUNet(im_chn, extra_chn=extra_chn, out_chn=im_chn, n_feat=n_feat,
+                               n_resblocks=n_resblocks, extra_mode=extra_mode)
+        self.precision = (precision or _default_precision()).lower()
+        self._engine = None
+
+    def engine(self):
+        from ..engine import DenoiseEngine
+        if self._engine is None or self._engine.precision != self.precision:
+            object.__setattr__(self, "_engine", DenoiseEngine(self, self.precision))
+        return self._engine
+
+    def forward(self, x):
+        eng = self.engine()
+        params = tuple(self.parameters())
+        mu, sigma = _WholeNetFn.apply(x, eng, *params)
+        return mu, sigma
+
+
+class VIRAttResUNetSR(nn.Module):
+    """Super-resolution variant (SNet + KNet + SFT-modulated RNet); returns (mu, kinfo, sigma)."""
+
+    def __init__(self, im_chn, sigma_chn=1, kernel_chn=3, n_feat=[64, 128, 192], dep_S=5, dep_K=8,
+                 noise_cond=True, kernel_cond=True, n_resblocks=1, extra_mode="Down", noise_avg=True,
+                 precision=None):
+        super().__init__()
+        self.noise_cond, self.noise_avg, self.kernel_cond = noise_cond, noise_avg, kernel_cond
+        extra_chn = (kernel_chn if kernel_cond else 0) + (sigma_chn if noise_cond else 0)
+        self.SNet = DnCNN(im_chn, sigma_chn, dep=dep_S, noise_avg=noise_avg)
+        self.KNet = KernelNet(im_chn, kernel_chn, num_blocks=dep_K)
+        self.RNet = AttResUNet(im_chn, extra_chn=extra_chn, out_chn=im_chn, n_feat=n_feat,
+                               n_resblocks=n_resblocks, extra_mode=extra_mode)
+        self.precision = (precision or _default_precision()).lower()
+        self._engine = None
+
+    def forward(self, x, sf):
+        raise NotImplementedError(
+            "VIRAttResUNetSR: the SISR engine (KNet + SFT modulation kernels) is the next hot-path row "
+            "(SURVEY.md §8 a5/a7/a8); parameters and state_dict layout are already reference-compatible")

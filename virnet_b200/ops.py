@@ -11,6 +11,7 @@ import torch
 
 from . import lib as _l
 from .lib import (VK_BF16, VK_TF32, VK_CONV3X3_S1, VK_CONV3X3_S2, VK_CONVT2X2_S2, VK_CONV1X1,
+                  VK_CONV2X2_S2, VK_CONV3X3_S2_DGRAD,
                   VK_EPI_STD, VK_EPI_NCHW_F32)
 
 TORCH_DTYPE = {VK_BF16: torch.bfloat16, VK_TF32: torch.float32}
@@ -80,7 +81,7 @@ def pack_convT_weight(w: torch.Tensor, dtype: int, ldx: int | None = None):
 # ---------------------------------------------------------------------------
 def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_STD, resid=None, mask=None,
                out1=None, out2=None, alpha=0.2, round_out2=False, act_expclamp=False, clamp=(0.0, 0.0),
-               crop=(0, 0), tune=None):
+               crop=(0, 0), out_hw=(0, 0), tune=None):
     """x: NHWC [n,ih,iw,ldx] tensor of the storage dtype; w_packed: [taps][wrows][ldx]."""
     assert x.is_cuda and x.is_contiguous() and w_packed.is_contiguous()
     assert x.dtype == TORCH_DTYPE[dtype] and w_packed.dtype == TORCH_DTYPE[dtype]
@@ -98,9 +99,106 @@ def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_S
     a.act_expclamp = int(act_expclamp)
     a.clamp_lo, a.clamp_hi = clamp
     a.crop_h, a.crop_w = crop
+    a.out_h, a.out_w = out_hw
     if tune:
         a.force_tiles_per_cta = tune.get("p", 0)
         a.force_chunk_bytes = tune.get("chunk", 0)
         a.force_stages = tune.get("stages", 0)
         a.force_tw = tune.get("tw", 0)
     _l.check(_l.load().vk_conv_igemm(C.byref(a), _stream()), "vk_conv_igemm")
+
+
+# ---------------------------------------------------------------------------
+# vk_conv_wgrad
+# ---------------------------------------------------------------------------
+def conv_wgrad(a, b, dw, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None):
+    """a: M operand NHWC (conv: dY; convT: X); b: N operand NHWC (conv: X; convT: dY_up).
+    dw: fp32 [taps, m_valid, n_valid] workspace, accumulated into."""
+    assert a.is_contiguous() and b.is_contiguous() and dw.is_contiguous() and dw.dtype == torch.float32
+    assert a.dtype == TORCH_DTYPE[dtype] and b.dtype == TORCH_DTYPE[dtype]
+    g = _l.vk_wgrad_args()
+    g.dtype, g.kind = dtype, kind
+    g.a, g.n, g.gh, g.gw, g.lda, g.m_valid = _ptr(a), a.shape[0], a.shape[1], a.shape[2], a.shape[3], m_valid
+    g.b, g.bh, g.bw, g.ldb, g.n_valid = _ptr(b), b.shape[1], b.shape[2], b.shape[3], n_valid
+    g.dw, g.dbias = _ptr(dw), _ptr(dbias)
+    if tune:
+        g.force_ksplit = tune.get("ksplit", 0)
+        g.force_k_rows = tune.get("k_rows", 0)
+        g.force_stages = tune.get("stages", 0)
+    _l.check(_l.load().vk_conv_wgrad(C.byref(g), _stream()), "vk_conv_wgrad")
+
+
+def wgrad_unpack(ws, out, accumulate=False):
+    """ws [taps, M, N] fp32 -> out [M, N, kh, kw] (parameter layout)."""
+    taps, m, n = ws.shape
+    assert out.numel() == ws.numel() and out.is_contiguous() and out.dtype == torch.float32
+    _l.check(_l.load().vk_wgrad_unpack(_ptr(ws), _ptr(out), taps, m, n, int(accumulate), _stream()), "vk_wgrad_unpack")
+
+
+# ---------------------------------------------------------------------------
+# HBM-bound kernels
+# ---------------------------------------------------------------------------
+def pack_input(img, out, *, dtype, sf=1, extra=None, extra_is_map=True, extra_sqrt_mask=0, esf=1):
+    """img NCHW fp32 -> out NHWC [n, hp, wp, ld] (reflect pad, nearest upsample, optional extra channels)."""
+    n, c, h, w = img.shape
+    _, hp, wp, ld = out.shape
+    assert img.dtype == torch.float32 and img.is_contiguous() and out.is_contiguous()
+    e = eh = ew = 0
+    if extra is not None:
+        assert extra.dtype == torch.float32 and extra.is_contiguous()
+        e = extra.shape[1]
+        if extra_is_map:
+            eh, ew = extra.shape[2], extra.shape[3]
+    _l.check(_l.load().vk_pack_input(dtype, _ptr(img), n, c, h, w, sf, _ptr(extra), e, int(extra_is_map),
+                                     extra_sqrt_mask, eh, ew, esf, _ptr(out), hp, wp, ld, _stream()), "vk_pack_input")
+
+
+def pack_grad(g, out, *, dtype):
+    n, c, h, w = g.shape
+    _, hp, wp, ld = out.shape
+    assert g.dtype == torch.float32 and g.is_contiguous() and out.is_contiguous()
+    _l.check(_l.load().vk_pack_grad(dtype, _ptr(g), n, c, h, w, _ptr(out), hp, wp, ld, _stream()), "vk_pack_grad")
+
+
+def sigma_head_bwd(sigma, g_sigma, g_in, chan, out, *, dtype, log_lo, log_hi):
+    n, sc, h, w = sigma.shape
+    ld = out.shape[-1]
+    hp = wp = ld_in = 0
+    if g_in is not None:
+        _, hp, wp, ld_in = g_in.shape
+    assert g_sigma is None or (g_sigma.is_contiguous() and g_sigma.dtype == torch.float32)
+    _l.check(_l.load().vk_sigma_head_bwd(dtype, _ptr(sigma), _ptr(g_sigma), _ptr(g_in), ld_in, chan, hp, wp, _ptr(out),
+                                         ld, n, sc, h, w, log_lo, log_hi, _stream()), "vk_sigma_head_bwd")
+
+
+def elbo_denoise(mu, sigma, noisy, gt, beta0, *, eps2, alpha0, digamma_am1, beta0_scale=1.0, grad_scale=1.0, d_mu=None, d_sigma=None,
+                 acc3=None, out4=None):
+    n, c, h, w = mu.shape
+    sc = sigma.shape[1]
+    for t in (mu, sigma, noisy, gt, beta0):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    if acc3 is None:
+        acc3 = torch.empty(3, device=mu.device, dtype=torch.float64)
+    if out4 is None:
+        out4 = torch.empty(4, device=mu.device, dtype=torch.float32)
+    _l.check(_l.load().vk_elbo_denoise(_ptr(mu), _ptr(sigma), _ptr(noisy), _ptr(gt), _ptr(beta0), beta0_scale, n, c, sc, h, w,
+                                       eps2, alpha0, digamma_am1, grad_scale, _ptr(d_mu), _ptr(d_sigma), _ptr(acc3),
+                                       _ptr(out4), _stream()), "vk_elbo_denoise")
+    return out4
+
+
+def pack_weights(descs_dev, ndesc, max_elems, *, dtype, round_tf32=True):
+    _l.check(_l.load().vk_pack_weights(dtype, _ptr(descs_dev), ndesc, max_elems, int(round_tf32), _stream()),
+             "vk_pack_weights")
+
+
+def channel_sum(x, c, out, *, dtype):
+    npix = x.numel() // x.shape[-1]
+    _l.check(_l.load().vk_channel_sum(dtype, _ptr(x), npix, x.shape[-1], c, _ptr(out), _stream()), "vk_channel_sum")
+
+
+def adam_clip_step(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_group_elems, sq_ws, *, grad_scale, lr,
+                   beta1, beta2, eps, step, norms_out=None):
+    _l.check(_l.load().vk_adam_clip_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(groups_dev),
+                                         ngroups, max_group_elems, _ptr(sq_ws), grad_scale, lr, beta1, beta2, eps,
+                                         step, _ptr(norms_out), _stream()), "vk_adam_clip_step")

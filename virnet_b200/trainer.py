@@ -1,0 +1,103 @@
+"""Data-parallel training step for the denoising network: the hot loop of the reference's
+train_denoising_syn.py:169-184, as one kernel-only CUDA program per step.
+
+    im_noisy, im_gt, sigma_gt  (host or device, NCHW fp32)
+      -> forward (SNet, RNet)            virnet_b200.engine.DenoiseEngine.forward
+      -> fused ELBO (loss + d_mu, d_sigma)          vk_elbo_denoise
+      -> backward (dgrad / wgrad kernels)           DenoiseEngine.backward
+      -> [world_size > 1] NCCL all-reduce (sum) of the flat fp32 gradient buffer over NVLink
+      -> per-sub-network grad-norm -> clip -> Adam  vk_adam_clip_step   (averaging folded in)
+
+Semantics follow the reference: each rank computes the mean loss over its local batch, DDP
+averages gradients over ranks, clip_grad_norm_ runs per sub-network (RNet / SNet) on the averaged
+gradients, Adam(lr, betas=(0.9, 0.999), eps=1e-8) without weight decay; the LR is not rescaled
+with the world size.  There is no host synchronisation inside a step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import lib as _l
+from . import ops
+from .loss.ELBO_simple import _digamma
+
+
+class DenoiseTrainer:
+    def __init__(self, net, lr=1e-4, clip_grad_R=1e3, clip_grad_S=1e2, alpha0=24.5, eps2=1e-6, betas=(0.9, 0.999),
+                 adam_eps=1e-8, process_group=None):
+        self.net = net
+        self.engine = net.engine()
+        self.engine._ensure_flat()
+        eng = self.engine
+        dev = eng.flat_params.device
+        self.lr, self.betas, self.adam_eps = lr, betas, adam_eps
+        self.alpha0, self.eps2 = float(alpha0), float(eps2)
+        self.digamma_am1 = _digamma(self.alpha0 - 1.0)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.step_count = 0
+        self.exp_avg = torch.zeros_like(eng.flat_params)
+        self.exp_avg_sq = torch.zeros_like(eng.flat_params)
+        # clip groups: contiguous ranges of the flat buffer (parameters() order is SNet..., RNet...)
+        groups = []
+        names = [n for n, _ in net.named_parameters()]
+        for key, max_norm in (("snet", clip_grad_S), ("rnet", clip_grad_R)):
+            idx = [i for i, n in enumerate(names) if key in n.lower()]
+            assert idx == list(range(idx[0], idx[-1] + 1)), "sub-network parameters must be contiguous"
+            begin = eng.flat_offsets[idx[0]]
+            end = eng.flat_offsets[idx[-1] + 1] if idx[-1] + 1 < len(names) else eng.flat_total
+            groups.append((begin, end, float(max_norm)))
+        arr = (_l.vk_adam_group * len(groups))()
+        for i, (b, e, m) in enumerate(groups):
+            arr[i].begin, arr[i].end, arr[i].max_norm = b, e, m
+        self.group_names = ["SNet", "RNet"]
+        self._groups_dev = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
+        self._ngroups = len(groups)
+        self._max_group = max(e - b for b, e, _ in groups)
+        self._sq_ws = torch.zeros(len(groups), device=dev, dtype=torch.float64)
+        self.grad_norms = torch.zeros(len(groups), device=dev, dtype=torch.float32)
+        self._acc3 = torch.zeros(3, device=dev, dtype=torch.float64)
+        self.losses = torch.zeros(4, device=dev, dtype=torch.float32)
+        self._d_mu = self._d_sigma = None
+        self._staging = {}
+
+    # -- host -> device staging (pinned host buffers are the caller's; copies are async) --
+    def _to_device(self, name, t):
+        if t.is_cuda:
+            return t
+        buf = self._staging.get(name)
+        if buf is None or buf.shape != t.shape:
+            buf = torch.empty(t.shape, device=self.engine.flat_params.device, dtype=torch.float32)
+            self._staging[name] = buf
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def step(self, im_noisy, im_gt, sigma_gt, lr: Optional[float] = None):
+        """One optimisation step; returns the device tensor [loss, lh, kl_gauss, kl_Igamma]
+        of the local batch (no host sync)."""
+        eng = self.engine
+        x = self._to_device("noisy", im_noisy)
+        gt = self._to_device("gt", im_gt)
+        sg = self._to_device("sigma_gt", sigma_gt)
+        mu, sigma = eng.forward(x, save=True)
+        if self._d_mu is None or self._d_mu.shape != mu.shape:
+            self._d_mu, self._d_sigma = torch.empty_like(mu), torch.empty_like(sigma)
+        # beta0 = alpha0 * sigma_gt (train_denoising_syn.py:172) is folded into the loss kernel
+        ops.elbo_denoise(mu, sigma, x, gt, sg, beta0_scale=self.alpha0, eps2=self.eps2, alpha0=self.alpha0,
+                         digamma_am1=self.digamma_am1, d_mu=self._d_mu, d_sigma=self._d_sigma, acc3=self._acc3,
+                         out4=self.losses)
+        eng.backward(self._d_mu, self._d_sigma)
+        if self.world > 1:
+            dist.all_reduce(eng.flat_grads, op=dist.ReduceOp.SUM, group=self.pg)
+        self.step_count += 1
+        ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
+                           self._ngroups, self._max_group, self._sq_ws, grad_scale=1.0 / self.world,
+                           lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1],
+                           eps=self.adam_eps, step=self.step_count, norms_out=self.grad_norms)
+        eng.mark_params_dirty()
+        self.last_mu, self.last_sigma = mu, sigma
+        return self.losses
