@@ -36,6 +36,62 @@ def _stream():
 
 
 # ---------------------------------------------------------------------------
+# optional per-launch timing (CUDA events on the launching stream); used by bench.py for the
+# roofline of the dominant kernel.  Off by default: zero overhead on the product path.
+# ---------------------------------------------------------------------------
+_PROFILE = None
+
+
+def start_profile():
+    global _PROFILE
+    _PROFILE = []
+    return _PROFILE
+
+
+def stop_profile():
+    """Returns [{family, flops, bytes, ms}] for every library call since start_profile()."""
+    global _PROFILE
+    recs, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    return [dict(family=f, flops=fl, bytes=by, ms=s.elapsed_time(e)) for f, fl, by, s, e in recs]
+
+
+class _Prof:
+    __slots__ = ("family", "flops", "bytes", "s")
+
+    def __init__(self, family, flops=0.0, nbytes=0.0):
+        self.family, self.flops, self.bytes = family, flops, nbytes
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            _PROFILE.append((self.family, self.flops, self.bytes, self.s, e))
+        return False
+
+
+def _conv_flops(kind, n, ih, iw, k, cout, wrows):
+    """Algorithmic FLOPs (2*MAC) of one vk_conv_igemm call."""
+    if kind == VK_CONV3X3_S1:
+        return 2.0 * n * ih * iw * 9 * k * cout
+    if kind in (VK_CONV3X3_S2, VK_CONV3X3_S2_DGRAD):
+        # S2: ih,iw = fine grid -> coarse output; S2_DGRAD: ih,iw = coarse grid; 9 taps per coarse pixel either way
+        pix = ((ih + 1) // 2) * ((iw + 1) // 2) if kind == VK_CONV3X3_S2 else ih * iw
+        return 2.0 * n * pix * 9 * k * cout
+    if kind == VK_CONVT2X2_S2:
+        return 2.0 * n * ih * iw * 4 * k * cout
+    if kind == VK_CONV2X2_S2:
+        return 2.0 * n * (ih // 2) * (iw // 2) * 4 * k * cout
+    return 2.0 * n * ih * iw * k * cout
+
+
+# ---------------------------------------------------------------------------
 # layout helpers (torch ops; used for parameter packing and in tests)
 # ---------------------------------------------------------------------------
 def to_nhwc(x_nchw: torch.Tensor, dtype: int, ld: int | None = None) -> torch.Tensor:
@@ -81,7 +137,7 @@ def pack_convT_weight(w: torch.Tensor, dtype: int, ldx: int | None = None):
 # ---------------------------------------------------------------------------
 def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_STD, resid=None, mask=None,
                out1=None, out2=None, alpha=0.2, round_out2=False, act_expclamp=False, clamp=(0.0, 0.0),
-               crop=(0, 0), out_hw=(0, 0), tune=None):
+               crop=(0, 0), out_hw=(0, 0), tune=None, cin=None):
     """x: NHWC [n,ih,iw,ldx] tensor of the storage dtype; w_packed: [taps][wrows][ldx]."""
     assert x.is_cuda and x.is_contiguous() and w_packed.is_contiguous()
     assert x.dtype == TORCH_DTYPE[dtype] and w_packed.dtype == TORCH_DTYPE[dtype]
@@ -105,7 +161,8 @@ def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_S
         a.force_chunk_bytes = tune.get("chunk", 0)
         a.force_stages = tune.get("stages", 0)
         a.force_tw = tune.get("tw", 0)
-    _l.check(_l.load().vk_conv_igemm(C.byref(a), _stream()), "vk_conv_igemm")
+    with _Prof("conv_igemm", _conv_flops(kind, n, ih, iw, cin or ldx, cout, a.wrows) if _PROFILE is not None else 0.0):
+        _l.check(_l.load().vk_conv_igemm(C.byref(a), _stream()), "vk_conv_igemm")
 
 
 # ---------------------------------------------------------------------------
@@ -125,14 +182,17 @@ def conv_wgrad(a, b, dw, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None
         g.force_ksplit = tune.get("ksplit", 0)
         g.force_k_rows = tune.get("k_rows", 0)
         g.force_stages = tune.get("stages", 0)
-    _l.check(_l.load().vk_conv_wgrad(C.byref(g), _stream()), "vk_conv_wgrad")
+    taps = dw.shape[0]
+    with _Prof("conv_wgrad", 2.0 * g.n * g.gh * g.gw * taps * m_valid * n_valid):
+        _l.check(_l.load().vk_conv_wgrad(C.byref(g), _stream()), "vk_conv_wgrad")
 
 
 def wgrad_unpack(ws, out, accumulate=False):
     """ws [taps, M, N] fp32 -> out [M, N, kh, kw] (parameter layout)."""
     taps, m, n = ws.shape
     assert out.numel() == ws.numel() and out.is_contiguous() and out.dtype == torch.float32
-    _l.check(_l.load().vk_wgrad_unpack(_ptr(ws), _ptr(out), taps, m, n, int(accumulate), _stream()), "vk_wgrad_unpack")
+    with _Prof("wgrad_unpack", 0.0, 8.0 * ws.numel()):
+        _l.check(_l.load().vk_wgrad_unpack(_ptr(ws), _ptr(out), taps, m, n, int(accumulate), _stream()), "vk_wgrad_unpack")
 
 
 # ---------------------------------------------------------------------------
@@ -149,15 +209,17 @@ def pack_input(img, out, *, dtype, sf=1, extra=None, extra_is_map=True, extra_sq
         e = extra.shape[1]
         if extra_is_map:
             eh, ew = extra.shape[2], extra.shape[3]
-    _l.check(_l.load().vk_pack_input(dtype, _ptr(img), n, c, h, w, sf, _ptr(extra), e, int(extra_is_map),
-                                     extra_sqrt_mask, eh, ew, esf, _ptr(out), hp, wp, ld, _stream()), "vk_pack_input")
+    with _Prof("pack_input"):
+        _l.check(_l.load().vk_pack_input(dtype, _ptr(img), n, c, h, w, sf, _ptr(extra), e, int(extra_is_map),
+                                         extra_sqrt_mask, eh, ew, esf, _ptr(out), hp, wp, ld, _stream()), "vk_pack_input")
 
 
 def pack_grad(g, out, *, dtype):
     n, c, h, w = g.shape
     _, hp, wp, ld = out.shape
     assert g.dtype == torch.float32 and g.is_contiguous() and out.is_contiguous()
-    _l.check(_l.load().vk_pack_grad(dtype, _ptr(g), n, c, h, w, _ptr(out), hp, wp, ld, _stream()), "vk_pack_grad")
+    with _Prof("pack_grad"):
+        _l.check(_l.load().vk_pack_grad(dtype, _ptr(g), n, c, h, w, _ptr(out), hp, wp, ld, _stream()), "vk_pack_grad")
 
 
 def sigma_head_bwd(sigma, g_sigma, g_in, chan, out, *, dtype, log_lo, log_hi):
@@ -167,8 +229,9 @@ def sigma_head_bwd(sigma, g_sigma, g_in, chan, out, *, dtype, log_lo, log_hi):
     if g_in is not None:
         _, hp, wp, ld_in = g_in.shape
     assert g_sigma is None or (g_sigma.is_contiguous() and g_sigma.dtype == torch.float32)
-    _l.check(_l.load().vk_sigma_head_bwd(dtype, _ptr(sigma), _ptr(g_sigma), _ptr(g_in), ld_in, chan, hp, wp, _ptr(out),
-                                         ld, n, sc, h, w, log_lo, log_hi, _stream()), "vk_sigma_head_bwd")
+    with _Prof("sigma_head_bwd"):
+        _l.check(_l.load().vk_sigma_head_bwd(dtype, _ptr(sigma), _ptr(g_sigma), _ptr(g_in), ld_in, chan, hp, wp, _ptr(out),
+                                             ld, n, sc, h, w, log_lo, log_hi, _stream()), "vk_sigma_head_bwd")
 
 
 def elbo_denoise(mu, sigma, noisy, gt, beta0, *, eps2, alpha0, digamma_am1, beta0_scale=1.0, grad_scale=1.0, d_mu=None, d_sigma=None,
@@ -181,24 +244,28 @@ def elbo_denoise(mu, sigma, noisy, gt, beta0, *, eps2, alpha0, digamma_am1, beta
         acc3 = torch.empty(3, device=mu.device, dtype=torch.float64)
     if out4 is None:
         out4 = torch.empty(4, device=mu.device, dtype=torch.float32)
-    _l.check(_l.load().vk_elbo_denoise(_ptr(mu), _ptr(sigma), _ptr(noisy), _ptr(gt), _ptr(beta0), beta0_scale, n, c, sc, h, w,
-                                       eps2, alpha0, digamma_am1, grad_scale, _ptr(d_mu), _ptr(d_sigma), _ptr(acc3),
-                                       _ptr(out4), _stream()), "vk_elbo_denoise")
+    with _Prof("elbo_denoise"):
+        _l.check(_l.load().vk_elbo_denoise(_ptr(mu), _ptr(sigma), _ptr(noisy), _ptr(gt), _ptr(beta0), beta0_scale, n, c, sc, h, w,
+                                           eps2, alpha0, digamma_am1, grad_scale, _ptr(d_mu), _ptr(d_sigma), _ptr(acc3),
+                                           _ptr(out4), _stream()), "vk_elbo_denoise")
     return out4
 
 
 def pack_weights(descs_dev, ndesc, max_elems, *, dtype, round_tf32=True):
-    _l.check(_l.load().vk_pack_weights(dtype, _ptr(descs_dev), ndesc, max_elems, int(round_tf32), _stream()),
-             "vk_pack_weights")
+    with _Prof("pack_weights"):
+        _l.check(_l.load().vk_pack_weights(dtype, _ptr(descs_dev), ndesc, max_elems, int(round_tf32), _stream()),
+                 "vk_pack_weights")
 
 
 def channel_sum(x, c, out, *, dtype):
     npix = x.numel() // x.shape[-1]
-    _l.check(_l.load().vk_channel_sum(dtype, _ptr(x), npix, x.shape[-1], c, _ptr(out), _stream()), "vk_channel_sum")
+    with _Prof("channel_sum"):
+        _l.check(_l.load().vk_channel_sum(dtype, _ptr(x), npix, x.shape[-1], c, _ptr(out), _stream()), "vk_channel_sum")
 
 
 def adam_clip_step(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_group_elems, sq_ws, *, grad_scale, lr,
                    beta1, beta2, eps, step, norms_out=None):
-    _l.check(_l.load().vk_adam_clip_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(groups_dev),
-                                         ngroups, max_group_elems, _ptr(sq_ws), grad_scale, lr, beta1, beta2, eps,
-                                         step, _ptr(norms_out), _stream()), "vk_adam_clip_step")
+    with _Prof("adam_clip"):
+        _l.check(_l.load().vk_adam_clip_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(groups_dev),
+                                             ngroups, max_group_elems, _ptr(sq_ws), grad_scale, lr, beta1, beta2, eps,
+                                             step, _ptr(norms_out), _stream()), "vk_adam_clip_step")
