@@ -1,0 +1,12 @@
+#!/bin/bash
+# One GPU call: parity tests, bench (both arms), ncu launch list, one full capture of the conv kernel.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -c 3000 gpurun_out/bench.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
+   python tools/profile_step.py --steps 3 > gpurun_out/launches.log 2>&1; echo "ncu list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 60 -c 6 -f -o gpurun_out/prof_conv \
+   python tools/profile_step.py --steps 2 > gpurun_out/prof_conv.log 2>&1; echo "ncu full rc=$?"
