@@ -79,6 +79,11 @@ typedef struct vk_conv_args {
   int32_t force_chunk_bytes;
   int32_t force_stages;
   int32_t force_tw;
+  int32_t force_impl; /* 0 auto; 1 generic kernel; 2 halo-slab kernel (3x3 s1 only) */
+  int32_t pad_;
+  /* optional: device buffer of int64[gridsize][8] receiving per-CTA cycle counters
+   * {start, mainloop end, epilogue end, producer wait, mma wait, 0, 0, 0}; NULL in production */
+  long long* cta_timing;
 } vk_conv_args;
 
 /* Forward / data-gradient convolution as an implicit GEMM on tcgen05.

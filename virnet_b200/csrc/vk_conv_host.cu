@@ -349,6 +349,7 @@ static int conv_igemm_impl(const vk_conv_args* a, void* stream, int phase) {
   prm.clamp_hi = a->clamp_hi;
   prm.crop_h = a->crop_h > 0 ? a->crop_h : prm.oh;
   prm.crop_w = a->crop_w > 0 ? a->crop_w : prm.ow;
+  prm.cta_timing = a->cta_timing;
 
   // ---- tensor maps ----
   CUtensorMap ta, tb;

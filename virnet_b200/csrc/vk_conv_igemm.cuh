@@ -15,8 +15,13 @@
 // out-of-bounds zero fill standing in for the padding, so no im2col buffer ever
 // exists.  Weights are pre-packed K-major as [tap][Cout][Cin].
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner),
-// warps 2-5 epilogue (TMEM -> registers -> fused epilogue -> global).
+// CTA = 13 warps.  Warp 0 and warps 6-8: TMA producers (one TMA instruction occupies its issuing
+// warp for ~800 cycles on B200 — measured, tools/probe — so the boxes of a stage are spread over
+// four warps).  Warp 1: MMA issuer (+TMEM owner); its loop is warp-uniform with only the tcgen05
+// instructions predicated on one elected lane, so descriptors live in uniform registers and the
+// shallow tensor-core queue is never starved by address arithmetic.  Warps 2-5 and 9-12: epilogue
+// (TMEM -> registers -> fused epilogue -> global); two warps share each TMEM lane quarter and
+// split the 16-column groups between them.
 // A CTA owns P pixel tiles x n_cta channels, i.e. P fp32 accumulators of
 // 128 lanes x n_cta columns in TMEM, so each weight tile read from L2 is
 // reused P times.
@@ -72,6 +77,7 @@ struct ConvIgemmParams {
   int act_expclamp;           // 1: v = exp(clamp(v, lo, hi))
   float clamp_lo, clamp_hi;
   int crop_h, crop_w;         // stored region (<= oh, ow); out/resid are [n][cout][crop_h][crop_w]
+  long long* cta_timing;      // optional per-CTA cycle counters (debug), or null
 };
 
 template <typename DT>
@@ -127,7 +133,8 @@ __device__ __forceinline__ float to_float(float x) { return x; }
 __device__ __forceinline__ void from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 __device__ __forceinline__ void from_float(float* p, float v) { *p = v; }
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 416;
+constexpr int kConvProducers = 4;
 
 template <typename DT, int kChunkBytes>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -162,6 +169,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int stage_bytes = P * box_bytes + prm.b_taps * b_tap_bytes;
   const int tiles_per_img = prm.tiles_x * prm.tiles_y;
   const int tw_mask = (1 << prm.tw_log2) - 1;
+  if (prm.cta_timing != nullptr && threadIdx.x == 0) {
+    long long* t = prm.cta_timing + (blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    t[0] = clock64();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    t[6] = smid;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < prm.stages; ++s) {
@@ -179,7 +193,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tmem_alloc(&tmem_base_slot, prm.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2 && prm.bias != nullptr) {
+  if (warp >= 2 && warp < 6 && prm.bias != nullptr) {
     // bias is the raw parameter [cout]; ConvT repeats it for each of the 4 sub-pixel quadrants
     for (int i = threadIdx.x - 64; i < prm.n_cta; i += 128) {
       const int c = (n0 + i) % prm.cq;
@@ -191,20 +205,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || (warp >= 6 && warp <= 8)) {
+    // ===================== TMA producers =====================
+    // producer `pw` issues the boxes whose running index is == pw (mod kConvProducers); producer 0
+    // also arms the barrier (a complete_tx that lands before the expect_tx is legal: the phase
+    // cannot complete before producer 0's arrival).
+    const int pw = warp == 0 ? 0 : warp - 5;
     if (elect_one()) {
       int it = 0;
+      int op = 0;
+      long long prod_wait = 0;
       for (int l = 0; l < prm.n_loads; ++l) {
         const ConvLoad& ld = prm.loads[l];
         for (int c = 0; c < prm.k_chunks; ++c, ++it) {
           const int s = it % prm.stages;
           const uint32_t ph = (it / prm.stages) & 1;
+          const long long tw0 = clock64();
           mbar_wait(&empty_bar[s], ph ^ 1);
+          prod_wait += clock64() - tw0;
           uint8_t* a_s = smem + s * stage_bytes;
           uint8_t* b_s = a_s + P * box_bytes;
-          mbar_arrive_expect_tx(&full_bar[s], nvalid * box_bytes + ld.ntaps * b_tap_bytes);
-          for (int p = 0; p < nvalid; ++p) {
+          if (pw == 0) mbar_arrive_expect_tx(&full_bar[s], nvalid * box_bytes + ld.ntaps * b_tap_bytes);
+          for (int p = 0; p < nvalid; ++p, ++op) {
+            if (op % kConvProducers != pw) continue;
             const int t = tile0 + p;
             const int img = t / tiles_per_img;
             const int r = t - img * tiles_per_img;
@@ -213,151 +236,212 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tma_load_4d(a_s + p * box_bytes, &tmap_a, &full_bar[s], c * kChunkElems, ox0 * prm.a_stride + ld.dx,
                         oy0 * prm.a_stride + ld.dy, img);
           }
-          for (int j = 0; j < ld.ntaps; ++j)
+          for (int j = 0; j < ld.ntaps; ++j, ++op) {
+            if (op % kConvProducers != pw) continue;
             tma_load_3d(b_s + j * b_tap_bytes, &tmap_b, &full_bar[s], c * kChunkElems, n0, ld.tap[j]);
+          }
         }
       }
+      if (prm.cta_timing != nullptr && pw == 0)
+        prm.cta_timing[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 3] = prod_wait;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
+    // The issuing thread runs on the (slow, in-order) uniform datapath: every instruction on the
+    // dependent chain in front of a tcgen05.mma delays it, so descriptors are kept as 32-bit "low
+    // words" (start address >> 4 | LBO) advanced by additions only; the high word is constant.
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc(DTraits<DT>::kFmt, 128, prm.n_cta, 0, 0);
-      int it = 0;
+      const uint64_t desc_hi = make_smem_desc(0, 16, kSBO, kLayout) & 0xFFFFFFFF00000000ull;
+      const uint32_t lbo_lo = 1u << 16;                       // LBO = 16 bytes (unused for swizzled K-major)
+      const uint32_t box16 = uint32_t(box_bytes) >> 4, btap16 = uint32_t(b_tap_bytes) >> 4;
+      const uint32_t stage16 = uint32_t(stage_bytes) >> 4;
+      const uint32_t smem16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      const uint32_t b_off16 = uint32_t(P) * box16;
+      const uint32_t acc_stride = prm.acc_stride;
+      int s = 0;
+      uint32_t ph = 0;
       uint32_t accum = 0;
+      long long mma_wait = 0;
       for (int l = 0; l < prm.n_loads; ++l) {
         const ConvLoad& ld = prm.loads[l];
-        for (int c = 0; c < prm.k_chunks; ++c, ++it) {
-          const int s = it % prm.stages;
-          const uint32_t ph = (it / prm.stages) & 1;
-          mbar_wait(&full_bar[s], ph);
+        const bool three = ld.ntaps > 1;
+        const uint32_t ro0 = uint32_t(ld.rowoff[0] * kChunkBytes) >> 4;
+        const uint32_t ro1 = uint32_t(ld.rowoff[1] * kChunkBytes) >> 4;
+        const uint32_t ro2 = uint32_t(ld.rowoff[2] * kChunkBytes) >> 4;
+        for (int c = 0; c < prm.k_chunks; ++c) {
+          if (prm.cta_timing != nullptr) {
+            const long long tw0 = clock64();
+            mbar_wait(&full_bar[s], ph);
+            mma_wait += clock64() - tw0;
+          } else {
+            mbar_wait(&full_bar[s], ph);
+          }
           tc_fence_after_sync();
-          const uint32_t a_s = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_s = a_s + P * box_bytes;
-          for (int p = 0; p < nvalid; ++p) {
-            uint32_t acc_p = accum;
-            for (int j = 0; j < ld.ntaps; ++j) {
-              const uint32_t a_tap = a_s + p * box_bytes + ld.rowoff[j] * kChunkBytes;
-              const uint32_t b_tap = b_s + j * b_tap_bytes;
+          const uint32_t a_lo = (smem16 + uint32_t(s) * stage16) | lbo_lo;
+          const uint32_t b_lo = a_lo + b_off16;
+          uint32_t a_p = a_lo, d_p = tmem_base;
+          for (int p = 0; p < nvalid; ++p, a_p += box16, d_p += acc_stride) {
+            // K step outer, tap inner: the accumulation order (load, channel, tap) does not depend on
+            // the chunk width picked by the host heuristics -> bit-identical results across batch sizes
+            if (leader) {
 #pragma unroll
               for (int k = 0; k < kMmasPerChunk; ++k) {
-                const uint64_t ad = make_smem_desc(a_tap + k * 32, 16, kSBO, kLayout);
-                const uint64_t bd = make_smem_desc(b_tap + k * 32, 16, kSBO, kLayout);
-                umma_ss<kTF32>(tmem_base + p * prm.acc_stride, ad, bd, idesc, acc_p);
-                acc_p = 1;
+                umma_ss<kTF32>(d_p, desc_hi | (a_p + ro0 + 2 * k), desc_hi | (b_lo + 2 * k), idesc,
+                               (k == 0) ? accum : 1u);
+                if (three) {
+                  umma_ss<kTF32>(d_p, desc_hi | (a_p + ro1 + 2 * k), desc_hi | (b_lo + btap16 + 2 * k), idesc, 1u);
+                  umma_ss<kTF32>(d_p, desc_hi | (a_p + ro2 + 2 * k), desc_hi | (b_lo + 2 * btap16 + 2 * k), idesc, 1u);
+                }
               }
             }
           }
           accum = 1;
-          umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
+          if (leader) umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
+          __syncwarp();
+          if (++s == prm.stages) s = 0, ph ^= 1;
         }
       }
-      umma_commit(&tmem_full_bar);      // accumulators complete
+      if (leader) {
+        umma_commit(&tmem_full_bar);      // accumulators complete
+        if (prm.cta_timing != nullptr) {
+          long long* t = prm.cta_timing + (blockIdx.y * gridDim.x + blockIdx.x) * 8;
+          t[4] = mma_wait;
+          t[5] = clock64();               // all MMAs issued
+        }
+      }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5 and 9..12) =====================
     const int q4 = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = warp >= 9 ? 1 : 0;         // which of the two warps of this quarter
     const int row = q4 * 32 + lane;             // GEMM row == pixel within the tile
     const int tyy = row >> prm.tw_log2, txx = row & tw_mask;
+    // everything that needs an integer division is hoisted out of the tile / column loops
+    const int us = prm.us;
+    const int quad = n0 / prm.cq + prm.quad_base;            // sub-pixel quadrant: constant per CTA
+    const int co0 = n0 - (n0 / prm.cq) * prm.cq;             // first channel (within the quadrant) of this CTA
+    const int qy = quad / us, qx = quad - qy * us;
+    const int ngroups = prm.n_cta >> 4;
+    const float alpha = prm.alpha;
+    const bool has_bias = prm.bias != nullptr;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after_sync();
-    const int us = prm.us;
+    if (prm.cta_timing != nullptr && threadIdx.x == 64)
+      prm.cta_timing[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 1] = clock64();
+    int img = tile0 / tiles_per_img;
+    int rt = tile0 - img * tiles_per_img;
     for (int p = 0; p < nvalid; ++p) {
-      const int t = tile0 + p;
-      const int img = t / tiles_per_img;
-      const int r = t - img * tiles_per_img;
-      const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
+      const int ty = rt / prm.tiles_x, tx = rt - ty * prm.tiles_x;
       const int oy = ty * prm.th + tyy, ox = (tx << prm.tw_log2) + txx;
       const bool pix_ok = (oy < prm.oh) && (ox < prm.ow);
       const uint32_t taddr = tmem_base + (uint32_t(q4 * 32) << 16) + p * prm.acc_stride;
-      for (int jc = 0; jc < prm.n_cta; jc += 16) {
-        uint32_t rr[16];
-        __syncwarp();                           // tcgen05.ld is warp-collective (.sync.aligned)
-        tmem_ld16(taddr + jc, rr);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
-        if (prm.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += bias_s[jc + i];
+      if (prm.epi == EPI_STD) {
+        const int yy = oy * us + qy, xx = ox * us + qx;
+        const bool out_ok = pix_ok && yy < prm.out_h && xx < prm.out_w;
+        const long long obase = ((static_cast<long long>(img) * prm.out_h + yy) * prm.out_w + xx) * prm.ldo + co0;
+        DT* const o1 = reinterpret_cast<DT*>(prm.out1);
+        DT* const o2 = reinterpret_cast<DT*>(prm.out2);
+        const DT* const rs = reinterpret_cast<const DT*>(prm.resid);
+        const DT* const mk = reinterpret_cast<const DT*>(prm.mask);
+        // software pipeline: the mask / residual vectors of the next group are in flight while this one is processed
+        float m_nx[16], r_nx[16];
+        int g = half;
+        if (g < ngroups && out_ok && co0 + g * 16 + 16 <= prm.cout) {
+          if (mk != nullptr) load16(mk + obase + g * 16, m_nx);
+          if (rs != nullptr) load16(rs + obase + g * 16, r_nx);
         }
-        const int cg = n0 + jc;                 // global GEMM column of v[0]
-        const int quad_c = cg / prm.cq;
-        const int co = cg - quad_c * prm.cq;    // channel within the quadrant
-        const int quad = quad_c + prm.quad_base;
-        const bool out_ok = pix_ok && (prm.epi != EPI_STD ||
-                                       ((oy * us + quad / us) < prm.out_h && (ox * us + quad % us) < prm.out_w));
-        const int nch = (out_ok && co < prm.cout) ? min(16, prm.cout - co) : 0;
-        if (nch == 0) {
-          // nothing to store for this thread (ragged tile edge / channel padding)
-        } else if (prm.epi == EPI_STD) {
-          const int qy = quad / us, qx = quad - qy * us;
-          const int yy = oy * us + qy, xx = ox * us + qx;
-          const long long opix = (static_cast<long long>(img) * prm.out_h + yy) * prm.out_w + xx;
-          const long long off = opix * prm.ldo + co;
-          DT* o1 = reinterpret_cast<DT*>(prm.out1);
-          DT* o2 = reinterpret_cast<DT*>(prm.out2);
-          const DT* rs = reinterpret_cast<const DT*>(prm.resid);
-          const DT* mk = reinterpret_cast<const DT*>(prm.mask);
+        for (; g < ngroups; g += 2) {
+          const int jc = g * 16;
+          uint32_t rr[16];
+          __syncwarp();                           // tcgen05.ld is warp-collective (.sync.aligned)
+          tmem_ld16(taddr + jc, rr);
+          float m[16], rv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m[i] = m_nx[i], rv[i] = r_nx[i];
+          const int gn = g + 2;
+          if (gn < ngroups && out_ok && co0 + gn * 16 + 16 <= prm.cout) {
+            if (mk != nullptr) load16(mk + obase + gn * 16, m_nx);
+            if (rs != nullptr) load16(rs + obase + gn * 16, r_nx);
+          }
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+          if (has_bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += bias_s[jc + i];
+          }
+          const int co = co0 + jc;
+          const int nch = (out_ok && co < prm.cout) ? min(16, prm.cout - co) : 0;
+          const long long off = obase + jc;
           if (nch == 16) {
             if (mk != nullptr) {
-              float m[16];
-              load16(mk + off, m);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : prm.alpha);
+              for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : alpha);
             }
             if (rs != nullptr) {
-              float m[16];
-              load16(rs + off, m);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += m[i];
+              for (int i = 0; i < 16; ++i) v[i] += rv[i];
             }
             if (o1 != nullptr) store16(o1 + off, v);
             if (o2 != nullptr) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                v[i] = lrelu(v[i], prm.alpha);
+                v[i] = lrelu(v[i], alpha);
                 if (kTF32 && prm.round_out2) v[i] = round_tf32(v[i]);
               }
               store16(o2 + off, v);
             }
-          } else {
+          } else if (nch > 0) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               if (i < nch) {
                 float x = v[i];
-                if (mk != nullptr) x *= (to_float(mk[off + i]) > 0.f ? 1.f : prm.alpha);
+                if (mk != nullptr) x *= (to_float(mk[off + i]) > 0.f ? 1.f : alpha);
                 if (rs != nullptr) x += to_float(rs[off + i]);
                 if (o1 != nullptr) from_float(o1 + off + i, x);
                 if (o2 != nullptr) {
-                  float y = lrelu(x, prm.alpha);
+                  float y = lrelu(x, alpha);
                   if (kTF32 && prm.round_out2) y = round_tf32(y);
                   from_float(o2 + off + i, y);
                 }
               }
             }
           }
-        } else {  // EPI_NCHW_F32
-          if (oy < prm.crop_h && ox < prm.crop_w) {
-            float* o1 = reinterpret_cast<float*>(prm.out1);
-            const float* rs = reinterpret_cast<const float*>(prm.resid);
-            const long long plane = static_cast<long long>(prm.crop_h) * prm.crop_w;
-            const long long base = (static_cast<long long>(img) * prm.cout + co) * plane +
-                                   static_cast<long long>(oy) * prm.crop_w + ox;
+        }
+      } else {  // EPI_NCHW_F32 (us == 1)
+        float* const o1 = reinterpret_cast<float*>(prm.out1);
+        const float* const rs = reinterpret_cast<const float*>(prm.resid);
+        const long long plane = static_cast<long long>(prm.crop_h) * prm.crop_w;
+        const bool in_crop = pix_ok && oy < prm.crop_h && ox < prm.crop_w;
+        for (int g = half; g < ngroups; g += 2) {
+          const int jc = g * 16;
+          uint32_t rr[16];
+          __syncwarp();
+          tmem_ld16(taddr + jc, rr);
+          tmem_ld_wait();
+          const int co = co0 + jc;
+          const int nch = (in_crop && co < prm.cout) ? min(16, prm.cout - co) : 0;
+          const long long base = (static_cast<long long>(img) * prm.cout + co) * plane +
+                                 static_cast<long long>(oy) * prm.crop_w + ox;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i < nch) {
-                float x = v[i];
-                if (prm.act_expclamp) x = expf(fminf(fmaxf(x, prm.clamp_lo), prm.clamp_hi));
-                if (rs != nullptr) x += __ldg(rs + base + i * plane);
-                o1[base + i * plane] = x;
-              }
+          for (int i = 0; i < 16; ++i) {
+            if (i < nch) {
+              float x = __uint_as_float(rr[i]) + (has_bias ? bias_s[jc + i] : 0.f);
+              if (prm.act_expclamp) x = expf(fminf(fmaxf(x, prm.clamp_lo), prm.clamp_hi));
+              if (rs != nullptr) x += __ldg(rs + base + i * plane);
+              o1[base + i * plane] = x;
             }
           }
         }
       }
+      if (++rt == tiles_per_img) rt = 0, ++img;
     }
     tc_fence_before_sync();
+    if (prm.cta_timing != nullptr && threadIdx.x == 64)
+      prm.cta_timing[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 2] = clock64();
   }
 
   __syncthreads();

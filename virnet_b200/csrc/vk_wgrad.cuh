@@ -59,7 +59,8 @@ __device__ __forceinline__ void red_add(float* p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
-constexpr int kWgradThreads = 192;
+constexpr int kWgradThreads = 288;   // warps 0, 6-8: TMA producers; 1: MMA; 2-5: epilogue
+constexpr int kWgradProducers = 4;
 
 template <typename DT>
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -117,7 +118,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     tmem_alloc(&tmem_base_slot, prm.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     // ones tile: the value 1.0 in the operand type; any layout of all-ones is all-ones
     const uint32_t one = kTF32 ? 0x3F800000u : 0x3F803F80u;
     uint32_t* o = reinterpret_cast<uint32_t*>(ones);
@@ -129,9 +130,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp >= 6) {
+    // ===================== TMA producers (boxes of a stage spread over 4 warps) =====================
+    const int pw = warp == 0 ? 0 : warp - 5;
     if (elect_one()) {
+      int op = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % prm.stages;
         const uint32_t ph = (it / prm.stages) & 1;
@@ -143,58 +146,80 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int x0 = tx << prm.tw_log2, y0 = ty * prm.th;
         uint8_t* a_s = smem + s * stage_bytes;
         uint8_t* b_s = a_s + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        for (int j = 0; j < prm.n_a_blocks; ++j)
+        if (pw == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        for (int j = 0; j < prm.n_a_blocks; ++j, ++op) {
+          if (op % kWgradProducers != pw) continue;
           tma_load_4d(a_s + j * a_block_bytes, &tmap_a, &full_bar[s], m0 + j * kBlockElems, x0, y0, img);
+        }
         for (int l = 0; l < prm.n_loads; ++l) {
           const WgradLoad& ld = prm.loads[group][l];
-          for (int j = 0; j < prm.n_b_blocks; ++j)
+          for (int j = 0; j < prm.n_b_blocks; ++j, ++op) {
+            if (op % kWgradProducers != pw) continue;
             tma_load_4d(b_s + l * b_bytes + j * b_block_bytes, &tmap_b, &full_bar[s], n0 + j * kBlockElems,
                         x0 * prm.b_stride + ld.dx, y0 * prm.b_stride + ld.dy, img);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
+    // descriptors are advanced by additions on their 32-bit low word only (see vk_conv_igemm.cuh: the
+    // uniform datapath in front of tcgen05.mma is slow, keep the dependent chain short)
+    {
+      const bool leader = elect_one();          // warp-uniform loop, only the tcgen05 instructions are predicated
       const uint32_t idesc = make_idesc(DTraits<DT>::kFmt, 128, prm.n_cta, 1, 1);
       const uint32_t idesc_bias = make_idesc(DTraits<DT>::kFmt, 128, 16, 1, 1);
-      const uint32_t ones_addr = smem_u32(ones);
+      const uint64_t desc_hi = make_smem_desc(0, 0, kSBO, kLayout) & 0xFFFFFFFF00000000ull;
+      const uint32_t a_lbo = ((uint32_t(a_block_bytes) >> 4) & 0x3FFFu) << 16;
+      const uint32_t b_lbo = ((uint32_t(b_block_bytes) >> 4) & 0x3FFFu) << 16;
+      const uint32_t ones_lo = ((smem_u32(ones) & 0x3FFFFu) >> 4) | (64u << 16);   // LBO 1024 B
+      const uint32_t smem16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      const uint32_t stage16 = uint32_t(stage_bytes) >> 4, a16 = uint32_t(a_bytes) >> 4;
+      constexpr uint32_t kAdv16 = uint32_t(kAdvance) >> 4;
       const int ksteps = prm.k_rows / kRowsPerMma;
+      const int n_taps = prm.n_taps;
+      uint32_t tap_off[3];
+#pragma unroll
+      for (int tp = 0; tp < 3; ++tp)
+        tap_off[tp] = (uint32_t(prm.taps[group][tp].load * b_bytes + prm.taps[group][tp].rowoff * 128) >> 4);
+      const uint32_t acc_stride = prm.acc_stride;
       uint32_t accum = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % prm.stages;
-        const uint32_t ph = (it / prm.stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after_sync();
-        const uint32_t a_s = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_s = a_s + a_bytes;
-        for (int tp = 0; tp < prm.n_taps; ++tp) {
-          const WgradTap& tap = prm.taps[group][tp];
-          const uint32_t b_tap = b_s + tap.load * b_bytes + tap.rowoff * 128;
-          uint32_t acc = accum;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t ad = make_smem_desc(a_s + kk * kAdvance, a_block_bytes, kSBO, kLayout);
-            const uint64_t bd = make_smem_desc(b_tap + kk * kAdvance, b_block_bytes, kSBO, kLayout);
-            umma_ss<kTF32>(tmem_base + tp * prm.acc_stride, ad, bd, idesc, acc);
-            acc = 1;
+        const uint32_t a_lo = (smem16 + uint32_t(s) * stage16) | a_lbo;
+        const uint32_t b_lo = (smem16 + uint32_t(s) * stage16 + a16) | b_lbo;
+        if (leader) {
+#pragma unroll
+          for (int tp = 0; tp < 3; ++tp) {
+            if (tp < n_taps) {
+              uint32_t ad = a_lo, bd = b_lo + tap_off[tp];
+              uint32_t acc = accum;
+              for (int kk = 0; kk < ksteps; ++kk, ad += kAdv16, bd += kAdv16) {
+                umma_ss<kTF32>(tmem_base + tp * acc_stride, desc_hi | ad, desc_hi | bd, idesc, acc);
+                acc = 1;
+              }
+            }
           }
-        }
-        if (do_bias) {
-          uint32_t acc = accum;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t ad = make_smem_desc(a_s + kk * kAdvance, a_block_bytes, kSBO, kLayout);
-            const uint64_t bd = make_smem_desc(ones_addr, 1024, kSBO, kLayout);
-            umma_ss<kTF32>(tmem_base + prm.n_taps * prm.acc_stride, ad, bd, idesc_bias, acc);
-            acc = 1;
+          if (do_bias) {
+            uint32_t ad = a_lo;
+            uint32_t acc = accum;
+            for (int kk = 0; kk < ksteps; ++kk, ad += kAdv16) {
+              umma_ss<kTF32>(tmem_base + n_taps * acc_stride, desc_hi | ad, desc_hi | ones_lo, idesc_bias, acc);
+              acc = 1;
+            }
           }
+          umma_commit(&empty_bar[s]);
         }
+        __syncwarp();
         accum = 1;
-        umma_commit(&empty_bar[s]);
+        if (++s == prm.stages) s = 0, ph ^= 1;
       }
-      umma_commit(&tmem_full_bar);
+      if (leader) umma_commit(&tmem_full_bar);
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue: TMEM -> fp32 red.add =====================
     const int q4 = warp & 3;
     const int m = m0 + q4 * 32 + lane;
