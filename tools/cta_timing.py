@@ -28,7 +28,7 @@ def run(c, h, n, epi, tune=None, impl=0):
     elif epi == "mask_resid":
         kw.update(resid=resid, mask=o2, out1=o1)
     t = dict(tune or {})
-    t["impl"] = impl
+    t["impl"] = impl or 1   # this tool reads the v1 per-CTA counters (v2: tools/v2_timing.py)
     for _ in range(3):
         ops.conv_igemm(x, w, tune=t, **kw)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

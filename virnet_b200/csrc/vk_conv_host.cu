@@ -148,6 +148,9 @@ constexpr int kSmemBudget = 200 * 1024;   // dynamic smem we allow one CTA (<= 2
 using namespace vk;
 
 static int conv_igemm_impl(const vk_conv_args* a, void* stream, int phase);
+namespace vk {
+int conv_v2_impl(const vk_conv_args* a, void* stream, int phase);   // vk_conv_v2_host.cu
+}
 
 extern "C" int vk_conv_igemm(const vk_conv_args* a, void* stream) {
   if (a == nullptr || a->x == nullptr || a->w == nullptr) return VK_E_BADARG;
@@ -168,6 +171,13 @@ static int conv_igemm_impl(const vk_conv_args* a, void* stream, int phase) {
   if (a->ldx <= 0 || a->ldx % chan_align) return VK_E_BADARG;
   if (a->wrows <= 0 || a->wrows % 16) return VK_E_BADARG;
   if (a->n <= 0 || a->ih <= 0 || a->iw <= 0 || a->cout <= 0) return VK_E_BADARG;
+  // persistent kernel first (force_impl: 0 auto, 1 = v1 only, 2 = v2 only); v1 serves what v2 declines
+  // (auto mode sends only the 3x3 stride-1 convolutions there: the strided / transposed kinds are
+  // 4 % of the FLOPs and still run faster on v1's larger per-CTA tile groups)
+  if (a->force_impl == 2 || (a->force_impl == 0 && a->kind == VK_CONV3X3_S1)) {
+    const int r = conv_v2_impl(a, stream, phase);
+    if (r != VK_E_UNSUPPORTED || a->force_impl == 2) return r;
+  }
 
   ConvIgemmParams prm{};
   int taps = 9;

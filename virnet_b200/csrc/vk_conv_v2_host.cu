@@ -1,0 +1,358 @@
+// vk_conv_v2_host.cu — host side of the persistent convolution kernel (vk_conv_v2.cuh): job /
+// stage heuristics under the TMEM (512 columns) and shared-memory (227 KB) budgets, the TMA
+// descriptors of the A / B operands and of the epilogue tensors, launch.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/virnet_b200.h"
+#include "vk_conv_v2.cuh"
+#include "vk_host.h"
+
+namespace vk {
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int next_pow2_cols(int x) {
+  int c = 32;
+  while (c < x) c <<= 1;
+  return c;
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+constexpr int kV2SmemBudget = 220 * 1024;   // dynamic smem incl. 1 KB alignment slack (static: ~4.6 KB)
+
+template <typename DT, int kChunk, int kNT>
+int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em, const ConvV2Params& prm, int grid,
+              int smem_bytes, cudaStream_t st) {
+  static int cur = 0;
+  static std::mutex mu;
+  auto kern = conv_v2_kernel<DT, kChunk, kNT>;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (smem_bytes > cur) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+      if (e != cudaSuccess) return int(e);
+      cur = smem_bytes;
+    }
+  }
+  kern<<<grid, kV2Threads, smem_bytes, st>>>(ta, tb, em, prm);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+template <typename DT>
+int dispatch_v2(int chunk, int nt, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
+                const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st) {
+#define VK_V2_CASE(C, T) \
+  if (chunk == C && nt == T) return launch_v2<DT, C, T>(ta, tb, em, prm, grid, smem_bytes, st);
+  VK_V2_CASE(128, 1) VK_V2_CASE(128, 3) VK_V2_CASE(128, 9)
+  VK_V2_CASE(64, 1) VK_V2_CASE(64, 3) VK_V2_CASE(64, 9)
+  VK_V2_CASE(32, 1) VK_V2_CASE(32, 3) VK_V2_CASE(32, 9)
+#undef VK_V2_CASE
+  return VK_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+// Returns VK_E_UNSUPPORTED when the shape does not fit this kernel (the caller falls back to v1).
+int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
+  const int esize = a->dtype == VK_BF16 ? 2 : 4;
+  const int chan_align = 32 / esize;
+  if (a->ldx <= 0 || a->ldx % chan_align) return VK_E_BADARG;
+  if (a->wrows <= 0 || a->wrows % 16 || a->wrows > 1024) return VK_E_UNSUPPORTED;
+
+  ConvV2Params prm{};
+  int taps = 9, us = 1;
+  bool slab = false;
+  switch (a->kind) {
+    case VK_CONV3X3_S1: prm.oh = a->ih, prm.ow = a->iw, prm.a_stride = 1, slab = true; break;
+    case VK_CONV3X3_S2: prm.oh = (a->ih + 1) / 2, prm.ow = (a->iw + 1) / 2, prm.a_stride = 2; break;
+    case VK_CONVT2X2_S2: prm.oh = a->ih, prm.ow = a->iw, prm.a_stride = 1, taps = 1, us = 2; break;
+    case VK_CONV1X1: prm.oh = a->ih, prm.ow = a->iw, prm.a_stride = 1, taps = 1; break;
+    case VK_CONV2X2_S2: prm.oh = a->ih / 2, prm.ow = a->iw / 2, prm.a_stride = 2, taps = 4; break;
+    case VK_CONV3X3_S2_DGRAD: {
+      if (a->out_h <= 0 || a->out_w <= 0 || (a->out_h + 1) / 2 != a->ih || (a->out_w + 1) / 2 != a->iw)
+        return VK_E_BADARG;
+      const int py = phase >> 1, px = phase & 1;
+      prm.oh = (a->out_h - py + 1) / 2, prm.ow = (a->out_w - px + 1) / 2;
+      prm.a_stride = 1, us = 2;
+      if (prm.oh <= 0 || prm.ow <= 0) return 0;
+      break;
+    }
+    default: return VK_E_BADARG;
+  }
+  const bool is_convT = a->kind == VK_CONVT2X2_S2;
+  const bool is_s2d = a->kind == VK_CONV3X3_S2_DGRAD;
+  prm.n_img = a->n;
+  prm.cout = a->cout;
+  prm.wrows = a->wrows;
+  prm.cq = is_convT ? a->wrows / 4 : a->wrows;
+  if (is_convT && (a->wrows % 64 || prm.cq < a->cout)) return VK_E_BADARG;
+  if (!is_convT && a->wrows < a->cout) return VK_E_BADARG;
+  const int fine_h = is_s2d ? a->out_h : prm.oh * us;      // spatial dims of the EPI_STD tensors
+  const int fine_w = is_s2d ? a->out_w : prm.ow * us;
+  if (a->epi == VK_EPI_STD) {
+    if (a->ldo <= 0 || a->ldo % (16 / esize) || a->ldo < a->cout) return VK_E_BADARG;
+  } else if (a->epi == VK_EPI_NCHW_F32) {
+    if (us != 1 || a->out1 == nullptr) return VK_E_BADARG;
+  } else {
+    return VK_E_BADARG;
+  }
+
+  // ---- pixel tile ----
+  int tw, th;
+  if (slab) {
+    tw = 8, th = 16;
+  } else {
+    static const int cand_tw[5] = {16, 8, 32, 64, 128};
+    int best_tw = 16;
+    long long best_cost = -1;
+    for (int i = 0; i < 5; ++i) {
+      const int w = cand_tw[i], h = 128 / w;
+      if (a->force_tw && a->force_tw != w) continue;
+      if (prm.a_stride == 2 && w * 2 > 256) continue;
+      const long long cost = (long long)((prm.ow + w - 1) / w) * ((prm.oh + h - 1) / h);
+      if (best_cost < 0 || cost < best_cost) best_cost = cost, best_tw = w;
+    }
+    tw = best_tw, th = 128 / tw;
+  }
+  prm.tw_log2 = 31 - __builtin_clz(tw);
+  prm.th = th;
+  prm.tiles_x = (prm.ow + tw - 1) / tw;
+  prm.tiles_y = (prm.oh + th - 1) / th;
+  prm.n_tiles = prm.tiles_x * prm.tiles_y * a->n;
+
+  // ---- K chunk ----
+  const int row_bytes = a->ldx * esize;
+  int chunk = 0;
+  for (int cb : {128, 64, 32}) {
+    if (a->force_chunk_bytes && a->force_chunk_bytes != cb) continue;
+    if (row_bytes % cb == 0) { chunk = cb; break; }
+  }
+  if (chunk == 0) return VK_E_UNSUPPORTED;
+  prm.k_chunks = row_bytes / chunk;
+
+  // ---- N split ----
+  int n_cta;
+  if (is_convT) {
+    n_cta = prm.cq;
+  } else {
+    const int parts = (a->wrows + 255) / 256;
+    n_cta = round_up((a->wrows + parts - 1) / parts, 16);
+    if (n_cta * parts != a->wrows) {
+      n_cta = 0;
+      for (int c = 256; c >= 16; c -= 16)
+        if (a->wrows % c == 0) { n_cta = c; break; }
+    }
+  }
+  if (n_cta <= 0 || n_cta > 256 || n_cta % 16 || a->wrows % n_cta) return VK_E_UNSUPPORTED;
+  if (a->epi == VK_EPI_NCHW_F32 && a->wrows != n_cta) return VK_E_UNSUPPORTED;
+  prm.n_cta = n_cta;
+  prm.n_blocks = a->wrows / n_cta;
+  prm.acc_stride = round_up(n_cta, 32);
+
+  // ---- loads / taps ----
+  int box_w, box_h;   // A box in pixels (before element strides)
+  int nt_opts[3], n_nt = 0;
+  if (slab) {
+    box_w = tw + 2, box_h = th + 2;
+    prm.n_loads = 1;
+    prm.loads[0] = {-1, -1, 0};
+    prm.a_sbo = box_w * chunk;
+    nt_opts[n_nt++] = 9, nt_opts[n_nt++] = 3, nt_opts[n_nt++] = 1;
+  } else {
+    box_w = tw, box_h = th;
+    prm.a_sbo = 8 * chunk;
+    nt_opts[n_nt++] = 1;
+    if (a->kind == VK_CONV3X3_S2) {
+      prm.n_loads = 9;
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) prm.loads[r * 3 + s] = {s - 1, r - 1, r * 3 + s};
+    } else if (a->kind == VK_CONV2X2_S2) {
+      prm.n_loads = 4;
+      for (int t = 0; t < 4; ++t) prm.loads[t] = {t & 1, t >> 1, t};
+    } else if (is_s2d) {
+      const int py = phase >> 1, px = phase & 1;
+      const int nr = py ? 2 : 1, ns = px ? 2 : 1;
+      const int rr[2] = {py ? 0 : 1, 2}, dyv[2] = {py ? 1 : 0, 0};
+      const int ss[2] = {px ? 0 : 1, 2}, dxv[2] = {px ? 1 : 0, 0};
+      prm.n_loads = 0;
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < ns; ++j) prm.loads[prm.n_loads++] = {dxv[j], dyv[i], rr[i] * 3 + ss[j]};
+    } else {
+      prm.n_loads = 1;
+      prm.loads[0] = {0, 0, 0};
+    }
+  }
+  const int a_rows = box_w * box_h;
+  prm.a_tx_bytes = a_rows * chunk;
+  prm.a_box_bytes = round_up(prm.a_tx_bytes, 1024);
+
+  // ---- epilogue staging ----
+  prm.epi = a->epi;
+  prm.has_resid = a->resid != nullptr, prm.has_mask = a->mask != nullptr;
+  prm.has_out1 = a->out1 != nullptr, prm.has_out2 = a->out2 != nullptr;
+  int ecols = 0, ecb = 0, epi_warp_bytes = 0;
+  if (a->epi == VK_EPI_STD) {
+    if (us == 2 && prm.has_mask) return VK_E_UNSUPPORTED;
+    ecb = (n_cta * esize) % 64 == 0 ? 64 : 32;
+    ecols = ecb / esize;
+    if (n_cta % ecols) return VK_E_UNSUPPORTED;
+    int off = 0;
+    const int unit = 32 * ecb;
+    prm.off_r = off; if (prm.has_resid) off += unit;
+    prm.off_k = off; if (prm.has_mask) off += unit;
+    prm.off_o1 = off; if (prm.has_out1) off += unit;
+    prm.off_o2 = off; if (prm.has_out2) off += unit;
+    epi_warp_bytes = round_up(std::max(off, unit), 1024);
+    prm.ebx = std::min(tw, 32), prm.eby = 32 / prm.ebx;
+  }
+  prm.ecb = ecb, prm.ecols = ecols, prm.n_ech = ecols ? n_cta / ecols : 1;
+  prm.epi_warp_bytes = epi_warp_bytes;
+  const int epi_bytes = 8 * epi_warp_bytes;
+
+  // ---- P, NT and ring depths ----
+  const int n_sm = sm_count();
+  const int p_max_tmem = std::max(1, 256 / prm.acc_stride);          // double-buffered accumulators
+  int p_hi = std::min(4, p_max_tmem);
+  if (a->force_tiles_per_cta) p_hi = std::min(p_hi, a->force_tiles_per_cta);
+  int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0;
+  double best_score = -1.0;
+  for (int P = p_hi; P >= 1; --P) {
+    if (a->force_tiles_per_cta && P != p_hi) break;
+    const long long jobs = (long long)((prm.n_tiles + P - 1) / P) * prm.n_blocks;
+    const long long rounds = (jobs + n_sm - 1) / n_sm;
+    const double eff = double(jobs) / double(rounds * n_sm);
+    for (int i = 0; i < n_nt; ++i) {
+      const int nt = nt_opts[i];
+      if (a->force_nt && slab && nt != a->force_nt) continue;
+      const int a_slot = P * prm.a_box_bytes;
+      const int b_slot = round_up(nt * n_cta * chunk, 1024);
+      const int total_b_items = prm.n_loads * prm.k_chunks * (slab ? 9 / nt : 1);
+      const int total_a_items = prm.n_loads * prm.k_chunks;
+      const int avail = kV2SmemBudget - 1024 - epi_bytes;
+      // depth: at least 2 of each; B ring as deep as fits (up to 8), A ring 2 (3 when cheap)
+      int as = std::min(2, std::max(1, total_a_items)) ;
+      if (as < 2) as = 2;
+      int bs = (avail - as * a_slot) / b_slot;
+      bs = std::min(bs, kV2MaxStages);
+      if (a->force_stages) bs = std::min(bs, a->force_stages);
+      if (bs < 2) continue;
+      // spend what is left on a third / fourth A slot
+      while (as < 4 && as * a_slot + bs * b_slot + a_slot <= avail && bs >= 3) ++as;
+      (void)total_b_items;
+      // score: fewer, larger B items (less barrier traffic per MMA), more tiles per job (weight reuse), full waves
+      const double mmas_per_b = double(P) * nt * (chunk / 32);
+      const double score = eff * (1.0 - 0.12 / P) * (1.0 - 1.5 / (mmas_per_b + 6.0)) * (bs >= 3 ? 1.0 : 0.9);
+      if (score > best_score) best_score = score, best_P = P, best_nt = nt, best_as = as, best_bs = bs;
+    }
+  }
+  if (best_P == 0) return VK_E_UNSUPPORTED;
+  const int P = best_P, nt = best_nt;
+  prm.P = P;
+  prm.nb = slab ? 9 / nt : 1;
+  prm.a_slot_bytes = P * prm.a_box_bytes;
+  prm.b_slot_bytes = round_up(nt * n_cta * chunk, 1024);
+  prm.b_tx_bytes = nt * n_cta * chunk;
+  prm.a_stages = best_as, prm.b_stages = best_bs;
+  prm.b_base = prm.a_stages * prm.a_slot_bytes;
+  prm.epi_base = prm.b_base + prm.b_stages * prm.b_slot_bytes;
+  for (int tap = 0; tap < 9; ++tap)
+    prm.a_off16[tap] = slab ? uint32_t(((tap / 3) * box_w + (tap % 3)) * chunk) >> 4 : 0u;
+  prm.n_jobs = ((prm.n_tiles + P - 1) / P) * prm.n_blocks;
+  prm.tmem_cols = next_pow2_cols(2 * P * prm.acc_stride);
+  if (prm.tmem_cols > 512) return VK_E_UNSUPPORTED;
+  const int smem_bytes = prm.epi_base + epi_bytes + 1024;
+  if (smem_bytes > kV2SmemBudget) return VK_E_UNSUPPORTED;
+
+  prm.alpha = a->alpha;
+  prm.round_out2 = a->round_out2;
+  prm.bias = a->bias;
+  prm.out1_ptr = a->out1;
+  prm.resid_ptr = a->resid;
+  prm.act_expclamp = a->act_expclamp;
+  prm.clamp_lo = a->clamp_lo, prm.clamp_hi = a->clamp_hi;
+  prm.crop_h = a->crop_h > 0 ? a->crop_h : prm.oh;
+  prm.crop_w = a->crop_w > 0 ? a->crop_w : prm.ow;
+  prm.timing = a->cta_timing;
+
+  // ---- tensor maps: operands ----
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[4] = {uint64_t(a->ldx), uint64_t(a->iw), uint64_t(a->ih), uint64_t(a->n)};
+    const uint64_t strides[3] = {uint64_t(row_bytes), uint64_t(row_bytes) * a->iw, uint64_t(row_bytes) * a->iw * a->ih};
+    const uint32_t s = prm.a_stride;
+    const uint32_t box[4] = {uint32_t(chunk / esize), uint32_t(box_w) * s, uint32_t(box_h) * s, 1u};
+    const uint32_t es[4] = {1u, s, s, 1u};
+    int r = make_tensor_map(&ta, a->dtype, 4, a->x, dims, strides, box, es, chunk);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[3] = {uint64_t(a->ldx), uint64_t(a->wrows), uint64_t(taps)};
+    const uint64_t strides[2] = {uint64_t(row_bytes), uint64_t(row_bytes) * a->wrows};
+    const uint32_t box[3] = {uint32_t(chunk / esize), uint32_t(n_cta), uint32_t(nt)};
+    const uint32_t es[3] = {1u, 1u, 1u};
+    int r = make_tensor_map(&tb, a->dtype, 3, a->w, dims, strides, box, es, chunk);
+    if (r) return r;
+  }
+  // ---- tensor maps: epilogue tensors (one strided view per sub-pixel quadrant when us == 2) ----
+  ConvV2Maps em;
+  std::memset(&em, 0, sizeof(em));
+  if (a->epi == VK_EPI_STD) {
+    const uint64_t pix_bytes = uint64_t(a->ldo) * esize;
+    auto make_view = [&](CUtensorMap* out, const void* base, int quad) -> int {
+      // quadrant (qy, qx) of the fine grid: pixel (us*y + qy, us*x + qx)
+      const int qy = us == 2 ? quad >> 1 : 0, qx = us == 2 ? quad & 1 : 0;
+      const int vw = us == 2 ? (fine_w - qx + 1) / 2 : fine_w;
+      const int vh = us == 2 ? (fine_h - qy + 1) / 2 : fine_h;
+      if (vw <= 0 || vh <= 0) return 0;
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(base) + (uint64_t(qy) * fine_w + qx) * pix_bytes;
+      const uint64_t dims[4] = {uint64_t(a->cout), uint64_t(vw), uint64_t(vh), uint64_t(a->n)};
+      const uint64_t strides[3] = {pix_bytes * us, pix_bytes * us * fine_w, pix_bytes * fine_w * fine_h};
+      const uint32_t box[4] = {uint32_t(ecols), uint32_t(prm.ebx), uint32_t(prm.eby), 1u};
+      const uint32_t es[4] = {1u, 1u, 1u, 1u};
+      return make_tensor_map(out, a->dtype, 4, p, dims, strides, box, es, ecb);
+    };
+    const int q_lo = is_s2d ? phase : 0;
+    const int nq = is_convT ? 4 : 1;
+    for (int q = 0; q < nq; ++q) {
+      int r = 0;
+      if (prm.has_out1) r = make_view(&em.out1[q], a->out1, q_lo + q);
+      if (!r && prm.has_out2) r = make_view(&em.out2[q], a->out2, q_lo + q);
+      if (!r && prm.has_resid) r = make_view(&em.resid[q], a->resid, q_lo + q);
+      if (r) return r;
+    }
+    if (prm.has_mask) {
+      int r = make_view(&em.mask, a->mask, 0);
+      if (r) return r;
+    }
+  }
+
+  const int grid = int(std::min<long long>(prm.n_jobs, n_sm));
+  static const bool debug = std::getenv("VK_V2_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr,
+            "vk v2: kind=%d n=%d %dx%d ldx=%d wrows=%d | tile %dx%d tiles=%d P=%d n_cta=%d jobs=%d grid=%d | chunk=%d nt=%d "
+            "nb=%d a_stages=%d(%d B) b_stages=%d(%d B) epi=%d B/warp ecb=%d tmem=%d smem=%d\n",
+            a->kind, a->n, a->ih, a->iw, a->ldx, a->wrows, tw, th, prm.n_tiles, P, n_cta, prm.n_jobs, grid, chunk, nt,
+            prm.nb, prm.a_stages, prm.a_slot_bytes, prm.b_stages, prm.b_slot_bytes, epi_warp_bytes, ecb, prm.tmem_cols,
+            smem_bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == VK_BF16) return dispatch_v2<__nv_bfloat16>(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st);
+  return dispatch_v2<float>(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st);
+}
+
+}  // namespace vk

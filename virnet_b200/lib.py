@@ -40,7 +40,7 @@ class vk_conv_args(C.Structure):
         ("out_h", C.c_int32), ("out_w", C.c_int32),
         ("force_tiles_per_cta", C.c_int32), ("force_chunk_bytes", C.c_int32),
         ("force_stages", C.c_int32), ("force_tw", C.c_int32),
-        ("force_impl", C.c_int32), ("pad_", C.c_int32),
+        ("force_impl", C.c_int32), ("force_nt", C.c_int32),
         ("cta_timing", C.c_void_p),
     ]
 

@@ -162,6 +162,7 @@ def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_S
         a.force_stages = tune.get("stages", 0)
         a.force_tw = tune.get("tw", 0)
         a.force_impl = tune.get("impl", 0)
+        a.force_nt = tune.get("nt", 0)
         a.cta_timing = _ptr(tune.get("cta_timing"))
     with _Prof("conv_igemm", _conv_flops(kind, n, ih, iw, cin or ldx, cout, a.wrows) if _PROFILE is not None else 0.0):
         _l.check(_l.load().vk_conv_igemm(C.byref(a), _stream()), "vk_conv_igemm")
