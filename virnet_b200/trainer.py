@@ -21,6 +21,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from . import dp
 from . import lib as _l
 from . import ops
 from .loss.ELBO_simple import _digamma
@@ -38,7 +39,8 @@ class DenoiseTrainer:
         self.alpha0, self.eps2 = float(alpha0), float(eps2)
         self.digamma_am1 = _digamma(self.alpha0 - 1.0)
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dp.world_size(process_group)
+        dp.broadcast_flat_params(eng.flat_params, 0, process_group)
         self.step_count = 0
         self.exp_avg = torch.zeros_like(eng.flat_params)
         self.exp_avg_sq = torch.zeros_like(eng.flat_params)
@@ -91,11 +93,10 @@ class DenoiseTrainer:
                          digamma_am1=self.digamma_am1, d_mu=self._d_mu, d_sigma=self._d_sigma, acc3=self._acc3,
                          out4=self.losses)
         eng.backward(self._d_mu, self._d_sigma)
-        if self.world > 1:
-            dist.all_reduce(eng.flat_grads, op=dist.ReduceOp.SUM, group=self.pg)
+        grad_scale = dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
         self.step_count += 1
         ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
-                           self._ngroups, self._max_group, self._sq_ws, grad_scale=1.0 / self.world,
+                           self._ngroups, self._max_group, self._sq_ws, grad_scale=grad_scale,
                            lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1],
                            eps=self.adam_eps, step=self.step_count, norms_out=self.grad_norms)
         eng.mark_params_dirty()
