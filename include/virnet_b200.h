@@ -79,7 +79,7 @@ typedef struct vk_conv_args {
   int32_t force_chunk_bytes;
   int32_t force_stages;
   int32_t force_tw;
-  int32_t force_impl; /* 0 auto; 1 generic kernel; 2 halo-slab kernel (3x3 s1 only) */
+  int32_t force_impl; /* 0 auto; 1 v1 kernel; 2 persistent v2 kernel; 3 v2 single CTAs; 4 v2 CTA pairs (cta_group::2) */
   int32_t force_nt;   /* v2 3x3 s1 only: filter taps per weight stage (1, 3 or 9) */
   /* optional: device buffer of int64[gridsize][8] receiving per-CTA cycle counters
    * {start, mainloop end, epilogue end, producer wait, mma wait, 0, 0, 0}; NULL in production */

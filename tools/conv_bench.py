@@ -51,13 +51,13 @@ def time_it(fn, iters=20):
     return s.elapsed_time(e) / iters * 1e3  # us
 
 
-def run(c_in, c_out, h, n, epi, dt=ops.VK_BF16, kind=ops.VK_CONV3X3_S1, tune=None, check=True):
+def run(c_in, c_out, h, n, epi, dt=ops.VK_BF16, kind=ops.VK_CONV3X3_S1, tune=None, check=True, impls=(1, 3, 4)):
     x, w, kw, o1, o2 = make(c_in, c_out, h, n, epi, dt, kind)
     res = {}
     oh = o1.shape[1]
     flops = 2.0 * n * oh * oh * 9 * c_in * c_out
     line = f"Cin={c_in} Cout={c_out} {h}x{h} n={n} epi={epi} {'bf16' if dt == ops.VK_BF16 else 'tf32'} tune={tune}:"
-    for impl in (1, 2):
+    for impl in impls:
         t = dict(tune or {})
         t["impl"] = impl
         if impl == 1:
@@ -72,12 +72,16 @@ def run(c_in, c_out, h, n, epi, dt=ops.VK_BF16, kind=ops.VK_CONV3X3_S1, tune=Non
         res[impl] = (o1.float().clone(), o2.float().clone())
         us = time_it(lambda: ops.conv_igemm(x, w, tune=t, **kw))
         line += f" v{impl}: {us:7.1f} us {flops / us / 1e6:6.0f} TF/s;"
-    if check and 1 in res and 2 in res:
-        errs = []
-        for a, b in zip(res[1], res[2]):
-            den = a.abs().max().item() or 1.0
-            errs.append((a - b).abs().max().item() / den)
-        line += f" max rel diff v1/v2 = {max(errs):.2e}"
+    if check and len(res) > 1:
+        first = impls[0]
+        for impl in impls[1:]:
+            if impl not in res or first not in res:
+                continue
+            errs = []
+            for a, b in zip(res[first], res[impl]):
+                den = a.abs().max().item() or 1.0
+                errs.append((a - b).abs().max().item() / den)
+            line += f" diff v{first}/v{impl} = {max(errs):.2e}"
     print(line, flush=True)
 
 

@@ -79,7 +79,7 @@ struct ConvV2Params {
   int act_expclamp;
   float clamp_lo, clamp_hi;
   int crop_h, crop_w;
-  long long* timing;         // optional int64[grid][16] stall counters (debug), or null
+  long long* timing;         // optional int64[grid][24] stall counters (debug), or null
 };
 
 struct ConvV2Maps {
@@ -181,7 +181,75 @@ __device__ __forceinline__ void stage_store(uint32_t unit, int row, int ecb, int
                       __float_as_uint(v[4 * j + 3])));
 }
 
-template <typename DT, int kChunkBytes, int kNT>
+
+// ---------------------------------------------------------------------------
+// Epilogue maths of one item row: ecb bytes = NCH 16-byte chunks of CPC channels each.
+//   v = acc (+bias, already added); v *= lrelu'(mask); v += resid; out1 = v; out2 = lrelu(v)
+// Compile-time flags keep the per-channel instruction count minimal: the epilogue warps share the issue
+// slots of the SM with nothing else that matters, and their instruction count is what bounds small-N layers.
+// ---------------------------------------------------------------------------
+template <typename DT>
+__device__ __forceinline__ void unpack_chunk(const uint4& raw, float (&f)[16 / sizeof(DT)]) {
+  if constexpr (sizeof(DT) == 4) {
+    f[0] = __uint_as_float(raw.x), f[1] = __uint_as_float(raw.y), f[2] = __uint_as_float(raw.z), f[3] = __uint_as_float(raw.w);
+  } else {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[2 * i] = __uint_as_float(w[i] << 16), f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+template <typename DT>
+__device__ __forceinline__ uint4 pack_chunk(const float (&f)[16 / sizeof(DT)]) {
+  if constexpr (sizeof(DT) == 4) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+template <typename DT, bool kMask, bool kResid, bool kOut1, bool kOut2, int kEcb>
+__device__ __forceinline__ void epi_item_math(const uint32_t (&acc)[2][16], const uint4 (&rraw)[4], const uint4 (&kraw)[4],
+                                              float alpha, bool rnd, uint32_t a_o1, uint32_t a_o2, int swz) {
+  constexpr int CPC = 16 / int(sizeof(DT));
+  constexpr int NCH = kEcb / 16;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    float v[CPC];
+#pragma unroll
+    for (int i = 0; i < CPC; ++i) v[i] = __uint_as_float(acc[(j * CPC + i) >> 4][(j * CPC + i) & 15]);
+    if constexpr (kMask) {
+      float m[CPC];
+      unpack_chunk<DT>(kraw[j], m);
+#pragma unroll
+      for (int i = 0; i < CPC; ++i) v[i] = m[i] > 0.f ? v[i] : v[i] * alpha;
+    }
+    if constexpr (kResid) {
+      float r[CPC];
+      unpack_chunk<DT>(rraw[j], r);
+#pragma unroll
+      for (int i = 0; i < CPC; ++i) v[i] += r[i];
+    }
+    const uint32_t sw = uint32_t((j ^ swz) << 4);
+    if constexpr (kOut1) sts128(a_o1 + sw, pack_chunk<DT>(v));
+    if constexpr (kOut2) {
+#pragma unroll
+      for (int i = 0; i < CPC; ++i) v[i] = fmaxf(v[i], v[i] * alpha);      // LeakyReLU for 0 < alpha < 1
+      if constexpr (sizeof(DT) == 4) {
+        if (rnd) {
+#pragma unroll
+          for (int i = 0; i < CPC; ++i) v[i] = round_tf32(v[i]);
+        }
+      }
+      sts128(a_o2 + sw, pack_chunk<DT>(v));
+    }
+  }
+}
+template <typename DT, int kChunkBytes, int kNT, bool kPair>
 __global__ void __launch_bounds__(kV2Threads, 1)
 conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvV2Maps emaps, const __grid_constant__ ConvV2Params prm) {
@@ -197,7 +265,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
   __shared__ __align__(8) uint64_t in_bar[8];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float bias_s[1024];
+  __shared__ __align__(16) float bias_s[1024];
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
@@ -209,8 +277,16 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int P = prm.P;
   const int tiles_per_img = prm.tiles_x * prm.tiles_y;
   const int n_a_items = prm.n_loads * prm.k_chunks;
+  // pair mode (cta_group::2): the two CTAs of a cluster walk the same job list; CTA `cta_rank` owns tile
+  // group 2 * pair_group + cta_rank and half of the weight rows, the leader (rank 0) issues M=256 MMAs
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int worker = kPair ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int n_workers = kPair ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int n_groups = (prm.n_tiles + P - 1) / P;
+  (void)n_groups;
   const bool prof = prm.timing != nullptr;
-  long long* const tslot = prof ? prm.timing + blockIdx.x * 16 : nullptr;
+  long long* const tslot = prof ? prm.timing + blockIdx.x * 24 : nullptr;
   const long long t_start = prof ? clock64() : 0;
 
   if (threadIdx.x == 0) {
@@ -219,7 +295,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&full_b[s], 1), mbar_init(&empty_b[s], 1);
       mbar_init(&in_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 8);
+    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], kPair ? 16 : 8);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -227,8 +303,13 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 12) {
-    tmem_alloc(&tmem_base_slot, prm.tmem_cols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_2sm(&tmem_base_slot, prm.tmem_cols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(&tmem_base_slot, prm.tmem_cols);
+      tmem_relinquish();
+    }
   }
   if (warp >= 4 && warp < 12) {
     for (int i = threadIdx.x - 128; i < prm.wrows; i += 256) {
@@ -237,7 +318,11 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (kPair) {
+    cluster_sync_all();          // the peer's barriers must be initialised before anything signals them
+  } else {
+    __syncthreads();
+  }
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -247,10 +332,11 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int sa = 0;
       uint32_t ph = 0;
       long long w_empty = 0;
-      for (int job = blockIdx.x; job < prm.n_jobs; job += gridDim.x) {
-        const int group = job / prm.n_blocks;
+      for (int job = worker; job < prm.n_jobs; job += n_workers) {
+        const int group = kPair ? 2 * (job / prm.n_blocks) + int(cta_rank) : job / prm.n_blocks;
         const int tile0 = group * P;
-        const int nvalid = min(P, prm.n_tiles - tile0);
+        // pair mode always moves P boxes per CTA (tiles past the end are fully out of bounds -> zero fill)
+        const int nvalid = kPair ? P : min(P, prm.n_tiles - tile0);
         int timg[4], tx0[4], ty0[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -264,13 +350,24 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int dx = prm.loads[l].dx, dy = prm.loads[l].dy;
           for (int c = 0; c < prm.k_chunks; ++c) {
             mbar_wait_t(&empty_a[sa], ph ^ 1, prof, w_empty);
-            mbar_arrive_expect_tx(&full_a[sa], nvalid * prm.a_tx_bytes);
             uint8_t* dst = smem_a + sa * prm.a_slot_bytes;
+            if constexpr (kPair) {
+              // both CTAs' boxes complete on the LEADER's barrier, armed by the leader with the pair's bytes
+              if (is_leader) mbar_arrive_expect_tx(&full_a[sa], 2 * P * prm.a_tx_bytes);
+              const uint32_t bar = mapa_shared(smem_u32(&full_a[sa]), 0);
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
-              if (p < nvalid)
-                tma_load_4d(dst + p * prm.a_box_bytes, &tmap_a, &full_a[sa], c * kChunkElems, tx0[p] + dx, ty0[p] + dy,
-                            timg[p]);
+              for (int p = 0; p < 4; ++p)
+                if (p < nvalid)
+                  tma_load_4d_2sm(dst + p * prm.a_box_bytes, &tmap_a, bar, c * kChunkElems, tx0[p] + dx, ty0[p] + dy,
+                                  timg[p]);
+            } else {
+              mbar_arrive_expect_tx(&full_a[sa], nvalid * prm.a_tx_bytes);
+#pragma unroll
+              for (int p = 0; p < 4; ++p)
+                if (p < nvalid)
+                  tma_load_4d(dst + p * prm.a_box_bytes, &tmap_a, &full_a[sa], c * kChunkElems, tx0[p] + dx,
+                              ty0[p] + dy, timg[p]);
+            }
             if (++sa == prm.a_stages) sa = 0, ph ^= 1;
           }
         }
@@ -284,16 +381,24 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int sb = 0, turn = 0;
       uint32_t ph = 0;
       long long w_empty = 0;
-      for (int job = blockIdx.x; job < prm.n_jobs; job += gridDim.x) {
-        const int n0 = (job % prm.n_blocks) * prm.n_cta;
+      for (int job = worker; job < prm.n_jobs; job += n_workers) {
+        // pair mode: this CTA supplies rows [n0, n0 + n_cta / 2) of the job's weight block
+        const int n0 = (job % prm.n_blocks) * prm.n_cta + (kPair ? int(cta_rank) * (prm.n_cta >> 1) : 0);
         for (int l = 0; l < prm.n_loads; ++l) {
           const int tap0 = prm.loads[l].tap0;
           for (int c = 0; c < prm.k_chunks; ++c) {
             for (int bi = 0; bi < prm.nb; ++bi) {
               if (turn == pw) {
                 mbar_wait_t(&empty_b[sb], ph ^ 1, prof, w_empty);
-                mbar_arrive_expect_tx(&full_b[sb], prm.b_tx_bytes);
-                tma_load_3d(smem_b + sb * prm.b_slot_bytes, &tmap_b, &full_b[sb], c * kChunkElems, n0, tap0 + bi * kNT);
+                if constexpr (kPair) {
+                  if (is_leader) mbar_arrive_expect_tx(&full_b[sb], 2 * prm.b_tx_bytes);
+                  tma_load_3d_2sm(smem_b + sb * prm.b_slot_bytes, &tmap_b, mapa_shared(smem_u32(&full_b[sb]), 0),
+                                  c * kChunkElems, n0, tap0 + bi * kNT);
+                } else {
+                  mbar_arrive_expect_tx(&full_b[sb], prm.b_tx_bytes);
+                  tma_load_3d(smem_b + sb * prm.b_slot_bytes, &tmap_b, &full_b[sb], c * kChunkElems, n0,
+                              tap0 + bi * kNT);
+                }
               }
               if (++turn == kV2BProducers) turn = 0;
               if (++sb == prm.b_stages) sb = 0, ph ^= 1;
@@ -304,9 +409,9 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (prof && pw == 0) tslot[6] = w_empty, tslot[12] = clock64() - t_start;
     }
   } else if (warp == 12) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (pair mode: leader CTA only) =====================
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc(DTraits<DT>::kFmt, 128, prm.n_cta, 0, 0);
+    const uint32_t idesc = make_idesc(DTraits<DT>::kFmt, kPair ? 256 : 128, prm.n_cta, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, prm.a_sbo, kLayout) & 0xFFFFFFFF00000000ull;
     const uint64_t desc_hi_b = make_smem_desc(0, 16, 8 * kChunkBytes, kLayout) & 0xFFFFFFFF00000000ull;
     const uint32_t lbo_lo = 1u << 16;
@@ -314,15 +419,15 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t b0_16 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | lbo_lo;
     const uint32_t aslot16 = uint32_t(prm.a_slot_bytes) >> 4, bslot16 = uint32_t(prm.b_slot_bytes) >> 4;
     const uint32_t box16 = uint32_t(prm.a_box_bytes) >> 4;
-    const uint32_t btap16 = uint32_t(prm.n_cta * kChunkBytes) >> 4;
+    const uint32_t btap16 = uint32_t((kPair ? prm.n_cta >> 1 : prm.n_cta) * kChunkBytes) >> 4;
     const uint32_t acc_stride = prm.acc_stride;
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, phacc = 0;
     uint32_t a_lo = a0_16, b_lo = b0_16;
     long long w_fa = 0, w_fb = 0, w_te = 0;
-    for (int job = blockIdx.x; job < prm.n_jobs; job += gridDim.x) {
+    for (int job = worker; job < prm.n_jobs && is_leader; job += n_workers) {
       const int tile0 = (job / prm.n_blocks) * P;
-      const int nvalid = min(P, prm.n_tiles - tile0);
+      const int nvalid = kPair ? P : min(P, prm.n_tiles - tile0);
       mbar_wait_t(&tmem_empty[as], phacc ^ 1, prof, w_te);
       tc_fence_after_sync();
       const uint32_t d0 = tmem_base + uint32_t(as * P) * acc_stride;
@@ -343,12 +448,18 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int t = 0; t < kNT; ++t) {
 #pragma unroll
                   for (int k = 0; k < kMmasPerChunk; ++k) {
-                    umma_ss<kTF32>(dp, desc_hi | (ap + prm.a_off16[(bi * kNT + t) % 9] + 2 * k),
-                                   desc_hi_b | (b_lo + t * btap16 + 2 * k), idesc, (k == 0 && t == 0) ? accum : 1u);
+                    if constexpr (kPair) {
+                      umma_ss_2sm<kTF32>(dp, desc_hi | (ap + prm.a_off16[(bi * kNT + t) % 9] + 2 * k),
+                                         desc_hi_b | (b_lo + t * btap16 + 2 * k), idesc,
+                                         (k == 0 && t == 0) ? accum : 1u);
+                    } else {
+                      umma_ss<kTF32>(dp, desc_hi | (ap + prm.a_off16[(bi * kNT + t) % 9] + 2 * k),
+                                     desc_hi_b | (b_lo + t * btap16 + 2 * k), idesc, (k == 0 && t == 0) ? accum : 1u);
+                    }
                   }
                 }
               }
-              umma_commit(&empty_b[sb]);
+              if constexpr (kPair) umma_commit_2sm(&empty_b[sb]); else umma_commit(&empty_b[sb]);
             }
             __syncwarp();
             accum = 1;
@@ -356,12 +467,16 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (++sb == prm.b_stages) sb = 0, phb ^= 1, b_lo = b0_16;
           }
         }
-        if (leader) umma_commit(&empty_a[sa]);
+        if (leader) {
+          if constexpr (kPair) umma_commit_2sm(&empty_a[sa]); else umma_commit(&empty_a[sa]);
+        }
         __syncwarp();
         a_lo += aslot16;
         if (++sa == prm.a_stages) sa = 0, pha ^= 1, a_lo = a0_16;
       }
-      if (leader) umma_commit(&tmem_full[as]);
+      if (leader) {
+        if constexpr (kPair) umma_commit_2sm(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+      }
       __syncwarp();
       if (++as == 2) as = 0, phacc ^= 1;
     }
@@ -372,81 +487,121 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q4 = warp & 3;                   // TMEM lane quarter of this warp
     const int half = ew >> 2;
     const int tw_mask = (1 << prm.tw_log2) - 1;
-    const int sub_x = (q4 * 32) & tw_mask, sub_y = (q4 * 32) >> prm.tw_log2;   // origin of the warp's 32 pixels
+    // the four warps of a `half` form a group that owns whole (tile, channel chunk) items: their 4 x 32 TMEM
+    // lanes are the 128 pixels of the tile, staged as rows of one buffer and moved by ONE TMA op per tensor
     const int row = q4 * 32 + lane;
     const int tyy = row >> prm.tw_log2, txx = row & tw_mask;
-    const uint32_t stg = smem_u32(smem_e + ew * prm.epi_warp_bytes);
-    const uint32_t buf_r = stg + prm.off_r, buf_k = stg + prm.off_k, buf_o1 = stg + prm.off_o1,
-                   buf_o2 = stg + prm.off_o2;
+    uint8_t* const stg_p = smem_e + half * prm.epi_warp_bytes;
+    const uint32_t stg = smem_u32(stg_p);
+    const int grp_bar = 1 + half;                         // named barrier of the group (128 threads)
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp_bar) : "memory"); };
+    const bool glead = (q4 == 0) && (lane == 0);          // the group's TMA-issuing thread
     const int ecb = prm.ecb, ecols = prm.ecols, n_ech = prm.n_ech;
+    const int swz = ecb == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1);      // TMA swizzle of this thread's staged row
+    const uint32_t row_base = stg + uint32_t(row * ecb);
+    const uint32_t off_r = prm.off_r, off_k = prm.off_k, off_o1 = prm.off_o1, off_o2 = prm.off_o2;
     const bool has_in = prm.epi == EPI_STD && (prm.has_resid || prm.has_mask);
-    const uint32_t in_bytes = uint32_t(32 * ecb) * uint32_t((prm.has_resid ? 1 : 0) + (prm.has_mask ? 1 : 0));
+    const uint32_t in_bytes = uint32_t(128 * ecb) * uint32_t((prm.has_resid ? 1 : 0) + (prm.has_mask ? 1 : 0));
     const float alpha = prm.alpha;
-    uint64_t* my_bar = &in_bar[ew];
+    uint64_t* my_bar = &in_bar[half];
     uint32_t in_ph = 0;
     int as = 0;
     uint32_t phacc = 0;
     const bool lead = lane == 0;
-    long long w_tf = 0, w_in = 0, w_rd = 0;
+    long long w_tf = 0, w_in = 0, w_rd = 0, w_ld = 0, w_math = 0, w_sync = 0, w_st = 0, w_misc = 0, w_fence = 0;
+    long long tq = 0;
+    auto lap = [&](long long& acc) {
+      if (prof) {
+        const long long now = clock64();
+        acc += now - tq;
+        tq = now;
+      }
+    };
 
-    for (int job = blockIdx.x; job < prm.n_jobs; job += gridDim.x) {
-      const int group = job / prm.n_blocks;
-      const int n0 = (job - group * prm.n_blocks) * prm.n_cta;
+    for (int job = worker; job < prm.n_jobs; job += n_workers) {
+      const int jgroup = job / prm.n_blocks;
+      const int group = kPair ? 2 * jgroup + int(cta_rank) : jgroup;
+      const int n0 = (job - jgroup * prm.n_blocks) * prm.n_cta;
       const int qi = n0 / prm.cq;
       const int cq0 = n0 - qi * prm.cq;
       const int tile0 = group * P;
-      const int nvalid = min(P, prm.n_tiles - tile0);
+      const int nvalid = max(0, min(P, prm.n_tiles - tile0));
       const uint32_t acc0 = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(as * P) * prm.acc_stride;
 
       if (prm.epi == EPI_STD) {
-        const int items = nvalid * n_ech;
-        // item -> (tile, channel chunk) -> TMA coordinates of this warp's sub-box
-        auto coords = [&](int idx, int& c0, int& x, int& y, int& img, int& p, int& kc) {
-          p = idx / n_ech;
-          kc = idx - p * n_ech;
-          const int t = tile0 + p;
-          img = t / tiles_per_img;
+        // Items of a job are (channel chunk kc, tile p), p fastest; group `half` takes every second one.  P is
+        // 1, 2 or 4, so the group only ever meets tiles p0 = half & (P-1) and (P == 4) p0 + 2: decode them once.
+        const int p0 = half & (P - 1);
+        const int ns = (P == 1 && half == 1) ? 0 : ((p0 < nvalid ? 1 : 0) + ((P == 4 && p0 + 2 < nvalid) ? 1 : 0));
+        int t_img[2], t_x[2], t_y[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int t = tile0 + p0 + 2 * sl;
+          const int img = t / tiles_per_img;
           const int r = t - img * tiles_per_img;
           const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
-          x = (tx << prm.tw_log2) + sub_x, y = ty * prm.th + sub_y;
-          c0 = cq0 + kc * ecols;
+          t_img[sl] = img, t_x[sl] = tx << prm.tw_log2, t_y[sl] = ty * prm.th;
+        }
+        // P == 1: both groups share tile 0 and alternate over the channel chunks instead
+        const int kc_step = P == 1 ? 2 : 1;
+        const int kc_first = P == 1 ? half : 0;
+        const int ns_eff = P == 1 ? (nvalid > 0 ? 1 : 0) : ns;
+        const int g_items = ns_eff == 0 ? 0 : ns_eff * ((n_ech - kc_first + kc_step - 1) / kc_step);
+        auto item_of = [&](int g, int& kc, int& sl) {     // g-th item of this group in this job
+          if (ns_eff == 2) {
+            kc = g >> 1, sl = g & 1;
+          } else {
+            kc = kc_first + g * kc_step, sl = 0;
+          }
         };
-        auto issue_in = [&](int idx) {
-          int c0, x, y, img, p, kc;
-          coords(idx, c0, x, y, img, p, kc);
+        auto issue_in = [&](int g) {
+          int kc, sl;
+          item_of(g, kc, sl);
+          const int c0 = cq0 + kc * ecols;
           mbar_arrive_expect_tx(my_bar, in_bytes);
           if (prm.has_resid)
-            tma_load_4d(reinterpret_cast<void*>(smem_e + ew * prm.epi_warp_bytes + prm.off_r), &emaps.resid[qi], my_bar,
-                        c0, x, y, img);
+            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_r), &emaps.resid[qi], my_bar, c0, sl ? t_x[1] : t_x[0],
+                        sl ? t_y[1] : t_y[0], sl ? t_img[1] : t_img[0]);
           if (prm.has_mask)
-            tma_load_4d(reinterpret_cast<void*>(smem_e + ew * prm.epi_warp_bytes + prm.off_k), &emaps.mask, my_bar, c0,
-                        x, y, img);
+            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_k), &emaps.mask, my_bar, c0, sl ? t_x[1] : t_x[0],
+                        sl ? t_y[1] : t_y[0], sl ? t_img[1] : t_img[0]);
         };
-        int idx = half;
-        if (has_in && idx < items && lead) issue_in(idx);
+        if (has_in && g_items > 0 && glead) issue_in(0);
         mbar_wait_t(&tmem_full[as], phacc, prof, w_tf);
         tc_fence_after_sync();
-        for (; idx < items; idx += 2) {
-          int c0, x, y, img, p, kc;
-          coords(idx, c0, x, y, img, p, kc);
+        for (int g = 0; g < g_items; ++g) {
+          if (prof) tq = clock64();
+          int kc, sl;
+          item_of(g, kc, sl);
+          const int p = p0 + 2 * sl;
           const uint32_t taddr = acc0 + uint32_t(p) * prm.acc_stride + uint32_t(kc * ecols);
-          // one item = 32 pixels x ecols channels; a staged row is ecb bytes = nchunks 16-byte chunks
-          constexpr int CPC = 16 / kElemBytes;            // channels per 16-byte chunk
-          const int nchunks = ecb >> 4;                   // 4 or 2
+          // ---- inputs: this thread's row of the staged residual / mask tiles ----
           uint4 rraw[4], kraw[4];
           if (has_in) {
             mbar_wait_t(my_bar, in_ph, prof, w_in);
             in_ph ^= 1;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (j < nchunks) {
-                if (prm.has_resid) rraw[j] = lds128(stage_addr(buf_r, lane, ecb, j));
-                if (prm.has_mask) kraw[j] = lds128(stage_addr(buf_k, lane, ecb, j));
+              if (j < (ecb >> 4)) {
+                if (prm.has_resid) rraw[j] = lds128(row_base + off_r + ((j ^ swz) << 4));
+                if (prm.has_mask) kraw[j] = lds128(row_base + off_k + ((j ^ swz) << 4));
               }
             }
-            __syncwarp();
-            if (idx + 2 < items && lead) issue_in(idx + 2);
           }
+          if (glead) {                            // previous stores have finished reading the out buffers
+            if (prof) {
+              const long long t0 = clock64();
+              bulk_wait_read0();
+              w_rd += clock64() - t0;
+            } else {
+              bulk_wait_read0();
+            }
+          }
+          lap(w_misc);
+          group_sync();                           // inputs consumed by all 4 warps, out buffers free
+          lap(w_sync);
+          if (has_in && g + 1 < g_items && glead) issue_in(g + 1);
+          // ---- accumulators ----
           uint32_t acc[2][16];
           __syncwarp();
           if (ecols >= 16) {
@@ -459,77 +614,50 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < 8; ++i) acc[0][i] = t8[i];
           }
           tmem_ld_wait();
-          if (lead) {                             // previous stores have finished reading the out buffers
-            if (prof) {
-              const long long t0 = clock64();
-              bulk_wait_read0();
-              w_rd += clock64() - t0;
-            } else {
-              bulk_wait_read0();
-            }
-          }
-          __syncwarp();
-          const float* bias_p = bias_s + n0 + kc * ecols;
+          lap(w_ld);
+          if (prm.bias != nullptr) {              // bias: 16-byte broadcast loads, added in place
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + n0 + kc * ecols);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nchunks) {
-              float v[CPC], rv[CPC], mv[CPC];
-              if constexpr (kTF32) {
-                rv[0] = __uint_as_float(rraw[j].x), rv[1] = __uint_as_float(rraw[j].y);
-                rv[2] = __uint_as_float(rraw[j].z), rv[3] = __uint_as_float(rraw[j].w);
-                mv[0] = __uint_as_float(kraw[j].x), mv[1] = __uint_as_float(kraw[j].y);
-                mv[2] = __uint_as_float(kraw[j].z), mv[3] = __uint_as_float(kraw[j].w);
-              } else {
-                const uint32_t rw[4] = {rraw[j].x, rraw[j].y, rraw[j].z, rraw[j].w};
-                const uint32_t kw[4] = {kraw[j].x, kraw[j].y, kraw[j].z, kraw[j].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  rv[2 * i] = __uint_as_float(rw[i] << 16), rv[2 * i + 1] = __uint_as_float(rw[i] & 0xFFFF0000u);
-                  mv[2 * i] = __uint_as_float(kw[i] << 16), mv[2 * i + 1] = __uint_as_float(kw[i] & 0xFFFF0000u);
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < CPC; ++i) {
-                const int col = j * CPC + i;
-                float x = __uint_as_float(acc[col >> 4][col & 15]) + bias_p[col];
-                if (prm.has_mask) x *= (mv[i] > 0.f ? 1.f : alpha);
-                if (prm.has_resid) x += rv[i];
-                v[i] = x;
-              }
-              auto pack = [&](const float (&f)[CPC]) -> uint4 {
-                if constexpr (kTF32) {
-                  return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                                    __float_as_uint(f[3]));
-                } else {
-                  uint32_t w[4];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                    w[i] = *reinterpret_cast<uint32_t*>(&h);
-                  }
-                  return make_uint4(w[0], w[1], w[2], w[3]);
-                }
-              };
-              if (prm.has_out1) sts128(stage_addr(buf_o1, lane, ecb, j), pack(v));
-              if (prm.has_out2) {
-#pragma unroll
-                for (int i = 0; i < CPC; ++i) {
-                  v[i] = lrelu(v[i], alpha);
-                  if (kTF32 && prm.round_out2) v[i] = round_tf32(v[i]);
-                }
-                sts128(stage_addr(buf_o2, lane, ecb, j), pack(v));
+            for (int i4 = 0; i4 < 8; ++i4) {
+              if (i4 * 4 < ecols) {
+                const float4 b = bp[i4];
+                uint32_t* a4 = &acc[(i4 * 4) >> 4][(i4 * 4) & 15];
+                a4[0] = __float_as_uint(__uint_as_float(a4[0]) + b.x), a4[1] = __float_as_uint(__uint_as_float(a4[1]) + b.y);
+                a4[2] = __float_as_uint(__uint_as_float(a4[2]) + b.z), a4[3] = __float_as_uint(__uint_as_float(a4[3]) + b.w);
               }
             }
           }
+          // ---- fused epilogue maths, specialised at compile time on the tensors present ----
+          const uint32_t a_o1 = row_base + off_o1, a_o2 = row_base + off_o2;
+          const int mode = (prm.has_mask ? 1 : 0) | (prm.has_resid ? 2 : 0) | (prm.has_out1 ? 4 : 0) | (prm.has_out2 ? 8 : 0);
+          const bool rnd = kTF32 && prm.round_out2;
+#define VK_EPI_CASE(M)                                                                                             \
+  case M:                                                                                                          \
+    if (ecb == 64)                                                                                                 \
+      epi_item_math<DT, (M & 1) != 0, (M & 2) != 0, (M & 4) != 0, (M & 8) != 0, 64>(acc, rraw, kraw, alpha, rnd, a_o1, \
+                                                                                    a_o2, swz);                    \
+    else                                                                                                           \
+      epi_item_math<DT, (M & 1) != 0, (M & 2) != 0, (M & 4) != 0, (M & 8) != 0, 32>(acc, rraw, kraw, alpha, rnd, a_o1, \
+                                                                                    a_o2, swz);                    \
+    break;
+          switch (mode) {
+            VK_EPI_CASE(4) VK_EPI_CASE(5) VK_EPI_CASE(6) VK_EPI_CASE(7) VK_EPI_CASE(8) VK_EPI_CASE(12) VK_EPI_CASE(14)
+            default: break;                       // the host only launches the combinations above
+          }
+#undef VK_EPI_CASE
+          lap(w_math);
           fence_proxy_async_smem();
-          __syncwarp();
-          if (lead) {
-            if (prm.has_out1)
-              tma_store_4d(&emaps.out1[qi], smem_e + ew * prm.epi_warp_bytes + prm.off_o1, c0, x, y, img);
-            if (prm.has_out2)
-              tma_store_4d(&emaps.out2[qi], smem_e + ew * prm.epi_warp_bytes + prm.off_o2, c0, x, y, img);
+          lap(w_fence);
+          group_sync();                           // the whole 128-pixel item is staged
+          lap(w_sync);
+          if (glead) {
+            const int c0 = cq0 + kc * ecols;
+            const int x = sl ? t_x[1] : t_x[0], y = sl ? t_y[1] : t_y[0], img = sl ? t_img[1] : t_img[0];
+            if (prm.has_out1) tma_store_4d(&emaps.out1[qi], stg_p + prm.off_o1, c0, x, y, img);
+            if (prm.has_out2) tma_store_4d(&emaps.out2[qi], stg_p + prm.off_o2, c0, x, y, img);
             bulk_commit();
           }
+          lap(w_st);
         }
       } else {
         // EPI_NCHW_F32: n_cta == 16 columns, direct stores (consecutive lanes = consecutive pixels of a row)
@@ -568,19 +696,25 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lead) mbar_arrive(&tmem_empty[as]);
+      if (lead) {
+        if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]);
+      }
       if (++as == 2) as = 0, phacc ^= 1;
     }
-    if (lead) bulk_wait0();                      // all stores of this warp have completed
-    if (prof && lead && ew == 0) tslot[7] = w_tf, tslot[8] = w_in, tslot[9] = w_rd, tslot[10] = clock64() - t_start;
+    if (glead) bulk_wait0();                     // all stores of this group have completed
+    if (prof && glead && half == 0) tslot[7] = w_tf, tslot[8] = w_in, tslot[9] = w_rd, tslot[10] = clock64() - t_start, tslot[13] = w_ld, tslot[14] = w_math, tslot[15] = w_sync, tslot[16] = w_st, tslot[17] = w_misc, tslot[18] = w_fence;
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (kPair) {
+    cluster_sync_all();          // neither CTA may retire while the other can still touch its smem / barriers / TMEM
+  } else {
+    __syncthreads();
+  }
   if (prof && threadIdx.x == 0) tslot[0] = clock64() - t_start;
   if (warp == 12) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, prm.tmem_cols);
+    if constexpr (kPair) tmem_dealloc_2sm(tmem_base, prm.tmem_cols); else tmem_dealloc(tmem_base, prm.tmem_cols);
   }
 }
 

@@ -34,12 +34,12 @@ int sm_count() {
 
 constexpr int kV2SmemBudget = 220 * 1024;   // dynamic smem incl. 1 KB alignment slack (static: ~4.6 KB)
 
-template <typename DT, int kChunk, int kNT>
+template <typename DT, int kChunk, int kNT, bool kPair>
 int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em, const ConvV2Params& prm, int grid,
               int smem_bytes, cudaStream_t st) {
   static int cur = 0;
   static std::mutex mu;
-  auto kern = conv_v2_kernel<DT, kChunk, kNT>;
+  auto kern = conv_v2_kernel<DT, kChunk, kNT, kPair>;
   {
     std::lock_guard<std::mutex> g(mu);
     if (smem_bytes > cur) {
@@ -48,16 +48,31 @@ int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em
       cur = smem_bytes;
     }
   }
-  kern<<<grid, kV2Threads, smem_bytes, st>>>(ta, tb, em, prm);
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return int(cudaGetLastError());
+  if constexpr (kPair) {
+    // CTA pairs: a cluster of two CTAs on one TPC shares every weight tile (tcgen05 cta_group::2)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kV2Threads), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, em, prm);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return e != cudaSuccess ? int(e) : int(cudaGetLastError());
+  } else {
+    kern<<<grid, kV2Threads, smem_bytes, st>>>(ta, tb, em, prm);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return int(cudaGetLastError());
+  }
 }
 
 template <typename DT>
-int dispatch_v2(int chunk, int nt, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
+int dispatch_v2(int chunk, int nt, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
                 const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st) {
-#define VK_V2_CASE(C, T) \
-  if (chunk == C && nt == T) return launch_v2<DT, C, T>(ta, tb, em, prm, grid, smem_bytes, st);
+#define VK_V2_CASE(C, T)                                                                           \
+  if (chunk == C && nt == T)                                                                       \
+    return pair ? launch_v2<DT, C, T, true>(ta, tb, em, prm, grid, smem_bytes, st)                 \
+                : launch_v2<DT, C, T, false>(ta, tb, em, prm, grid, smem_bytes, st);
   VK_V2_CASE(128, 1) VK_V2_CASE(128, 3) VK_V2_CASE(128, 9)
   VK_V2_CASE(64, 1) VK_V2_CASE(64, 3) VK_V2_CASE(64, 9)
   VK_V2_CASE(32, 1) VK_V2_CASE(32, 3) VK_V2_CASE(32, 9)
@@ -208,21 +223,31 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   int ecols = 0, ecb = 0, epi_warp_bytes = 0;
   if (a->epi == VK_EPI_STD) {
     if (us == 2 && prm.has_mask) return VK_E_UNSUPPORTED;
+    {  // tensor combinations the epilogue is specialised for (everything the network uses); others -> v1
+      const int mode = prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3);
+      if (mode != 4 && mode != 5 && mode != 6 && mode != 7 && mode != 8 && mode != 12 && mode != 14) return VK_E_UNSUPPORTED;
+    }
     ecb = (n_cta * esize) % 64 == 0 ? 64 : 32;
     ecols = ecb / esize;
     if (n_cta % ecols) return VK_E_UNSUPPORTED;
     int off = 0;
-    const int unit = 32 * ecb;
+    const int unit = 128 * ecb;                 // one 128-pixel tile x ecols channels
     prm.off_r = off; if (prm.has_resid) off += unit;
     prm.off_k = off; if (prm.has_mask) off += unit;
     prm.off_o1 = off; if (prm.has_out1) off += unit;
     prm.off_o2 = off; if (prm.has_out2) off += unit;
     epi_warp_bytes = round_up(std::max(off, unit), 1024);
-    prm.ebx = std::min(tw, 32), prm.eby = 32 / prm.ebx;
+    prm.ebx = tw, prm.eby = th;
   }
   prm.ecb = ecb, prm.ecols = ecols, prm.n_ech = ecols ? n_cta / ecols : 1;
   prm.epi_warp_bytes = epi_warp_bytes;
-  const int epi_bytes = 8 * epi_warp_bytes;
+  const int epi_bytes = 2 * epi_warp_bytes;   // one staging area per epilogue group (4 warps)
+
+  // ---- CTA pairs (cta_group::2): M = 256 per MMA, each CTA stages half of the weight rows ----
+  // force_impl: 0/2 automatic, 3 single CTAs, 4 pairs
+  bool pair = a->force_impl == 4 || (a->force_impl != 3 && slab && n_cta % 32 == 0);
+  if (n_cta % 32) pair = false;                 // each half must be a multiple of 16 rows (N % 16, swizzle atoms)
+  const int b_rows = pair ? n_cta / 2 : n_cta;  // weight rows staged per CTA
 
   // ---- P, NT and ring depths ----
   const int n_sm = sm_count();
@@ -231,16 +256,19 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   if (a->force_tiles_per_cta) p_hi = std::min(p_hi, a->force_tiles_per_cta);
   int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0;
   double best_score = -1.0;
-  for (int P = p_hi; P >= 1; --P) {
+  if (p_hi == 3) p_hi = 2;                      // the epilogue's item <-> tile mapping wants P in {1, 2, 4}
+  for (int P = p_hi; P >= 1; P >>= 1) {
     if (a->force_tiles_per_cta && P != p_hi) break;
-    const long long jobs = (long long)((prm.n_tiles + P - 1) / P) * prm.n_blocks;
-    const long long rounds = (jobs + n_sm - 1) / n_sm;
-    const double eff = double(jobs) / double(rounds * n_sm);
+    const long long groups = (prm.n_tiles + P - 1) / P;
+    const long long jobs = (pair ? (groups + 1) / 2 : groups) * prm.n_blocks;
+    const long long workers = pair ? n_sm / 2 : n_sm;
+    const long long rounds = (jobs + workers - 1) / workers;
+    const double eff = double(groups * prm.n_blocks) / double(rounds * workers * (pair ? 2 : 1));
     for (int i = 0; i < n_nt; ++i) {
       const int nt = nt_opts[i];
       if (a->force_nt && slab && nt != a->force_nt) continue;
       const int a_slot = P * prm.a_box_bytes;
-      const int b_slot = round_up(nt * n_cta * chunk, 1024);
+      const int b_slot = round_up(nt * b_rows * chunk, 1024);
       const int total_b_items = prm.n_loads * prm.k_chunks * (slab ? 9 / nt : 1);
       const int total_a_items = prm.n_loads * prm.k_chunks;
       const int avail = kV2SmemBudget - 1024 - epi_bytes;
@@ -265,14 +293,17 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   prm.P = P;
   prm.nb = slab ? 9 / nt : 1;
   prm.a_slot_bytes = P * prm.a_box_bytes;
-  prm.b_slot_bytes = round_up(nt * n_cta * chunk, 1024);
-  prm.b_tx_bytes = nt * n_cta * chunk;
+  prm.b_slot_bytes = round_up(nt * b_rows * chunk, 1024);
+  prm.b_tx_bytes = nt * b_rows * chunk;
   prm.a_stages = best_as, prm.b_stages = best_bs;
   prm.b_base = prm.a_stages * prm.a_slot_bytes;
   prm.epi_base = prm.b_base + prm.b_stages * prm.b_slot_bytes;
   for (int tap = 0; tap < 9; ++tap)
     prm.a_off16[tap] = slab ? uint32_t(((tap / 3) * box_w + (tap % 3)) * chunk) >> 4 : 0u;
-  prm.n_jobs = ((prm.n_tiles + P - 1) / P) * prm.n_blocks;
+  {
+    const int groups = (prm.n_tiles + P - 1) / P;
+    prm.n_jobs = (pair ? (groups + 1) / 2 : groups) * prm.n_blocks;
+  }
   prm.tmem_cols = next_pow2_cols(2 * P * prm.acc_stride);
   if (prm.tmem_cols > 512) return VK_E_UNSUPPORTED;
   const int smem_bytes = prm.epi_base + epi_bytes + 1024;
@@ -303,7 +334,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   {
     const uint64_t dims[3] = {uint64_t(a->ldx), uint64_t(a->wrows), uint64_t(taps)};
     const uint64_t strides[2] = {uint64_t(row_bytes), uint64_t(row_bytes) * a->wrows};
-    const uint32_t box[3] = {uint32_t(chunk / esize), uint32_t(n_cta), uint32_t(nt)};
+    const uint32_t box[3] = {uint32_t(chunk / esize), uint32_t(b_rows), uint32_t(nt)};
     const uint32_t es[3] = {1u, 1u, 1u};
     int r = make_tensor_map(&tb, a->dtype, 3, a->w, dims, strides, box, es, chunk);
     if (r) return r;
@@ -341,18 +372,18 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
     }
   }
 
-  const int grid = int(std::min<long long>(prm.n_jobs, n_sm));
+  const int grid = pair ? 2 * int(std::min<long long>(prm.n_jobs, n_sm / 2)) : int(std::min<long long>(prm.n_jobs, n_sm));
   static const bool debug = std::getenv("VK_V2_DEBUG") != nullptr;
   if (debug)
     fprintf(stderr,
             "vk v2: kind=%d n=%d %dx%d ldx=%d wrows=%d | tile %dx%d tiles=%d P=%d n_cta=%d jobs=%d grid=%d | chunk=%d nt=%d "
-            "nb=%d a_stages=%d(%d B) b_stages=%d(%d B) epi=%d B/warp ecb=%d tmem=%d smem=%d\n",
+            "nb=%d a_stages=%d(%d B) b_stages=%d(%d B) epi=%d B/warp ecb=%d tmem=%d smem=%d pair=%d\n",
             a->kind, a->n, a->ih, a->iw, a->ldx, a->wrows, tw, th, prm.n_tiles, P, n_cta, prm.n_jobs, grid, chunk, nt,
             prm.nb, prm.a_stages, prm.a_slot_bytes, prm.b_stages, prm.b_slot_bytes, epi_warp_bytes, ecb, prm.tmem_cols,
-            smem_bytes);
+            smem_bytes, int(pair));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->dtype == VK_BF16) return dispatch_v2<__nv_bfloat16>(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st);
-  return dispatch_v2<float>(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st);
+  if (a->dtype == VK_BF16) return dispatch_v2<__nv_bfloat16>(chunk, nt, pair, ta, tb, em, prm, grid, smem_bytes, st);
+  return dispatch_v2<float>(chunk, nt, pair, ta, tb, em, prm, grid, smem_bytes, st);
 }
 
 }  // namespace vk
