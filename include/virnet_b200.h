@@ -120,6 +120,14 @@ int vk_conv_wgrad(const vk_wgrad_args* args, void* stream);
 int vk_wgrad_unpack(const float* ws, float* out, int32_t taps, int32_t m, int32_t n, int32_t accumulate,
                     void* stream);
 
+/* The same for every layer of a network in ONE launch.  descs_dev: device array of vk_unpack_desc. */
+typedef struct vk_unpack_desc {
+  const float* ws; /* [taps][mn] */
+  float* out;      /* [mn][taps] */
+  int32_t taps, mn;
+} vk_unpack_desc;
+int vk_wgrad_unpack_batched(const void* descs_dev, int32_t ndesc, int64_t max_mn, int32_t accumulate, void* stream);
+
 uint32_t vk_sizeof_wgrad_args(void);
 
 /* ---- HBM-bound kernels ------------------------------------------------- */

@@ -280,4 +280,22 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restr
   }
 }
 
+
+// all layers in one launch: blockIdx.y = layer
+struct WgradUnpackDesc {
+  const float* ws;
+  float* out;
+  int taps, mn;
+};
+__global__ void wgrad_unpack_batched_kernel(const WgradUnpackDesc* __restrict__ descs, int accumulate) {
+  const WgradUnpackDesc d = descs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.mn; i += gridDim.x * blockDim.x) {
+    for (int t = 0; t < d.taps; ++t) {
+      const float v = d.ws[static_cast<long long>(t) * d.mn + i];
+      float* o = d.out + static_cast<long long>(i) * d.taps + t;
+      *o = accumulate ? *o + v : v;
+    }
+  }
+}
+
 }  // namespace vk

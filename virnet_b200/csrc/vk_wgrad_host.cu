@@ -128,7 +128,14 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   prm.n_tiles = prm.tiles_x * prm.tiles_y * a->n;
 
   const int base_ctas = m_blocks * parts * prm.n_groups;
-  int ksplit = std::max(1, (148 + base_ctas - 1) / base_ctas);
+  // one CTA per SM (its smem ring fills the SM): never launch a partial second wave
+  int n_sm = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  int ksplit = std::max(1, n_sm / base_ctas);
   if (a->force_ksplit) ksplit = a->force_ksplit;
   ksplit = std::min(ksplit, prm.n_tiles);
   prm.ksplit = ksplit;
@@ -171,6 +178,17 @@ extern "C" int vk_wgrad_unpack(const float* ws, float* out, int32_t taps, int32_
   const int mn = m * n;
   wgrad_unpack_kernel<<<(mn + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ws, out, taps, mn,
                                                                                             accumulate);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+extern "C" int vk_wgrad_unpack_batched(const void* descs_dev, int32_t ndesc, int64_t max_mn, int32_t accumulate,
+                                       void* stream) {
+  if (descs_dev == nullptr || ndesc <= 0 || max_mn <= 0) return VK_E_BADARG;
+  static_assert(sizeof(WgradUnpackDesc) == sizeof(vk_unpack_desc), "descriptor layout");
+  const int bx = int(std::min<int64_t>((max_mn + 255) / 256, 64));
+  wgrad_unpack_batched_kernel<<<dim3(bx, ndesc), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const WgradUnpackDesc*>(descs_dev), accumulate);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
 }

@@ -188,11 +188,18 @@ class DenoiseEngine:
         # wgrad workspace: [taps][M][N] per layer, one flat buffer
         self.flat_ws = torch.zeros(ws_total, device=dev, dtype=torch.float32)
         o = 0
+        udescs = []
         for ly in self.layers:
             n = ly.weight.numel()
             m_, n_ = (ly.cin, ly.cout) if ly.kind == "convT" else (ly.cout, ly.cin)
             ly.ws = self.flat_ws[o:o + n].view(ly.taps, m_, n_)
             o += n
+            d = _l.vk_unpack_desc()
+            d.ws, d.out, d.taps, d.mn = ly.ws.data_ptr(), self.grad_view(ly.weight).data_ptr(), ly.taps, m_ * n_
+            udescs.append(d)
+        arr = (_l.vk_unpack_desc * len(udescs))(*udescs)
+        self._unpack_descs = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
+        self._unpack_n, self._unpack_max = len(udescs), max(d.mn for d in udescs)
 
     def mark_params_dirty(self):
         self._packed_version = None
@@ -420,6 +427,5 @@ class DenoiseEngine:
                     self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
                     g = gn
         # ---- workspace -> parameter-layout gradients ----
-        for ly in self.layers:
-            ops.wgrad_unpack(ly.ws, self.grad_view(ly.weight), accumulate=False)
+        ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
         self.saved = None

@@ -64,6 +64,10 @@ class vk_pack_desc(C.Structure):
                 ("mode", C.c_int32), ("pad_", C.c_int32)]
 
 
+class vk_unpack_desc(C.Structure):
+    _fields_ = [("ws", C.c_void_p), ("out", C.c_void_p), ("taps", C.c_int32), ("mn", C.c_int32)]
+
+
 class vk_adam_group(C.Structure):
     _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("max_norm", C.c_float), ("pad_", C.c_int32)]
 
@@ -75,6 +79,7 @@ _SIGNATURES = {
     "vk_conv_igemm": (C.c_int, [C.POINTER(vk_conv_args), C.c_void_p]),
     "vk_conv_wgrad": (C.c_int, [C.POINTER(vk_wgrad_args), C.c_void_p]),
     "vk_wgrad_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vk_wgrad_unpack_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "vk_sizeof_wgrad_args": (C.c_uint32, []),
     "vk_pack_input": (C.c_int, [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] + [C.c_int32] * 6
                       + [C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p]),

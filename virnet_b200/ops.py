@@ -198,6 +198,13 @@ def wgrad_unpack(ws, out, accumulate=False):
         _l.check(_l.load().vk_wgrad_unpack(_ptr(ws), _ptr(out), taps, m, n, int(accumulate), _stream()), "vk_wgrad_unpack")
 
 
+def wgrad_unpack_batched(descs_dev, ndesc, max_mn, accumulate=False):
+    """All layers' [taps, M, N] workspaces -> parameter-layout gradients in one launch."""
+    with _Prof("wgrad_unpack"):
+        _l.check(_l.load().vk_wgrad_unpack_batched(_ptr(descs_dev), ndesc, max_mn, int(accumulate), _stream()),
+                 "vk_wgrad_unpack_batched")
+
+
 # ---------------------------------------------------------------------------
 # HBM-bound kernels
 # ---------------------------------------------------------------------------
