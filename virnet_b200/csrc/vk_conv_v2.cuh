@@ -51,7 +51,8 @@ struct ConvV2Params {
   int a_slot_bytes, b_slot_bytes;
   int a_stages, b_stages;
   // ---- jobs ----
-  int P;                     // pixel tiles per job
+  int P;                     // pixel tiles per job (1, 2 or 4; <= epilogue groups)
+  int p_log2;
   int n_cta, n_blocks;       // GEMM N per job, N blocks
   int n_jobs;
   int acc_stride;            // TMEM columns between accumulators
@@ -97,7 +98,11 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
   }
 }
 
-constexpr int kV2Threads = 416;
+// 4 producer warps + kEpiGroups x 4 epilogue warps + 1 MMA warp.
+// (measured: 4 groups per CTA are slower than 2 — the 96-register cap spills and the larger staging area
+// shrinks the weight ring; profiles/r01_v2_*)
+constexpr int v2_epi_groups(bool pair) { return pair ? 2 : 2; }
+constexpr int v2_threads(bool pair) { return (4 + 4 * v2_epi_groups(pair) + 1) * 32; }
 constexpr int kV2MaxStages = 8;
 constexpr int kV2BProducers = 3;
 
@@ -250,7 +255,7 @@ __device__ __forceinline__ void epi_item_math(const uint32_t (&acc)[2][16], cons
   }
 }
 template <typename DT, int kChunkBytes, int kNT, bool kPair>
-__global__ void __launch_bounds__(kV2Threads, 1)
+__global__ void __launch_bounds__(v2_threads(kPair), 1)
 conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvV2Maps emaps, const __grid_constant__ ConvV2Params prm) {
   constexpr bool kTF32 = DTraits<DT>::kTF32;
@@ -258,6 +263,8 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int kChunkElems = kChunkBytes / kElemBytes;
   constexpr int kMmasPerChunk = kChunkBytes / 32;
   constexpr uint32_t kLayout = layout_type_for_swizzle(kChunkBytes);
+  constexpr int kGroups = v2_epi_groups(kPair);
+  constexpr int kMmaWarp = 4 + 4 * kGroups;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_a[kV2MaxStages], empty_a[kV2MaxStages];
@@ -295,14 +302,14 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&full_b[s], 1), mbar_init(&empty_b[s], 1);
       mbar_init(&in_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], kPair ? 16 : 8);
+    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], (kPair ? 2 : 1) * 4 * kGroups);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
   }
-  if (warp == 12) {
+  if (warp == kMmaWarp) {
     if constexpr (kPair) {
       tmem_alloc_2sm(&tmem_base_slot, prm.tmem_cols);
       tmem_relinquish_2sm();
@@ -311,8 +318,8 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tmem_relinquish();
     }
   }
-  if (warp >= 4 && warp < 12) {
-    for (int i = threadIdx.x - 128; i < prm.wrows; i += 256) {
+  if (warp >= 4 && warp < kMmaWarp) {
+    for (int i = threadIdx.x - 128; i < prm.wrows; i += 128 * kGroups) {
       const int c = i % prm.cq;
       bias_s[i] = (prm.bias != nullptr && c < prm.cout) ? __ldg(prm.bias + c) : 0.f;
     }
@@ -408,7 +415,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       if (prof && pw == 0) tslot[6] = w_empty, tslot[12] = clock64() - t_start;
     }
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (pair mode: leader CTA only) =====================
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc(DTraits<DT>::kFmt, kPair ? 256 : 128, prm.n_cta, 0, 0);
@@ -482,7 +489,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     if (prof && leader) tslot[1] = w_fa, tslot[2] = w_fb, tslot[3] = w_te, tslot[4] = clock64() - t_start;
   } else {
-    // ===================== epilogue (warps 4..11) =====================
+    // ===================== epilogue (warps 4 .. 4 + 4 * kGroups - 1) =====================
     const int ew = warp - 4;
     const int q4 = warp & 3;                   // TMEM lane quarter of this warp
     const int half = ew >> 2;
@@ -529,51 +536,35 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t acc0 = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(as * P) * prm.acc_stride;
 
       if (prm.epi == EPI_STD) {
-        // Items of a job are (channel chunk kc, tile p), p fastest; group `half` takes every second one.  P is
-        // 1, 2 or 4, so the group only ever meets tiles p0 = half & (P-1) and (P == 4) p0 + 2: decode them once.
-        const int p0 = half & (P - 1);
-        const int ns = (P == 1 && half == 1) ? 0 : ((p0 < nvalid ? 1 : 0) + ((P == 4 && p0 + 2 < nvalid) ? 1 : 0));
-        int t_img[2], t_x[2], t_y[2];
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int t = tile0 + p0 + 2 * sl;
-          const int img = t / tiles_per_img;
-          const int r = t - img * tiles_per_img;
+        // Items of a job are (channel chunk kc, tile p), p fastest, dealt round-robin to the kGroups groups.
+        // P is a power of two <= kGroups, so a group meets ONE tile per job, p = half & (P-1), and every
+        // (kGroups / P)-th channel chunk starting at half / P.
+        const int p = half & (P - 1);
+        const int kc_first = half >> prm.p_log2;
+        const int kc_step = kGroups >> prm.p_log2;
+        const int g_items = (p < nvalid && kc_first < n_ech) ? (n_ech - kc_first + kc_step - 1) / kc_step : 0;
+        int t_img, t_x, t_y;
+        {
+          const int t = tile0 + p;
+          t_img = t / tiles_per_img;
+          const int r = t - t_img * tiles_per_img;
           const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
-          t_img[sl] = img, t_x[sl] = tx << prm.tw_log2, t_y[sl] = ty * prm.th;
+          t_x = tx << prm.tw_log2, t_y = ty * prm.th;
         }
-        // P == 1: both groups share tile 0 and alternate over the channel chunks instead
-        const int kc_step = P == 1 ? 2 : 1;
-        const int kc_first = P == 1 ? half : 0;
-        const int ns_eff = P == 1 ? (nvalid > 0 ? 1 : 0) : ns;
-        const int g_items = ns_eff == 0 ? 0 : ns_eff * ((n_ech - kc_first + kc_step - 1) / kc_step);
-        auto item_of = [&](int g, int& kc, int& sl) {     // g-th item of this group in this job
-          if (ns_eff == 2) {
-            kc = g >> 1, sl = g & 1;
-          } else {
-            kc = kc_first + g * kc_step, sl = 0;
-          }
-        };
         auto issue_in = [&](int g) {
-          int kc, sl;
-          item_of(g, kc, sl);
-          const int c0 = cq0 + kc * ecols;
+          const int c0 = cq0 + (kc_first + g * kc_step) * ecols;
           mbar_arrive_expect_tx(my_bar, in_bytes);
           if (prm.has_resid)
-            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_r), &emaps.resid[qi], my_bar, c0, sl ? t_x[1] : t_x[0],
-                        sl ? t_y[1] : t_y[0], sl ? t_img[1] : t_img[0]);
+            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_r), &emaps.resid[qi], my_bar, c0, t_x, t_y, t_img);
           if (prm.has_mask)
-            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_k), &emaps.mask, my_bar, c0, sl ? t_x[1] : t_x[0],
-                        sl ? t_y[1] : t_y[0], sl ? t_img[1] : t_img[0]);
+            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_k), &emaps.mask, my_bar, c0, t_x, t_y, t_img);
         };
         if (has_in && g_items > 0 && glead) issue_in(0);
         mbar_wait_t(&tmem_full[as], phacc, prof, w_tf);
         tc_fence_after_sync();
         for (int g = 0; g < g_items; ++g) {
           if (prof) tq = clock64();
-          int kc, sl;
-          item_of(g, kc, sl);
-          const int p = p0 + 2 * sl;
+          const int kc = kc_first + g * kc_step;
           const uint32_t taddr = acc0 + uint32_t(p) * prm.acc_stride + uint32_t(kc * ecols);
           // ---- inputs: this thread's row of the staged residual / mask tiles ----
           uint4 rraw[4], kraw[4];
@@ -652,9 +643,8 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           lap(w_sync);
           if (glead) {
             const int c0 = cq0 + kc * ecols;
-            const int x = sl ? t_x[1] : t_x[0], y = sl ? t_y[1] : t_y[0], img = sl ? t_img[1] : t_img[0];
-            if (prm.has_out1) tma_store_4d(&emaps.out1[qi], stg_p + prm.off_o1, c0, x, y, img);
-            if (prm.has_out2) tma_store_4d(&emaps.out2[qi], stg_p + prm.off_o2, c0, x, y, img);
+            if (prm.has_out1) tma_store_4d(&emaps.out1[qi], stg_p + prm.off_o1, c0, t_x, t_y, t_img);
+            if (prm.has_out2) tma_store_4d(&emaps.out2[qi], stg_p + prm.off_o2, c0, t_x, t_y, t_img);
             bulk_commit();
           }
           lap(w_st);
@@ -666,7 +656,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         float* const o1 = reinterpret_cast<float*>(prm.out1_ptr);
         const float* const rs = reinterpret_cast<const float*>(prm.resid_ptr);
         const long long plane = static_cast<long long>(prm.crop_h) * prm.crop_w;
-        for (int p = half; p < nvalid; p += 2) {
+        for (int p = half; p < nvalid; p += kGroups) {
           const int t = tile0 + p;
           const int img = t / tiles_per_img;
           const int r = t - img * tiles_per_img;
@@ -712,7 +702,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
   }
   if (prof && threadIdx.x == 0) tslot[0] = clock64() - t_start;
-  if (warp == 12) {
+  if (warp == kMmaWarp) {
     tc_fence_after_sync();
     if constexpr (kPair) tmem_dealloc_2sm(tmem_base, prm.tmem_cols); else tmem_dealloc(tmem_base, prm.tmem_cols);
   }

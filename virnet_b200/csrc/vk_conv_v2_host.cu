@@ -51,7 +51,7 @@ int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em
   if constexpr (kPair) {
     // CTA pairs: a cluster of two CTAs on one TPC shares every weight tile (tcgen05 cta_group::2)
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kV2Threads), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(v2_threads(true)), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
@@ -60,7 +60,7 @@ int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return e != cudaSuccess ? int(e) : int(cudaGetLastError());
   } else {
-    kern<<<grid, kV2Threads, smem_bytes, st>>>(ta, tb, em, prm);
+    kern<<<grid, v2_threads(false), smem_bytes, st>>>(ta, tb, em, prm);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return int(cudaGetLastError());
   }
@@ -241,18 +241,20 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   }
   prm.ecb = ecb, prm.ecols = ecols, prm.n_ech = ecols ? n_cta / ecols : 1;
   prm.epi_warp_bytes = epi_warp_bytes;
-  const int epi_bytes = 2 * epi_warp_bytes;   // one staging area per epilogue group (4 warps)
+  // (epi_bytes depends on the pair decision below)
 
   // ---- CTA pairs (cta_group::2): M = 256 per MMA, each CTA stages half of the weight rows ----
   // force_impl: 0/2 automatic, 3 single CTAs, 4 pairs
-  bool pair = a->force_impl == 4 || (a->force_impl != 3 && slab && n_cta % 32 == 0);
+  bool pair = a->force_impl == 4 || (a->force_impl != 3 && slab && n_cta % 32 == 0 && n_cta >= 96);
   if (n_cta % 32) pair = false;                 // each half must be a multiple of 16 rows (N % 16, swizzle atoms)
   const int b_rows = pair ? n_cta / 2 : n_cta;  // weight rows staged per CTA
+  const int epi_groups = v2_epi_groups(pair);
+  const int epi_bytes = epi_groups * epi_warp_bytes;   // one staging area per epilogue group (4 warps)
 
   // ---- P, NT and ring depths ----
   const int n_sm = sm_count();
   const int p_max_tmem = std::max(1, 256 / prm.acc_stride);          // double-buffered accumulators
-  int p_hi = std::min(4, p_max_tmem);
+  int p_hi = std::min(std::min(4, epi_groups), p_max_tmem);
   if (a->force_tiles_per_cta) p_hi = std::min(p_hi, a->force_tiles_per_cta);
   int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0;
   double best_score = -1.0;
@@ -278,7 +280,9 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
       int bs = (avail - as * a_slot) / b_slot;
       bs = std::min(bs, kV2MaxStages);
       if (a->force_stages) bs = std::min(bs, a->force_stages);
-      if (bs < 2) continue;
+      // >= kV2BProducers: a B producer warp handles every 3rd item, so with fewer slots it could run two
+      // barrier phases ahead of the consumer and its parity wait would alias
+      if (bs < kV2BProducers) continue;
       // spend what is left on a third / fourth A slot
       while (as < 4 && as * a_slot + bs * b_slot + a_slot <= avail && bs >= 3) ++as;
       (void)total_b_items;
@@ -291,6 +295,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   if (best_P == 0) return VK_E_UNSUPPORTED;
   const int P = best_P, nt = best_nt;
   prm.P = P;
+  prm.p_log2 = P == 4 ? 2 : (P == 2 ? 1 : 0);
   prm.nb = slab ? 9 / nt : 1;
   prm.a_slot_bytes = P * prm.a_box_bytes;
   prm.b_slot_bytes = round_up(nt * b_rows * chunk, 1024);
