@@ -74,6 +74,13 @@ typedef struct vk_conv_args {
   float clamp_lo, clamp_hi;
   int32_t crop_h, crop_w;
   int32_t out_h, out_w; /* VK_CONV3X3_S2_DGRAD only: fine-grid size (the forward conv's input size) */
+  /* SFT modulation of out2 only (AttLayer, networks/AttResUNet.py:27-32,54-58), or NULL:
+   * out2 = lrelu(v * sft_mul[img][c] + sft_add[img][c]); fp32 [n][sft_ld] per-sample scalars
+   * (spatially constant conditioning maps).  Served by the persistent kernel only. */
+  const float* sft_mul;
+  const float* sft_add;
+  int32_t sft_ld;
+  int32_t pad_;
   /* tuning overrides, 0 = automatic */
   int32_t force_tiles_per_cta;
   int32_t force_chunk_bytes;
@@ -129,6 +136,35 @@ typedef struct vk_unpack_desc {
 int vk_wgrad_unpack_batched(const void* descs_dev, int32_t ndesc, int64_t max_mn, int32_t accumulate, void* stream);
 
 uint32_t vk_sizeof_wgrad_args(void);
+
+/* ---- super-resolution forward path: small per-sample kernels ------------- */
+
+/* KernelNet head, nn.Conv2d(c, cout, 9, stride 4, padding 4, bias=False) (networks/KNet.py:45):
+ * x NCHW fp32 [n][c][h][w], w OIHW fp32 [cout][c][9][9] -> out NHWC `dtype` [n][oh][ow][ld]. */
+int vk_knet_head(int32_t dtype, const float* x, const float* w, void* out, int32_t n, int32_t c, int32_t h, int32_t wd,
+                 int32_t cout, int32_t ld, void* stream);
+
+/* CALayer + skip of RB_Layer (networks/KNet.py:23-26, 37-39): out = f * sigmoid(W2 lrelu(W1 mean(f) + b1) + b2) + skip.
+ * f, skip, out: NHWC `dtype` [n][npix][ld]; w1 [r][c], w2 [c][r] are the 1x1 conv parameters. */
+int vk_ca_layer(int32_t dtype, const void* f, const void* skip, const float* w1, const float* b1, const float* w2,
+                const float* b2, void* out, int32_t n, int32_t npix, int32_t c, int32_t r, int32_t ld, float alpha,
+                void* stream);
+
+/* Global average over NCHW fp32 planes [n][c][hw] + head: exp(clamp(mean, lo, hi)) for channels in exp_mask,
+ * tanh(mean) for channels in tanh_mask -> out [n][c].  nn.AdaptiveAvgPool2d of SNet (networks/DnCNN.py:30-33,
+ * VIRNet.py:81) and of KNet's tail (networks/KNet.py:49,55-58). */
+int vk_gap_head(const float* x, int32_t n, int32_t c, int32_t hw, uint32_t exp_mask, uint32_t tanh_mask, float lo,
+                float hi, float* out, void* stream);
+
+/* AttLayer MLP (networks/AttResUNet.py:27-32) on per-sample constant conditioning values extra[n][e]
+ * (sqrt applied to the entries in sqrt_mask): mul = sigmoid(Wm f2 + bm), add = Wa f2 + ba, fp32 [n][c]. */
+int vk_sft_mlp(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask, const float* w1, const float* b1,
+               int32_t c1, const float* w2, const float* b2, int32_t c2, const float* wm, const float* bm,
+               const float* wa, const float* ba, int32_t c, float alpha, float* mul, float* add, void* stream);
+
+/* F.interpolate(x, scale_factor=sf, mode="nearest") on NCHW fp32 (networks/VIRNet.py:83). */
+int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
+                        void* stream);
 
 /* ---- HBM-bound kernels ------------------------------------------------- */
 

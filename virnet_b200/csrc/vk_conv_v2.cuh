@@ -66,6 +66,9 @@ struct ConvV2Params {
   int round_out2;
   int has_resid, has_mask, has_out1, has_out2;
   const float* bias;
+  const float* sft_mul;      // per-sample modulation of out2 (fp32 [n][sft_ld]) or null
+  const float* sft_add;
+  int sft_ld;
   int ecb;                   // bytes per staged row (64 or 32)
   int ecols;                 // channels per item
   int n_ech;                 // items per tile = n_cta / ecols
@@ -254,6 +257,39 @@ __device__ __forceinline__ void epi_item_math(const uint32_t (&acc)[2][16], cons
     }
   }
 }
+
+// out2 = lrelu(v * mul + add) with per-(sample, channel) SFT scalars (AttLayer on constant conditioning maps);
+// out1 = v.  Runtime flags: only the super-resolution forward path comes through here.
+template <typename DT>
+__device__ __forceinline__ void epi_item_math_sft(const uint32_t (&acc)[2][16], const uint4 (&rraw)[4], int nch,
+                                                  bool has_resid, bool has_out1, const float* __restrict__ mul,
+                                                  const float* __restrict__ add, int c_valid, float alpha, bool rnd,
+                                                  uint32_t a_o1, uint32_t a_o2, int swz) {
+  constexpr int CPC = 16 / int(sizeof(DT));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < nch) {
+      float v[CPC], r[CPC];
+      unpack_chunk<DT>(rraw[j], r);
+#pragma unroll
+      for (int i = 0; i < CPC; ++i) {
+        v[i] = __uint_as_float(acc[(j * CPC + i) >> 4][(j * CPC + i) & 15]);
+        if (has_resid) v[i] += r[i];
+      }
+      const uint32_t sw = uint32_t((j ^ swz) << 4);
+      if (has_out1) sts128(a_o1 + sw, pack_chunk<DT>(v));
+#pragma unroll
+      for (int i = 0; i < CPC; ++i) {
+        const int c = j * CPC + i;
+        const float m = c < c_valid ? __ldg(mul + c) : 1.f, a = c < c_valid ? __ldg(add + c) : 0.f;
+        v[i] = lrelu(fmaf(v[i], m, a), alpha);
+        if (sizeof(DT) == 4 && rnd) v[i] = round_tf32(v[i]);
+      }
+      sts128(a_o2 + sw, pack_chunk<DT>(v));
+    }
+  }
+}
+
 template <typename DT, int kChunkBytes, int kNT, bool kPair>
 __global__ void __launch_bounds__(v2_threads(kPair), 1)
 conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -631,6 +667,13 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       epi_item_math<DT, (M & 1) != 0, (M & 2) != 0, (M & 4) != 0, (M & 8) != 0, 32>(acc, rraw, kraw, alpha, rnd, a_o1, \
                                                                                     a_o2, swz);                    \
     break;
+          if (prm.sft_mul != nullptr) {
+            const int c0 = cq0 + kc * ecols;
+            epi_item_math_sft<DT>(acc, rraw, ecb >> 4, prm.has_resid != 0, prm.has_out1 != 0,
+                                  prm.sft_mul + static_cast<long long>(t_img) * prm.sft_ld + c0,
+                                  prm.sft_add + static_cast<long long>(t_img) * prm.sft_ld + c0, prm.cout - c0, alpha,
+                                  rnd, a_o1, a_o2, swz);
+          } else
           switch (mode) {
             VK_EPI_CASE(4) VK_EPI_CASE(5) VK_EPI_CASE(6) VK_EPI_CASE(7) VK_EPI_CASE(8) VK_EPI_CASE(12) VK_EPI_CASE(14)
             default: break;                       // the host only launches the combinations above

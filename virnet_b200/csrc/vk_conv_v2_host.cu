@@ -223,6 +223,8 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   int ecols = 0, ecb = 0, epi_warp_bytes = 0;
   if (a->epi == VK_EPI_STD) {
     if (us == 2 && prm.has_mask) return VK_E_UNSUPPORTED;
+    if ((a->sft_mul != nullptr) != (a->sft_add != nullptr)) return VK_E_BADARG;
+    if (a->sft_mul != nullptr && (!prm.has_out2 || prm.has_mask || us != 1 || a->sft_ld < a->cout)) return VK_E_BADARG;
     {  // tensor combinations the epilogue is specialised for (everything the network uses); others -> v1
       const int mode = prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3);
       if (mode != 4 && mode != 5 && mode != 6 && mode != 7 && mode != 8 && mode != 12 && mode != 14) return VK_E_UNSUPPORTED;
@@ -317,6 +319,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   prm.alpha = a->alpha;
   prm.round_out2 = a->round_out2;
   prm.bias = a->bias;
+  prm.sft_mul = a->sft_mul, prm.sft_add = a->sft_add, prm.sft_ld = a->sft_ld;
   prm.out1_ptr = a->out1;
   prm.resid_ptr = a->resid;
   prm.act_expclamp = a->act_expclamp;

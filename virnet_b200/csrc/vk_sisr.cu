@@ -1,0 +1,270 @@
+// vk_sisr.cu — the small, latency-bound kernels of the super-resolution forward path (sm_100a):
+// KernelNet's 9x9 stride-4 head and channel-attention layers (networks/KNet.py:12-59), the global-average
+// heads of SNet / KNet (networks/DnCNN.py:30-33,42, networks/KNet.py:55-58, networks/VIRNet.py:81) and
+// the SFT modulation MLPs of AttLayer (networks/AttResUNet.py:11-32).  The 3x3 convolutions between
+// them run on the tcgen05 kernels of vk_conv_*.  All of these touch a few hundred KB: one CTA per
+// sample, everything staged through shared memory / registers, no atomics.
+#include <algorithm>
+#include <cstdio>
+
+#include "../../include/virnet_b200.h"
+#include "vk_common.cuh"
+#include "vk_host.h"
+
+namespace vk {
+
+template <typename DT>
+__device__ __forceinline__ float ld_f(const DT* p);
+template <>
+__device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename DT>
+__device__ __forceinline__ void st_f(DT* p, float v);
+template <>
+__device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------
+// KNet head: Conv2d(c -> cout, k = 9, stride 4, pad 4, no bias), NCHW fp32 in, NHWC DT out.
+// One thread per (output pixel, output channel); the 9x9xc window is read through L1 (every
+// input pixel is shared by ~5 windows and all `cout` threads of a pixel).
+// ---------------------------------------------------------------------------
+template <typename DT>
+__global__ void knet_head_kernel(const float* __restrict__ x, const float* __restrict__ w, DT* __restrict__ out, int N,
+                                 int C, int H, int W, int OH, int OW, int cout, int ld) {
+  const long long total = static_cast<long long>(N) * OH * OW * ld;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = int(i % ld);
+    const long long pix = i / ld;
+    const int ox = int(pix % OW), oy = int((pix / OW) % OH), n = int(pix / (static_cast<long long>(OW) * OH));
+    float acc = 0.f;
+    if (co < cout) {
+      for (int c = 0; c < C; ++c) {
+        const float* xp = x + (static_cast<long long>(n) * C + c) * H * W;
+        const float* wp = w + (static_cast<long long>(co) * C + c) * 81;
+        for (int r = 0; r < 9; ++r) {
+          const int iy = oy * 4 - 4 + r;
+          if (iy < 0 || iy >= H) continue;
+          for (int s = 0; s < 9; ++s) {
+            const int ix = ox * 4 - 4 + s;
+            if (ix < 0 || ix >= W) continue;
+            acc = fmaf(__ldg(xp + iy * W + ix), __ldg(wp + r * 9 + s), acc);
+          }
+        }
+      }
+    }
+    st_f<DT>(out + i, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CALayer + residual of RB_Layer (networks/KNet.py:23-26, 37-39), one CTA per sample:
+//   y = mean_pix f;  z = LReLU(W1 y + b1);  s = sigmoid(W2 z + b2);  out = f * s + skip
+// ---------------------------------------------------------------------------
+template <typename DT>
+__global__ void ca_layer_kernel(const DT* __restrict__ f, const DT* __restrict__ skip, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, DT* __restrict__ out, int npix, int C, int R, int ld,
+                                float alpha) {
+  extern __shared__ float sm[];          // [blockDim.x / C][C] partial sums, then y[C], z[R], s[C]
+  const int n = blockIdx.x;
+  const DT* fp = f + static_cast<long long>(n) * npix * ld;
+  const DT* sp = skip + static_cast<long long>(n) * npix * ld;
+  DT* op = out + static_cast<long long>(n) * npix * ld;
+  const int lanes = blockDim.x / C;      // pixel lanes
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  float part = 0.f;
+  if (pl < lanes)
+    for (int p = pl; p < npix; p += lanes) part += ld_f<DT>(fp + static_cast<long long>(p) * ld + c);
+  float* partial = sm;
+  float* y = sm + lanes * C;
+  float* z = y + C;
+  float* s = z + R;
+  if (pl < lanes) partial[pl * C + c] = part;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += partial[l * C + threadIdx.x];
+    y[threadIdx.x] = t / float(npix);
+  }
+  __syncthreads();
+  if (threadIdx.x < R) {
+    float t = b1[threadIdx.x];
+    for (int k = 0; k < C; ++k) t = fmaf(w1[threadIdx.x * C + k], y[k], t);
+    z[threadIdx.x] = t > 0.f ? t : t * alpha;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = b2[threadIdx.x];
+    for (int k = 0; k < R; ++k) t = fmaf(w2[threadIdx.x * R + k], z[k], t);
+    s[threadIdx.x] = 1.f / (1.f + expf(-t));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npix * ld; i += blockDim.x) {
+    const int cc = i % ld;
+    float v = 0.f;
+    if (cc < C) v = ld_f<DT>(fp + i) * s[cc] + ld_f<DT>(sp + i);
+    st_f<DT>(op + i, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Global average over NCHW fp32 planes followed by a per-channel head:
+//   exp(clamp(mean, lo, hi)) for channels in exp_mask, tanh(mean) for channels in tanh_mask.
+// SNet with noise_avg (DnCNN.py:30-33 + VIRNet.py:81) and KNet's tail (KNet.py:55-58).
+// ---------------------------------------------------------------------------
+__global__ void gap_head_kernel(const float* __restrict__ x, int hw, int C, unsigned exp_mask, unsigned tanh_mask,
+                                float lo, float hi, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int plane = blockIdx.x;          // n * C + c
+  const int c = plane % C;
+  const float* p = x + static_cast<long long>(plane) * hw;
+  float t = 0.f;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) t += p[i];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < int(blockDim.x >> 5); ++i) tot += red[i];
+    float m = tot / float(hw);
+    if (exp_mask & (1u << c)) m = expf(fminf(fmaxf(m, lo), hi));
+    if (tanh_mask & (1u << c)) m = tanhf(m);
+    out[plane] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// AttLayer (networks/AttResUNet.py:27-32) on per-sample CONSTANT conditioning maps: the 1x1-conv MLP
+// commutes with the spatial repeat, so (mul, add) are per-(sample, channel) scalars:
+//   f1 = LReLU(W1 e + b1); f2 = LReLU(W2 f1 + b2); mul = sigmoid(Wm f2 + bm); add = Wa f2 + ba
+// e[n][k] = sqrt(extra[n][k]) for k in sqrt_mask (the noise variance), extra[n][k] otherwise.
+// ---------------------------------------------------------------------------
+__global__ void sft_mlp_kernel(const float* __restrict__ extra, int E, unsigned sqrt_mask, const float* __restrict__ w1,
+                               const float* __restrict__ b1, int C1, const float* __restrict__ w2,
+                               const float* __restrict__ b2, int C2, const float* __restrict__ wm,
+                               const float* __restrict__ bm, const float* __restrict__ wa,
+                               const float* __restrict__ ba, int C, float alpha, float* __restrict__ mul,
+                               float* __restrict__ add) {
+  extern __shared__ float sm[];          // e[E], f1[C1], f2[C2]
+  float* e = sm;
+  float* f1 = e + E;
+  float* f2 = f1 + C1;
+  const int n = blockIdx.x;
+  if (threadIdx.x < E) {
+    float v = extra[n * E + threadIdx.x];
+    e[threadIdx.x] = (sqrt_mask & (1u << threadIdx.x)) ? sqrtf(v) : v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C1; i += blockDim.x) {
+    float t = b1[i];
+    for (int k = 0; k < E; ++k) t = fmaf(w1[i * E + k], e[k], t);
+    f1[i] = t > 0.f ? t : t * alpha;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C2; i += blockDim.x) {
+    float t = b2[i];
+    for (int k = 0; k < C1; ++k) t = fmaf(w2[i * C1 + k], f1[k], t);
+    f2[i] = t > 0.f ? t : t * alpha;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float tm = bm[i], ta = ba[i];
+    for (int k = 0; k < C2; ++k) {
+      tm = fmaf(wm[i * C2 + k], f2[k], tm);
+      ta = fmaf(wa[i * C2 + k], f2[k], ta);
+    }
+    mul[n * C + i] = 1.f / (1.f + expf(-tm));
+    add[n * C + i] = ta;
+  }
+}
+
+// F.interpolate(x, scale_factor=sf, mode='nearest') on NCHW fp32 (networks/VIRNet.py:83): the global residual of RNet
+__global__ void upsample_nearest_kernel(const float* __restrict__ x, float* __restrict__ out, long long planes, int h,
+                                        int w, int sf) {
+  const int H = h * sf, W = w * sf;
+  const long long total = planes * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = int(i % W), Y = int((i / W) % H);
+    const long long pl = i / (static_cast<long long>(W) * H);
+    out[i] = __ldg(x + (pl * h + Y / sf) * w + X / sf);
+  }
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+#define VK_ST(s) reinterpret_cast<cudaStream_t>(s)
+#define VK_LAUNCHED()                                        \
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);    \
+  return int(cudaGetLastError())
+
+extern "C" int vk_knet_head(int32_t dtype, const float* x, const float* w, void* out, int32_t n, int32_t c, int32_t h,
+                            int32_t wd, int32_t cout, int32_t ld, void* stream) {
+  if (!x || !w || !out || n <= 0 || c <= 0 || h <= 0 || wd <= 0 || cout <= 0 || cout > ld) return VK_E_BADARG;
+  const int oh = (h - 1) / 4 + 1, ow = (wd - 1) / 4 + 1;
+  const long long total = static_cast<long long>(n) * oh * ow * ld;
+  const int grid = int(std::min<long long>((total + 255) / 256, 148 * 8));
+  if (dtype == VK_BF16)
+    knet_head_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(x, w, reinterpret_cast<__nv_bfloat16*>(out), n, c,
+                                                                    h, wd, oh, ow, cout, ld);
+  else if (dtype == VK_TF32)
+    knet_head_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(x, w, reinterpret_cast<float*>(out), n, c, h, wd, oh, ow,
+                                                            cout, ld);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_ca_layer(int32_t dtype, const void* f, const void* skip, const float* w1, const float* b1,
+                           const float* w2, const float* b2, void* out, int32_t n, int32_t npix, int32_t c, int32_t r,
+                           int32_t ld, float alpha, void* stream) {
+  if (!f || !skip || !w1 || !b1 || !w2 || !b2 || !out || n <= 0 || npix <= 0 || c <= 0 || r <= 0 || c > ld || c > 256)
+    return VK_E_BADARG;
+  const int threads = std::max(c, 256 / c * c);
+  const size_t smem = (size_t(threads / c) * c + 2 * c + r) * sizeof(float);
+  if (dtype == VK_BF16)
+    ca_layer_kernel<__nv_bfloat16><<<n, threads, smem, VK_ST(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(f), reinterpret_cast<const __nv_bfloat16*>(skip), w1, b1, w2, b2,
+        reinterpret_cast<__nv_bfloat16*>(out), npix, c, r, ld, alpha);
+  else if (dtype == VK_TF32)
+    ca_layer_kernel<float><<<n, threads, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(f),
+                                                              reinterpret_cast<const float*>(skip), w1, b1, w2, b2,
+                                                              reinterpret_cast<float*>(out), npix, c, r, ld, alpha);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_gap_head(const float* x, int32_t n, int32_t c, int32_t hw, uint32_t exp_mask, uint32_t tanh_mask,
+                           float lo, float hi, float* out, void* stream) {
+  if (!x || !out || n <= 0 || c <= 0 || c > 32 || hw <= 0) return VK_E_BADARG;
+  gap_head_kernel<<<n * c, 256, 0, VK_ST(stream)>>>(x, hw, c, exp_mask, tanh_mask, lo, hi, out);
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_sft_mlp(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask, const float* w1,
+                          const float* b1, int32_t c1, const float* w2, const float* b2, int32_t c2, const float* wm,
+                          const float* bm, const float* wa, const float* ba, int32_t c, float alpha, float* mul,
+                          float* add, void* stream) {
+  if (!extra || !w1 || !b1 || !w2 || !b2 || !wm || !bm || !wa || !ba || !mul || !add) return VK_E_BADARG;
+  if (n <= 0 || e <= 0 || e > 32 || c1 <= 0 || c2 <= 0 || c <= 0) return VK_E_BADARG;
+  const size_t smem = size_t(e + c1 + c2) * sizeof(float);
+  sft_mlp_kernel<<<n, 128, smem, VK_ST(stream)>>>(extra, e, sqrt_mask, w1, b1, c1, w2, b2, c2, wm, bm, wa, ba, c, alpha,
+                                                 mul, add);
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
+                                   void* stream) {
+  if (!x || !out || n <= 0 || c <= 0 || h <= 0 || w <= 0 || sf <= 0) return VK_E_BADARG;
+  const long long total = static_cast<long long>(n) * c * h * sf * w * sf;
+  const int grid = int(std::min<long long>((total + 255) / 256, 148 * 8));
+  upsample_nearest_kernel<<<grid, 256, 0, VK_ST(stream)>>>(x, out, static_cast<long long>(n) * c, h, w, sf);
+  VK_LAUNCHED();
+}

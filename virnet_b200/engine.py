@@ -29,6 +29,7 @@ from .ops import (VK_BF16, VK_TF32, VK_CONV3X3_S1, VK_CONV3X3_S2, VK_CONVT2X2_S2
                   VK_CONV3X3_S2_DGRAD, VK_EPI_NCHW_F32)
 
 SNET_LOG_MAX, SNET_LOG_MIN = math.log(1e2), math.log(1e-10)     # networks/VIRNet.py:15-16
+KNET_LOG_MAX, KNET_LOG_MIN = math.log(1e2), math.log(1e-4)      # networks/KNet.py:5-6
 
 PRECISIONS = {"bf16": VK_BF16, "tf32": VK_TF32}
 
@@ -60,8 +61,9 @@ class _Layer:
 
 
 class DenoiseEngine:
-    def __init__(self, net: nn.Module, precision: str = "tf32"):
+    def __init__(self, net: nn.Module, precision: str = "tf32", sr: bool = False):
         self.net = net
+        self.sr = sr
         self.precision = precision
         self.dtype = PRECISIONS[precision]
         self.tdt = ops.TORCH_DTYPE[self.dtype]
@@ -70,11 +72,14 @@ class DenoiseEngine:
         self.sigma_chn = snet.conv_last.out_channels
         self.noise_cond = bool(net.noise_cond)
         self.extra_mode = rnet.extra_mode
-        if self.extra_mode in ("down", "both"):
-            raise NotImplementedError("extra_mode 'Down'/'Both' (SFT modulation) belongs to the SISR engine")
-        if snet.noise_avg:
-            raise NotImplementedError("noise_avg=True belongs to the SISR engine")
-        self.head_extra = self.sigma_chn if (self.noise_cond and self.extra_mode == "input") else 0
+        if not sr:
+            if self.extra_mode in ("down", "both"):
+                raise NotImplementedError("extra_mode 'Down'/'Both' (SFT modulation) belongs to the SISR engine")
+            if snet.noise_avg:
+                raise NotImplementedError("noise_avg=True belongs to the SISR engine")
+            self.head_extra = self.sigma_chn if (self.noise_cond and self.extra_mode == "input") else 0
+        else:
+            self.head_extra = rnet.extra_chn if self.extra_mode in ("input", "both") else 0
         self.depth, self.n_feat, self.n_res = rnet.depth, rnet.n_feat, rnet.n_resblocks
 
         # ---- layer table (forward order) ----
@@ -108,6 +113,17 @@ class DenoiseEngine:
                 L += [a, b]
         self.tail = _Layer("RNet.tail", rnet.tail, "conv", True)
         L.append(self.tail)
+        # KNet (super-resolution only): the 3x3 convs run on the tensor-core kernels, the 9x9 head, the
+        # channel-attention MLPs and the SFT MLPs read their fp32 parameters directly (vk_sisr.cu)
+        self.k_blocks, self.k_tail = [], None
+        if sr:
+            knet = net.KNet
+            for b, rb in enumerate(knet.body):
+                self.k_blocks.append((_Layer(f"KNet.body{b}.conv1", rb.body[0], "conv", False),
+                                      _Layer(f"KNet.body{b}.conv2", rb.body[2], "conv", False), rb.body[3]))
+                L += [self.k_blocks[-1][0], self.k_blocks[-1][1]]
+            self.k_tail = _Layer("KNet.tail", knet.tail[0], "conv", False)
+            L.append(self.k_tail)
         self.layers = L
 
         self._flat_key = None
@@ -429,3 +445,136 @@ class DenoiseEngine:
         # ---- workspace -> parameter-layout gradients ----
         ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
         self.saved = None
+
+
+    # ------------------------------------------------------------------
+    # super-resolution forward (networks/VIRNet.py:80-97); inference only in this round
+    # ------------------------------------------------------------------
+    def forward_sr(self, x: torch.Tensor, sf: int):
+        """x: LR image NCHW fp32 -> (mu [N,C,H*sf,W*sf], kinfo [N,3], sigma [N,1,1,1])."""
+        net = self.net
+        if not (net.noise_cond and net.kernel_cond and net.noise_avg and self.extra_mode == "both"):
+            raise NotImplementedError(
+                "the SISR engine implements the shipped configuration (noise_cond, kernel_cond, noise_avg=True, "
+                "extra_mode='Both'): the SFT maps are then per-sample constants; spatially varying maps are not built")
+        self._ensure_flat()
+        self._ensure_packed()
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise _l.VkError("input must be a CUDA fp32 NCHW tensor")
+        x = x.contiguous()
+        N, C, h, w = x.shape
+        dt, dev = self.dtype, x.device
+        cp = lambda c: ops.chan_pad(c, dt)
+        f32 = torch.float32
+
+        # ---- SNet with global average of the log-variance (DnCNN.py:30-33,42; VIRNet.py:81) ----
+        xs = self._buf("sr.xs", (N, h, w, cp(C)))
+        ops.pack_input(x, xs, dtype=dt)
+        cur = xs
+        for i, ly in enumerate(self.s_layers[:-1]):
+            o = self._buf(f"sr.s{i}", (N, h, w, cp(ly.cout)))
+            self._conv(cur, ly, VK_CONV3X3_S1, ldo=cp(ly.cout), out2=o, alpha=0.25)
+            cur = o
+        logvar = self._buf("sr.logvar", (N, self.sigma_chn, h, w), f32)
+        self._conv(cur, self.s_layers[-1], VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=logvar)
+        sigma = torch.empty(N, self.sigma_chn, 1, 1, device=dev, dtype=f32)
+        ops.gap_head(logvar, sigma, exp_mask=(1 << self.sigma_chn) - 1, lo=SNET_LOG_MIN, hi=SNET_LOG_MAX)
+
+        # ---- KNet (KNet.py:52-59) ----
+        knet = net.KNet
+        nf = knet.head.out_channels
+        kh, kw = (h - 1) // 4 + 1, (w - 1) // 4 + 1
+        H = self._buf("sr.k.h0", (N, kh, kw, cp(nf)))
+        ops.knet_head(x, knet.head.weight, H, dtype=dt)
+        for b, (c1, c2, ca) in enumerate(self.k_blocks):
+            A = self._buf("sr.k.a", (N, kh, kw, cp(nf)))
+            self._conv(H, c1, VK_CONV3X3_S1, ldo=cp(nf), out2=A, alpha=0.2)
+            F_ = self._buf("sr.k.f", (N, kh, kw, cp(nf)))
+            self._conv(A, c2, VK_CONV3X3_S1, ldo=cp(nf), out1=F_)
+            Hn = self._buf(f"sr.k.h{1 + (b & 1)}", (N, kh, kw, cp(nf)))
+            ops.ca_layer(F_, H, ca.body[0].weight, ca.body[0].bias, ca.body[2].weight, ca.body[2].bias, Hn, dtype=dt,
+                         c=nf, alpha=0.2)
+            H = Hn
+        kc = self.k_tail.cout
+        kraw = self._buf("sr.k.raw", (N, kc, kh, kw), f32)
+        self._conv(H, self.k_tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=kraw)
+        kinfo = torch.empty(N, kc, device=dev, dtype=f32)
+        ops.gap_head(kraw, kinfo, exp_mask=0b011, tanh_mask=1 << (kc - 1), lo=KNET_LOG_MIN, hi=KNET_LOG_MAX)
+
+        # ---- conditioning values per sample: [kinfo (3), sigma (1)]; sqrt of the variance at use (VIRNet.py:89-92) ----
+        E = kc + self.sigma_chn
+        extra = self._buf("sr.extra", (N, E), f32)
+        extra[:, :kc].copy_(kinfo)
+        extra[:, kc:].copy_(sigma.view(N, self.sigma_chn))
+        sqrt_mask = ((1 << self.sigma_chn) - 1) << kc
+        nfeat = self.n_feat
+        rnet = net.RNet
+        sft = {}
+        for ii, blk in enumerate(rnet.down_path):
+            for b, rb in enumerate(blk.body):
+                for which in ("sft1", "sft2"):
+                    mul = self._buf(f"sr.sft.{ii}.{b}.{which}.m", (N, nfeat[ii]), f32)
+                    add = self._buf(f"sr.sft.{ii}.{b}.{which}.a", (N, nfeat[ii]), f32)
+                    ops.sft_mlp(extra, getattr(rb, which), mul, add, sqrt_mask=sqrt_mask)
+                    sft[(ii, b, which)] = (mul, add)
+
+        # ---- RNet on the nearest-upsampled image (VIRNet.py:83; AttResUNet.py:141-175, extra_mode 'Both') ----
+        Hh, Ww = h * sf, w * sf
+        mod = 2 ** (self.depth - 1)
+        Hp, Wp = (Hh + mod - 1) // mod * mod, (Ww + mod - 1) // mod * mod
+        if Hp > 2 * Hh - 1 or Wp > 2 * Ww - 1:
+            raise _l.VkError("image too small for reflect padding")
+        cin0 = C + self.head_extra
+        r0 = self._buf("sr.r0", (N, Hp, Wp, cp(cin0)))
+        ops.pack_input(x, r0, dtype=dt, sf=sf, extra=extra, extra_is_map=False, extra_sqrt_mask=sqrt_mask)
+        hh, ww = Hp, Wp
+        X = self._buf("sr.X.head", (N, hh, ww, nfeat[0]))
+        Act = self._buf("sr.A.head", (N, hh, ww, nfeat[0]))
+        self._conv(r0, self.head, VK_CONV3X3_S1, ldo=nfeat[0], out1=X, out2=Act, alpha=0.2, sft=sft[(0, 0, "sft1")])
+        bridges, dims = [], [(hh, ww)]
+        for ii, (res, ds) in enumerate(self.down):
+            c = nfeat[ii]
+            for b, (c1, c2) in enumerate(res):
+                Bt = self._buf(f"sr.d{ii}.{b}.B", (N, hh, ww, c))
+                self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out2=Bt, alpha=0.2, sft=sft[(ii, b, "sft2")])
+                Xn = self._buf(f"sr.d{ii}.{b}.X", (N, hh, ww, c))
+                last = b == len(res) - 1
+                if last:
+                    self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn)
+                    X, Act = Xn, None
+                else:
+                    An = self._buf(f"sr.d{ii}.{b}.A", (N, hh, ww, c))
+                    self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2,
+                               sft=sft[(ii, b + 1, "sft1")])
+                    X, Act = Xn, An
+            if ds is not None:
+                bridges.append(X)
+                h2, w2 = (hh + 1) // 2, (ww + 1) // 2
+                Xd = self._buf(f"sr.d{ii}.ds.X", (N, h2, w2, nfeat[ii + 1]))
+                Ad = self._buf(f"sr.d{ii}.ds.A", (N, h2, w2, nfeat[ii + 1]))
+                self._conv(X, ds, VK_CONV3X3_S2, ldo=nfeat[ii + 1], out1=Xd, out2=Ad, alpha=0.2,
+                           sft=sft[(ii + 1, 0, "sft1")])
+                X, Act, hh, ww = Xd, Ad, h2, w2
+                dims.append((hh, ww))
+        for k, (us, res) in enumerate(self.up):
+            lvl = self.depth - 2 - k
+            c = nfeat[lvl]
+            hh, ww = dims[lvl]
+            Xu = self._buf(f"sr.u{k}.us.X", (N, hh, ww, c))
+            Au = self._buf(f"sr.u{k}.us.A", (N, hh, ww, c))
+            self._conv(X, us, VK_CONVT2X2_S2, ldo=c, resid=bridges[lvl], out1=Xu, out2=Au, alpha=0.2)
+            X, Act = Xu, Au
+            for b, (c1, c2) in enumerate(res):
+                Bt = self._buf(f"sr.u{k}.{b}.B", (N, hh, ww, c))
+                self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out2=Bt, alpha=0.2)
+                Xn = self._buf(f"sr.u{k}.{b}.X", (N, hh, ww, c))
+                last = b == len(res) - 1
+                An = None if last else self._buf(f"sr.u{k}.{b}.A", (N, hh, ww, c))
+                self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2)
+                X, Act = Xn, An
+        # tail: + bias, crop, + x_up (the nearest-upsampled LR image, AttResUNet.py:173) -> NCHW fp32
+        x_up = self._buf("sr.xup", (N, C, Hh, Ww), f32)
+        ops.upsample_nearest_nchw(x, x_up, sf)
+        mu = torch.empty(N, C, Hh, Ww, device=dev, dtype=f32)
+        self._conv(X, self.tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, resid=x_up, out1=mu, crop=(Hh, Ww))
+        return mu, kinfo, sigma

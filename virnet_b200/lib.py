@@ -38,6 +38,7 @@ class vk_conv_args(C.Structure):
         ("clamp_lo", C.c_float), ("clamp_hi", C.c_float),
         ("crop_h", C.c_int32), ("crop_w", C.c_int32),
         ("out_h", C.c_int32), ("out_w", C.c_int32),
+        ("sft_mul", C.c_void_p), ("sft_add", C.c_void_p), ("sft_ld", C.c_int32), ("pad_", C.c_int32),
         ("force_tiles_per_cta", C.c_int32), ("force_chunk_bytes", C.c_int32),
         ("force_stages", C.c_int32), ("force_tw", C.c_int32),
         ("force_impl", C.c_int32), ("force_nt", C.c_int32),
@@ -91,6 +92,14 @@ _SIGNATURES = {
     "vk_channel_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "vk_adam_clip_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p] + [C.c_float] * 5
                           + [C.c_int32, C.c_void_p, C.c_void_p]),
+    "vk_knet_head": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    "vk_ca_layer": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
+    "vk_gap_head": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                              C.c_void_p, C.c_void_p]),
+    "vk_sft_mlp": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                             C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vk_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
     "vk_sizeof_conv_args": (C.c_uint32, []),
     "vk_version": (C.c_char_p, []),
     "vk_launch_count": (C.c_uint64, []),

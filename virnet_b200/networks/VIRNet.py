@@ -90,7 +90,18 @@ class VIRAttResUNetSR(nn.Module):
         self.precision = (precision or _default_precision()).lower()
         self._engine = None
 
+    def engine(self):
+        from ..engine import DenoiseEngine
+        if self._engine is None or self._engine.precision != self.precision:
+            object.__setattr__(self, "_engine", DenoiseEngine(self, self.precision, sr=True))
+        return self._engine
+
     def forward(self, x, sf):
-        raise NotImplementedError(
-            "VIRAttResUNetSR: the SISR engine (KNet + SFT modulation kernels) is the next hot-path row "
-            "(SURVEY.md §8 a5/a7/a8); parameters and state_dict layout are already reference-compatible")
+        """(mu, kinfo_est [N,3], sigma [N,1,1,1]) as networks/VIRNet.py:80-97.  Forward only in this round: the
+        backward pass of the SISR rows is not built, so calling it with autograd
+        recording and trainable parameters raises instead of returning tensors that silently lack a graph."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("VIRAttResUNetSR: only the forward (inference) path is built; call it under "
+                                      "torch.no_grad() / .eval()")
+        with torch.no_grad():
+            return self.engine().forward_sr(x, int(sf))

@@ -137,7 +137,7 @@ def pack_convT_weight(w: torch.Tensor, dtype: int, ldx: int | None = None):
 # ---------------------------------------------------------------------------
 def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_STD, resid=None, mask=None,
                out1=None, out2=None, alpha=0.2, round_out2=False, act_expclamp=False, clamp=(0.0, 0.0),
-               crop=(0, 0), out_hw=(0, 0), tune=None, cin=None):
+               crop=(0, 0), out_hw=(0, 0), tune=None, cin=None, sft=None):
     """x: NHWC [n,ih,iw,ldx] tensor of the storage dtype; w_packed: [taps][wrows][ldx]."""
     assert x.is_cuda and x.is_contiguous() and w_packed.is_contiguous()
     assert x.dtype == TORCH_DTYPE[dtype] and w_packed.dtype == TORCH_DTYPE[dtype]
@@ -156,6 +156,11 @@ def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_S
     a.clamp_lo, a.clamp_hi = clamp
     a.crop_h, a.crop_w = crop
     a.out_h, a.out_w = out_hw
+    if sft is not None:
+        mul, add = sft                                   # fp32 [n, C] per-sample modulation of out2
+        assert mul.dtype == torch.float32 and add.dtype == torch.float32 and mul.shape == add.shape
+        assert mul.is_contiguous() and add.is_contiguous() and mul.shape[0] == n and mul.shape[1] >= cout
+        a.sft_mul, a.sft_add, a.sft_ld = _ptr(mul), _ptr(add), mul.shape[1]
     if tune:
         a.force_tiles_per_cta = tune.get("p", 0)
         a.force_chunk_bytes = tune.get("chunk", 0)
@@ -279,3 +284,55 @@ def adam_clip_step(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_
         _l.check(_l.load().vk_adam_clip_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(groups_dev),
                                              ngroups, max_group_elems, _ptr(sq_ws), grad_scale, lr, beta1, beta2, eps,
                                              step, _ptr(norms_out), _stream()), "vk_adam_clip_step")
+
+
+# ---------------------------------------------------------------------------
+# super-resolution forward path: small per-sample kernels
+# ---------------------------------------------------------------------------
+def knet_head(x, w, out, *, dtype):
+    """x NCHW fp32, w [cout, c, 9, 9] fp32 -> out NHWC [n, oh, ow, ld] (Conv2d k9 s4 p4, no bias)."""
+    n, c, h, wd = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous() and out.is_contiguous()
+    assert out.shape[1] == (h - 1) // 4 + 1 and out.shape[2] == (wd - 1) // 4 + 1
+    with _Prof("knet_head"):
+        _l.check(_l.load().vk_knet_head(dtype, _ptr(x), _ptr(w), _ptr(out), n, c, h, wd, w.shape[0], out.shape[-1],
+                                        _stream()), "vk_knet_head")
+
+
+def ca_layer(f, skip, w1, b1, w2, b2, out, *, dtype, c, alpha=0.2):
+    """out = f * sigmoid(W2 lrelu(W1 mean(f) + b1) + b2) + skip; f/skip/out NHWC [n, h, w, ld]."""
+    n, ld = f.shape[0], f.shape[-1]
+    npix = f.shape[1] * f.shape[2]
+    for t in (f, skip, out):
+        assert t.is_contiguous() and t.shape == f.shape
+    with _Prof("ca_layer"):
+        _l.check(_l.load().vk_ca_layer(dtype, _ptr(f), _ptr(skip), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(out), n,
+                                       npix, c, w1.shape[0], ld, alpha, _stream()), "vk_ca_layer")
+
+
+def gap_head(x, out, *, exp_mask=0, tanh_mask=0, lo=0.0, hi=0.0):
+    """x NCHW fp32 -> out [n, c] = head(mean over pixels)."""
+    n, c = x.shape[0], x.shape[1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.numel() == n * c
+    with _Prof("gap_head"):
+        _l.check(_l.load().vk_gap_head(_ptr(x), n, c, x.shape[2] * x.shape[3], exp_mask, tanh_mask, lo, hi, _ptr(out),
+                                       _stream()), "vk_gap_head")
+
+
+def sft_mlp(extra, att, mul, add, *, sqrt_mask=0, alpha=0.2):
+    """att: an AttLayer container (conv1, conv2, mul_conv, add_conv 1x1 convs); extra fp32 [n, e]."""
+    n, e = extra.shape
+    c1, c2, c = att.conv1.out_channels, att.conv2.out_channels, att.mul_conv.out_channels
+    assert extra.dtype == torch.float32 and extra.is_contiguous() and mul.shape == (n, c) and add.shape == (n, c)
+    with _Prof("sft_mlp"):
+        _l.check(_l.load().vk_sft_mlp(_ptr(extra), n, e, sqrt_mask, _ptr(att.conv1.weight), _ptr(att.conv1.bias), c1,
+                                      _ptr(att.conv2.weight), _ptr(att.conv2.bias), c2, _ptr(att.mul_conv.weight),
+                                      _ptr(att.mul_conv.bias), _ptr(att.add_conv.weight), _ptr(att.add_conv.bias), c,
+                                      alpha, _ptr(mul), _ptr(add), _stream()), "vk_sft_mlp")
+
+
+def upsample_nearest_nchw(x, out, sf):
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.shape == (n, c, h * sf, w * sf)
+    with _Prof("upsample_nearest"):
+        _l.check(_l.load().vk_upsample_nearest(_ptr(x), _ptr(out), n, c, h, w, sf, _stream()), "vk_upsample_nearest")
