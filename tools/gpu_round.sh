@@ -8,5 +8,5 @@ tail -c 3000 gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
    python tools/profile_step.py --steps 3 > gpurun_out/launches.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 60 -c 6 -f -o gpurun_out/prof_conv \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_v2 -s 60 -c 6 -f -o gpurun_out/prof_conv \
    python tools/profile_step.py --steps 2 > gpurun_out/prof_conv.log 2>&1; echo "ncu full rc=$?"
