@@ -239,11 +239,16 @@ def run_ours(args):
     final_loss = float(loss_host[0])
 
     # ---- roofline of the dominant kernel (conv_igemm: fprop + dgrad launches), measured live ----
+    # (per-launch CUDA events need the launches serialised on one stream: the weight-gradient side stream of
+    # the product path is switched off for these two extra steps only; `value` / `e2e` above ran with it on)
+    side = trainer.engine.wgrad_side_stream
+    trainer.engine.wgrad_side_stream = False
     prof = ops.start_profile()
     for _ in range(2):
         step_resident()
     torch.cuda.synchronize()
     recs = ops.stop_profile()
+    trainer.engine.wgrad_side_stream = side
     fam = {}
     for r in recs:
         f = fam.setdefault(r["family"], {"ms": 0.0, "flops": 0.0, "n": 0})
@@ -280,7 +285,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (fprop+dgrad launches)",
+            "roofline": {"bound": "tensor", "kernel": "vk_conv_igemm launches (conv_v2_kernel + conv_igemm_kernel; fprop+dgrad), serialised",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": f"{peak_src} bf16_tflops_sustained" + (" x0.5 (tf32)" if args.precision == "tf32" else ""),
                          "traffic": traffic, "launches_per_step": conv["n"] // 2,

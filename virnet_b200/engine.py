@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -126,6 +127,8 @@ class DenoiseEngine:
             L.append(self.k_tail)
         self.layers = L
 
+        self.wgrad_side_stream = os.environ.get("VIRNET_B200_WGRAD_STREAM", "1") != "0"
+        self._wg_stream, self._wg_events, self._wg_i = None, [], 0
         self._flat_key = None
         self._packed_version = None
         self._bufs: Dict = {}
@@ -351,7 +354,18 @@ class DenoiseEngine:
         dbias = None
         if ly.bias is not None and ly.kind != "convT":
             dbias = self.grad_view(ly.bias)
-        ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias)
+        ws = self._wg_stream
+        if ws is None:
+            ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias)
+            return
+        # weight gradients are leaves of the backward graph: run them on a side stream so their CTAs fill the SMs
+        # the persistent dgrad kernels leave idle in their last (partial) round
+        ev = self._wg_events[self._wg_i % len(self._wg_events)]
+        self._wg_i += 1
+        ev.record()
+        ws.wait_event(ev)
+        with torch.cuda.stream(ws):
+            ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias)
 
     def _dgrad(self, g, ly: _Layer, kind, cout, **kw):
         ops.conv_igemm(g, ly.wd, dtype=self.dtype, kind=kind, cout=cout, bias=None, **kw)
@@ -379,6 +393,11 @@ class DenoiseEngine:
         nf = self.n_feat
         self.flat_grads.zero_()
         self.flat_ws.zero_()
+        if self.wgrad_side_stream and self._wg_stream is None:
+            self._wg_stream = torch.cuda.Stream(device=self.flat_params.device)
+            self._wg_events = [torch.cuda.Event() for _ in range(8)]
+        if not self.wgrad_side_stream:
+            self._wg_stream = None
         gR0 = None
         if g_mu is not None:
             g_mu = g_mu.contiguous().float()
@@ -443,6 +462,8 @@ class DenoiseEngine:
                     self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
                     g = gn
         # ---- workspace -> parameter-layout gradients ----
+        if self._wg_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._wg_stream)
         ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
         self.saved = None
 
