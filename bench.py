@@ -305,7 +305,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=16, help="patches per GPU per step (reference batch_size=16)")
+    ap.add_argument("--batch", type=int, default=32,
+                    help="patches per GPU per step (weak scaling; the reference trains with a GLOBAL batch of 16)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
