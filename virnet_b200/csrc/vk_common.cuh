@@ -226,6 +226,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// Same without the cluster-scope release fence (a MEMBAR + ERRBAR, ~1000 cycles): for signals that publish no
+// shared / global memory writes, e.g. "this TMEM accumulator has been drained" after tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
 // TMA loads whose completion is signalled on a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t cluster_bar_addr, int c0,
                                                 int c1, int c2) {

@@ -538,7 +538,8 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t stg = smem_u32(stg_p);
     const int grp_bar = 1 + half;                         // named barrier of the group (128 threads)
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp_bar) : "memory"); };
-    const bool glead = (q4 == 0) && (lane == 0);          // the group's TMA-issuing thread
+    const bool glead = (q4 == 0) && (lane == 0);          // the group's TMA-load-issuing thread
+    const bool slead = (q4 == 1) && (lane == 0);          // ... and its TMA-store-issuing thread (bulk groups are per thread)
     const int ecb = prm.ecb, ecols = prm.ecols, n_ech = prm.n_ech;
     const int swz = ecb == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1);      // TMA swizzle of this thread's staged row
     const uint32_t row_base = stg + uint32_t(row * ecb);
@@ -615,15 +616,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
-          if (glead) {                            // previous stores have finished reading the out buffers
-            if (prof) {
-              const long long t0 = clock64();
-              bulk_wait_read0();
-              w_rd += clock64() - t0;
-            } else {
-              bulk_wait_read0();
-            }
-          }
+          if (slead) bulk_wait_read0();           // previous stores have finished reading the out buffers
           lap(w_misc);
           group_sync();                           // inputs consumed by all 4 warps, out buffers free
           lap(w_sync);
@@ -684,7 +677,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           lap(w_fence);
           group_sync();                           // the whole 128-pixel item is staged
           lap(w_sync);
-          if (glead) {
+          if (slead) {
             const int c0 = cq0 + kc * ecols;
             if (prm.has_out1) tma_store_4d(&emaps.out1[qi], stg_p + prm.off_o1, c0, t_x, t_y, t_img);
             if (prm.has_out2) tma_store_4d(&emaps.out2[qi], stg_p + prm.off_o2, c0, t_x, t_y, t_img);
@@ -730,11 +723,11 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before_sync();
       __syncwarp();
       if (lead) {
-        if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]);
+        if constexpr (kPair) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]);
       }
       if (++as == 2) as = 0, phacc ^= 1;
     }
-    if (glead) bulk_wait0();                     // all stores of this group have completed
+    if (slead) bulk_wait0();                     // all stores of this group have completed
     if (prof && glead && half == 0) tslot[7] = w_tf, tslot[8] = w_in, tslot[9] = w_rd, tslot[10] = clock64() - t_start, tslot[13] = w_ld, tslot[14] = w_math, tslot[15] = w_sync, tslot[16] = w_st, tslot[17] = w_misc, tslot[18] = w_fence;
   }
 
