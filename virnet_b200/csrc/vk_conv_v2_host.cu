@@ -173,6 +173,8 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
         if (a->wrows % c == 0) { n_cta = c; break; }
     }
   }
+  // wide layers whose even split is not a multiple of 32 (288 = 2 x 144) cannot pair; three blocks of 96 can
+  if (!is_convT && slab && a->wrows > 256 && n_cta % 32 && a->wrows % 96 == 0 && a->force_impl != 3) n_cta = 96;
   if (n_cta <= 0 || n_cta > 256 || n_cta % 16 || a->wrows % n_cta) return VK_E_UNSUPPORTED;
   if (a->epi == VK_EPI_NCHW_F32 && a->wrows != n_cta) return VK_E_UNSUPPORTED;
   prm.n_cta = n_cta;
