@@ -102,7 +102,7 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
 }
 
 // 4 producer warps + kEpiGroups x 4 epilogue warps + 1 MMA warp.
-// (measured: 4 groups per CTA are slower than 2 — the 96-register cap spills and the larger staging area
+// (measured: 3 or 4 groups per CTA are slower than 2 — the register cap spills and the larger staging area
 // shrinks the weight ring; profiles/r01_v2_*)
 constexpr int v2_epi_groups(bool pair) { return pair ? 2 : 2; }
 constexpr int v2_threads(bool pair) { return (4 + 4 * v2_epi_groups(pair) + 1) * 32; }
@@ -573,35 +573,41 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t acc0 = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(as * P) * prm.acc_stride;
 
       if (prm.epi == EPI_STD) {
-        // Items of a job are (channel chunk kc, tile p), p fastest, dealt round-robin to the kGroups groups.
-        // P is a power of two <= kGroups, so a group meets ONE tile per job, p = half & (P-1), and every
-        // (kGroups / P)-th channel chunk starting at half / P.
-        const int p = half & (P - 1);
-        const int kc_first = half >> prm.p_log2;
-        const int kc_step = kGroups >> prm.p_log2;
-        const int g_items = (p < nvalid && kc_first < n_ech) ? (n_ech - kc_first + kc_step - 1) / kc_step : 0;
-        int t_img, t_x, t_y;
-        {
-          const int t = tile0 + p;
-          t_img = t / tiles_per_img;
-          const int r = t - t_img * tiles_per_img;
+        // Items of a job are (channel chunk kc, tile p), p fastest (P is 1 or 2), dealt round-robin to the
+        // kGroups groups: group `half` takes items half, half + kGroups, ...  Tiles past the end of the image
+        // list decode to an image index >= n_img, i.e. fully out of bounds for TMA: their loads return zeros
+        // and their stores write nothing, so no item needs special casing.
+        const int n_items = P * n_ech;
+        const int g_items = nvalid > 0 && half < n_items ? (n_items - half + kGroups - 1) / kGroups : 0;
+        int tc_img[2], tc_x[2], tc_y[2];
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          const int t = tile0 + pp;
+          tc_img[pp] = t / tiles_per_img;
+          const int r = t - tc_img[pp] * tiles_per_img;
           const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
-          t_x = tx << prm.tw_log2, t_y = ty * prm.th;
+          tc_x[pp] = tx << prm.tw_log2, tc_y[pp] = ty * prm.th;
         }
         auto issue_in = [&](int g) {
-          const int c0 = cq0 + (kc_first + g * kc_step) * ecols;
+          const int idx = half + g * kGroups;
+          const int pp = idx & (P - 1);
+          const int c0 = cq0 + (idx >> prm.p_log2) * ecols;
+          const int x = pp ? tc_x[1] : tc_x[0], y = pp ? tc_y[1] : tc_y[0], img = pp ? tc_img[1] : tc_img[0];
           mbar_arrive_expect_tx(my_bar, in_bytes);
           if (prm.has_resid)
-            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_r), &emaps.resid[qi], my_bar, c0, t_x, t_y, t_img);
+            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_r), &emaps.resid[qi], my_bar, c0, x, y, img);
           if (prm.has_mask)
-            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_k), &emaps.mask, my_bar, c0, t_x, t_y, t_img);
+            tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_k), &emaps.mask, my_bar, c0, x, y, img);
         };
         if (has_in && g_items > 0 && glead) issue_in(0);
         mbar_wait_t(&tmem_full[as], phacc, prof, w_tf);
         tc_fence_after_sync();
         for (int g = 0; g < g_items; ++g) {
           if (prof) tq = clock64();
-          const int kc = kc_first + g * kc_step;
+          const int idx = half + g * kGroups;
+          const int p = idx & (P - 1);
+          const int kc = idx >> prm.p_log2;
+          const int t_x = p ? tc_x[1] : tc_x[0], t_y = p ? tc_y[1] : tc_y[0], t_img = p ? tc_img[1] : tc_img[0];
           const uint32_t taddr = acc0 + uint32_t(p) * prm.acc_stride + uint32_t(kc * ecols);
           // ---- inputs: this thread's row of the staged residual / mask tiles ----
           uint4 rraw[4], kraw[4];

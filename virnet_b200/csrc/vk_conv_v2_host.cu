@@ -258,7 +258,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   // ---- P, NT and ring depths ----
   const int n_sm = sm_count();
   const int p_max_tmem = std::max(1, 256 / prm.acc_stride);          // double-buffered accumulators
-  int p_hi = std::min(std::min(4, epi_groups), p_max_tmem);
+  int p_hi = std::min(2, p_max_tmem);          // the epilogue caches the coordinates of two tiles per job
   if (a->force_tiles_per_cta) p_hi = std::min(p_hi, a->force_tiles_per_cta);
   int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0;
   double best_score = -1.0;
