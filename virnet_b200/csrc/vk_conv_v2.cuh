@@ -50,6 +50,7 @@ struct ConvV2Params {
   int b_tx_bytes;            // bytes one B item transfers (NT * n_cta * chunk)
   int a_slot_bytes, b_slot_bytes;
   int a_stages, b_stages;
+  int b_resident;            // 1: the weight ring holds ALL items of a job and n_blocks == 1 -> loaded once per CTA
   // ---- jobs ----
   int P;                     // pixel tiles per job (1, 2 or 4; <= epilogue groups)
   int p_log2;
@@ -425,6 +426,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t ph = 0;
       long long w_empty = 0;
       for (int job = worker; job < prm.n_jobs; job += n_workers) {
+        if (prm.b_resident && job != worker) break;    // weights stay in shared memory after the first job
         // pair mode: this CTA supplies rows [n0, n0 + n_cta / 2) of the job's weight block
         const int n0 = (job % prm.n_blocks) * prm.n_cta + (kPair ? int(cta_rank) * (prm.n_cta >> 1) : 0);
         for (int l = 0; l < prm.n_loads; ++l) {
@@ -480,7 +482,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int bi = 0; bi < 9; ++bi) {
           if (bi * kNT < 9 && bi < prm.nb) {
-            mbar_wait_t(&full_b[sb], phb, prof, w_fb);
+            if (!prm.b_resident || job == worker) mbar_wait_t(&full_b[sb], phb, prof, w_fb);
             tc_fence_after_sync();
             if (leader) {
               uint32_t ap = a_lo, dp = d0;
@@ -502,7 +504,9 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   }
                 }
               }
-              if constexpr (kPair) umma_commit_2sm(&empty_b[sb]); else umma_commit(&empty_b[sb]);
+              if (!prm.b_resident) {
+                if constexpr (kPair) umma_commit_2sm(&empty_b[sb]); else umma_commit(&empty_b[sb]);
+              }
             }
             __syncwarp();
             accum = 1;

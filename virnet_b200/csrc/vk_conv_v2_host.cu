@@ -260,7 +260,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   const int p_max_tmem = std::max(1, 256 / prm.acc_stride);          // double-buffered accumulators
   int p_hi = std::min(2, p_max_tmem);          // the epilogue caches the coordinates of two tiles per job
   if (a->force_tiles_per_cta) p_hi = std::min(p_hi, a->force_tiles_per_cta);
-  int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0;
+  int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0, best_res = 0;
   double best_score = -1.0;
   if (p_hi == 3) p_hi = 2;                      // the epilogue's item <-> tile mapping wants P in {1, 2, 4}
   for (int P = p_hi; P >= 1; P >>= 1) {
@@ -284,16 +284,22 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
       int bs = (avail - as * a_slot) / b_slot;
       bs = std::min(bs, kV2MaxStages);
       if (a->force_stages) bs = std::min(bs, a->force_stages);
+      // resident weights: one N block and every weight item of a job fits the ring -> loaded once per CTA,
+      // no weight traffic (L2 -> smem writes compete with the MMA's operand fetch) after the first job
+      const bool resident = prm.n_blocks == 1 && total_b_items <= bs && !a->force_stages &&
+                            std::getenv("VK_V2_NO_RESIDENT") == nullptr;
+      if (resident) bs = total_b_items;
       // >= kV2BProducers: a B producer warp handles every 3rd item, so with fewer slots it could run two
       // barrier phases ahead of the consumer and its parity wait would alias
-      if (bs < kV2BProducers) continue;
+      if (!resident && bs < kV2BProducers) continue;
       // spend what is left on a third / fourth A slot
-      while (as < 4 && as * a_slot + bs * b_slot + a_slot <= avail && bs >= 3) ++as;
+      while (as < 4 && as * a_slot + bs * b_slot + a_slot <= avail && (bs >= 3 || resident)) ++as;
       (void)total_b_items;
       // score: fewer, larger B items (less barrier traffic per MMA), more tiles per job (weight reuse), full waves
       const double mmas_per_b = double(P) * nt * (chunk / 32);
-      const double score = eff * (1.0 - 0.12 / P) * (1.0 - 1.5 / (mmas_per_b + 6.0)) * (bs >= 3 ? 1.0 : 0.9);
-      if (score > best_score) best_score = score, best_P = P, best_nt = nt, best_as = as, best_bs = bs;
+      const double score = eff * (1.0 - 0.12 / P) * (1.0 - 1.5 / (mmas_per_b + 6.0)) * (resident ? 1.15 : 1.0);
+      if (score > best_score)
+        best_score = score, best_P = P, best_nt = nt, best_as = as, best_bs = bs, best_res = resident ? 1 : 0;
     }
   }
   if (best_P == 0) return VK_E_UNSUPPORTED;
@@ -305,6 +311,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   prm.b_slot_bytes = round_up(nt * b_rows * chunk, 1024);
   prm.b_tx_bytes = nt * b_rows * chunk;
   prm.a_stages = best_as, prm.b_stages = best_bs;
+  prm.b_resident = best_res;
   prm.b_base = prm.a_stages * prm.a_slot_bytes;
   prm.epi_base = prm.b_base + prm.b_stages * prm.b_slot_bytes;
   for (int tap = 0; tap < 9; ++tap)
@@ -387,10 +394,10 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   if (debug)
     fprintf(stderr,
             "vk v2: kind=%d n=%d %dx%d ldx=%d wrows=%d | tile %dx%d tiles=%d P=%d n_cta=%d jobs=%d grid=%d | chunk=%d nt=%d "
-            "nb=%d a_stages=%d(%d B) b_stages=%d(%d B) epi=%d B/warp ecb=%d tmem=%d smem=%d pair=%d\n",
+            "nb=%d a_stages=%d(%d B) b_stages=%d(%d B) epi=%d B/warp ecb=%d tmem=%d smem=%d pair=%d resident=%d\n",
             a->kind, a->n, a->ih, a->iw, a->ldx, a->wrows, tw, th, prm.n_tiles, P, n_cta, prm.n_jobs, grid, chunk, nt,
             prm.nb, prm.a_stages, prm.a_slot_bytes, prm.b_stages, prm.b_slot_bytes, epi_warp_bytes, ecb, prm.tmem_cols,
-            smem_bytes, int(pair));
+            smem_bytes, int(pair), prm.b_resident);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->dtype == VK_BF16) return dispatch_v2<__nv_bfloat16>(chunk, nt, pair, ta, tb, em, prm, grid, smem_bytes, st);
   return dispatch_v2<float>(chunk, nt, pair, ta, tb, em, prm, grid, smem_bytes, st);
