@@ -188,3 +188,34 @@ def test_autograd_path_equals_trainer_path():
     g_engine = torch.cat([eng.grad_view(p).flatten() for p in net.parameters()])
     # wgrad uses fp32 atomics (split-K): not bit-identical run to run, but equal to ~1e-6
     assert rel(g_engine, g_autograd) < 1e-5
+
+
+def test_denoising_real_architecture_forward_backward_vs_oracle():
+    """configs/denoising_real.json: sigma_chn=3 (head sees 6 channels), dep_S=8, four levels
+    n_feat=[96,160,224,288] (reflect pad to a multiple of 8), n_resblocks=3 — the third trainer's network
+     on the same kernels.  Ragged 2x3x43x50 input, tf32 mode, forward and gradients vs the oracle."""
+    import virnet_b200
+    from oracle import virnet_oracle as O
+    from virnet_b200.loss.ELBO_simple import elbo_denoising_simple
+    n_feat = (96, 160, 224, 288)
+    torch.manual_seed(1234)
+    net = virnet_b200.VIRAttResUNet(im_chn=3, sigma_chn=3, n_feat=list(n_feat), dep_S=8, n_resblocks=3, noise_cond=True,
+                                    extra_mode="Input", noise_avg=False, precision="tf32")
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    cfg = O.NetCfg(sigma_chn=3, n_feat=n_feat, dep_S=8, n_resblocks=3)
+    g = torch.Generator().manual_seed(11)
+    im_gt = torch.rand(2, 3, 43, 50, generator=g)
+    sig = 5 / 255 + torch.rand(2, 3, 43, 50, generator=g) * 40 / 255
+    im_noisy = im_gt + torch.randn(2, 3, 43, 50, generator=g) * sig
+    sigma_gt = (sig ** 2).clamp_min(1e-10)
+    mu, sigma = net(im_noisy.cuda())
+    loss, *_ = elbo_denoising_simple(mu, sigma, im_noisy.cuda(), im_gt.cuda(), EPS2, ALPHA0, (ALPHA0 * sigma_gt).cuda())
+    loss.backward()
+    (loss_o, *_), mu_o, sg_o, grads_o = O.denoise_loss_and_grads(sd, cfg, im_noisy, im_gt, sigma_gt, ALPHA0, EPS2)
+    assert mu.shape == (2, 3, 43, 50) and sigma.shape == (2, 3, 43, 50)
+    assert rel(mu.detach().cpu(), mu_o) < 1e-3 and rel(sigma.detach().cpu(), sg_o) < 1e-3
+    # the loss is (mu - gt)^2 / eps2 dominated (1e6 scale): a 1e-3 forward error shows up a few times larger here
+    assert abs(loss.item() - loss_o.item()) / abs(loss_o.item()) < 5e-3
+    worst = max(rel(p.grad.cpu(), grads_o[k]) for k, p in net.named_parameters())
+    assert worst < 3e-2, worst
