@@ -168,7 +168,32 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+class _StdoutToStderr:
+    """Native libraries (NCCL prints its version banner) write to file descriptor 1; the driver wants exactly ONE
+    JSON line on stdout, so fd 1 points at stderr while the benchmark runs and is restored for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_ours(args):
+    with _StdoutToStderr():
+        line = _run_ours(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def _run_ours(args):
     import torch
     import torch.distributed as dist
     import virnet_b200
@@ -294,10 +319,11 @@ def run_ours(args):
                          "whole_step_tflops": value * TRAIN_GFLOP_PER_PATCH / 1e3 / world},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line
 
 
 def main():
