@@ -62,7 +62,10 @@ __device__ __forceinline__ void red_add(float* p, float a) {
 constexpr int kWgradThreads = 288;   // warps 0, 6-8: TMA producers; 1: MMA; 2-5: epilogue
 constexpr int kWgradProducers = 4;
 
-template <typename DT>
+// kRows = pixels per K tile (compile time: the MMA issue loop is fully unrolled with immediate descriptor
+// offsets — with a run-time trip count the issuing thread spends ~87 clk per MMA on R2UR / address arithmetic,
+// which is what bounded this kernel; tools/probe `mma`)
+template <typename DT, int kRows>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ WgradParams prm) {
@@ -90,7 +93,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int n_block = blockIdx.y - m_block * prm.n_blocks_n;
   const int m0 = m_block * 128;
   const int n0 = n_block * prm.n_cta;
-  const bool do_bias = (prm.dbias != nullptr) && group == 0 && n_block == 0;
+  // bias gradient (column sums of the M operand): the tap groups of a K slice share it round-robin over the K
+  // tiles, so no CTA carries all the extra N=16 MMAs (one group doing them all made it 33 % longer than the rest)
+  const bool bias_en = (prm.dbias != nullptr) && n_block == 0;
 
   const int a_block_bytes = prm.k_rows * 128;
   const int b_block_bytes = prm.box_rows * 128;
@@ -176,14 +181,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const uint32_t smem16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
       const uint32_t stage16 = uint32_t(stage_bytes) >> 4, a16 = uint32_t(a_bytes) >> 4;
       constexpr uint32_t kAdv16 = uint32_t(kAdvance) >> 4;
-      const int ksteps = prm.k_rows / kRowsPerMma;
+      constexpr int ksteps = kRows / kRowsPerMma;
       const int n_taps = prm.n_taps;
       uint32_t tap_off[3];
 #pragma unroll
       for (int tp = 0; tp < 3; ++tp)
         tap_off[tp] = (uint32_t(prm.taps[group][tp].load * b_bytes + prm.taps[group][tp].rowoff * 128) >> 4);
       const uint32_t acc_stride = prm.acc_stride;
-      uint32_t accum = 0;
+      uint32_t accum = 0, bias_accum = 0;
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -197,18 +202,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             if (tp < n_taps) {
               uint32_t ad = a_lo, bd = b_lo + tap_off[tp];
               uint32_t acc = accum;
-              for (int kk = 0; kk < ksteps; ++kk, ad += kAdv16, bd += kAdv16) {
-                umma_ss<kTF32>(tmem_base + tp * acc_stride, desc_hi | ad, desc_hi | bd, idesc, acc);
-                acc = 1;
+#pragma unroll
+              for (int kk = 0; kk < ksteps; ++kk) {
+                umma_ss<kTF32>(tmem_base + tp * acc_stride, desc_hi | (ad + kk * kAdv16), desc_hi | (bd + kk * kAdv16),
+                               idesc, kk == 0 ? acc : 1u);
               }
             }
           }
-          if (do_bias) {
+          if (bias_en && (it % prm.n_groups) == group) {
             uint32_t ad = a_lo;
-            uint32_t acc = accum;
-            for (int kk = 0; kk < ksteps; ++kk, ad += kAdv16) {
-              umma_ss<kTF32>(tmem_base + n_taps * acc_stride, desc_hi | ad, desc_hi | ones_lo, idesc_bias, acc);
-              acc = 1;
+            uint32_t acc = bias_accum;
+            bias_accum = 1;
+#pragma unroll
+            for (int kk = 0; kk < ksteps; ++kk) {
+              umma_ss<kTF32>(tmem_base + n_taps * acc_stride, desc_hi | (ad + kk * kAdv16), desc_hi | ones_lo, idesc_bias,
+                             kk == 0 ? acc : 1u);
             }
           }
           umma_commit(&empty_bar[s]);
@@ -251,7 +259,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
       }
     }
-    if (do_bias) {
+    if (bias_en && group < my_tiles) {
       uint32_t rr[16];
       __syncwarp();
       tmem_ld16(lane_addr + prm.n_taps * prm.acc_stride, rr);

@@ -17,11 +17,11 @@ inline int next_pow2_cols(int x) {
 }
 constexpr int kWgradSmemBudget = 216 * 1024;
 
-template <typename DT>
-int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
-                 cudaStream_t st) {
+template <typename DT, int kRows>
+int launch_wgrad_k(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
+                   cudaStream_t st) {
   static int cur = 0;
-  auto kern = wgrad_kernel<DT>;
+  auto kern = wgrad_kernel<DT, kRows>;
   if (smem_bytes > cur) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return int(e);
@@ -30,6 +30,17 @@ int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams
   kern<<<grid, kWgradThreads, smem_bytes, st>>>(ta, tb, prm);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
+}
+template <typename DT>
+int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
+                 cudaStream_t st) {
+  switch (prm.k_rows) {
+    case 128: return launch_wgrad_k<DT, 128>(ta, tb, prm, grid, smem_bytes, st);
+    case 64: return launch_wgrad_k<DT, 64>(ta, tb, prm, grid, smem_bytes, st);
+    case 32: return launch_wgrad_k<DT, 32>(ta, tb, prm, grid, smem_bytes, st);
+    case 16: return launch_wgrad_k<DT, 16>(ta, tb, prm, grid, smem_bytes, st);
+    default: return VK_E_UNSUPPORTED;
+  }
 }
 }  // namespace
 
