@@ -66,32 +66,85 @@ class DenoiseTrainer:
         self.losses = torch.zeros(4, device=dev, dtype=torch.float32)
         self._d_mu = self._d_sigma = None
         self._staging = {}
+        self._copy_stream, self._ev = None, None
+        self._pf_free = self._pf_ready = self._pf_used = self._pf_key = None
+        self._pf_next = 0
 
-    # -- host -> device staging (pinned host buffers are the caller's; copies are async) --
-    def _to_device(self, name, t):
-        if t.is_cuda:
-            return t
+    # -- host -> device staging (pinned host buffers are the caller's) --------------------------------------
+    # The copies run on a side stream: the noisy patches are needed first (the weight packing of this step
+    # overlaps their copy), the clean patches and the variance map only at the loss, a forward pass later.
+    def _stage(self, name, t, stream):
         buf = self._staging.get(name)
         if buf is None or buf.shape != t.shape:
             buf = torch.empty(t.shape, device=self.engine.flat_params.device, dtype=torch.float32)
             self._staging[name] = buf
-        buf.copy_(t, non_blocking=True)
+        with torch.cuda.stream(stream):
+            buf.copy_(t, non_blocking=True)
         return buf
+
+    def prefetch(self, im_noisy, im_gt, sigma_gt):
+        """Start copying the NEXT batch (pinned host tensors) while the current step computes: what a
+        DataLoader with pin_memory + non_blocking copies does for the reference loop (train_denoising_syn.py:169-171).
+        The following step() call with the same host tensors picks the device copies up."""
+        eng = self.engine
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=eng.flat_params.device)
+            self._ev = [torch.cuda.Event() for _ in range(3)]
+        if self._pf_free is None:
+            self._pf_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._pf_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._pf_used = [False, False]
+        k = self._pf_next
+        self._pf_next ^= 1
+        cs = self._copy_stream
+        if self._pf_used[k]:
+            cs.wait_event(self._pf_free[k])     # the step that last read this staging set has passed its loss
+        bufs = [self._stage(f"pf{k}.{nm}", t, cs) for nm, t in (("noisy", im_noisy), ("gt", im_gt), ("sg", sigma_gt))]
+        self._pf_ready[k].record(cs)
+        self._pf_key = (k, im_noisy.data_ptr(), im_gt.data_ptr(), sigma_gt.data_ptr(), bufs)
 
     def step(self, im_noisy, im_gt, sigma_gt, lr: Optional[float] = None):
         """One optimisation step; returns the device tensor [loss, lh, kl_gauss, kl_Igamma]
         of the local batch (no host sync)."""
         eng = self.engine
-        x = self._to_device("noisy", im_noisy)
-        gt = self._to_device("gt", im_gt)
-        sg = self._to_device("sigma_gt", sigma_gt)
+        main = torch.cuda.current_stream()
+        ev_late = None
+        pf_set = None
+        if (self._pf_key is not None and not im_noisy.is_cuda
+                and self._pf_key[1:4] == (im_noisy.data_ptr(), im_gt.data_ptr(), sigma_gt.data_ptr())):
+            pf_set, x, gt, sg = self._pf_key[0], *self._pf_key[4]
+            self._pf_key = None
+            main.wait_event(self._pf_ready[pf_set])
+        elif not (im_noisy.is_cuda and im_gt.is_cuda and sigma_gt.is_cuda):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=eng.flat_params.device)
+                self._ev = [torch.cuda.Event() for _ in range(3)]
+            cs = self._copy_stream
+            self._ev[2].record(main)            # the previous step has finished reading the staging buffers
+            cs.wait_event(self._ev[2])
+            x = im_noisy if im_noisy.is_cuda else self._stage("noisy", im_noisy, cs)
+            self._ev[0].record(cs)
+            gt = im_gt if im_gt.is_cuda else self._stage("gt", im_gt, cs)
+            sg = sigma_gt if sigma_gt.is_cuda else self._stage("sigma_gt", sigma_gt, cs)
+            self._ev[1].record(cs)
+            ev_late = self._ev[1]
+            eng._ensure_flat()
+            eng._ensure_packed()                # runs while the first copy is in flight
+            main.wait_event(self._ev[0])
+        else:
+            x, gt, sg = im_noisy, im_gt, sigma_gt
         mu, sigma = eng.forward(x, save=True)
         if self._d_mu is None or self._d_mu.shape != mu.shape:
             self._d_mu, self._d_sigma = torch.empty_like(mu), torch.empty_like(sigma)
+        if ev_late is not None:
+            main.wait_event(ev_late)
         # beta0 = alpha0 * sigma_gt (train_denoising_syn.py:172) is folded into the loss kernel
         ops.elbo_denoise(mu, sigma, x, gt, sg, beta0_scale=self.alpha0, eps2=self.eps2, alpha0=self.alpha0,
                          digamma_am1=self.digamma_am1, d_mu=self._d_mu, d_sigma=self._d_sigma, acc3=self._acc3,
                          out4=self.losses)
+        if pf_set is not None:
+            self._pf_free[pf_set].record(main)   # inputs are not read after the loss kernel
+            self._pf_used[pf_set] = True
         eng.backward(self._d_mu, self._d_sigma)
         grad_scale = dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
         self.step_count += 1
