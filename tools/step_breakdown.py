@@ -16,8 +16,10 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(1234)
 net = virnet_b200.VIRAttResUNet(im_chn=3, sigma_chn=1, n_feat=bench.N_FEAT, dep_S=bench.DEP_S, n_resblocks=bench.N_RES,
                                 noise_cond=True, extra_mode="Input", noise_avg=False, precision="bf16").to(dev)
-batch = bench.synth_batch(16, 0, dev)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+batch = bench.synth_batch(B, 0, dev)
 tr = DenoiseTrainer(net)
+tr.engine.wgrad_side_stream = False   # serialise launches so per-launch events are meaningful
 for _ in range(3):
     tr.step(*batch)
 ops.start_profile()

@@ -172,10 +172,8 @@ static int conv_igemm_impl(const vk_conv_args* a, void* stream, int phase) {
   if (a->wrows <= 0 || a->wrows % 16) return VK_E_BADARG;
   if (a->n <= 0 || a->ih <= 0 || a->iw <= 0 || a->cout <= 0) return VK_E_BADARG;
   // persistent kernel first (force_impl: 0 auto, 1 = v1 only, 2 = v2 only); v1 serves what v2 declines
-  // (auto mode sends only the 3x3 stride-1 convolutions there: the strided / transposed kinds are
-  // 4 % of the FLOPs and still run faster on v1's larger per-CTA tile groups)
   if (a->sft_mul != nullptr && a->epi != VK_EPI_STD) return VK_E_BADARG;
-  if (a->force_impl >= 2 || a->sft_mul != nullptr || (a->force_impl == 0 && a->kind == VK_CONV3X3_S1)) {
+  if (a->force_impl != 1) {
     const int r = conv_v2_impl(a, stream, phase);
     if (r != VK_E_UNSUPPORTED || a->force_impl >= 2 || a->sft_mul != nullptr) return r;   // v1 has no SFT epilogue
   }

@@ -28,8 +28,12 @@
 namespace vk {
 
 struct ConvV2Load {
-  int dx, dy;   // A box origin = tile origin * a_stride + (dx, dy)
-  int tap0;     // weight tap of (bi = 0, t = 0); tap = tap0 + bi * NT + t
+  int dx, dy;          // A box origin = tile origin * a_stride + (dx, dy)
+  int tap0;            // slab mode: weight tap of (bi = 0, t = 0); tap = tap0 + bi * NT + t
+  // full-K mode (strided / transposed / 1x1 kinds): this load's box feeds `nb` single-tap weight items
+  int nb;
+  int tap[4];          // weight tap of item bi
+  uint32_t aoff16[4];  // A descriptor start offset of item bi inside the box (bytes >> 4)
 };
 
 struct ConvV2Params {
@@ -42,6 +46,9 @@ struct ConvV2Params {
   int n_loads;
   ConvV2Load loads[9];
   int k_chunks;
+  int full_k;                // 1: an A item is one load x one GROUP of kg K chunks (kg boxes per tile) and a B item is
+                             // one tap x the same chunks; 0 (3x3 s1 slab): A item = one chunk, B item = NT taps
+  int kg;                    // K chunks per group (full_k mode)
   int nb;                    // B items per A item (1, 3 or 9)
   uint32_t a_off16[9];       // [tap = bi * NT + t]: A descriptor start offset (bytes >> 4) inside the box
   int a_box_bytes;           // smem bytes reserved per A box (multiple of 1024)
@@ -291,7 +298,7 @@ __device__ __forceinline__ void epi_item_math_sft(const uint32_t (&acc)[2][16], 
   }
 }
 
-template <typename DT, int kChunkBytes, int kNT, bool kPair>
+template <typename DT, int kChunkBytes, int kNT, bool kPair, bool kFullK>
 __global__ void __launch_bounds__(v2_threads(kPair), 1)
 conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvV2Maps emaps, const __grid_constant__ ConvV2Params prm) {
@@ -320,7 +327,16 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int P = prm.P;
   const int tiles_per_img = prm.tiles_x * prm.tiles_y;
-  const int n_a_items = prm.n_loads * prm.k_chunks;
+  // full-K mode: item ai = (load l, chunk group g) -> chunks [c0, c0 + ns); slab mode: item = (load 0, chunk c0), ns = 1
+  const int n_kgroups = kFullK ? (prm.k_chunks + prm.kg - 1) / prm.kg : prm.k_chunks;
+  const int n_a_items = prm.n_loads * n_kgroups;
+  const int sub_max = kFullK ? prm.kg : 1;               // A boxes per tile per A item (slot layout)
+  auto item_of = [&](int ai, int& l, int& c0, int& ns) {
+    l = ai / n_kgroups;
+    const int g = ai - l * n_kgroups;
+    c0 = kFullK ? g * prm.kg : g;
+    ns = kFullK ? min(prm.kg, prm.k_chunks - c0) : 1;
+  };
   // pair mode (cta_group::2): the two CTAs of a cluster walk the same job list; CTA `cta_rank` owns tile
   // group 2 * pair_group + cta_rank and half of the weight rows, the leader (rank 0) issues M=256 MMAs
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
@@ -390,30 +406,32 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
           timg[p] = img, tx0[p] = (tx << prm.tw_log2) * prm.a_stride, ty0[p] = ty * prm.th * prm.a_stride;
         }
-        for (int l = 0; l < prm.n_loads; ++l) {
+        for (int ai = 0; ai < n_a_items; ++ai) {
+          int l, c0, n_sub;
+          item_of(ai, l, c0, n_sub);
           const int dx = prm.loads[l].dx, dy = prm.loads[l].dy;
-          for (int c = 0; c < prm.k_chunks; ++c) {
-            mbar_wait_t(&empty_a[sa], ph ^ 1, prof, w_empty);
-            uint8_t* dst = smem_a + sa * prm.a_slot_bytes;
-            if constexpr (kPair) {
-              // both CTAs' boxes complete on the LEADER's barrier, armed by the leader with the pair's bytes
-              if (is_leader) mbar_arrive_expect_tx(&full_a[sa], 2 * P * prm.a_tx_bytes);
-              const uint32_t bar = mapa_shared(smem_u32(&full_a[sa]), 0);
+          mbar_wait_t(&empty_a[sa], ph ^ 1, prof, w_empty);
+          uint8_t* dst = smem_a + sa * prm.a_slot_bytes;
+          if constexpr (kPair) {
+            // both CTAs' boxes complete on the LEADER's barrier, armed by the leader with the pair's bytes
+            if (is_leader) mbar_arrive_expect_tx(&full_a[sa], 2 * P * n_sub * prm.a_tx_bytes);
+            const uint32_t bar = mapa_shared(smem_u32(&full_a[sa]), 0);
 #pragma unroll
-              for (int p = 0; p < 4; ++p)
-                if (p < nvalid)
-                  tma_load_4d_2sm(dst + p * prm.a_box_bytes, &tmap_a, bar, c * kChunkElems, tx0[p] + dx, ty0[p] + dy,
-                                  timg[p]);
-            } else {
-              mbar_arrive_expect_tx(&full_a[sa], nvalid * prm.a_tx_bytes);
+            for (int p = 0; p < 4; ++p)
+              if (p < nvalid)
+                for (int c = 0; c < n_sub; ++c)
+                  tma_load_4d_2sm(dst + (p * sub_max + c) * prm.a_box_bytes, &tmap_a, bar, (c0 + c) * kChunkElems,
+                                  tx0[p] + dx, ty0[p] + dy, timg[p]);
+          } else {
+            mbar_arrive_expect_tx(&full_a[sa], nvalid * n_sub * prm.a_tx_bytes);
 #pragma unroll
-              for (int p = 0; p < 4; ++p)
-                if (p < nvalid)
-                  tma_load_4d(dst + p * prm.a_box_bytes, &tmap_a, &full_a[sa], c * kChunkElems, tx0[p] + dx,
-                              ty0[p] + dy, timg[p]);
-            }
-            if (++sa == prm.a_stages) sa = 0, ph ^= 1;
+            for (int p = 0; p < 4; ++p)
+              if (p < nvalid)
+                for (int c = 0; c < n_sub; ++c)
+                  tma_load_4d(dst + (p * sub_max + c) * prm.a_box_bytes, &tmap_a, &full_a[sa], (c0 + c) * kChunkElems,
+                              tx0[p] + dx, ty0[p] + dy, timg[p]);
           }
+          if (++sa == prm.a_stages) sa = 0, ph ^= 1;
         }
       }
       if (prof) tslot[5] = w_empty, tslot[11] = clock64() - t_start;
@@ -429,25 +447,43 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (prm.b_resident && job != worker) break;    // weights stay in shared memory after the first job
         // pair mode: this CTA supplies rows [n0, n0 + n_cta / 2) of the job's weight block
         const int n0 = (job % prm.n_blocks) * prm.n_cta + (kPair ? int(cta_rank) * (prm.n_cta >> 1) : 0);
-        for (int l = 0; l < prm.n_loads; ++l) {
-          const int tap0 = prm.loads[l].tap0;
-          for (int c = 0; c < prm.k_chunks; ++c) {
-            for (int bi = 0; bi < prm.nb; ++bi) {
-              if (turn == pw) {
-                mbar_wait_t(&empty_b[sb], ph ^ 1, prof, w_empty);
+        for (int ai = 0; ai < n_a_items; ++ai) {
+          int l, c, n_sub;
+          item_of(ai, l, c, n_sub);
+          const int nb_l = kFullK ? prm.loads[l].nb : prm.nb;
+          for (int bi = 0; bi < nb_l; ++bi) {
+            if (turn == pw) {
+              mbar_wait_t(&empty_b[sb], ph ^ 1, prof, w_empty);
+              void* dst = smem_b + sb * prm.b_slot_bytes;
+              if constexpr (kFullK) {
+                // one tap, all K chunks: k_chunks boxes [rows][chunk bytes] one after the other
+                const int tap = prm.loads[l].tap[bi];
+                const int cb = prm.b_tx_bytes;          // bytes of ONE chunk of a weight item (full-K mode)
+                if constexpr (kPair) {
+                  if (is_leader) mbar_arrive_expect_tx(&full_b[sb], 2 * n_sub * cb);
+                  const uint32_t bar = mapa_shared(smem_u32(&full_b[sb]), 0);
+                  for (int cc = 0; cc < n_sub; ++cc)
+                    tma_load_3d_2sm(reinterpret_cast<uint8_t*>(dst) + cc * cb, &tmap_b, bar, (c + cc) * kChunkElems, n0,
+                                    tap);
+                } else {
+                  mbar_arrive_expect_tx(&full_b[sb], n_sub * cb);
+                  for (int cc = 0; cc < n_sub; ++cc)
+                    tma_load_3d(reinterpret_cast<uint8_t*>(dst) + cc * cb, &tmap_b, &full_b[sb], (c + cc) * kChunkElems,
+                                n0, tap);
+                }
+              } else {
+                const int tap = prm.loads[l].tap0 + bi * kNT;
                 if constexpr (kPair) {
                   if (is_leader) mbar_arrive_expect_tx(&full_b[sb], 2 * prm.b_tx_bytes);
-                  tma_load_3d_2sm(smem_b + sb * prm.b_slot_bytes, &tmap_b, mapa_shared(smem_u32(&full_b[sb]), 0),
-                                  c * kChunkElems, n0, tap0 + bi * kNT);
+                  tma_load_3d_2sm(dst, &tmap_b, mapa_shared(smem_u32(&full_b[sb]), 0), c * kChunkElems, n0, tap);
                 } else {
                   mbar_arrive_expect_tx(&full_b[sb], prm.b_tx_bytes);
-                  tma_load_3d(smem_b + sb * prm.b_slot_bytes, &tmap_b, &full_b[sb], c * kChunkElems, n0,
-                              tap0 + bi * kNT);
+                  tma_load_3d(dst, &tmap_b, &full_b[sb], c * kChunkElems, n0, tap);
                 }
               }
-              if (++turn == kV2BProducers) turn = 0;
-              if (++sb == prm.b_stages) sb = 0, ph ^= 1;
             }
+            if (++turn == kV2BProducers) turn = 0;
+            if (++sb == prm.b_stages) sb = 0, ph ^= 1;
           }
         }
       }
@@ -465,6 +501,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t aslot16 = uint32_t(prm.a_slot_bytes) >> 4, bslot16 = uint32_t(prm.b_slot_bytes) >> 4;
     const uint32_t box16 = uint32_t(prm.a_box_bytes) >> 4;
     const uint32_t btap16 = uint32_t((kPair ? prm.n_cta >> 1 : prm.n_cta) * kChunkBytes) >> 4;
+    const uint32_t bchunk16 = btap16;           // full-K mode: K chunk c of a weight item follows chunk c - 1
     const uint32_t acc_stride = prm.acc_stride;
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, phacc = 0;
@@ -479,30 +516,39 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t accum = 0;
       for (int ai = 0; ai < n_a_items; ++ai) {
         mbar_wait_t(&full_a[sa], pha, prof, w_fa);
+        int l_, c0_, n_sub;
+        item_of(ai, l_, c0_, n_sub);
+        const int nb_l = kFullK ? prm.loads[l_].nb : prm.nb;
 #pragma unroll
         for (int bi = 0; bi < 9; ++bi) {
-          if (bi * kNT < 9 && bi < prm.nb) {
+          if (bi * kNT < 9 && bi < nb_l) {
             if (!prm.b_resident || job == worker) mbar_wait_t(&full_b[sb], phb, prof, w_fb);
             tc_fence_after_sync();
             if (leader) {
-              uint32_t ap = a_lo, dp = d0;
-              for (int p = 0; p < nvalid; ++p, ap += box16, dp += acc_stride) {
+              // full-K mode: item bi of load ai reads its tap view at aoff16[bi]; sub-box c is K chunk c
+              const uint32_t a_item = a_lo + (kFullK ? prm.loads[l_].aoff16[bi & 3] : 0u);
+              uint32_t dp = d0;
+              for (int p = 0; p < nvalid; ++p, dp += acc_stride) {
+               for (int c = 0; c < n_sub; ++c) {
+                const uint32_t ap = a_item + uint32_t(p * sub_max + c) * box16;
+                const uint32_t bq = b_lo + uint32_t(c) * bchunk16;
                 // tap outer, K step inner: the accumulation order (load, chunk, tap, k) depends on neither the
                 // taps-per-stage nor the tiles-per-job picked by the host -> bit-identical across batch sizes
 #pragma unroll
                 for (int t = 0; t < kNT; ++t) {
 #pragma unroll
                   for (int k = 0; k < kMmasPerChunk; ++k) {
+                    const uint32_t acc_flag = (k == 0 && t == 0 && c == 0) ? accum : 1u;
                     if constexpr (kPair) {
                       umma_ss_2sm<kTF32>(dp, desc_hi | (ap + prm.a_off16[(bi * kNT + t) % 9] + 2 * k),
-                                         desc_hi_b | (b_lo + t * btap16 + 2 * k), idesc,
-                                         (k == 0 && t == 0) ? accum : 1u);
+                                         desc_hi_b | (bq + t * btap16 + 2 * k), idesc, acc_flag);
                     } else {
                       umma_ss<kTF32>(dp, desc_hi | (ap + prm.a_off16[(bi * kNT + t) % 9] + 2 * k),
-                                     desc_hi_b | (b_lo + t * btap16 + 2 * k), idesc, (k == 0 && t == 0) ? accum : 1u);
+                                     desc_hi_b | (bq + t * btap16 + 2 * k), idesc, acc_flag);
                     }
                   }
                 }
+               }
               }
               if (!prm.b_resident) {
                 if constexpr (kPair) umma_commit_2sm(&empty_b[sb]); else umma_commit(&empty_b[sb]);

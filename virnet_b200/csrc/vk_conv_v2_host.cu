@@ -34,12 +34,12 @@ int sm_count() {
 
 constexpr int kV2SmemBudget = 220 * 1024;   // dynamic smem incl. 1 KB alignment slack (static: ~4.6 KB)
 
-template <typename DT, int kChunk, int kNT, bool kPair>
+template <typename DT, int kChunk, int kNT, bool kPair, bool kFullK>
 int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em, const ConvV2Params& prm, int grid,
               int smem_bytes, cudaStream_t st) {
   static int cur = 0;
   static std::mutex mu;
-  auto kern = conv_v2_kernel<DT, kChunk, kNT, kPair>;
+  auto kern = conv_v2_kernel<DT, kChunk, kNT, kPair, kFullK>;
   {
     std::lock_guard<std::mutex> g(mu);
     if (smem_bytes > cur) {
@@ -70,9 +70,15 @@ template <typename DT>
 int dispatch_v2(int chunk, int nt, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
                 const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st) {
 #define VK_V2_CASE(C, T)                                                                           \
-  if (chunk == C && nt == T)                                                                       \
-    return pair ? launch_v2<DT, C, T, true>(ta, tb, em, prm, grid, smem_bytes, st)                 \
-                : launch_v2<DT, C, T, false>(ta, tb, em, prm, grid, smem_bytes, st);
+  if (chunk == C && nt == T && !prm.full_k)                                                        \
+    return pair ? launch_v2<DT, C, T, true, false>(ta, tb, em, prm, grid, smem_bytes, st)          \
+                : launch_v2<DT, C, T, false, false>(ta, tb, em, prm, grid, smem_bytes, st);
+#define VK_V2_FULLK(C)                                                                             \
+  if (chunk == C && prm.full_k)                                                                    \
+    return pair ? launch_v2<DT, C, 1, true, true>(ta, tb, em, prm, grid, smem_bytes, st)           \
+                : launch_v2<DT, C, 1, false, true>(ta, tb, em, prm, grid, smem_bytes, st);
+  VK_V2_FULLK(128) VK_V2_FULLK(64) VK_V2_FULLK(32)
+#undef VK_V2_FULLK
   VK_V2_CASE(128, 1) VK_V2_CASE(128, 3) VK_V2_CASE(128, 9)
   VK_V2_CASE(64, 1) VK_V2_CASE(64, 3) VK_V2_CASE(64, 9)
   VK_V2_CASE(32, 1) VK_V2_CASE(32, 3) VK_V2_CASE(32, 9)
@@ -128,22 +134,9 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   }
 
   // ---- pixel tile ----
-  int tw, th;
-  if (slab) {
-    tw = 8, th = 16;
-  } else {
-    static const int cand_tw[5] = {16, 8, 32, 64, 128};
-    int best_tw = 16;
-    long long best_cost = -1;
-    for (int i = 0; i < 5; ++i) {
-      const int w = cand_tw[i], h = 128 / w;
-      if (a->force_tw && a->force_tw != w) continue;
-      if (prm.a_stride == 2 && w * 2 > 256) continue;
-      const long long cost = (long long)((prm.ow + w - 1) / w) * ((prm.oh + h - 1) / h);
-      if (best_cost < 0 || cost < best_cost) best_cost = cost, best_tw = w;
-    }
-    tw = best_tw, th = 128 / tw;
-  }
+  // 8 x 16 pixel tiles: a tile row is one 8-row UMMA core-matrix group, so tap views of a wider box (halo slab,
+  // stride-2 phase slab) are plain row-shifted descriptors with SBO = box width
+  const int tw = 8, th = 16;
   prm.tw_log2 = 31 - __builtin_clz(tw);
   prm.th = th;
   prm.tiles_x = (prm.ow + tw - 1) / tw;
@@ -174,7 +167,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
     }
   }
   // wide layers whose even split is not a multiple of 32 (288 = 2 x 144) cannot pair; three blocks of 96 can
-  if (!is_convT && slab && a->wrows > 256 && n_cta % 32 && a->wrows % 96 == 0 && a->force_impl != 3) n_cta = 96;
+  if (!is_convT && a->wrows > 256 && n_cta % 32 && a->wrows % 96 == 0 && a->force_impl != 3) n_cta = 96;
   if (n_cta <= 0 || n_cta > 256 || n_cta % 16 || a->wrows % n_cta) return VK_E_UNSUPPORTED;
   if (a->epi == VK_EPI_NCHW_F32 && a->wrows != n_cta) return VK_E_UNSUPPORTED;
   prm.n_cta = n_cta;
@@ -191,28 +184,55 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
     prm.a_sbo = box_w * chunk;
     nt_opts[n_nt++] = 9, nt_opts[n_nt++] = 3, nt_opts[n_nt++] = 1;
   } else {
-    box_w = tw, box_h = th;
-    prm.a_sbo = 8 * chunk;
+    // full-K mode: an A item is one load (box) with all K chunks, each weight item is one tap with all K chunks
+    prm.full_k = 1;
     nt_opts[n_nt++] = 1;
+    std::memset(prm.loads, 0, sizeof(prm.loads));
+    auto aoff = [&](int dyo, int dxo, int bw) { return uint32_t((dyo * bw + dxo) * chunk) >> 4; };
     if (a->kind == VK_CONV3X3_S2) {
-      prm.n_loads = 9;
-      for (int r = 0; r < 3; ++r)
-        for (int s = 0; s < 3; ++s) prm.loads[r * 3 + s] = {s - 1, r - 1, r * 3 + s};
-    } else if (a->kind == VK_CONV2X2_S2) {
+      // the 9 taps read the four (row parity, column parity) phase images of the input: each phase is ONE
+      // strided (tw+1) x (th+1) box whose taps are row-shifted views (1, 2, 2 and 4 taps)
+      box_w = tw + 1, box_h = th + 1;
       prm.n_loads = 4;
-      for (int t = 0; t < 4; ++t) prm.loads[t] = {t & 1, t >> 1, t};
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          ConvV2Load& l = prm.loads[py * 2 + px];
+          l.dx = px ? -1 : 0, l.dy = py ? -1 : 0;
+          for (int r = 0; r < 3; ++r)
+            for (int s2 = 0; s2 < 3; ++s2)
+              if ((r != 1) == (py != 0) && (s2 != 1) == (px != 0)) {
+                l.tap[l.nb] = r * 3 + s2;
+                l.aoff16[l.nb] = aoff(r == 2 ? 1 : 0, s2 == 2 ? 1 : 0, box_w);
+                ++l.nb;
+              }
+        }
+    } else if (a->kind == VK_CONV2X2_S2) {
+      box_w = tw, box_h = th;
+      prm.n_loads = 4;
+      for (int t = 0; t < 4; ++t) {
+        ConvV2Load& l = prm.loads[t];
+        l.dx = t & 1, l.dy = t >> 1, l.nb = 1, l.tap[0] = t, l.aoff16[0] = 0;
+      }
     } else if (is_s2d) {
       const int py = phase >> 1, px = phase & 1;
       const int nr = py ? 2 : 1, ns = px ? 2 : 1;
       const int rr[2] = {py ? 0 : 1, 2}, dyv[2] = {py ? 1 : 0, 0};
       const int ss[2] = {px ? 0 : 1, 2}, dxv[2] = {px ? 1 : 0, 0};
-      prm.n_loads = 0;
-      for (int i = 0; i < nr; ++i)
-        for (int j = 0; j < ns; ++j) prm.loads[prm.n_loads++] = {dxv[j], dyv[i], rr[i] * 3 + ss[j]};
-    } else {
+      box_w = tw + 1, box_h = th + 1;
       prm.n_loads = 1;
-      prm.loads[0] = {0, 0, 0};
+      ConvV2Load& l = prm.loads[0];
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < ns; ++j) {
+          l.tap[l.nb] = rr[i] * 3 + ss[j];
+          l.aoff16[l.nb] = aoff(dyv[i], dxv[j], box_w);
+          ++l.nb;
+        }
+    } else {
+      box_w = tw, box_h = th;
+      prm.n_loads = 1;
+      prm.loads[0].nb = 1;
     }
+    prm.a_sbo = box_w * chunk;
   }
   const int a_rows = box_w * box_h;
   prm.a_tx_bytes = a_rows * chunk;
@@ -249,7 +269,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
 
   // ---- CTA pairs (cta_group::2): M = 256 per MMA, each CTA stages half of the weight rows ----
   // force_impl: 0/2 automatic, 3 single CTAs, 4 pairs
-  bool pair = a->force_impl == 4 || (a->force_impl != 3 && slab && n_cta % 32 == 0 && n_cta >= 96);
+  bool pair = a->force_impl == 4 || (a->force_impl != 3 && n_cta % 32 == 0 && n_cta >= 96);
   if (n_cta % 32) pair = false;                 // each half must be a multiple of 16 rows (N % 16, swizzle atoms)
   const int b_rows = pair ? n_cta / 2 : n_cta;  // weight rows staged per CTA
   const int epi_groups = v2_epi_groups(pair);
@@ -260,7 +280,22 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   const int p_max_tmem = std::max(1, 256 / prm.acc_stride);          // double-buffered accumulators
   int p_hi = std::min(2, p_max_tmem);          // the epilogue caches the coordinates of two tiles per job
   if (a->force_tiles_per_cta) p_hi = std::min(p_hi, a->force_tiles_per_cta);
-  int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0, best_res = 0;
+  int best_P = 0, best_nt = 0, best_as = 0, best_bs = 0, best_res = 0, best_kg = 1;
+  // full-K mode: the K-chunk group size fixes the accumulation order (load, group, tap, chunk, k), so it must
+  // depend on the layer only, never on the batch: the largest group that fits with the TMEM-maximal P, two A
+  // slots and three B slots
+  int kg_fixed = 1;
+  if (!slab) {
+    const int p_cap = std::min(2, p_max_tmem);
+    const int avail = kV2SmemBudget - 1024 - epi_bytes;
+    kg_fixed = 0;
+    for (int kg = prm.k_chunks; kg >= 1; --kg) {
+      const int a_slot = p_cap * kg * prm.a_box_bytes;
+      const int b_slot = round_up(kg * b_rows * chunk, 1024);
+      if (2 * a_slot + kV2BProducers * b_slot <= avail) { kg_fixed = kg; break; }
+    }
+    if (kg_fixed == 0) return VK_E_UNSUPPORTED;
+  }
   double best_score = -1.0;
   if (p_hi == 3) p_hi = 2;                      // the epilogue's item <-> tile mapping wants P in {1, 2, 4}
   for (int P = p_hi; P >= 1; P >>= 1) {
@@ -270,13 +305,20 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
     const long long workers = pair ? n_sm / 2 : n_sm;
     const long long rounds = (jobs + workers - 1) / workers;
     const double eff = double(groups * prm.n_blocks) / double(rounds * workers * (pair ? 2 : 1));
-    for (int i = 0; i < n_nt; ++i) {
-      const int nt = nt_opts[i];
+    // slab mode iterates the taps-per-stage options; full-K mode uses the fixed K-chunk group size
+    const int n_opts = slab ? n_nt : 1;
+    for (int i = 0; i < n_opts; ++i) {
+      const int nt = slab ? nt_opts[i] : 1;
+      const int kg = slab ? 1 : kg_fixed;
       if (a->force_nt && slab && nt != a->force_nt) continue;
-      const int a_slot = P * prm.a_box_bytes;
-      const int b_slot = round_up(nt * b_rows * chunk, 1024);
-      const int total_b_items = prm.n_loads * prm.k_chunks * (slab ? 9 / nt : 1);
-      const int total_a_items = prm.n_loads * prm.k_chunks;
+      const int n_sub = kg;                                      // boxes per tile per A item
+      const int n_kgroups = slab ? prm.k_chunks : (prm.k_chunks + kg - 1) / kg;
+      const int a_slot = P * n_sub * prm.a_box_bytes;
+      const int b_slot = round_up((slab ? nt : kg) * b_rows * chunk, 1024);
+      int gen_b_items = 0;
+      for (int l = 0; l < prm.n_loads; ++l) gen_b_items += prm.loads[l].nb;
+      const int total_b_items = slab ? prm.k_chunks * (9 / nt) : gen_b_items * n_kgroups;
+      const int total_a_items = slab ? prm.k_chunks : prm.n_loads * n_kgroups;
       const int avail = kV2SmemBudget - 1024 - epi_bytes;
       // depth: at least 2 of each; B ring as deep as fits (up to 8), A ring 2 (3 when cheap)
       int as = std::min(2, std::max(1, total_a_items)) ;
@@ -296,10 +338,10 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
       while (as < 4 && as * a_slot + bs * b_slot + a_slot <= avail && (bs >= 3 || resident)) ++as;
       (void)total_b_items;
       // score: fewer, larger B items (less barrier traffic per MMA), more tiles per job (weight reuse), full waves
-      const double mmas_per_b = double(P) * nt * (chunk / 32);
+      const double mmas_per_b = double(P) * (slab ? nt : kg) * (chunk / 32);
       const double score = eff * (1.0 - 0.12 / P) * (1.0 - 1.5 / (mmas_per_b + 6.0)) * (resident ? 1.15 : 1.0);
       if (score > best_score)
-        best_score = score, best_P = P, best_nt = nt, best_as = as, best_bs = bs, best_res = resident ? 1 : 0;
+        best_score = score, best_P = P, best_nt = nt, best_as = as, best_bs = bs, best_res = resident ? 1 : 0, best_kg = kg;
     }
   }
   if (best_P == 0) return VK_E_UNSUPPORTED;
@@ -307,9 +349,10 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   prm.P = P;
   prm.p_log2 = P == 4 ? 2 : (P == 2 ? 1 : 0);
   prm.nb = slab ? 9 / nt : 1;
-  prm.a_slot_bytes = P * prm.a_box_bytes;
-  prm.b_slot_bytes = round_up(nt * b_rows * chunk, 1024);
-  prm.b_tx_bytes = nt * b_rows * chunk;
+  prm.kg = best_kg;
+  prm.a_slot_bytes = P * best_kg * prm.a_box_bytes;
+  prm.b_slot_bytes = round_up((slab ? nt : best_kg) * b_rows * chunk, 1024);
+  prm.b_tx_bytes = (slab ? nt : 1) * b_rows * chunk;        // full-K mode: bytes of ONE chunk of a weight item
   prm.a_stages = best_as, prm.b_stages = best_bs;
   prm.b_resident = best_res;
   prm.b_base = prm.a_stages * prm.a_slot_bytes;
