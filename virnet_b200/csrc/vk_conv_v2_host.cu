@@ -9,7 +9,7 @@
 #include <unordered_map>
 
 #include "../../include/virnet_b200.h"
-#include "vk_conv_v2.cuh"
+#include "vk_conv_v2_launch.h"
 #include "vk_host.h"
 
 namespace vk {
@@ -34,58 +34,7 @@ int sm_count() {
 
 constexpr int kV2SmemBudget = 220 * 1024;   // dynamic smem incl. 1 KB alignment slack (static: ~4.6 KB)
 
-template <typename DT, int kChunk, int kNT, bool kPair, bool kFullK>
-int launch_v2(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em, const ConvV2Params& prm, int grid,
-              int smem_bytes, cudaStream_t st) {
-  static int cur = 0;
-  static std::mutex mu;
-  auto kern = conv_v2_kernel<DT, kChunk, kNT, kPair, kFullK>;
-  {
-    std::lock_guard<std::mutex> g(mu);
-    if (smem_bytes > cur) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-      if (e != cudaSuccess) return int(e);
-      cur = smem_bytes;
-    }
-  }
-  if constexpr (kPair) {
-    // CTA pairs: a cluster of two CTAs on one TPC shares every weight tile (tcgen05 cta_group::2)
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(v2_threads(true)), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, em, prm);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return e != cudaSuccess ? int(e) : int(cudaGetLastError());
-  } else {
-    kern<<<grid, v2_threads(false), smem_bytes, st>>>(ta, tb, em, prm);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return int(cudaGetLastError());
-  }
-}
-
-template <typename DT>
-int dispatch_v2(int chunk, int nt, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
-                const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st) {
-#define VK_V2_CASE(C, T)                                                                           \
-  if (chunk == C && nt == T && !prm.full_k)                                                        \
-    return pair ? launch_v2<DT, C, T, true, false>(ta, tb, em, prm, grid, smem_bytes, st)          \
-                : launch_v2<DT, C, T, false, false>(ta, tb, em, prm, grid, smem_bytes, st);
-#define VK_V2_FULLK(C)                                                                             \
-  if (chunk == C && prm.full_k)                                                                    \
-    return pair ? launch_v2<DT, C, 1, true, true>(ta, tb, em, prm, grid, smem_bytes, st)           \
-                : launch_v2<DT, C, 1, false, true>(ta, tb, em, prm, grid, smem_bytes, st);
-  VK_V2_FULLK(128) VK_V2_FULLK(64) VK_V2_FULLK(32)
-#undef VK_V2_FULLK
-  VK_V2_CASE(128, 1) VK_V2_CASE(128, 3) VK_V2_CASE(128, 9)
-  VK_V2_CASE(64, 1) VK_V2_CASE(64, 3) VK_V2_CASE(64, 9)
-  VK_V2_CASE(32, 1) VK_V2_CASE(32, 3) VK_V2_CASE(32, 9)
-#undef VK_V2_CASE
-  return VK_E_UNSUPPORTED;
-}
-
+// kernel instantiations live in vk_conv_v2_inst_*.cu (one translation unit per dtype x pair mode, built in parallel)
 }  // namespace
 
 // Returns VK_E_UNSUPPORTED when the shape does not fit this kernel (the caller falls back to v1).
@@ -442,8 +391,11 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
             prm.nb, prm.a_stages, prm.a_slot_bytes, prm.b_stages, prm.b_slot_bytes, epi_warp_bytes, ecb, prm.tmem_cols,
             smem_bytes, int(pair), prm.b_resident);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->dtype == VK_BF16) return dispatch_v2<__nv_bfloat16>(chunk, nt, pair, ta, tb, em, prm, grid, smem_bytes, st);
-  return dispatch_v2<float>(chunk, nt, pair, ta, tb, em, prm, grid, smem_bytes, st);
+  if (a->dtype == VK_BF16)
+    return pair ? v2_launch_bf16_pair(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st)
+                : v2_launch_bf16_single(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st);
+  return pair ? v2_launch_tf32_pair(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st)
+              : v2_launch_tf32_single(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st);
 }
 
 }  // namespace vk

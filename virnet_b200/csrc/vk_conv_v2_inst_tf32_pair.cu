@@ -1,0 +1,5 @@
+// conv_v2_kernel instantiations: tf32_pair (see vk_conv_v2_inst.inc)
+#define VK_INST_DT float
+#define VK_INST_PAIR true
+#define VK_INST_NAME v2_launch_tf32_pair
+#include "vk_conv_v2_inst.inc"

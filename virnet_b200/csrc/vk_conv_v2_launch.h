@@ -1,0 +1,15 @@
+// vk_conv_v2_launch.h — launch entry points of the persistent conv kernel, one per (dtype, pair mode);
+// each is defined in its own translation unit (vk_conv_v2_inst_*.cu) so the 48 kernel instantiations build in parallel.
+#pragma once
+#include "vk_conv_v2.cuh"
+
+namespace vk {
+#define VK_V2_DECL(NAME)                                                                                              \
+  int NAME(int chunk, int nt, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em, const ConvV2Params& prm, \
+           int grid, int smem_bytes, cudaStream_t st);
+VK_V2_DECL(v2_launch_bf16_single)
+VK_V2_DECL(v2_launch_bf16_pair)
+VK_V2_DECL(v2_launch_tf32_single)
+VK_V2_DECL(v2_launch_tf32_pair)
+#undef VK_V2_DECL
+}  // namespace vk
