@@ -24,6 +24,29 @@ __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// One NHWC pixel row of `ld` channels, written with 16-byte stores (ld * sizeof(DT) is a multiple of 32);
+// f(c) yields channel c as float.
+template <typename DT, typename F>
+__device__ __forceinline__ void store_row_vec(DT* __restrict__ o, int ld, F f) {
+  constexpr int V = 16 / int(sizeof(DT));
+  for (int c0 = 0; c0 < ld; c0 += V) {
+    uint4 q;
+    if constexpr (sizeof(DT) == 4) {
+      q = make_uint4(__float_as_uint(f(c0)), __float_as_uint(f(c0 + 1)), __float_as_uint(f(c0 + 2)),
+                     __float_as_uint(f(c0 + 3)));
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f(c0 + 2 * i), f(c0 + 2 * i + 1));
+        w[i] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      q = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(o + c0) = q;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // pack_input: NCHW fp32 image (+ conditioning maps) -> NHWC DT, reflect-padded
 //   out[n][y][x][c] = c <  C      : img[n][c][ry/sf][rx/sf]
@@ -44,19 +67,16 @@ __global__ void pack_input_kernel(const float* __restrict__ img, int C, int h, i
     const int y = int((p / Wp) % Hp);
     const int n = int(p / (static_cast<long long>(Wp) * Hp));
     const int ry = reflect_idx(y, H), rx = reflect_idx(x, W);
-    DT* o = out + p * ld;
-    int c = 0;
-    for (; c < C; ++c) o[c] = cvt_out<DT>(__ldg(img + ((static_cast<long long>(n) * C + c) * h + ry / sf) * w + rx / sf));
-    for (int e = 0; e < E; ++e, ++c) {
-      float v;
-      if (extra_is_map)
-        v = __ldg(extra + ((static_cast<long long>(n) * E + e) * eh + ry / esf) * ew + rx / esf);
-      else
-        v = __ldg(extra + static_cast<long long>(n) * E + e);
+    const int iy = ry / sf, ix = rx / sf, ey = ry / esf, ex = rx / esf;
+    store_row_vec<DT>(out + p * ld, ld, [&](int c) -> float {
+      if (c < C) return __ldg(img + ((static_cast<long long>(n) * C + c) * h + iy) * w + ix);
+      const int e = c - C;
+      if (e >= E) return 0.f;
+      float v = extra_is_map ? __ldg(extra + ((static_cast<long long>(n) * E + e) * eh + ey) * ew + ex)
+                             : __ldg(extra + static_cast<long long>(n) * E + e);
       if (extra_sqrt & (1 << e)) v = sqrtf(v);
-      o[c] = cvt_out<DT>(v);
-    }
-    for (; c < ld; ++c) o[c] = cvt_out<DT>(0.f);
+      return v;
+    });
   }
 }
 
@@ -73,12 +93,9 @@ __global__ void pack_grad_kernel(const float* __restrict__ g, int C, int h, int 
     const int y = int((p / Wp) % Hp);
     const int n = int(p / (static_cast<long long>(Wp) * Hp));
     const bool in = (y < h) && (x < w);
-    DT* o = out + p * ld;
-    for (int c = 0; c < ld; ++c) {
-      float v = 0.f;
-      if (in && c < C) v = __ldg(g + ((static_cast<long long>(n) * C + c) * h + y) * w + x);
-      o[c] = cvt_out<DT>(v);
-    }
+    store_row_vec<DT>(out + p * ld, ld, [&](int c) -> float {
+      return (in && c < C) ? __ldg(g + ((static_cast<long long>(n) * C + c) * h + y) * w + x) : 0.f;
+    });
   }
 }
 
@@ -104,8 +121,7 @@ __global__ void sigma_head_bwd_kernel(const float* __restrict__ sigma, const flo
     // mirrored partners of (y, x) inside the padded grid
     const int y2 = 2 * (h - 1) - y, x2 = 2 * (w - 1) - x;
     const bool my = (y2 >= h) && (y2 < Hp), mx = (x2 >= w) && (x2 < Wp);
-    DT* o = out + p * ld;
-    for (int c = 0; c < ld; ++c) {
+    store_row_vec<DT>(out + p * ld, ld, [&](int c) -> float {
       float v = 0.f;
       if (c < SC) {
         const long long si = ((static_cast<long long>(n) * SC + c) * h + y) * w + x;
@@ -122,8 +138,8 @@ __global__ void sigma_head_bwd_kernel(const float* __restrict__ sigma, const flo
         const bool in_range = (sg > sig_lo) && (sg < sig_hi);
         v = in_range ? sg * (gsig + gs * 0.5f * rsqrtf(sg)) : 0.f;
       }
-      o[c] = cvt_out<DT>(v);
-    }
+      return v;
+    });
   }
 }
 
@@ -331,7 +347,7 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
-static inline int grid_for(long long total, int threads, int max_waves = 8) {
+static inline int grid_for(long long total, int threads, int max_waves = 16) {
   long long b = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(kSMs) * max_waves;
   if (b > cap) b = cap;
