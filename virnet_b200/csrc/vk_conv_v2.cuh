@@ -1,25 +1,32 @@
-// vk_conv_v2.cuh — persistent implicit-GEMM convolution for sm_100a (second generation of
-// vk_conv_igemm.cuh; same maths, same C ABI entry point, selected by the host heuristics).
+// vk_conv_v2.cuh — persistent implicit-GEMM convolution for sm_100a: serves every dense convolution on
+// the VIRNet hot path in both directions (reference call sites: networks/AttResUNet.py:43,46,67,80,117-119,139,
+// networks/DnCNN.py:22-29, networks/KNet.py:32-34,49).  vk_conv_igemm.cuh ("v1") is kept as the fallback for
+// shapes the host heuristics decline.
 //
-// What changed against v1 (measured on B200, profiles/r01_*):
-//   * v1 serialised mainloop and epilogue inside one CTA per tile group and paid TMEM allocation,
-//     barrier set-up and the pipeline fill once per group.  v2 is PERSISTENT: one CTA per SM walks
-//     the job list, the fp32 accumulators are double-buffered in TMEM (2 x P tiles x N columns), so
-//     the epilogue of job j overlaps the TMA/MMA mainloop of job j+1.
-//   * 3x3 stride-1 convolutions load ONE halo slab per (tile, K chunk): a (tw+2) x (th+2) pixel box
-//     with tw = 8.  A tile row is then exactly one 8-row UMMA core-matrix group, so each of the 9
-//     filter taps is the same slab read through a descriptor whose start address is shifted by
-//     (r * slab_w + s) rows and whose group pitch (SBO) is slab_w rows — no im2col, and the slab is
-//     fetched from L2 once instead of three times (the swizzle is a function of the absolute
-//     shared-memory address, so row-shifted descriptors stay consistent; tools/probe `shift`).
-//   * A (activation slabs) and B (weights) move through two independent mbarrier rings, so a weight
-//     block of `NT` taps can be much smaller than the slab it is multiplied with.
-//   * The epilogue no longer issues per-thread 32-byte global accesses (32 cache lines per warp
-//     instruction).  Each epilogue warp owns a 32-pixel x `ecols`-channel item: residual / mask
-//     arrive by TMA into a private swizzled staging buffer, results leave by TMA store.
+// GEMM view: M = 128 output pixels (an 8 x 16 patch of one image), N = output channels of the job, K = taps x
+// input channels; activations NHWC, weights pre-packed K-major [tap][Cout][Cin].
 //
-// Warp roles (13 warps): 0 = A producer, 1-3 = B producers, 4-11 = epilogue (two warps per TMEM lane
-// quarter), 12 = MMA issuer and TMEM owner.
+//   * PERSISTENT: one CTA per SM walks the job list; fp32 accumulators are double-buffered in TMEM
+//     (2 x P tiles x N columns <= 512), so the epilogue of job j overlaps the TMA/MMA mainloop of job j+1.
+//   * CTA PAIRS (kPair, tcgen05 cta_group::2): a cluster of two CTAs walks the same job list; each CTA owns its
+//     own pixel tiles and stages HALF of the weight rows; the leader issues M = 256 MMAs.  TMA loads of both CTAs
+//     complete on the leader's barriers, commits are multicast, the peer signals "accumulator drained" remotely.
+//   * SLAB mode (3x3 stride 1): ONE halo slab per (tile, K chunk), a (8+2) x (16+2) pixel box.  A tile row is
+//     exactly one 8-row UMMA core-matrix group, so each of the 9 taps is the same slab read through a descriptor
+//     shifted by (r * slab_w + s) rows with group pitch (SBO) slab_w rows — no im2col, one L2 fetch per input
+//     pixel (the swizzle is a function of the absolute smem address; tools/probe `shift`).
+//   * FULL-K mode (kFullK: stride-2, transposed, 1x1, 2x2 kinds): an A item is one box with a group of K chunks,
+//     a weight item one tap with the same chunks; a stride-2 conv reads the four parity phase images of its input
+//     as strided boxes whose taps are row-shifted views.
+//   * A (activations) and B (weights) move through two independent mbarrier rings; weights of a one-block layer
+//     that fit the ring stay resident after the first job.
+//   * EPILOGUE by TMA: two groups of four warps own (128-pixel tile x 32-channel chunk) items; residual / mask
+//     tiles arrive by TMA into a swizzled staging buffer (prefetched one item ahead), results leave by ONE TMA
+//     store per output tensor; the maths is specialised at compile time per tensor combination.
+//
+// Warp roles (13 warps): 0 = A producer, 1-3 = B producers, 4-11 = epilogue (one warp per TMEM lane quarter in
+// each of the two groups), 12 = MMA issuer and TMEM owner.  Optional per-role stall counters (prm.timing) feed
+// tools/v2_timing.py.
 #pragma once
 #include <type_traits>
 
