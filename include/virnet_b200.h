@@ -162,6 +162,34 @@ int vk_sft_mlp(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask, con
                int32_t c1, const float* w2, const float* b2, int32_t c2, const float* wm, const float* bm,
                const float* wa, const float* ba, int32_t c, float alpha, float* mul, float* add, void* stream);
 
+/* ---- backward of the same layers (autograd of the reference modules) ---- */
+
+/* SFT backward after the producing dgrad applied lrelu': gx = g * mul (+ resid); dmul/dadd [n][c] += sums over pixels
+ * of g * x and g (accumulated: zero them first).  g, x, resid, gx: NHWC `dtype` [n][npix][ld]. */
+int vk_sft_bwd(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx, float* dmul,
+               float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, void* stream);
+
+/* AttLayer MLP backward: parameter gradients are ACCUMULATED into gw1..gba (same shapes as the parameters),
+ * d_extra [n][e] += dL/d(raw conditioning values). */
+int vk_sft_mlp_bwd(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask, const float* w1, const float* b1,
+                   int32_t c1, const float* w2, const float* b2, int32_t c2, const float* wm, const float* bm,
+                   const float* wa, const float* ba, int32_t c, float alpha, const float* dmul, const float* dadd,
+                   float* gw1, float* gb1, float* gw2, float* gb2, float* gwm, float* gbm, float* gwa, float* gba,
+                   float* d_extra, void* stream);
+
+/* CALayer + skip backward: df = g * s + dy / npix (the skip gradient is g); parameter gradients accumulated. */
+int vk_ca_layer_bwd(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1, const float* w2,
+                    const float* b2, void* df, float* gw1, float* gb1, float* gw2, float* gb2, int32_t n, int32_t npix,
+                    int32_t c, int32_t r, int32_t ld, float alpha, void* stream);
+
+/* Backward of vk_gap_head: gx NHWC `dtype` [n][hw][ld] = gout[n][c] * head'(outv[n][c]) / hw (0 for c >= C). */
+int vk_gap_head_bwd(int32_t dtype, const float* gout, const float* outv, int32_t n, int32_t c, int32_t hw,
+                    uint32_t exp_mask, uint32_t tanh_mask, float lo, float hi, void* gx, int32_t ld, void* stream);
+
+/* Weight gradient of vk_knet_head, ACCUMULATED into gw [cout][c][9][9]; g NHWC `dtype` [n][oh][ow][ld]. */
+int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c, int32_t h,
+                       int32_t wd, int32_t cout, int32_t ld, void* stream);
+
 /* F.interpolate(x, scale_factor=sf, mode="nearest") on NCHW fp32 (networks/VIRNet.py:83). */
 int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
                         void* stream);

@@ -55,8 +55,54 @@ def test_sisr_forward_vs_oracle_ragged(shape, sf):
     assert rel(mu.cpu(), mu_o) < 1e-3
 
 
-def test_sisr_training_mode_raises():
+@pytest.mark.parametrize("precision,tol", [("tf32", 2e-2), ("bf16", 8e-2)])
+@pytest.mark.parametrize("shape,sf", [((2, 3, 16, 16), 4), ((1, 3, 21, 30), 2)])
+def test_sisr_backward_vs_oracle(precision, tol, shape, sf):
+    """Gradients of every parameter (SNet, KNet incl. the 9x9 head and channel attention, RNet incl. the SFT
+    MLPs) of a random linear functional of (mu, kinfo, sigma) against torch autograd through the CPU oracle.
+    Tolerance: relative L2 per sub-network, same bar as the denoising backward tests (tf32 2e-2, bf16 8e-2)."""
+    from oracle import virnet_oracle as O
+    net, sd = make_sr(precision, n_feat=(32, 64, 96), n_res=2, dep_K=3)
+    net.train()
+    cfg = O.NetCfg(n_feat=(32, 64, 96), n_resblocks=2, extra_mode="Both", noise_avg=True, sisr=True, dep_K=3)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(*shape, generator=g)
+    N, C, h, w = shape
+    w_mu = torch.randn(N, C, h * sf, w * sf, generator=g) / (h * sf)
+    w_k = torch.randn(N, 3, generator=g)
+    w_s = torch.randn(N, 1, 1, 1, generator=g) * 10
+
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    mu_o, kinfo_o, sigma_o = O.vir_sisr_forward(sdr, x, sf, cfg)
+    ((mu_o * w_mu).sum() + (kinfo_o * w_k).sum() + (sigma_o * w_s).sum()).backward()
+
+    mu, kinfo, sigma = net(x.cuda(), sf)
+    ((mu * w_mu.cuda()).sum() + (kinfo * w_k.cuda()).sum() + (sigma * w_s.cuda()).sum()).backward()
+    got = {k: p.grad.detach().cpu() for k, p in net.named_parameters()}
+    assert set(got) == set(sdr)
+    for sub in ("SNet.", "KNet.", "RNet."):
+        a = torch.cat([got[k].flatten() for k in sdr if k.startswith(sub)])
+        b = torch.cat([sdr[k].grad.flatten() for k in sdr if k.startswith(sub)])
+        assert rel(a, b) < tol, (sub, rel(a, b))
+    # the small layers individually (their gradients are tiny next to the 3x3 convs' in the sub-network norm)
+    groups = {"knet_head": ["KNet.head.weight"],
+              "knet_ca": [k for k in sdr if k.startswith("KNet.body") and ".body.3." in k],
+              "sft": [k for k in sdr if ".sft1." in k or ".sft2." in k]}
+    for name, keys in groups.items():
+        assert keys, name
+        a = torch.cat([got[k].flatten() for k in keys])
+        b = torch.cat([sdr[k].grad.flatten() for k in keys])
+        assert rel(a, b) < tol, (name, rel(a, b))
+
+
+def test_sisr_backward_then_inference_consistent():
+    """A no-grad forward after a training forward/backward returns the same outputs (buffers are not clobbered)."""
     net, _ = make_sr("tf32", n_feat=(32, 64, 96), n_res=1, dep_K=2)
     net.train()
-    with pytest.raises(NotImplementedError):
-        net(torch.rand(1, 3, 16, 16, device="cuda"), 4)
+    x = torch.rand(1, 3, 16, 16, device="cuda")
+    mu, kinfo, sigma = net(x, 4)
+    mu_keep = mu.clone()
+    (mu.sum() + kinfo.sum() + sigma.sum()).backward()
+    with torch.no_grad():
+        mu2, _, _ = net(x, 4)
+    assert torch.equal(mu2, mu_keep)

@@ -195,6 +195,253 @@ __global__ void upsample_nearest_kernel(const float* __restrict__ x, float* __re
   }
 }
 
+
+// ===========================================================================
+// Backward pass of the super-resolution network's small layers
+// ===========================================================================
+
+// SFT backward (autograd of a = lrelu(x * mul + add), networks/AttResUNet.py:54-58), after the producing dgrad
+// has already applied lrelu'(a):  g = dL/d(x * mul + add), NHWC DT [n][npix][ld]
+//   gx = g * mul[n][c] (+ resid),  dmul[n][c] += sum_pix g * x,  dadd[n][c] += sum_pix g
+// block = 8 pixel lanes x 32 channel lanes over one sample's pixel chunk; blockIdx.y = sample.
+template <typename DT>
+__global__ void sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* __restrict__ mul,
+                               const DT* __restrict__ resid, DT* __restrict__ gx, float* __restrict__ dmul,
+                               float* __restrict__ dadd, int npix, int C, int ld, int pix_per_block) {
+  __shared__ float pm[8][33], pa[8][33];
+  const int n = blockIdx.y;
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const long long base = static_cast<long long>(n) * npix * ld;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  for (int c0 = 0; c0 < ld; c0 += 32) {
+    const int c = c0 + cl;
+    float sm_ = 0.f, sa_ = 0.f;
+    if (c < ld) {
+      const float m = c < C ? mul[n * C + c] : 0.f;
+      for (int p = p0 + pl; p < p1; p += 8) {
+        const long long i = base + static_cast<long long>(p) * ld + c;
+        const float gv = c < C ? ld_f<DT>(g + i) : 0.f;
+        float o = gv * m;
+        if (resid != nullptr) o += ld_f<DT>(resid + i);
+        st_f<DT>(gx + i, c < C ? o : 0.f);
+        sm_ += gv * (c < C ? ld_f<DT>(x + i) : 0.f);
+        sa_ += gv;
+      }
+    }
+    pm[pl][cl] = sm_, pa[pl][cl] = sa_;
+    __syncthreads();
+    if (pl == 0 && c < C) {
+      float tm = 0.f, ta = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tm += pm[j][cl], ta += pa[j][cl];
+      atomicAdd(dmul + n * C + c, tm);
+      atomicAdd(dadd + n * C + c, ta);
+    }
+    __syncthreads();
+  }
+}
+
+// AttLayer MLP backward (one block, samples in sequence so parameter gradients need no atomics):
+// recomputes the forward of sft_mlp_kernel, then back-propagates (dmul, dadd) to the four 1x1 convs and to the
+// conditioning values.  d_extra[n][e] += dL/d(raw extra) (the sqrt of the masked entries is chained here).
+__global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E, unsigned sqrt_mask,
+                                   const float* __restrict__ w1, const float* __restrict__ b1, int C1,
+                                   const float* __restrict__ w2, const float* __restrict__ b2, int C2,
+                                   const float* __restrict__ wm, const float* __restrict__ bm,
+                                   const float* __restrict__ wa, const float* __restrict__ ba, int C, float alpha,
+                                   const float* __restrict__ dmul, const float* __restrict__ dadd, float* __restrict__ gw1,
+                                   float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2,
+                                   float* __restrict__ gwm, float* __restrict__ gbm, float* __restrict__ gwa,
+                                   float* __restrict__ gba, float* __restrict__ d_extra) {
+  extern __shared__ float sm[];   // e[E] f1p[C1] f1[C1] f2p[C2] f2[C2] gmp[C] gad[C] gf2[C2] gf1[C1]
+  float* e = sm;
+  float* f1p = e + E;
+  float* f1 = f1p + C1;
+  float* f2p = f1 + C1;
+  float* f2 = f2p + C2;
+  float* gmp = f2 + C2;
+  float* gad = gmp + C;
+  float* gf2 = gad + C;
+  float* gf1 = gf2 + C2;
+  const int T = blockDim.x, t = threadIdx.x;
+  for (int n = 0; n < N; ++n) {
+    if (t < E) {
+      const float v = extra[n * E + t];
+      e[t] = (sqrt_mask & (1u << t)) ? sqrtf(v) : v;
+    }
+    __syncthreads();
+    for (int i = t; i < C1; i += T) {
+      float a = b1[i];
+      for (int k = 0; k < E; ++k) a = fmaf(w1[i * E + k], e[k], a);
+      f1p[i] = a, f1[i] = a > 0.f ? a : a * alpha;
+    }
+    __syncthreads();
+    for (int i = t; i < C2; i += T) {
+      float a = b2[i];
+      for (int k = 0; k < C1; ++k) a = fmaf(w2[i * C1 + k], f1[k], a);
+      f2p[i] = a, f2[i] = a > 0.f ? a : a * alpha;
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += T) {
+      float a = bm[c];
+      for (int k = 0; k < C2; ++k) a = fmaf(wm[c * C2 + k], f2[k], a);
+      const float mu = 1.f / (1.f + expf(-a));
+      const float g1 = dmul[n * C + c] * mu * (1.f - mu), g2 = dadd[n * C + c];
+      gmp[c] = g1, gad[c] = g2;
+      gbm[c] += g1, gba[c] += g2;
+      for (int k = 0; k < C2; ++k) gwm[c * C2 + k] += g1 * f2[k], gwa[c * C2 + k] += g2 * f2[k];
+    }
+    __syncthreads();
+    for (int k = t; k < C2; k += T) {
+      float a = 0.f;
+      for (int c = 0; c < C; ++c) a = fmaf(wm[c * C2 + k], gmp[c], fmaf(wa[c * C2 + k], gad[c], a));
+      a *= f2p[k] > 0.f ? 1.f : alpha;
+      gf2[k] = a;
+      gb2[k] += a;
+      for (int j = 0; j < C1; ++j) gw2[k * C1 + j] += a * f1[j];
+    }
+    __syncthreads();
+    for (int j = t; j < C1; j += T) {
+      float a = 0.f;
+      for (int k = 0; k < C2; ++k) a = fmaf(w2[k * C1 + j], gf2[k], a);
+      a *= f1p[j] > 0.f ? 1.f : alpha;
+      gf1[j] = a;
+      gb1[j] += a;
+      for (int i = 0; i < E; ++i) gw1[j * E + i] += a * e[i];
+    }
+    __syncthreads();
+    if (t < E) {
+      float a = 0.f;
+      for (int j = 0; j < C1; ++j) a = fmaf(w1[j * E + t], gf1[j], a);
+      if (sqrt_mask & (1u << t)) a *= 0.5f / fmaxf(e[t], 1e-20f);
+      d_extra[n * E + t] += a;
+    }
+    __syncthreads();
+  }
+}
+
+// CALayer + skip backward (autograd of out = f * s(mean f) + skip), one CTA per sample:
+//   d_f = g * s + dy / npix,  the skip gradient is g itself;  parameter gradients by atomicAdd over samples.
+template <typename DT>
+__global__ void ca_layer_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ f, const float* __restrict__ w1,
+                                    const float* __restrict__ b1, const float* __restrict__ w2,
+                                    const float* __restrict__ b2, DT* __restrict__ df, float* __restrict__ gw1,
+                                    float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2, int npix,
+                                    int C, int R, int ld, float alpha) {
+  extern __shared__ float sm[];   // part_y[L][C] part_d[L][C] y[C] ds[C] s[C] gsp[C] dy[C] zp[R] z[R] gzp[R]
+  const int n = blockIdx.x;
+  const long long base = static_cast<long long>(n) * npix * ld;
+  const int lanes = blockDim.x / C;
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  float* part_y = sm;
+  float* part_d = part_y + lanes * C;
+  float* y = part_d + lanes * C;
+  float* ds = y + C;
+  float* s = ds + C;
+  float* gsp = s + C;
+  float* dy = gsp + C;
+  float* zp = dy + C;
+  float* z = zp + R;
+  float* gzp = z + R;
+  float py = 0.f, pd = 0.f;
+  if (pl < lanes)
+    for (int p = pl; p < npix; p += lanes) {
+      const float fv = ld_f<DT>(f + base + static_cast<long long>(p) * ld + c);
+      py += fv;
+      pd += fv * ld_f<DT>(g + base + static_cast<long long>(p) * ld + c);
+    }
+  if (pl < lanes) part_y[pl * C + c] = py, part_d[pl * C + c] = pd;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) a += part_y[l * C + threadIdx.x], b += part_d[l * C + threadIdx.x];
+    y[threadIdx.x] = a / float(npix), ds[threadIdx.x] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < R) {
+    float a = b1[threadIdx.x];
+    for (int k = 0; k < C; ++k) a = fmaf(w1[threadIdx.x * C + k], y[k], a);
+    zp[threadIdx.x] = a, z[threadIdx.x] = a > 0.f ? a : a * alpha;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = b2[threadIdx.x];
+    for (int k = 0; k < R; ++k) a = fmaf(w2[threadIdx.x * R + k], z[k], a);
+    const float sv = 1.f / (1.f + expf(-a));
+    s[threadIdx.x] = sv;
+    const float gs = ds[threadIdx.x] * sv * (1.f - sv);
+    gsp[threadIdx.x] = gs;
+    atomicAdd(gb2 + threadIdx.x, gs);
+    for (int k = 0; k < R; ++k) atomicAdd(gw2 + threadIdx.x * R + k, gs * z[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < R) {
+    float a = 0.f;
+    for (int cc = 0; cc < C; ++cc) a = fmaf(w2[cc * R + threadIdx.x], gsp[cc], a);
+    a *= zp[threadIdx.x] > 0.f ? 1.f : alpha;
+    gzp[threadIdx.x] = a;
+    atomicAdd(gb1 + threadIdx.x, a);
+    for (int cc = 0; cc < C; ++cc) atomicAdd(gw1 + threadIdx.x * C + cc, a * y[cc]);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.f;
+    for (int k = 0; k < R; ++k) a = fmaf(w1[k * C + threadIdx.x], gzp[k], a);
+    dy[threadIdx.x] = a / float(npix);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npix * ld; i += blockDim.x) {
+    const int cc = i % ld;
+    float v = 0.f;
+    if (cc < C) v = ld_f<DT>(g + base + i) * s[cc] + dy[cc];
+    st_f<DT>(df + base + i, v);
+  }
+}
+
+// Backward of gap_head_kernel: the gradient w.r.t. every pixel of plane (n, c) is
+//   g[n][c] * head'(.) / hw,  head' = out (exp head, inside the clamp range) or 1 - out^2 (tanh); NHWC DT output.
+template <typename DT>
+__global__ void gap_head_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ outv, int C, int hw,
+                                    unsigned exp_mask, unsigned tanh_mask, float out_lo, float out_hi,
+                                    DT* __restrict__ gx, int ld, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = int(i % ld);
+    const long long n = i / (static_cast<long long>(ld) * hw);
+    float v = 0.f;
+    if (c < C) {
+      const float o = outv[n * C + c];
+      float d = 1.f;
+      if (exp_mask & (1u << c)) d = (o > out_lo && o < out_hi) ? o : 0.f;
+      if (tanh_mask & (1u << c)) d = 1.f - o * o;
+      v = gout[n * C + c] * d / float(hw);
+    }
+    st_f<DT>(gx + i, v);
+  }
+}
+
+// Weight gradient of the KNet head (9x9, stride 4, pad 4): one thread per weight element.
+template <typename DT>
+__global__ void knet_head_wgrad_kernel(const float* __restrict__ x, const DT* __restrict__ g, float* __restrict__ gw,
+                                       int N, int C, int H, int W, int OH, int OW, int cout, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * C * 81) return;
+  const int s = i % 9, r = (i / 9) % 9, c = (i / 81) % C, co = i / (81 * C);
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n)
+    for (int oy = 0; oy < OH; ++oy) {
+      const int iy = oy * 4 - 4 + r;
+      if (iy < 0 || iy >= H) continue;
+      for (int ox = 0; ox < OW; ++ox) {
+        const int ix = ox * 4 - 4 + s;
+        if (ix < 0 || ix >= W) continue;
+        acc = fmaf(ld_f<DT>(g + ((static_cast<long long>(n) * OH + oy) * OW + ox) * ld + co),
+                   __ldg(x + ((static_cast<long long>(n) * C + c) * H + iy) * W + ix), acc);
+      }
+    }
+  gw[i] += acc;
+}
+
 }  // namespace vk
 
 using namespace vk;
@@ -266,5 +513,95 @@ extern "C" int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_
   const long long total = static_cast<long long>(n) * c * h * sf * w * sf;
   const int grid = int(std::min<long long>((total + 255) / 256, 148 * 8));
   upsample_nearest_kernel<<<grid, 256, 0, VK_ST(stream)>>>(x, out, static_cast<long long>(n) * c, h, w, sf);
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_sft_bwd(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx,
+                          float* dmul, float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, void* stream) {
+  if (!g || !x || !mul || !gx || !dmul || !dadd || n <= 0 || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
+  const int ppb = 256;
+  dim3 grid((npix + ppb - 1) / ppb, n);
+  if (dtype == VK_BF16)
+    sft_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), mul,
+        reinterpret_cast<const __nv_bfloat16*>(resid), reinterpret_cast<__nv_bfloat16*>(gx), dmul, dadd, npix, c, ld, ppb);
+  else if (dtype == VK_TF32)
+    sft_bwd_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(g),
+                                                           reinterpret_cast<const float*>(x), mul,
+                                                           reinterpret_cast<const float*>(resid),
+                                                           reinterpret_cast<float*>(gx), dmul, dadd, npix, c, ld, ppb);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_sft_mlp_bwd(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask, const float* w1,
+                              const float* b1, int32_t c1, const float* w2, const float* b2, int32_t c2,
+                              const float* wm, const float* bm, const float* wa, const float* ba, int32_t c, float alpha,
+                              const float* dmul, const float* dadd, float* gw1, float* gb1, float* gw2, float* gb2,
+                              float* gwm, float* gbm, float* gwa, float* gba, float* d_extra, void* stream) {
+  if (!extra || !w1 || !b1 || !w2 || !b2 || !wm || !bm || !wa || !ba || !dmul || !dadd || !gw1 || !gb1 || !gw2 ||
+      !gb2 || !gwm || !gbm || !gwa || !gba || !d_extra)
+    return VK_E_BADARG;
+  if (n <= 0 || e <= 0 || e > 32 || c1 <= 0 || c2 <= 0 || c <= 0) return VK_E_BADARG;
+  const size_t smem = size_t(e + 3 * c1 + 3 * c2 + 2 * c) * sizeof(float);
+  sft_mlp_bwd_kernel<<<1, 256, smem, VK_ST(stream)>>>(extra, n, e, sqrt_mask, w1, b1, c1, w2, b2, c2, wm, bm, wa, ba, c,
+                                                     alpha, dmul, dadd, gw1, gb1, gw2, gb2, gwm, gbm, gwa, gba, d_extra);
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_ca_layer_bwd(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1,
+                               const float* w2, const float* b2, void* df, float* gw1, float* gb1, float* gw2,
+                               float* gb2, int32_t n, int32_t npix, int32_t c, int32_t r, int32_t ld, float alpha,
+                               void* stream) {
+  if (!g || !f || !w1 || !b1 || !w2 || !b2 || !df || !gw1 || !gb1 || !gw2 || !gb2) return VK_E_BADARG;
+  if (n <= 0 || npix <= 0 || c <= 0 || r <= 0 || c > ld || c > 256) return VK_E_BADARG;
+  const int threads = std::max(c, 256 / c * c);
+  const size_t smem = (size_t(2 * (threads / c)) * c + 5 * c + 3 * r) * sizeof(float);
+  if (dtype == VK_BF16)
+    ca_layer_bwd_kernel<__nv_bfloat16><<<n, threads, smem, VK_ST(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(f), w1, b1, w2, b2,
+        reinterpret_cast<__nv_bfloat16*>(df), gw1, gb1, gw2, gb2, npix, c, r, ld, alpha);
+  else if (dtype == VK_TF32)
+    ca_layer_bwd_kernel<float><<<n, threads, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(g),
+                                                                  reinterpret_cast<const float*>(f), w1, b1, w2, b2,
+                                                                  reinterpret_cast<float*>(df), gw1, gb1, gw2, gb2,
+                                                                  npix, c, r, ld, alpha);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_gap_head_bwd(int32_t dtype, const float* gout, const float* outv, int32_t n, int32_t c, int32_t hw,
+                               uint32_t exp_mask, uint32_t tanh_mask, float lo, float hi, void* gx, int32_t ld,
+                               void* stream) {
+  if (!gout || !outv || !gx || n <= 0 || c <= 0 || c > 32 || hw <= 0 || c > ld) return VK_E_BADARG;
+  const long long total = static_cast<long long>(n) * hw * ld;
+  const int grid = int(std::min<long long>((total + 255) / 256, 148 * 8));
+  const float olo = expf(lo), ohi = expf(hi);
+  if (dtype == VK_BF16)
+    gap_head_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(gout, outv, c, hw, exp_mask, tanh_mask, olo, ohi,
+                                                                       reinterpret_cast<__nv_bfloat16*>(gx), ld, total);
+  else if (dtype == VK_TF32)
+    gap_head_bwd_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(gout, outv, c, hw, exp_mask, tanh_mask, olo, ohi,
+                                                               reinterpret_cast<float*>(gx), ld, total);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c,
+                                  int32_t h, int32_t wd, int32_t cout, int32_t ld, void* stream) {
+  if (!x || !g || !gw || n <= 0 || c <= 0 || h <= 0 || wd <= 0 || cout <= 0 || cout > ld) return VK_E_BADARG;
+  const int oh = (h - 1) / 4 + 1, ow = (wd - 1) / 4 + 1;
+  const int total = cout * c * 81;
+  if (dtype == VK_BF16)
+    knet_head_wgrad_kernel<__nv_bfloat16><<<(total + 127) / 128, 128, 0, VK_ST(stream)>>>(
+        x, reinterpret_cast<const __nv_bfloat16*>(g), gw, n, c, h, wd, oh, ow, cout, ld);
+  else if (dtype == VK_TF32)
+    knet_head_wgrad_kernel<float><<<(total + 127) / 128, 128, 0, VK_ST(stream)>>>(x, reinterpret_cast<const float*>(g),
+                                                                                gw, n, c, h, wd, oh, ow, cout, ld);
+  else
+    return VK_E_BADARG;
   VK_LAUNCHED();
 }

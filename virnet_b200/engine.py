@@ -120,10 +120,10 @@ class DenoiseEngine:
         if sr:
             knet = net.KNet
             for b, rb in enumerate(knet.body):
-                self.k_blocks.append((_Layer(f"KNet.body{b}.conv1", rb.body[0], "conv", False),
-                                      _Layer(f"KNet.body{b}.conv2", rb.body[2], "conv", False), rb.body[3]))
+                self.k_blocks.append((_Layer(f"KNet.body{b}.conv1", rb.body[0], "conv", True),
+                                      _Layer(f"KNet.body{b}.conv2", rb.body[2], "conv", True), rb.body[3]))
                 L += [self.k_blocks[-1][0], self.k_blocks[-1][1]]
-            self.k_tail = _Layer("KNet.tail", knet.tail[0], "conv", False)
+            self.k_tail = _Layer("KNet.tail", knet.tail[0], "conv", True)
             L.append(self.k_tail)
         self.layers = L
 
@@ -469,9 +469,9 @@ class DenoiseEngine:
 
 
     # ------------------------------------------------------------------
-    # super-resolution forward (networks/VIRNet.py:80-97); inference only in this round
+    # super-resolution network (networks/VIRNet.py:80-97): forward, and backward w.r.t. every parameter
     # ------------------------------------------------------------------
-    def forward_sr(self, x: torch.Tensor, sf: int):
+    def forward_sr(self, x: torch.Tensor, sf: int, save: bool = False):
         """x: LR image NCHW fp32 -> (mu [N,C,H*sf,W*sf], kinfo [N,3], sigma [N,1,1,1])."""
         net = self.net
         if not (net.noise_cond and net.kernel_cond and net.noise_avg and self.extra_mode == "both"):
@@ -487,14 +487,17 @@ class DenoiseEngine:
         dt, dev = self.dtype, x.device
         cp = lambda c: ops.chan_pad(c, dt)
         f32 = torch.float32
+        S: Dict[str, torch.Tensor] = {}
 
         # ---- SNet with global average of the log-variance (DnCNN.py:30-33,42; VIRNet.py:81) ----
         xs = self._buf("sr.xs", (N, h, w, cp(C)))
         ops.pack_input(x, xs, dtype=dt)
+        S["xs"] = xs
         cur = xs
         for i, ly in enumerate(self.s_layers[:-1]):
             o = self._buf(f"sr.s{i}", (N, h, w, cp(ly.cout)))
             self._conv(cur, ly, VK_CONV3X3_S1, ldo=cp(ly.cout), out2=o, alpha=0.25)
+            S[f"s{i}"] = o
             cur = o
         logvar = self._buf("sr.logvar", (N, self.sigma_chn, h, w), f32)
         self._conv(cur, self.s_layers[-1], VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=logvar)
@@ -503,19 +506,21 @@ class DenoiseEngine:
 
         # ---- KNet (KNet.py:52-59) ----
         knet = net.KNet
-        nf = knet.head.out_channels
+        nfk = knet.head.out_channels
         kh, kw = (h - 1) // 4 + 1, (w - 1) // 4 + 1
-        H = self._buf("sr.k.h0", (N, kh, kw, cp(nf)))
+        H = self._buf("sr.k.h0", (N, kh, kw, cp(nfk)))
         ops.knet_head(x, knet.head.weight, H, dtype=dt)
         for b, (c1, c2, ca) in enumerate(self.k_blocks):
-            A = self._buf("sr.k.a", (N, kh, kw, cp(nf)))
-            self._conv(H, c1, VK_CONV3X3_S1, ldo=cp(nf), out2=A, alpha=0.2)
-            F_ = self._buf("sr.k.f", (N, kh, kw, cp(nf)))
-            self._conv(A, c2, VK_CONV3X3_S1, ldo=cp(nf), out1=F_)
-            Hn = self._buf(f"sr.k.h{1 + (b & 1)}", (N, kh, kw, cp(nf)))
+            A = self._buf(f"sr.k{b}.a", (N, kh, kw, cp(nfk)))
+            self._conv(H, c1, VK_CONV3X3_S1, ldo=cp(nfk), out2=A, alpha=0.2)
+            F_ = self._buf(f"sr.k{b}.f", (N, kh, kw, cp(nfk)))
+            self._conv(A, c2, VK_CONV3X3_S1, ldo=cp(nfk), out1=F_)
+            Hn = self._buf(f"sr.k.h{b + 1}", (N, kh, kw, cp(nfk)))
             ops.ca_layer(F_, H, ca.body[0].weight, ca.body[0].bias, ca.body[2].weight, ca.body[2].bias, Hn, dtype=dt,
-                         c=nf, alpha=0.2)
+                         c=nfk, alpha=0.2)
+            S[f"k{b}.h"], S[f"k{b}.a"], S[f"k{b}.f"] = H, A, F_
             H = Hn
+        S["k.hlast"] = H
         kc = self.k_tail.cout
         kraw = self._buf("sr.k.raw", (N, kc, kh, kw), f32)
         self._conv(H, self.k_tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=kraw)
@@ -548,6 +553,7 @@ class DenoiseEngine:
         cin0 = C + self.head_extra
         r0 = self._buf("sr.r0", (N, Hp, Wp, cp(cin0)))
         ops.pack_input(x, r0, dtype=dt, sf=sf, extra=extra, extra_is_map=False, extra_sqrt_mask=sqrt_mask)
+        S["r0"] = r0
         hh, ww = Hp, Wp
         X = self._buf("sr.X.head", (N, hh, ww, nfeat[0]))
         Act = self._buf("sr.A.head", (N, hh, ww, nfeat[0]))
@@ -556,20 +562,24 @@ class DenoiseEngine:
         for ii, (res, ds) in enumerate(self.down):
             c = nfeat[ii]
             for b, (c1, c2) in enumerate(res):
-                Bt = self._buf(f"sr.d{ii}.{b}.B", (N, hh, ww, c))
-                self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out2=Bt, alpha=0.2, sft=sft[(ii, b, "sft2")])
-                Xn = self._buf(f"sr.d{ii}.{b}.X", (N, hh, ww, c))
-                last = b == len(res) - 1
-                if last:
+                tag = f"d{ii}.{b}"
+                Bt = self._buf(f"sr.{tag}.B", (N, hh, ww, c))
+                F1 = self._buf(f"sr.{tag}.F1", (N, hh, ww, c)) if save else None
+                # conv1 emits a2 = lrelu(fea1 * mul2 + add2); training also keeps fea1 (needed for d mul2)
+                self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out1=F1, out2=Bt, alpha=0.2, sft=sft[(ii, b, "sft2")])
+                S[tag + ".x"], S[tag + ".a"], S[tag + ".f1"], S[tag + ".b"] = X, Act, F1, Bt
+                Xn = self._buf(f"sr.{tag}.X", (N, hh, ww, c))
+                if b == len(res) - 1:
                     self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn)
                     X, Act = Xn, None
                 else:
-                    An = self._buf(f"sr.d{ii}.{b}.A", (N, hh, ww, c))
+                    An = self._buf(f"sr.{tag}.A", (N, hh, ww, c))
                     self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2,
                                sft=sft[(ii, b + 1, "sft1")])
                     X, Act = Xn, An
             if ds is not None:
                 bridges.append(X)
+                S[f"d{ii}.xlast"] = X
                 h2, w2 = (hh + 1) // 2, (ww + 1) // 2
                 Xd = self._buf(f"sr.d{ii}.ds.X", (N, h2, w2, nfeat[ii + 1]))
                 Ad = self._buf(f"sr.d{ii}.ds.A", (N, h2, w2, nfeat[ii + 1]))
@@ -580,22 +590,170 @@ class DenoiseEngine:
         for k, (us, res) in enumerate(self.up):
             lvl = self.depth - 2 - k
             c = nfeat[lvl]
+            S[f"u{k}.x"] = X
             hh, ww = dims[lvl]
             Xu = self._buf(f"sr.u{k}.us.X", (N, hh, ww, c))
             Au = self._buf(f"sr.u{k}.us.A", (N, hh, ww, c))
             self._conv(X, us, VK_CONVT2X2_S2, ldo=c, resid=bridges[lvl], out1=Xu, out2=Au, alpha=0.2)
             X, Act = Xu, Au
             for b, (c1, c2) in enumerate(res):
+                S[f"u{k}.{b}.a"] = Act
                 Bt = self._buf(f"sr.u{k}.{b}.B", (N, hh, ww, c))
                 self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out2=Bt, alpha=0.2)
+                S[f"u{k}.{b}.b"] = Bt
                 Xn = self._buf(f"sr.u{k}.{b}.X", (N, hh, ww, c))
                 last = b == len(res) - 1
                 An = None if last else self._buf(f"sr.u{k}.{b}.A", (N, hh, ww, c))
                 self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2)
                 X, Act = Xn, An
+        S["tail.x"] = X
         # tail: + bias, crop, + x_up (the nearest-upsampled LR image, AttResUNet.py:173) -> NCHW fp32
         x_up = self._buf("sr.xup", (N, C, Hh, Ww), f32)
         ops.upsample_nearest_nchw(x, x_up, sf)
         mu = torch.empty(N, C, Hh, Ww, device=dev, dtype=f32)
         self._conv(X, self.tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, resid=x_up, out1=mu, crop=(Hh, Ww))
+        if save:
+            S["x"], S["sigma"], S["kinfo"], S["extra"], S["sft"] = x, sigma, kinfo, extra, sft
+            S["shape"] = (N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask)
+            self.saved = S
         return mu, kinfo, sigma
+
+    def _sft_block_bwd(self, ii, b, c1, c2, gX, shape, dm, dd):
+        """Backward of one SFT-modulated AttResBlock (AttResUNet.py:48-60); returns the gradient w.r.t. its input."""
+        S = self.saved
+        N, hh, ww, c = shape
+        tag = f"d{ii}.{b}"
+        m1 = S["sft"][(ii, b, "sft1")][0]
+        m2 = S["sft"][(ii, b, "sft2")][0]
+        self._wgrad(c2, gX, S[tag + ".b"], VK_CONV3X3_S1)
+        G2 = self._buf(f"g.sr.{tag}.G2", (N, hh, ww, c))
+        self._dgrad(gX, c2, VK_CONV3X3_S1, c, ldo=c, mask=S[tag + ".b"], out1=G2, alpha=0.2)
+        gF1 = self._buf(f"g.sr.{tag}.F1", (N, hh, ww, c))
+        ops.sft_bwd(G2, S[tag + ".f1"], m2, gF1, dm[(ii, b, "sft2")], dd[(ii, b, "sft2")], dtype=self.dtype, c=c)
+        self._wgrad(c1, gF1, S[tag + ".a"], VK_CONV3X3_S1)
+        G1 = self._buf(f"g.sr.{tag}.G1", (N, hh, ww, c))
+        self._dgrad(gF1, c1, VK_CONV3X3_S1, c, ldo=c, mask=S[tag + ".a"], out1=G1, alpha=0.2)
+        gXp = self._buf(f"g.sr.{tag}.X", (N, hh, ww, c))
+        ops.sft_bwd(G1, S[tag + ".x"], m1, gXp, dm[(ii, b, "sft1")], dd[(ii, b, "sft1")], dtype=self.dtype, c=c, resid=gX)
+        return gXp
+
+    def backward_sr(self, g_mu, g_kinfo, g_sigma):
+        """Accumulates the gradients of every parameter (SNet, KNet, RNet incl. the SFT MLPs) into flat_grads."""
+        S = self.saved
+        if S is None or "sft" not in S:
+            raise _l.VkError("backward_sr called without a saved super-resolution forward")
+        N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask = S["shape"]
+        dt, dev, f32 = self.dtype, S["x"].device, torch.float32
+        cp = lambda c: ops.chan_pad(c, dt)
+        nf = self.n_feat
+        net = self.net
+        kc, sc = self.k_tail.cout, self.sigma_chn
+        E = kc + sc
+        self.flat_grads.zero_()
+        self.flat_ws.zero_()
+        if self.wgrad_side_stream and self._wg_stream is None:
+            self._wg_stream = torch.cuda.Stream(device=dev)
+            self._wg_events = [torch.cuda.Event() for _ in range(8)]
+        if not self.wgrad_side_stream:
+            self._wg_stream = None
+        d_extra = torch.zeros(N, E, device=dev, dtype=f32)
+        if g_mu is not None:
+            G = self._buf("g.sr.mu", (N, Hp, Wp, cp(C)))
+            ops.pack_grad(g_mu.contiguous().float(), G, dtype=dt)
+            self._wgrad(self.tail, G, S["tail.x"], VK_CONV3X3_S1)
+            hh, ww = dims[0]
+            gX = self._buf("g.sr.tail.X", (N, hh, ww, nf[0]))
+            self._dgrad(G, self.tail, VK_CONV3X3_S1, nf[0], ldo=nf[0], out1=gX)
+            g_bridge = {}
+            for k in reversed(range(len(self.up))):
+                us, res = self.up[k]
+                lvl = self.depth - 2 - k
+                c = nf[lvl]
+                hh, ww = dims[lvl]
+                for b in reversed(range(len(res))):
+                    gX = self._resblock_bwd(f"u{k}.{b}", res[b][0], res[b][1], gX, (N, hh, ww, c))
+                g_bridge[lvl] = gX
+                self._wgrad(us, S[f"u{k}.x"], gX, VK_CONVT2X2_S2)
+                ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt)
+                hl, wl = dims[lvl + 1]
+                gXl = self._buf(f"g.sr.u{k}.low", (N, hl, wl, nf[lvl + 1]))
+                self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
+                gX = gXl
+            dm, dd = {}, {}
+            for key, (mul, _) in S["sft"].items():
+                dm[key] = torch.zeros_like(mul)
+                dd[key] = torch.zeros_like(mul)
+            for ii in reversed(range(self.depth)):
+                res, ds = self.down[ii]
+                c = nf[ii]
+                hh, ww = dims[ii]
+                if ds is not None:
+                    self._wgrad(ds, gX, S[f"d{ii}.xlast"], VK_CONV3X3_S2)
+                    gXf = self._buf(f"g.sr.d{ii}.ds", (N, hh, ww, c))
+                    self._dgrad(gX, ds, VK_CONV3X3_S2_DGRAD, c, ldo=c, resid=g_bridge[ii], out1=gXf, out_hw=(hh, ww))
+                    gX = gXf
+                for b in reversed(range(len(res))):
+                    gX = self._sft_block_bwd(ii, b, res[b][0], res[b][1], gX, (N, hh, ww, c), dm, dd)
+            # head conv: weight gradient, and the gradient w.r.t. its (per-sample constant) conditioning channels
+            self._wgrad(self.head, gX, S["r0"], VK_CONV3X3_S1)
+            cin0 = C + self.head_extra
+            gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))
+            self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
+            hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
+            for n in range(N):
+                ops.channel_sum(gR0[n], cin0, hsum[n], dtype=dt)
+            # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values
+            rnet = net.RNet
+            for (ii, b, which), _ in S["sft"].items():
+                att = getattr(rnet.down_path[ii].body[b], which)
+                ops.sft_mlp_bwd(S["extra"], att, dm[(ii, b, which)], dd[(ii, b, which)], self.grad_view, d_extra,
+                                sqrt_mask=sqrt_mask)
+            # the head saw [kinfo, sqrt(sigma)] as constant planes: chain the sqrt for the variance channels
+            hext = hsum[:, C:C + E].clone()
+            hext[:, kc:] = hext[:, kc:] * 0.5 / S["extra"][:, kc:].sqrt().clamp_min(1e-20)
+            d_extra += hext
+        gk = d_extra[:, :kc].clone()
+        if g_kinfo is not None:
+            gk += g_kinfo.reshape(N, kc).float()
+        gs = d_extra[:, kc:].clone()
+        if g_sigma is not None:
+            gs += g_sigma.reshape(N, sc).float()
+        # ---- KNet ----
+        knet = net.KNet
+        nfk = knet.head.out_channels
+        Gt = self._buf("g.sr.k.tail", (N, kh, kw, cp(kc)))
+        ops.gap_head_bwd(gk.contiguous(), S["kinfo"], Gt, dtype=dt, c=kc, exp_mask=0b011, tanh_mask=1 << (kc - 1),
+                         lo=KNET_LOG_MIN, hi=KNET_LOG_MAX)
+        self._wgrad(self.k_tail, Gt, S["k.hlast"], VK_CONV3X3_S1)
+        gH = self._buf("g.sr.k.h", (N, kh, kw, cp(nfk)))
+        self._dgrad(Gt, self.k_tail, VK_CONV3X3_S1, nfk, ldo=cp(nfk), out1=gH)
+        for b in reversed(range(len(self.k_blocks))):
+            c1, c2, ca = self.k_blocks[b]
+            dF = self._buf(f"g.sr.k{b}.df", (N, kh, kw, cp(nfk)))
+            ops.ca_layer_bwd(gH, S[f"k{b}.f"], ca, dF, self.grad_view, dtype=dt, c=nfk)
+            self._wgrad(c2, dF, S[f"k{b}.a"], VK_CONV3X3_S1)
+            gA = self._buf(f"g.sr.k{b}.ga", (N, kh, kw, cp(nfk)))
+            self._dgrad(dF, c2, VK_CONV3X3_S1, nfk, ldo=cp(nfk), mask=S[f"k{b}.a"], out1=gA, alpha=0.2)
+            self._wgrad(c1, gA, S[f"k{b}.h"], VK_CONV3X3_S1)
+            gHn = self._buf(f"g.sr.k{b}.gh", (N, kh, kw, cp(nfk)))
+            self._dgrad(gA, c1, VK_CONV3X3_S1, nfk, ldo=cp(nfk), resid=gH, out1=gHn)
+            gH = gHn
+        ops.knet_head_wgrad(S["x"], gH, self.grad_view(knet.head.weight), dtype=dt)
+        # ---- SNet (global average head) ----
+        GS = self._buf("g.sr.sig", (N, h, w, cp(sc)))
+        ops.gap_head_bwd(gs.contiguous(), S["sigma"].reshape(N, sc), GS, dtype=dt, c=sc, exp_mask=(1 << sc) - 1,
+                         lo=SNET_LOG_MIN, hi=SNET_LOG_MAX)
+        g = GS
+        nS = len(self.s_layers)
+        for i in reversed(range(nS)):
+            ly = self.s_layers[i]
+            inp = S["xs"] if i == 0 else S[f"s{i - 1}"]
+            self._wgrad(ly, g, inp, VK_CONV3X3_S1)
+            if i > 0:
+                gn = self._buf(f"g.sr.s{i - 1}", (N, h, w, cp(ly.cin)))
+                self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
+                g = gn
+        if self._wg_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._wg_stream)
+        ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
+        self.saved = None

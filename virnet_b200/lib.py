@@ -99,6 +99,14 @@ _SIGNATURES = {
     "vk_sft_mlp": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                              C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vk_sft_bwd": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p]),
+    "vk_sft_mlp_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_float] + [C.c_void_p] * 12),
+    "vk_ca_layer_bwd": (C.c_int, [C.c_int32] + [C.c_void_p] * 11 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
+    "vk_gap_head_bwd": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
+                                  C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vk_knet_head_wgrad": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vk_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
     "vk_sizeof_conv_args": (C.c_uint32, []),
     "vk_version": (C.c_char_p, []),

@@ -47,6 +47,25 @@ class _WholeNetFn(torch.autograd.Function):
         return (None, None) + grads
 
 
+class _SRNetFn(torch.autograd.Function):
+    """One autograd node for SNet + KNet + the SFT-modulated RNet (parameter gradients only: the reference never
+    differentiates w.r.t. the LR image, train_SISR.py)."""
+
+    @staticmethod
+    def forward(ctx, x, sf, engine, *params):
+        need_grad = any(ctx.needs_input_grad[3:])
+        mu, kinfo, sigma = engine.forward_sr(x, sf, save=need_grad)
+        ctx.engine, ctx.params = engine, params
+        return mu, kinfo, sigma
+
+    @staticmethod
+    def backward(ctx, g_mu, g_kinfo, g_sigma):
+        eng = ctx.engine
+        eng.backward_sr(g_mu, g_kinfo, g_sigma)
+        grads = tuple(eng.grad_view(p).clone() if p.requires_grad else None for p in ctx.params)
+        return (None, None, None) + grads
+
+
 class VIRAttResUNet(nn.Module):
     """Denoising: sigma = exp(clamp(SNet(x))), mu = RNet(x, sqrt(sigma)); returns (mu, sigma)."""
 
@@ -97,11 +116,7 @@ class VIRAttResUNetSR(nn.Module):
         return self._engine
 
     def forward(self, x, sf):
-        """(mu, kinfo_est [N,3], sigma [N,1,1,1]) as networks/VIRNet.py:80-97.  Forward only in this round: the
-        backward pass of the SISR rows is not built, so calling it with autograd
-        recording and trainable parameters raises instead of returning tensors that silently lack a graph."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("VIRAttResUNetSR: only the forward (inference) path is built; call it under "
-                                      "torch.no_grad() / .eval()")
-        with torch.no_grad():
-            return self.engine().forward_sr(x, int(sf))
+        """(mu, kinfo_est [N,3], sigma [N,1,1,1]) as networks/VIRNet.py:80-97; differentiable w.r.t. the parameters."""
+        eng = self.engine()
+        params = tuple(self.parameters())
+        return _SRNetFn.apply(x, int(sf), eng, *params)

@@ -336,3 +336,60 @@ def upsample_nearest_nchw(x, out, sf):
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.shape == (n, c, h * sf, w * sf)
     with _Prof("upsample_nearest"):
         _l.check(_l.load().vk_upsample_nearest(_ptr(x), _ptr(out), n, c, h, w, sf, _stream()), "vk_upsample_nearest")
+
+
+# ---------------------------------------------------------------------------
+# backward of the super-resolution network's small layers
+# ---------------------------------------------------------------------------
+def sft_bwd(g, x, mul, gx, dmul, dadd, *, dtype, c, resid=None):
+    """gx = g * mul (+ resid); dmul/dadd [n, c] += sums over pixels of g * x and g.  NHWC tensors [n, h, w, ld]."""
+    n, ld = g.shape[0], g.shape[-1]
+    npix = g.shape[1] * g.shape[2]
+    for t in (g, x, gx) + ((resid,) if resid is not None else ()):
+        assert t.is_contiguous() and t.shape == g.shape
+    assert mul.shape == (n, c) and dmul.shape == (n, c) and dadd.shape == (n, c)
+    with _Prof("sft_bwd"):
+        _l.check(_l.load().vk_sft_bwd(dtype, _ptr(g), _ptr(x), _ptr(mul), _ptr(resid), _ptr(gx), _ptr(dmul), _ptr(dadd), n,
+                                      npix, c, ld, _stream()), "vk_sft_bwd")
+
+
+def sft_mlp_bwd(extra, att, dmul, dadd, grads, d_extra, *, sqrt_mask=0, alpha=0.2):
+    """att: AttLayer container; grads: dict parameter -> gradient view (accumulated); d_extra [n, e] accumulated."""
+    n, e = extra.shape
+    c1, c2, c = att.conv1.out_channels, att.conv2.out_channels, att.mul_conv.out_channels
+    gp = [grads(p) for p in (att.conv1.weight, att.conv1.bias, att.conv2.weight, att.conv2.bias, att.mul_conv.weight,
+                             att.mul_conv.bias, att.add_conv.weight, att.add_conv.bias)]
+    with _Prof("sft_mlp_bwd"):
+        _l.check(_l.load().vk_sft_mlp_bwd(
+            _ptr(extra), n, e, sqrt_mask, _ptr(att.conv1.weight), _ptr(att.conv1.bias), c1, _ptr(att.conv2.weight),
+            _ptr(att.conv2.bias), c2, _ptr(att.mul_conv.weight), _ptr(att.mul_conv.bias), _ptr(att.add_conv.weight),
+            _ptr(att.add_conv.bias), c, alpha, _ptr(dmul), _ptr(dadd), *[_ptr(t) for t in gp], _ptr(d_extra), _stream()),
+            "vk_sft_mlp_bwd")
+
+
+def ca_layer_bwd(g, f, ca, df, grads, *, dtype, c, alpha=0.2):
+    """ca: CALayer container (body[0], body[2] 1x1 convs); df = g * s + dy / npix; parameter grads accumulated."""
+    n, ld = g.shape[0], g.shape[-1]
+    npix = g.shape[1] * g.shape[2]
+    w1, b1, w2, b2 = ca.body[0].weight, ca.body[0].bias, ca.body[2].weight, ca.body[2].bias
+    with _Prof("ca_layer_bwd"):
+        _l.check(_l.load().vk_ca_layer_bwd(dtype, _ptr(g), _ptr(f), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(df),
+                                           _ptr(grads(w1)), _ptr(grads(b1)), _ptr(grads(w2)), _ptr(grads(b2)), n, npix, c,
+                                           w1.shape[0], ld, alpha, _stream()), "vk_ca_layer_bwd")
+
+
+def gap_head_bwd(gout, outv, gx, *, dtype, c, exp_mask=0, tanh_mask=0, lo=0.0, hi=0.0):
+    """gx NHWC [n, h, w, ld] = gout[n, c] * head'(outv[n, c]) / (h * w)."""
+    n, ld = gx.shape[0], gx.shape[-1]
+    hw = gx.shape[1] * gx.shape[2]
+    assert gout.is_contiguous() and outv.is_contiguous() and gout.numel() == n * c and outv.numel() == n * c
+    with _Prof("gap_head_bwd"):
+        _l.check(_l.load().vk_gap_head_bwd(dtype, _ptr(gout), _ptr(outv), n, c, hw, exp_mask, tanh_mask, lo, hi, _ptr(gx),
+                                           ld, _stream()), "vk_gap_head_bwd")
+
+
+def knet_head_wgrad(x, g, gw, *, dtype):
+    n, c, h, wd = x.shape
+    with _Prof("knet_head_wgrad"):
+        _l.check(_l.load().vk_knet_head_wgrad(dtype, _ptr(x), _ptr(g), _ptr(gw), n, c, h, wd, gw.shape[0], g.shape[-1],
+                                              _stream()), "vk_knet_head_wgrad")
