@@ -285,6 +285,118 @@ def elbo_denoising_simple(mu, sigma_est, im_noisy, im_gt, eps2, alpha0, beta0):
 
 
 # --------------------------------------------------------------------------------------
+# SISR loss restatement (loss/ELBO_simple.py:55-138, utils/util_sisr.py:26-58,127-144,
+# ResizeRight/resize_right.py:29-76,146-320, ResizeRight/interp_methods.py:34-42)
+# --------------------------------------------------------------------------------------
+def _cubic(x):
+    """ResizeRight/interp_methods.py:34-42 (Keys cubic, a = -0.5), numpy float64."""
+    import numpy as np
+    ax = np.abs(x)
+    ax2, ax3 = ax ** 2, ax ** 3
+    return ((1.5 * ax3 - 2.5 * ax2 + 1.0) * (ax <= 1.0) +
+            (-0.5 * ax3 + 2.5 * ax2 - 4.0 * ax + 2.0) * ((1.0 < ax) & (ax <= 2.0)))
+
+
+def resize_matrix(in_sz: int, sf: int, downsampler: str = "bicubic"):
+    """The 1-D operator applied along one axis by `conv_multi_kernel_tensor`'s down-sampler, as a dense
+    [out_sz, in_sz] float32 matrix.  'direct': rows select every sf-th sample (util_sisr.py:137-138).
+    'bicubic': ResizeRight.resize(scale_factors=1/sf), antialiased cubic — projected grid
+    (resize_right.py:251-262), field of view with mirror folding (:265-285), stretched kernel
+    (:304-315), weights normalised per output (:288-299); torch float32 arithmetic as the reference runs it."""
+    import numpy as np
+    if downsampler.lower() == "direct":
+        out_sz = (in_sz + sf - 1) // sf
+        m = np.zeros((out_sz, in_sz), dtype=np.float32)
+        m[np.arange(out_sz), np.arange(out_sz) * sf] = 1.0
+        return torch.from_numpy(m)
+    if downsampler.lower() != "bicubic":
+        raise ValueError("downsampler must be Direct or Bicubic")
+    scale = 1.0 / sf
+    out_sz = int(math.ceil(scale * in_sz))
+    eps = float(np.finfo(np.float32).eps)
+    support = 4.0 / scale
+    # the reference evaluates these in torch: arange is int64, divisions promote to float32
+    grid = (torch.arange(out_sz) / scale + (in_sz - 1) / 2 - (out_sz - 1) / (2 * scale))
+    left = (grid - support / 2 - eps).ceil().long()
+    fov = left[:, None] + torch.arange(int(math.ceil(support - eps)))
+    mirror = torch.cat((torch.arange(in_sz), torch.arange(in_sz - 1, -1, -1)))
+    fov = mirror[torch.remainder(fov, mirror.shape[0])]
+    d = (grid[:, None] - fov).to(torch.float32)
+    w = scale * torch.from_numpy(_cubic((scale * d).numpy().astype(np.float32)).astype(np.float32))
+    sw = w.sum(1, keepdim=True)
+    sw[sw == 0] = 1
+    w = w / sw
+    m = torch.zeros(out_sz, in_sz, dtype=torch.float32)
+    m.scatter_add_(1, fov, w)
+    return m
+
+
+def sigma2kernel(k_cov: Tensor, k_size: int, sf: int, shift: bool) -> Tensor:
+    """utils/util_sisr.py:26-58: softmax over the k x k grid of -0.5 z^T Sigma^-1 z; N x 1 x k x k."""
+    inv = torch.inverse(k_cov)
+    center = k_size // 2 + 0.5 * (sf - k_size % 2) if shift else k_size // 2
+    ax = torch.arange(k_size, dtype=k_cov.dtype)
+    X, Y = torch.meshgrid(ax, ax, indexing="ij")
+    Z = torch.stack((X, Y), dim=2).view(1, -1, 2, 1) - center
+    q = -0.5 * Z.transpose(2, 3).matmul(inv).matmul(Z).squeeze(-1).squeeze(-1)
+    return F.softmax(q, dim=1).view(-1, 1, k_size, k_size)
+
+
+def blur_downsample(im_hr: Tensor, kernel: Tensor, sf: int, downsampler: str) -> Tensor:
+    """utils/util_sisr.py:127-144: reflect pad k//2, per-sample cross-correlation (grouped conv3d), then
+    ::sf sampling or the antialiased cubic resize along H and W."""
+    n, c, h, w = im_hr.shape
+    k = kernel.shape[-1]
+    pad = F.pad(im_hr, (k // 2,) * 4, mode="reflect")
+    blur = F.conv2d(pad.reshape(1, n * c, h + k - 1, w + k - 1),
+                    kernel.expand(n, c, k, k).reshape(n * c, 1, k, k), groups=n * c).view(n, c, h, w)
+    mh, mw = resize_matrix(h, sf, downsampler), resize_matrix(w, sf, downsampler)
+    return torch.einsum("yh,nchw,xw->ncyx", mh.to(blur), blur, mw.to(blur))
+
+
+def elbo_sisr(mu, sigma_est, kinfo_est, im_hr, im_lr, sigma_prior, alpha0, kinfo_gt, kappa0, r2, eps2, sf, k_size,
+              penalty_K, shift, downsampler, *, gamma_draw, rho_draw, z_draw):
+    """loss/ELBO_simple.py:82-138 with the three random draws made explicit:
+      gamma_draw [N,2] ~ Gamma(kappa0-1, 1)  (Gamma(alpha, beta).rsample() == gamma_draw / beta, :61-64)
+      rho_draw   [N,1] ~ N(0,1)              (:76)
+      z_draw     like mu ~ N(0,1)            (:56)
+    Returns (loss, [lh, kl_rnet, kl_snet, kl_knet, kl_knet0, kl_knet1, kl_knet2, kernel])."""
+    kl_rnet = kl_gauss_simple(mu, im_hr, eps2)
+    beta0 = sigma_prior * alpha0
+    beta = sigma_est * alpha0
+    kl_snet = kl_inverse_gamma_simple(beta, alpha0 - 1, beta0)
+    kl_k0 = kl_inverse_gamma_simple(kappa0 * kinfo_est[:, 0], kappa0 - 1, kappa0 * kinfo_gt[:, 0])
+    kl_k1 = kl_inverse_gamma_simple(kappa0 * kinfo_est[:, 1], kappa0 - 1, kappa0 * kinfo_gt[:, 1])
+    kl_k2 = kl_gauss_simple(kinfo_est[:, 2], kinfo_gt[:, 2], r2) * penalty_K[0]
+    kl_knet = (kl_k0 + kl_k1 + kl_k2) / 3 * penalty_K[1]
+    # reparameterised covariance (:66-80)
+    k_var = 1.0 / (gamma_draw / (kinfo_est[:, :2] * kappa0))
+    v1, v2 = torch.chunk(k_var, 2, dim=1)
+    rho = kinfo_est[:, 2].unsqueeze(1) + math.sqrt(r2) * rho_draw
+    direction = v1.detach().sqrt() * v2.detach().sqrt() * torch.clamp(rho, min=-1, max=1)
+    k_cov = torch.cat([v1, direction, direction, v2], dim=1).view(-1, 1, 2, 2)
+    kernel = sigma2kernel(k_cov, k_size, sf, shift)
+    # likelihood (:55-59)
+    zz = mu + z_draw * math.sqrt(eps2)
+    zz_blur = blur_downsample(zz, kernel, sf, downsampler)
+    alpha_q = torch.as_tensor(alpha0 - 1, dtype=torch.float32)
+    lh = (0.5 * math.log(2 * math.pi) + 0.5 * (beta.log() - torch.digamma(alpha_q)) +
+          0.5 * alpha_q / beta * (im_lr - zz_blur) ** 2).mean()
+    loss = lh + kl_rnet + kl_snet + kl_knet
+    return loss, [lh, kl_rnet, kl_snet, kl_knet, kl_k0, kl_k1, kl_k2, kernel]
+
+
+def reference_draws(n: int, mu_shape, kappa0: float, generator=None, device="cpu"):
+    """The reference's draw ORDER (Gamma rsample -> randn_like(rho) -> randn_like(mu)) on torch's global
+    generator: calling this right after the same `torch.manual_seed` reproduces what elbo_sisr consumes."""
+    conc = torch.full((n, 2), float(kappa0 - 1), device=device)
+    gamma_draw = torch._standard_gamma(conc)
+    rho_draw = torch.randn(n, 1, device=device)
+    z_draw = torch.randn(*mu_shape, device=device)
+    return gamma_draw, rho_draw, z_draw
+
+
+# --------------------------------------------------------------------------------------
 # one reference training step (train_denoising_syn.py:175-184), used as the CPU baseline
 # --------------------------------------------------------------------------------------
 def clip_grad_norm_(params: List[Tensor], max_norm: float) -> Tensor:
