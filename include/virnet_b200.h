@@ -194,6 +194,48 @@ int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, float* gw, 
 int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
                         void* stream);
 
+/* ---- super-resolution negative ELBO ------------------------------------- */
+
+/* loss/ELBO_simple.py:82-138 (elbo_sisr) with its helpers (:55-80), utils/util_sisr.py:26-58 (sigma2kernel) and
+ * :127-144 (conv_multi_kernel_tensor), and ResizeRight/resize_right.py:29-76 as the dense 1-D operators rh / rw.
+ * One call computes the 8 scalar terms AND the gradients of `loss` w.r.t. mu, sigma_est and kinfo_est.
+ * All tensors are fp32, images NCHW.  The three random draws the reference makes inside the loss are inputs:
+ * gamma_draw [n][2] ~ Gamma(kappa0-1, 1), rho_draw [n] ~ N(0,1), z_draw like mu ~ N(0,1).
+ * prior_mean / prior_logmean [n]: per-sample mean of sigma_prior and of log(sigma_prior) (equal to
+ * sigma_prior and its log for the N x 1 x 1 x 1 Gaussian-noise prior of train_SISR.py:202).
+ * terms[8] = loss, lh, kl_rnet, kl_snet, kl_knet, kl_knet0, kl_knet1, kl_knet2 (the reference's return order);
+ * kernel [n][k_size*k_size] is the re-sampled blur kernel (last entry of the reference's detail list). */
+typedef struct vk_elbo_sisr_args {
+  const float* mu;            /* [n][c][H][W] */
+  const float* im_hr;         /* [n][c][H][W] */
+  const float* im_lr;         /* [n][c][h][w] */
+  const float* sigma_est;     /* [n] */
+  const float* kinfo_est;     /* [n][3] */
+  const float* kinfo_gt;      /* [n][3] */
+  const float* prior_mean;    /* [n] */
+  const float* prior_logmean; /* [n] */
+  const float* gamma_draw;    /* [n][2] */
+  const float* rho_draw;      /* [n] */
+  const float* z_draw;        /* [n][c][H][W] */
+  const float* rh;            /* [h][H] down-sampling operator along rows */
+  const float* rw;            /* [w][W] down-sampling operator along columns */
+  float* d_mu;                /* [n][c][H][W] */
+  float* d_sigma;             /* [n] */
+  float* d_kinfo;             /* [n][3] */
+  float* kernel;              /* [n][k_size*k_size] */
+  float* terms;               /* [8] */
+  void* ws;                   /* workspace of at least vk_elbo_sisr_ws_bytes() bytes */
+  int64_t ws_bytes;
+  int32_t n, c, H, W, h, w, k_size;
+  float center;               /* kernel centre: k_size/2, + 0.5*(sf - k_size%2) when shifted (util_sisr.py:43-46) */
+  float alpha0, digamma_am1;  /* digamma(alpha0 - 1) */
+  float kappa0, r2, eps2, pk0, pk1;
+} vk_elbo_sisr_args;
+
+int64_t vk_elbo_sisr_ws_bytes(int32_t n, int32_t c, int32_t H, int32_t W, int32_t h, int32_t w, int32_t k_size);
+uint32_t vk_sizeof_elbo_sisr_args(void);
+int vk_elbo_sisr(const vk_elbo_sisr_args* args, void* stream);
+
 /* ---- HBM-bound kernels ------------------------------------------------- */
 
 /* NCHW fp32 image (+ conditioning channels) -> NHWC `dtype`, reflect-padded bottom/right

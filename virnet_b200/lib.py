@@ -58,6 +58,15 @@ class vk_wgrad_args(C.Structure):
     ]
 
 
+class vk_elbo_sisr_args(C.Structure):
+    _fields_ = ([(k, C.c_void_p) for k in ("mu", "im_hr", "im_lr", "sigma_est", "kinfo_est", "kinfo_gt", "prior_mean",
+                                           "prior_logmean", "gamma_draw", "rho_draw", "z_draw", "rh", "rw", "d_mu",
+                                           "d_sigma", "d_kinfo", "kernel", "terms", "ws")] +
+                [("ws_bytes", C.c_int64)] +
+                [(k, C.c_int32) for k in ("n", "c", "H", "W", "h", "w", "k_size")] +
+                [(k, C.c_float) for k in ("center", "alpha0", "digamma_am1", "kappa0", "r2", "eps2", "pk0", "pk1")])
+
+
 class vk_pack_desc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
                 ("dim0", C.c_int32), ("dim1", C.c_int32), ("taps", C.c_int32),
@@ -108,6 +117,9 @@ _SIGNATURES = {
                                   C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "vk_knet_head_wgrad": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vk_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
+    "vk_elbo_sisr_ws_bytes": (C.c_int64, [C.c_int32] * 7),
+    "vk_sizeof_elbo_sisr_args": (C.c_uint32, []),
+    "vk_elbo_sisr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vk_sizeof_conv_args": (C.c_uint32, []),
     "vk_version": (C.c_char_p, []),
     "vk_launch_count": (C.c_uint64, []),
@@ -133,7 +145,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     if (lib.vk_sizeof_conv_args() != C.sizeof(vk_conv_args)
-            or lib.vk_sizeof_wgrad_args() != C.sizeof(vk_wgrad_args)):
+            or lib.vk_sizeof_wgrad_args() != C.sizeof(vk_wgrad_args)
+            or lib.vk_sizeof_elbo_sisr_args() != C.sizeof(vk_elbo_sisr_args)):
         raise VkError("argument struct layout mismatch between lib.py and the built library; rebuild")
     _lib = lib
     return lib

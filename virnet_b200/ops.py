@@ -393,3 +393,51 @@ def knet_head_wgrad(x, g, gw, *, dtype):
     with _Prof("knet_head_wgrad"):
         _l.check(_l.load().vk_knet_head_wgrad(dtype, _ptr(x), _ptr(g), _ptr(gw), n, c, h, wd, gw.shape[0], g.shape[-1],
                                               _stream()), "vk_knet_head_wgrad")
+
+
+# ---------------------------------------------------------------------------
+# super-resolution negative ELBO (forward value + gradients in one call)
+# ---------------------------------------------------------------------------
+_SISR_WS = {}
+
+
+def elbo_sisr(mu, im_hr, im_lr, sigma_est, kinfo_est, kinfo_gt, prior_mean, prior_logmean, gamma_draw, rho_draw,
+              z_draw, rh, rw, *, k_size, center, alpha0, digamma_am1, kappa0, r2, eps2, pk0, pk1):
+    """All tensors fp32 contiguous CUDA.  Returns (terms[8], kernel [n,1,k,k], d_mu, d_sigma [n], d_kinfo [n,3])."""
+    n, c, H, W = mu.shape
+    h, w = im_lr.shape[2], im_lr.shape[3]
+    for t in (mu, im_hr, im_lr, sigma_est, kinfo_est, kinfo_gt, prior_mean, prior_logmean, gamma_draw, rho_draw,
+              z_draw, rh, rw):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+    assert im_hr.shape == mu.shape and z_draw.shape == mu.shape and im_lr.shape[:2] == (n, c)
+    assert rh.shape == (h, H) and rw.shape == (w, W), "down-sampling operators do not match the LR / HR sizes"
+    assert sigma_est.numel() == n and kinfo_est.shape == (n, 3) and kinfo_gt.shape == (n, 3)
+    assert gamma_draw.shape == (n, 2) and rho_draw.numel() == n and prior_mean.numel() == n
+    lib = _l.load()
+    need = lib.vk_elbo_sisr_ws_bytes(n, c, H, W, h, w, k_size)
+    if need < 0:
+        raise _l.VkError("vk_elbo_sisr_ws_bytes: bad shape")
+    key = (mu.device, need)
+    ws = _SISR_WS.get(key)
+    if ws is None:
+        _SISR_WS.clear()
+        ws = torch.empty(need, dtype=torch.uint8, device=mu.device)
+        _SISR_WS[key] = ws
+    dev = mu.device
+    d_mu = torch.empty_like(mu)
+    d_sigma = torch.empty(n, device=dev, dtype=torch.float32)
+    d_kinfo = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    kernel = torch.empty(n, 1, k_size, k_size, device=dev, dtype=torch.float32)
+    terms = torch.empty(8, device=dev, dtype=torch.float32)
+    a = _l.vk_elbo_sisr_args()
+    a.mu, a.im_hr, a.im_lr, a.sigma_est = _ptr(mu), _ptr(im_hr), _ptr(im_lr), _ptr(sigma_est)
+    a.kinfo_est, a.kinfo_gt, a.prior_mean, a.prior_logmean = _ptr(kinfo_est), _ptr(kinfo_gt), _ptr(prior_mean), _ptr(prior_logmean)
+    a.gamma_draw, a.rho_draw, a.z_draw, a.rh, a.rw = _ptr(gamma_draw), _ptr(rho_draw), _ptr(z_draw), _ptr(rh), _ptr(rw)
+    a.d_mu, a.d_sigma, a.d_kinfo, a.kernel, a.terms = _ptr(d_mu), _ptr(d_sigma), _ptr(d_kinfo), _ptr(kernel), _ptr(terms)
+    a.ws, a.ws_bytes = _ptr(ws), need
+    a.n, a.c, a.H, a.W, a.h, a.w, a.k_size = n, c, H, W, h, w, k_size
+    a.center, a.alpha0, a.digamma_am1 = center, alpha0, digamma_am1
+    a.kappa0, a.r2, a.eps2, a.pk0, a.pk1 = kappa0, r2, eps2, pk0, pk1
+    with _Prof("elbo_sisr"):
+        _l.check(lib.vk_elbo_sisr(C.byref(a), _stream()), "vk_elbo_sisr")
+    return terms, kernel, d_mu, d_sigma, d_kinfo
