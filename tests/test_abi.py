@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def declared_functions():
     text = (ROOT / "include" / "virnet_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+)?(?:int|uint32_t|uint64_t|char\s*\*|const char\s*\*)\s+\**(vk_\w+)\s*\(", text, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|int64_t|uint32_t|uint64_t|char\s*\*|const char\s*\*)\s+\**(vk_\w+)\s*\(", text, flags=re.M)
     return sorted(set(names))
 
 
