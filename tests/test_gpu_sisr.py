@@ -106,3 +106,86 @@ def test_sisr_backward_then_inference_consistent():
     with torch.no_grad():
         mu2, _, _ = net(x, 4)
     assert torch.equal(mu2, mu_keep)
+
+
+def _sisr_batch(n, h, w, sf, seed=9):
+    g = torch.Generator().manual_seed(seed)
+    im_hr = torch.rand(n, 3, h * sf, w * sf, generator=g)
+    im_lr = torch.nn.functional.avg_pool2d(im_hr, sf) + 0.02 * torch.randn(n, 3, h, w, generator=g)
+    kinfo_gt = torch.stack([0.5 + 3 * torch.rand(n, generator=g), 0.5 + 3 * torch.rand(n, generator=g),
+                            torch.rand(n, generator=g) - 0.5], dim=1)
+    nlevel = (0.02 ** 2 * torch.ones(n, 1, 1, 1))
+    return im_hr, im_lr, kinfo_gt, nlevel
+
+
+def test_sisr_trainer_step_matches_oracle_step():
+    """One SISRTrainer.step (forward, SISR ELBO, backward, per-sub-network clip, Adam; kernel-only) vs the oracle
+    doing train_SISR.py:206-229 on the CPU with the same random draws; more steps must lower the loss."""
+    from oracle import virnet_oracle as O
+    from virnet_b200.trainer import SISRTrainer
+    sf, n, h, w = 4, 2, 16, 16
+    net, sd = make_sr("tf32", n_feat=(32, 64, 96), n_res=2, dep_K=3)
+    net.train()
+    cfg = O.NetCfg(n_feat=(32, 64, 96), n_resblocks=2, extra_mode="Both", noise_avg=True, sisr=True, dep_K=3)
+    im_hr, im_lr, kinfo_gt, nlevel = _sisr_batch(n, h, w, sf)
+    torch.manual_seed(77)
+    draws = O.reference_draws(n, im_hr.shape, 50.0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    mu, kinfo, sigma = O.vir_sisr_forward(params, im_lr, sf, cfg)
+    alpha0 = 0.5 * 9 ** 2
+    loss_o, det_o = O.elbo_sisr(mu, sigma, kinfo, im_hr, im_lr, nlevel, alpha0, kinfo_gt, 50.0, 1e-4, 1e-5, sf, 21,
+                                [0.02, 2], False, "Bicubic", gamma_draw=draws[0], rho_draw=draws[1], z_draw=draws[2])
+    loss_o.backward()
+    norms_o = {nm: O.clip_grad_norm_([v for k, v in params.items() if k.lower().startswith(nm.lower())], mx).item()
+               for nm, mx in (("RNet", 5e2), ("SNet", 1e2), ("KNet", 5e2))}
+    opt.step()
+
+    tr = SISRTrainer(net, sf, lr=1e-4, clip_grad_R=5e2, clip_grad_S=1e2, clip_grad_K=5e2)
+    batch = [t.cuda() for t in (im_hr, im_lr, kinfo_gt, nlevel)]
+    dd = tuple(d.cuda() for d in draws)
+    terms = tr.step(*batch, draws=dd).clone()
+    assert abs(terms[0].item() - loss_o.item()) < 5e-3 * abs(loss_o.item()), (terms.tolist(), loss_o.item())
+    for i in range(1, 8):
+        ref_v = det_o[i - 1].item()
+        assert abs(terms[i].item() - ref_v) < 1e-2 * max(abs(ref_v), 1e-3), (i, terms[i].item(), ref_v)
+    norms = dict(zip(tr.group_names, tr.grad_norms.tolist()))
+    for nm in ("RNet", "SNet", "KNet"):
+        assert abs(norms[nm] - norms_o[nm]) < 2e-2 * norms_o[nm], (nm, norms[nm], norms_o[nm])
+    agree = tot = 0
+    for name, p in net.named_parameters():
+        d_ours = p.detach().cpu() - sd[name]
+        d_ref = params[name].detach() - sd[name]
+        big = d_ref.abs() > 0.5e-4
+        agree += (torch.sign(d_ours[big]) == torch.sign(d_ref[big])).sum().item()
+        tot += big.sum().item()
+        assert (d_ours.abs() <= 1.0001e-4).all(), name
+    assert agree / tot > 0.97, agree / tot
+    first = terms[0].item()
+    for _ in range(30):
+        terms = tr.step(*batch, draws=dd)
+    assert terms[0].item() < 0.9 * first, (first, terms[0].item())
+
+
+def test_sisr_autograd_path_equals_trainer_path():
+    """net(...) -> elbo_sisr -> loss.backward() (what train_SISR.py calls) fills p.grad with the gradients the
+    fused trainer path uses."""
+    from virnet_b200.loss.ELBO_simple import elbo_sisr, sisr_draws
+    from virnet_b200.trainer import SISRTrainer
+    sf, n, h, w = 2, 2, 16, 20
+    net, _ = make_sr("tf32", n_feat=(32, 64, 96), n_res=1, dep_K=2)
+    net.train()
+    im_hr, im_lr, kinfo_gt, nlevel = [t.cuda() for t in _sisr_batch(n, h, w, sf)]
+    torch.manual_seed(5)
+    draws = sisr_draws(kinfo_gt, im_hr, 50.0)
+    mu, kinfo, sigma = net(im_lr, sf)
+    loss, detail = elbo_sisr(mu, sigma, kinfo, im_hr, im_lr, nlevel, torch.tensor([40.5]).cuda(), kinfo_gt,
+                             torch.tensor([50.0]).cuda(), 1e-4, 1e-5, sf, 21, [0.02, 2], False, "Bicubic", draws=draws)
+    loss.backward()
+    g_autograd = torch.cat([p.grad.flatten() for p in net.parameters()])
+    tr = SISRTrainer(net, sf, lr=0.0)
+    eng = net.engine()
+    terms = tr.step(im_hr, im_lr, kinfo_gt, nlevel, draws=draws)
+    g_fused = torch.cat([eng.grad_view(p).flatten() for p in net.parameters()])
+    assert abs(terms[0].item() - loss.item()) < 1e-5 * abs(loss.item())
+    assert rel(g_fused, g_autograd) < 1e-5

@@ -24,7 +24,26 @@ import torch.distributed as dist
 from . import dp
 from . import lib as _l
 from . import ops
-from .loss.ELBO_simple import _digamma
+from .loss.ELBO_simple import _digamma, sisr_draws
+from .loss.resize_right import downsample_matrix
+
+
+def _clip_groups(net, eng, spec):
+    """Contiguous ranges of the flat parameter buffer per sub-network: [(key, max_norm)] -> device descriptor table."""
+    names = [n for n, _ in net.named_parameters()]
+    groups = []
+    for key, max_norm in spec:
+        idx = [i for i, n in enumerate(names) if n.lower().startswith(key)]
+        assert idx and idx == list(range(idx[0], idx[-1] + 1)), "sub-network parameters must be contiguous"
+        begin = eng.flat_offsets[idx[0]]
+        end = eng.flat_offsets[idx[-1] + 1] if idx[-1] + 1 < len(names) else eng.flat_total
+        groups.append((begin, end, float(max_norm)))
+    arr = (_l.vk_adam_group * len(groups))()
+    for i, (b, e, m) in enumerate(groups):
+        arr[i].begin, arr[i].end, arr[i].max_norm = b, e, m
+    dev = eng.flat_params.device
+    table = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
+    return table, len(groups), max(e - b for b, e, _ in groups)
 
 
 class DenoiseTrainer:
@@ -155,3 +174,73 @@ class DenoiseTrainer:
         eng.mark_params_dirty()
         self.last_mu, self.last_sigma = mu, sigma
         return self.losses
+
+
+class SISRTrainer:
+    """The hot loop of the reference's train_SISR.py:197-229 as one kernel-only CUDA program per step:
+
+        im_hr, im_lr, kinfo_gt, sigma_prior
+          -> forward (SNet, KNet, SFT-modulated RNet)      DenoiseEngine.forward_sr
+          -> SISR negative ELBO + gradients                 vk_elbo_sisr
+          -> backward                                       DenoiseEngine.backward_sr
+          -> [world_size > 1] NCCL all-reduce of the flat gradient buffer
+          -> clip_grad_norm_ per sub-network (R / S / K) -> Adam   vk_adam_clip_step
+
+    The loss's random draws come from torch's CUDA generator in the reference's order (loss/ELBO_simple.py)."""
+
+    def __init__(self, net, sf, lr=1e-4, clip_grad_R=5e2, clip_grad_S=1e2, clip_grad_K=5e2, var_window=9, kappa0=50.0,
+                 r2=1e-4, eps2=1e-5, k_size=21, penalty_K=(0.02, 2), kernel_shift=False, downsampler="Bicubic",
+                 betas=(0.9, 0.999), adam_eps=1e-8, process_group=None):
+        self.net, self.sf = net, int(sf)
+        self.engine = eng = net.engine()
+        eng._ensure_flat()
+        dev = eng.flat_params.device
+        self.lr, self.betas, self.adam_eps = lr, betas, adam_eps
+        self.alpha0 = 0.5 * float(var_window) ** 2                       # train_SISR.py:180
+        self.kappa0, self.r2, self.eps2, self.k_size = float(kappa0), float(r2), float(eps2), int(k_size)
+        self.penalty_K, self.shift, self.downsampler = tuple(penalty_K), bool(kernel_shift), downsampler
+        self.pg = process_group
+        self.world = dp.world_size(process_group)
+        dp.broadcast_flat_params(eng.flat_params, 0, process_group)
+        self.step_count = 0
+        self.exp_avg = torch.zeros_like(eng.flat_params)
+        self.exp_avg_sq = torch.zeros_like(eng.flat_params)
+        self.group_names = ["RNet", "SNet", "KNet"]
+        self._groups_dev, self._ngroups, self._max_group = _clip_groups(
+            net, eng, (("rnet", clip_grad_R), ("snet", clip_grad_S), ("knet", clip_grad_K)))
+        self._sq_ws = torch.zeros(self._ngroups, device=dev, dtype=torch.float64)
+        self.grad_norms = torch.zeros(self._ngroups, device=dev, dtype=torch.float32)
+        self.losses = None
+
+    def step(self, im_hr, im_lr, kinfo_gt, sigma_prior, lr: Optional[float] = None, draws=None):
+        """One optimisation step; returns the device tensor [loss, lh, kl_rnet, kl_snet, kl_knet, kl_k0, kl_k1, kl_k2]."""
+        eng = self.engine
+        dev = eng.flat_params.device
+        im_hr, im_lr, kinfo_gt, sigma_prior = [t if t.is_cuda else t.to(dev, non_blocking=True)
+                                               for t in (im_hr, im_lr, kinfo_gt, sigma_prior)]
+        n = im_lr.shape[0]
+        mu, kinfo, sigma = eng.forward_sr(im_lr, self.sf, save=True)
+        if draws is None:
+            draws = sisr_draws(kinfo, mu, self.kappa0)
+        H, W = mu.shape[2], mu.shape[3]
+        rh = downsample_matrix(H, self.sf, self.downsampler, dev)
+        rw = downsample_matrix(W, self.sf, self.downsampler, dev)
+        sp = sigma_prior.float().expand(n, *sigma_prior.shape[1:]).reshape(n, -1)
+        center = self.k_size // 2 + 0.5 * (self.sf - self.k_size % 2) if self.shift else float(self.k_size // 2)
+        terms, kernel, d_mu, d_sigma, d_kinfo = ops.elbo_sisr(
+            mu, im_hr.contiguous(), im_lr.contiguous(), sigma.reshape(n), kinfo, kinfo_gt.contiguous().float(),
+            sp.mean(1).contiguous(), sp.log().mean(1).contiguous(), draws[0].contiguous(),
+            draws[1].reshape(n).contiguous(), draws[2].contiguous(), rh, rw, k_size=self.k_size, center=float(center),
+            alpha0=self.alpha0, digamma_am1=_digamma(self.alpha0 - 1.0), kappa0=self.kappa0, r2=self.r2, eps2=self.eps2,
+            pk0=float(self.penalty_K[0]), pk1=float(self.penalty_K[1]))
+        eng.backward_sr(d_mu, d_kinfo, d_sigma)
+        grad_scale = dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
+        self.step_count += 1
+        ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
+                           self._ngroups, self._max_group, self._sq_ws, grad_scale=grad_scale,
+                           lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1],
+                           eps=self.adam_eps, step=self.step_count, norms_out=self.grad_norms)
+        eng.mark_params_dirty()
+        self.losses, self.last_kernel = terms, kernel
+        self.last_mu, self.last_kinfo, self.last_sigma = mu, kinfo, sigma
+        return terms
