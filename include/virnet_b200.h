@@ -290,6 +290,10 @@ int vk_pack_weights(int32_t dtype, const void* descs_dev, int32_t ndesc, int64_t
 /* out[c] += sum over pixels of x[p][c] (NHWC `dtype`, pitch ld): ConvTranspose2d bias gradient. */
 int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_t ld, int32_t c, float* out, void* stream);
 
+/* Per-sample form: out[s][c] += sum over the npix pixels of sample s (x is [n][npix][ld]). */
+int vk_channel_sum_batched(int32_t dtype, const void* x, int32_t n, int64_t npix, int32_t ld, int32_t c, float* out,
+                           void* stream);
+
 /* Per-sub-network gradient L2 norm -> clip coefficient -> Adam update over flat fp32 buffers, no
  * host synchronisation (train_denoising_syn.py:182-184).  groups_dev: device array of
  * vk_adam_group; sq_ws: ngroups doubles of scratch; grads are first multiplied by grad_scale

@@ -274,8 +274,10 @@ __global__ void pack_weights_kernel(const PackDesc* __restrict__ descs, int roun
 // ---------------------------------------------------------------------------
 template <typename DT>
 __global__ void channel_sum_kernel(const DT* __restrict__ x, long long npix, int ld, int C, float* __restrict__ out) {
-  // block = 256 threads = 8 pixel lanes x 32 channel lanes
+  // block = 256 threads = 8 pixel lanes x 32 channel lanes; blockIdx.y = sample (batched form: per-sample sums)
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  x += static_cast<long long>(blockIdx.y) * npix * ld;
+  out += static_cast<long long>(blockIdx.y) * C;
   __shared__ float part[8][33];
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int c = c0 + cl;
@@ -461,6 +463,20 @@ extern "C" int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_
                               void* stream) {
   if (x == nullptr || out == nullptr || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
   const int grid = int(std::min<long long>((npix + 7) / 8, kSMs * 4));
+  if (dtype == VK_BF16)
+    channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                      npix, ld, c, out);
+  else if (dtype == VK_TF32)
+    channel_sum_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c, out);
+  else
+    return VK_E_BADARG;
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_channel_sum_batched(int32_t dtype, const void* x, int32_t n, int64_t npix, int32_t ld, int32_t c,
+                                      float* out, void* stream) {
+  if (x == nullptr || out == nullptr || n <= 0 || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
+  const dim3 grid(unsigned(std::min<long long>((npix + 7) / 8, std::max(1, kSMs * 4 / n))), unsigned(n));
   if (dtype == VK_BF16)
     channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                                       npix, ld, c, out);

@@ -203,45 +203,99 @@ __global__ void upsample_nearest_kernel(const float* __restrict__ x, float* __re
 // SFT backward (autograd of a = lrelu(x * mul + add), networks/AttResUNet.py:54-58), after the producing dgrad
 // has already applied lrelu'(a):  g = dL/d(x * mul + add), NHWC DT [n][npix][ld]
 //   gx = g * mul[n][c] (+ resid),  dmul[n][c] += sum_pix g * x,  dadd[n][c] += sum_pix g
-// block = 8 pixel lanes x 32 channel lanes over one sample's pixel chunk; blockIdx.y = sample.
+// HBM-bound (3-4 tensors streamed once): every thread moves 16-byte vectors of one channel group and keeps the
+// group's partial sums in registers; lanes are reduced through shared memory, one atomicAdd per (block, channel).
+// blockIdx.y = sample, blockIdx.x = pixel chunk.
 template <typename DT>
-__global__ void sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* __restrict__ mul,
-                               const DT* __restrict__ resid, DT* __restrict__ gx, float* __restrict__ dmul,
-                               float* __restrict__ dadd, int npix, int C, int ld, int pix_per_block) {
-  __shared__ float pm[8][33], pa[8][33];
+struct SftVec;
+template <>
+struct SftVec<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x, v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+template <>
+struct SftVec<float> {
+  static constexpr int kN = 4;
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x, v[1] = r.y, v[2] = r.z, v[3] = r.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <typename DT>
+__global__ void __launch_bounds__(256)
+sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* __restrict__ mul,
+               const DT* __restrict__ resid, DT* __restrict__ gx, float* __restrict__ dmul, float* __restrict__ dadd,
+               int npix, int C, int ld, int pix_per_block) {
+  constexpr int V = SftVec<DT>::kN;
+  extern __shared__ float sm[];            // [lanes][ld] x 2
   const int n = blockIdx.y;
-  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int groups = ld / V, lanes = 256 / groups;
+  const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long long base = static_cast<long long>(n) * npix * ld;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
-  for (int c0 = 0; c0 < ld; c0 += 32) {
-    const int c = c0 + cl;
-    float sm_ = 0.f, sa_ = 0.f;
-    if (c < ld) {
-      const float m = c < C ? mul[n * C + c] : 0.f;
-      for (int p = p0 + pl; p < p1; p += 8) {
-        const long long i = base + static_cast<long long>(p) * ld + c;
-        const float gv = c < C ? ld_f<DT>(g + i) : 0.f;
-        float o = gv * m;
-        if (resid != nullptr) o += ld_f<DT>(resid + i);
-        st_f<DT>(gx + i, c < C ? o : 0.f);
-        sm_ += gv * (c < C ? ld_f<DT>(x + i) : 0.f);
-        sa_ += gv;
-      }
-    }
-    pm[pl][cl] = sm_, pa[pl][cl] = sa_;
-    __syncthreads();
-    if (pl == 0 && c < C) {
-      float tm = 0.f, ta = 0.f;
+  float m[V], sm_[V], sa_[V];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tm += pm[j][cl], ta += pa[j][cl];
-      atomicAdd(dmul + n * C + c, tm);
-      atomicAdd(dadd + n * C + c, ta);
+  for (int i = 0; i < V; ++i) {
+    const int c = cg * V + i;
+    m[i] = c < C ? mul[n * C + c] : 0.f;
+    sm_[i] = sa_[i] = 0.f;
+  }
+  if (pl < lanes)
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const long long i0 = base + static_cast<long long>(p) * ld + cg * V;
+      float gv[V], xv[V], o[V];
+      SftVec<DT>::load(g + i0, gv);
+      SftVec<DT>::load(x + i0, xv);
+      if (resid != nullptr) {
+        SftVec<DT>::load(resid + i0, o);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = fmaf(gv[i], m[i], o[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = gv[i] * m[i];
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sm_[i] = fmaf(gv[i], xv[i], sm_[i]);
+        sa_[i] += gv[i];
+      }
+      SftVec<DT>::store(gx + i0, o);
     }
-    __syncthreads();
+  float* pm = sm;
+  float* pa = sm + lanes * ld;
+  if (pl < lanes) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) pm[pl * ld + cg * V + i] = sm_[i], pa[pl * ld + cg * V + i] = sa_[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float tm = 0.f, ta = 0.f;
+    for (int l = 0; l < lanes; ++l) tm += pm[l * ld + c], ta += pa[l * ld + c];
+    atomicAdd(dmul + n * C + c, tm);
+    atomicAdd(dadd + n * C + c, ta);
   }
 }
 
-// AttLayer MLP backward (one block, samples in sequence so parameter gradients need no atomics):
+// AttLayer MLP backward, one block per sample (parameter gradients by atomicAdd over samples):
 // recomputes the forward of sft_mlp_kernel, then back-propagates (dmul, dadd) to the four 1x1 convs and to the
 // conditioning values.  d_extra[n][e] += dL/d(raw extra) (the sqrt of the masked entries is chained here).
 __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E, unsigned sqrt_mask,
@@ -264,7 +318,8 @@ __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E
   float* gf2 = gad + C;
   float* gf1 = gf2 + C2;
   const int T = blockDim.x, t = threadIdx.x;
-  for (int n = 0; n < N; ++n) {
+  {
+    const int n = blockIdx.x;
     if (t < E) {
       const float v = extra[n * E + t];
       e[t] = (sqrt_mask & (1u << t)) ? sqrtf(v) : v;
@@ -288,8 +343,8 @@ __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E
       const float mu = 1.f / (1.f + expf(-a));
       const float g1 = dmul[n * C + c] * mu * (1.f - mu), g2 = dadd[n * C + c];
       gmp[c] = g1, gad[c] = g2;
-      gbm[c] += g1, gba[c] += g2;
-      for (int k = 0; k < C2; ++k) gwm[c * C2 + k] += g1 * f2[k], gwa[c * C2 + k] += g2 * f2[k];
+      atomicAdd(gbm + c, g1), atomicAdd(gba + c, g2);
+      for (int k = 0; k < C2; ++k) atomicAdd(gwm + c * C2 + k, g1 * f2[k]), atomicAdd(gwa + c * C2 + k, g2 * f2[k]);
     }
     __syncthreads();
     for (int k = t; k < C2; k += T) {
@@ -297,8 +352,8 @@ __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E
       for (int c = 0; c < C; ++c) a = fmaf(wm[c * C2 + k], gmp[c], fmaf(wa[c * C2 + k], gad[c], a));
       a *= f2p[k] > 0.f ? 1.f : alpha;
       gf2[k] = a;
-      gb2[k] += a;
-      for (int j = 0; j < C1; ++j) gw2[k * C1 + j] += a * f1[j];
+      atomicAdd(gb2 + k, a);
+      for (int j = 0; j < C1; ++j) atomicAdd(gw2 + k * C1 + j, a * f1[j]);
     }
     __syncthreads();
     for (int j = t; j < C1; j += T) {
@@ -306,8 +361,8 @@ __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E
       for (int k = 0; k < C2; ++k) a = fmaf(w2[k * C1 + j], gf2[k], a);
       a *= f1p[j] > 0.f ? 1.f : alpha;
       gf1[j] = a;
-      gb1[j] += a;
-      for (int i = 0; i < E; ++i) gw1[j * E + i] += a * e[i];
+      atomicAdd(gb1 + j, a);
+      for (int i = 0; i < E; ++i) atomicAdd(gw1 + j * E + i, a * e[i]);
     }
     __syncthreads();
     if (t < E) {
@@ -316,7 +371,6 @@ __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E
       if (sqrt_mask & (1u << t)) a *= 0.5f / fmaxf(e[t], 1e-20f);
       d_extra[n * E + t] += a;
     }
-    __syncthreads();
   }
 }
 
@@ -420,7 +474,7 @@ __global__ void gap_head_bwd_kernel(const float* __restrict__ gout, const float*
   }
 }
 
-// Weight gradient of the KNet head (9x9, stride 4, pad 4): one thread per weight element.
+// Weight gradient of the KNet head (9x9, stride 4, pad 4): one thread per (weight element, sample), atomicAdd over samples.
 template <typename DT>
 __global__ void knet_head_wgrad_kernel(const float* __restrict__ x, const DT* __restrict__ g, float* __restrict__ gw,
                                        int N, int C, int H, int W, int OH, int OW, int cout, int ld) {
@@ -428,7 +482,8 @@ __global__ void knet_head_wgrad_kernel(const float* __restrict__ x, const DT* __
   if (i >= cout * C * 81) return;
   const int s = i % 9, r = (i / 9) % 9, c = (i / 81) % C, co = i / (81 * C);
   float acc = 0.f;
-  for (int n = 0; n < N; ++n)
+  {
+    const int n = blockIdx.y;
     for (int oy = 0; oy < OH; ++oy) {
       const int iy = oy * 4 - 4 + r;
       if (iy < 0 || iy >= H) continue;
@@ -439,7 +494,8 @@ __global__ void knet_head_wgrad_kernel(const float* __restrict__ x, const DT* __
                    __ldg(x + ((static_cast<long long>(n) * C + c) * H + iy) * W + ix), acc);
       }
     }
-  gw[i] += acc;
+  }
+  atomicAdd(gw + i, acc);
 }
 
 }  // namespace vk
@@ -519,14 +575,18 @@ extern "C" int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_
 extern "C" int vk_sft_bwd(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx,
                           float* dmul, float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, void* stream) {
   if (!g || !x || !mul || !gx || !dmul || !dadd || n <= 0 || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
-  const int ppb = 256;
+  const int vec = dtype == VK_BF16 ? 8 : 4;
+  if (ld % vec != 0 || ld / vec > 256) return VK_E_BADARG;
+  const int ppb = 512;
+  const size_t smem = size_t(2) * (256 / (ld / vec)) * ld * sizeof(float);
+  if (smem > 48 * 1024) return VK_E_BADARG;
   dim3 grid((npix + ppb - 1) / ppb, n);
   if (dtype == VK_BF16)
-    sft_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(
+    sft_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, VK_ST(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), mul,
         reinterpret_cast<const __nv_bfloat16*>(resid), reinterpret_cast<__nv_bfloat16*>(gx), dmul, dadd, npix, c, ld, ppb);
   else if (dtype == VK_TF32)
-    sft_bwd_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(g),
+    sft_bwd_kernel<float><<<grid, 256, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(g),
                                                            reinterpret_cast<const float*>(x), mul,
                                                            reinterpret_cast<const float*>(resid),
                                                            reinterpret_cast<float*>(gx), dmul, dadd, npix, c, ld, ppb);
@@ -545,7 +605,7 @@ extern "C" int vk_sft_mlp_bwd(const float* extra, int32_t n, int32_t e, uint32_t
     return VK_E_BADARG;
   if (n <= 0 || e <= 0 || e > 32 || c1 <= 0 || c2 <= 0 || c <= 0) return VK_E_BADARG;
   const size_t smem = size_t(e + 3 * c1 + 3 * c2 + 2 * c) * sizeof(float);
-  sft_mlp_bwd_kernel<<<1, 256, smem, VK_ST(stream)>>>(extra, n, e, sqrt_mask, w1, b1, c1, w2, b2, c2, wm, bm, wa, ba, c,
+  sft_mlp_bwd_kernel<<<n, 128, smem, VK_ST(stream)>>>(extra, n, e, sqrt_mask, w1, b1, c1, w2, b2, c2, wm, bm, wa, ba, c,
                                                      alpha, dmul, dadd, gw1, gb1, gw2, gb2, gwm, gbm, gwa, gba, d_extra);
   VK_LAUNCHED();
 }
@@ -596,10 +656,10 @@ extern "C" int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, 
   const int oh = (h - 1) / 4 + 1, ow = (wd - 1) / 4 + 1;
   const int total = cout * c * 81;
   if (dtype == VK_BF16)
-    knet_head_wgrad_kernel<__nv_bfloat16><<<(total + 127) / 128, 128, 0, VK_ST(stream)>>>(
+    knet_head_wgrad_kernel<__nv_bfloat16><<<dim3((total + 127) / 128, n), 128, 0, VK_ST(stream)>>>(
         x, reinterpret_cast<const __nv_bfloat16*>(g), gw, n, c, h, wd, oh, ow, cout, ld);
   else if (dtype == VK_TF32)
-    knet_head_wgrad_kernel<float><<<(total + 127) / 128, 128, 0, VK_ST(stream)>>>(x, reinterpret_cast<const float*>(g),
+    knet_head_wgrad_kernel<float><<<dim3((total + 127) / 128, n), 128, 0, VK_ST(stream)>>>(x, reinterpret_cast<const float*>(g),
                                                                                 gw, n, c, h, wd, oh, ow, cout, ld);
   else
     return VK_E_BADARG;

@@ -700,8 +700,7 @@ class DenoiseEngine:
             gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))
             self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
             hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
-            for n in range(N):
-                ops.channel_sum(gR0[n], cin0, hsum[n], dtype=dt)
+            ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
             # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values
             rnet = net.RNet
             for (ii, b, which), _ in S["sft"].items():

@@ -99,6 +99,8 @@ _SIGNATURES = {
     "vk_elbo_denoise": (C.c_int, [C.c_void_p] * 5 + [C.c_float] + [C.c_int32] * 5 + [C.c_float] * 4 + [C.c_void_p] * 5),
     "vk_pack_weights": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "vk_channel_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vk_channel_sum_batched": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p]),
     "vk_adam_clip_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p] + [C.c_float] * 5
                           + [C.c_int32, C.c_void_p, C.c_void_p]),
     "vk_knet_head": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),

@@ -278,6 +278,16 @@ def channel_sum(x, c, out, *, dtype):
         _l.check(_l.load().vk_channel_sum(dtype, _ptr(x), npix, x.shape[-1], c, _ptr(out), _stream()), "vk_channel_sum")
 
 
+def channel_sum_batched(x, c, out, *, dtype):
+    """x [n, ..., ld] -> out [n, c] += per-sample sums over the pixels."""
+    n = x.shape[0]
+    npix = x.numel() // (x.shape[-1] * n)
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == (n, c) and out.dtype == torch.float32
+    with _Prof("channel_sum"):
+        _l.check(_l.load().vk_channel_sum_batched(dtype, _ptr(x), n, npix, x.shape[-1], c, _ptr(out), _stream()),
+                 "vk_channel_sum_batched")
+
+
 def adam_clip_step(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_group_elems, sq_ws, *, grad_scale, lr,
                    beta1, beta2, eps, step, norms_out=None):
     with _Prof("adam_clip"):
