@@ -194,6 +194,19 @@ int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, float* gw, 
 int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
                         void* stream);
 
+/* ---- real-noise denoising trainer: data-side operators ------------------- */
+
+/* utils/util_denoising.py:54-63 (noise_estimate_fun): out = clamp_min(window (*) (noisy - gt)^2, floor) per plane with
+ * reflect padding; `window` is the k_size x k_size normalised Gaussian of inverse_gamma_kernel (:24-35), fp32 on the
+ * device; tensors are [planes][h][w] fp32 (planes = N * C). */
+int vk_noise_estimate(const float* noisy, const float* gt, const float* window, int32_t k_size, float* out,
+                      int32_t planes, int32_t h, int32_t w, float floor_, void* stream);
+
+/* datasets/data_tools.py:21-30 (MixUp_AUG.aug): out_x[i] = lam[i] * x[i] + (1 - lam[i]) * x[perm[i]] for x in {a, b};
+ * [n][per_sample] fp32, per_sample a multiple of 4; perm int64 [n], lam fp32 [n] on the device; out must not alias in. */
+int vk_mixup(const float* a, const float* b, const int64_t* perm, const float* lam, float* out_a, float* out_b, int32_t n,
+             int64_t per_sample, void* stream);
+
 /* ---- super-resolution negative ELBO ------------------------------------- */
 
 /* loss/ELBO_simple.py:82-138 (elbo_sisr) with its helpers (:55-80), utils/util_sisr.py:26-58 (sigma2kernel) and

@@ -397,6 +397,35 @@ def reference_draws(n: int, mu_shape, kappa0: float, generator=None, device="cpu
 
 
 # --------------------------------------------------------------------------------------
+# real-noise trainer's data-side operators (utils/util_denoising.py:24-63, datasets/data_tools.py:12-30)
+# --------------------------------------------------------------------------------------
+def inverse_gamma_window(k_size: int) -> Tensor:
+    """utils/util_denoising.py:24-41: cv2.getGaussianKernel(k, s) (s > 0: exp(-(i-(k-1)/2)^2 / 2s^2), sum 1)
+    outer product, renormalised; float64 -> float32."""
+    scale = 0.3 * ((k_size - 1) * 0.5 - 1) + 0.8
+    i = torch.arange(k_size, dtype=torch.float64)
+    k1 = torch.exp(-((i - (k_size - 1) / 2) ** 2) / (2 * scale ** 2))
+    k1 = k1 / k1.sum()
+    k2 = k1[:, None] * k1[None, :]
+    return (k2 / k2.sum()).to(torch.float32)
+
+
+def noise_estimate_fun(im_noisy: Tensor, im_gt: Tensor, k_size: int) -> Tensor:
+    """utils/util_denoising.py:43-63: depthwise Gaussian-window mean of the squared error, reflect pad, clamp 1e-10."""
+    c = im_noisy.shape[1]
+    kernel = inverse_gamma_window(k_size).expand(c, 1, k_size, k_size)
+    err2 = (im_noisy - im_gt) ** 2
+    out = F.conv2d(F.pad(err2, [k_size // 2] * 4, mode="reflect"), kernel, groups=c)
+    return out.clamp_(min=1e-10)
+
+
+def mixup(rgb_gt: Tensor, rgb_noisy: Tensor, indices: Tensor, lam: Tensor):
+    """datasets/data_tools.py:21-30 with the draws (randperm, Beta(0.6, 0.6) rsample) made explicit."""
+    lam = lam.view(-1, 1, 1, 1)
+    return lam * rgb_gt + (1 - lam) * rgb_gt[indices], lam * rgb_noisy + (1 - lam) * rgb_noisy[indices]
+
+
+# --------------------------------------------------------------------------------------
 # one reference training step (train_denoising_syn.py:175-184), used as the CPU baseline
 # --------------------------------------------------------------------------------------
 def clip_grad_norm_(params: List[Tensor], max_norm: float) -> Tensor:

@@ -451,3 +451,33 @@ def elbo_sisr(mu, im_hr, im_lr, sigma_est, kinfo_est, kinfo_gt, prior_mean, prio
     with _Prof("elbo_sisr"):
         _l.check(lib.vk_elbo_sisr(C.byref(a), _stream()), "vk_elbo_sisr")
     return terms, kernel, d_mu, d_sigma, d_kinfo
+
+
+# ---------------------------------------------------------------------------
+# real-noise denoising trainer: variance-map prior and MixUp
+# ---------------------------------------------------------------------------
+def noise_estimate(im_noisy, im_gt, window, out=None, floor=1e-10):
+    """out = clamp_min(window (*) (im_noisy - im_gt)^2, floor), reflect padding; NCHW fp32, window [k, k] fp32."""
+    n, c, h, w = im_noisy.shape
+    for t in (im_noisy, im_gt, window):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+    assert im_gt.shape == im_noisy.shape and window.shape[0] == window.shape[1]
+    if out is None:
+        out = torch.empty_like(im_noisy)
+    with _Prof("noise_estimate"):
+        _l.check(_l.load().vk_noise_estimate(_ptr(im_noisy), _ptr(im_gt), _ptr(window), window.shape[0], _ptr(out), n * c,
+                                             h, w, floor, _stream()), "vk_noise_estimate")
+    return out
+
+
+def mixup(a, b, perm, lam):
+    """(lam * a + (1 - lam) * a[perm], same for b); a, b [n, ...] fp32, perm int64 [n], lam fp32 [n] (all CUDA)."""
+    n = a.shape[0]
+    for t in (a, b, lam):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+    assert a.shape == b.shape and perm.dtype == torch.int64 and perm.is_cuda and perm.numel() == n and lam.numel() == n
+    out_a, out_b = torch.empty_like(a), torch.empty_like(b)
+    with _Prof("mixup"):
+        _l.check(_l.load().vk_mixup(_ptr(a), _ptr(b), _ptr(perm), _ptr(lam), _ptr(out_a), _ptr(out_b), n, a.numel() // n,
+                                    _stream()), "vk_mixup")
+    return out_a, out_b

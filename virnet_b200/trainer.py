@@ -122,6 +122,18 @@ class DenoiseTrainer:
         self._pf_ready[k].record(cs)
         self._pf_key = (k, im_noisy.data_ptr(), im_gt.data_ptr(), sigma_gt.data_ptr(), bufs)
 
+    def step_real(self, im_noisy, im_gt, var_window=7, mixup=None, lr: Optional[float] = None):
+        """The real-noise trainer's iteration (train_denoising_real.py:158-176): MixUp of the (clean, noisy) pairs,
+        variance-map prior from the squared error under a var_window Gaussian, then the same step.  `mixup`: a
+        virnet_b200.datasets.data_tools.MixUp_AUG (None = no MixUp)."""
+        from .utils.util_denoising import noise_estimate_fun
+        dev = self.engine.flat_params.device
+        im_noisy, im_gt = [t if t.is_cuda else t.to(dev, non_blocking=True) for t in (im_noisy, im_gt)]
+        if mixup is not None:
+            im_gt, im_noisy = mixup.aug(im_gt, im_noisy)
+        sigma_gt = noise_estimate_fun(im_noisy, im_gt, var_window)
+        return self.step(im_noisy, im_gt, sigma_gt, lr=lr)
+
     def step(self, im_noisy, im_gt, sigma_gt, lr: Optional[float] = None):
         """One optimisation step; returns the device tensor [loss, lh, kl_gauss, kl_Igamma]
         of the local batch (no host sync)."""
