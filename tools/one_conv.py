@@ -17,8 +17,11 @@ ap.add_argument("--n", type=int, default=16)
 ap.add_argument("--epi", default="resid_dual")
 ap.add_argument("--impl", type=int, default=0)
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--cout", type=int, default=0)
+ap.add_argument("--s2", action="store_true", help="3x3 stride-2 kind")
 args = ap.parse_args()
-x, w, kw, o1, o2 = make(args.c, args.c, args.h, args.n, args.epi, ops.VK_BF16)
+x, w, kw, o1, o2 = make(args.c, args.cout or args.c, args.h, args.n, args.epi, ops.VK_BF16,
+                        ops.VK_CONV3X3_S2 if args.s2 else ops.VK_CONV3X3_S1)
 for _ in range(args.iters):
     ops.conv_igemm(x, w, tune=dict(impl=args.impl), **kw)
 torch.cuda.synchronize()

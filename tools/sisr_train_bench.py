@@ -50,11 +50,12 @@ tr.step(im_hr, im_lr, kinfo_gt, nlevel)
 recs = ops.stop_profile()
 agg = defaultdict(lambda: [0.0, 0.0, 0])
 for r in recs:
-    agg[r["family"]][0] += r["ms"]
-    agg[r["family"]][1] += r["flops"]
-    agg[r["family"]][2] += 1
+    key = r["family"] if r["flops"] == 0 else f'{r["family"]} {r["flops"] / 1e9:7.2f}GF'
+    agg[key][0] += r["ms"]
+    agg[key][1] += r["flops"]
+    agg[key][2] += 1
 tot = sum(v[0] for v in agg.values())
 print(f"serialised launches total {tot:.3f} ms")
 for fam, (m, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     tf = fl / (m * 1e-3) / 1e12 if m > 0 else 0
-    print(f"{fam:18s} n={n:4d} ms={m:8.3f} ({100 * m / tot:4.1f}%) {tf:7.0f} TF/s")
+    print(f"{fam:28s} n={n:4d} ms={m:8.3f} ({100 * m / tot:4.1f}%) {tf:7.0f} TF/s")
