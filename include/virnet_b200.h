@@ -207,6 +207,15 @@ int vk_noise_estimate(const float* noisy, const float* gt, const float* window, 
 int vk_mixup(const float* a, const float* b, const int64_t* perm, const float* lam, float* out_a, float* out_b, int32_t n,
              int64_t per_sample, void* stream);
 
+/* ---- device-side synthesis of denoising training batches ----------------- */
+
+/* datasets/DenoisingDatasets.py:180-253 (SimulateTrain.__getitem__) after cropping: patches uint8 [n][p][p][c] (RGB, HWC);
+ * params fp64 [n][6] = {center_h, center_w, scale, up, down, iid_level} (scale <= 0: constant 'iid' map = iid_level);
+ * aug int32 [n] in 0..7 (utils/util_image.py:391-436); noise fp32 [n][p][p][c] ~ N(0,1) (the reference's
+ * torch.randn(im_gt.shape)); outputs NCHW fp32: im_noisy, im_gt [n][c][p][p], sigma_gt [n][1][p][p] = max(sigma^2, 1e-10). */
+int vk_synth_denoise(const uint8_t* patches, const double* params, const int32_t* aug, const float* noise, int32_t n,
+                     int32_t p, int32_t c, int32_t clip, float* im_noisy, float* im_gt, float* sigma_gt, void* stream);
+
 /* ---- super-resolution negative ELBO ------------------------------------- */
 
 /* loss/ELBO_simple.py:82-138 (elbo_sisr) with its helpers (:55-80), utils/util_sisr.py:26-58 (sigma2kernel) and

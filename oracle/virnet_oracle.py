@@ -426,6 +426,57 @@ def mixup(rgb_gt: Tensor, rgb_noisy: Tensor, indices: Tensor, lam: Tensor):
 
 
 # --------------------------------------------------------------------------------------
+# synthetic denoising batches (datasets/DenoisingDatasets.py:180-253, utils/util_denoising.py:12-22,
+# utils/util_image.py:391-436) — numpy, one sample at a time like the reference
+# --------------------------------------------------------------------------------------
+def data_aug_np(image, mode: int):
+    """utils/util_image.py:391-436."""
+    import numpy as np
+    if mode == 0:
+        out = image
+    elif mode == 1:
+        out = np.flipud(image)
+    elif mode in (2, 3):
+        out = np.rot90(image)
+    elif mode in (4, 5):
+        out = np.rot90(image, k=2)
+    elif mode in (6, 7):
+        out = np.rot90(image, k=3)
+    else:
+        raise ValueError("Invalid choice of image transformation")
+    if mode in (3, 5, 7):
+        out = np.flipud(out)
+    return out.copy()
+
+
+def synth_denoise_sample(patch_u8, params, aug_flag: int, noise, clip: bool = False):
+    """SimulateTrain.__getitem__ (:216-253) after crop_patch, with its random draws as arguments:
+    params = [center_h, center_w, scale, up (after swap and + 5/255), down, iid_level]; scale <= 0 -> 'iid'.
+    patch_u8 HWC uint8, noise HWC float32 ~ N(0,1).  Returns (im_noisy, im_gt, sigma_map_gt) CHW float32 tensors."""
+    import numpy as np
+    P = patch_u8.shape[0]
+    im_gt = np.multiply(np.asarray(patch_u8), 1.0 / 255, dtype=np.float32)      # skimage.img_as_float32 on uint8
+    ch, cw, scale, up, down, level = [float(v) for v in params]
+    if scale > 0:
+        ii, jj = [x.astype(np.float64) for x in np.meshgrid(np.arange(P), np.arange(P), indexing="ij")]
+        kk = np.exp((-(ii - ch) ** 2 - (jj - cw) ** 2) / (2 * scale ** 2))
+        kk /= kk.sum()
+        sigma_map = (down + (kk - kk.min()) / (kk.max() - kk.min()) * (up - down)).astype(np.float32)
+    else:
+        sigma_map = (np.ones([P, P]) * level).astype(np.float32)
+    sigma_map = sigma_map[:, :, np.newaxis]
+    nz = np.asarray(noise, dtype=np.float32) * sigma_map
+    im_noisy = im_gt + nz.astype(np.float32)
+    if clip:
+        im_noisy = np.clip(im_noisy, 0.0, 1.0)
+    im_gt, im_noisy, sigma_map = [data_aug_np(x, aug_flag) for x in (im_gt, im_noisy, sigma_map)]
+    sg = np.square(sigma_map)
+    sg = np.where(sg < 1e-10, 1e-10, sg)
+    tt = lambda x: torch.from_numpy(x.transpose((2, 0, 1)).copy())
+    return tt(im_noisy), tt(im_gt), tt(sg.astype(np.float32))
+
+
+# --------------------------------------------------------------------------------------
 # one reference training step (train_denoising_syn.py:175-184), used as the CPU baseline
 # --------------------------------------------------------------------------------------
 def clip_grad_norm_(params: List[Tensor], max_norm: float) -> Tensor:

@@ -119,6 +119,7 @@ _SIGNATURES = {
                                   C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "vk_knet_head_wgrad": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vk_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
+    "vk_synth_denoise": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 4),
     "vk_noise_estimate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_float, C.c_void_p]),
     "vk_mixup": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int64, C.c_void_p]),

@@ -481,3 +481,21 @@ def mixup(a, b, perm, lam):
         _l.check(_l.load().vk_mixup(_ptr(a), _ptr(b), _ptr(perm), _ptr(lam), _ptr(out_a), _ptr(out_b), n, a.numel() // n,
                                     _stream()), "vk_mixup")
     return out_a, out_b
+
+
+def synth_denoise(patches_u8, params, aug, noise, *, clip=False):
+    """patches uint8 [n, p, p, c]; params fp64 [n, 6]; aug int32 [n]; noise fp32 [n, p, p, c] (all CUDA, contiguous).
+    Returns (im_noisy, im_gt, sigma_gt) NCHW fp32."""
+    n, p, p2, c = patches_u8.shape
+    assert p == p2 and patches_u8.dtype == torch.uint8 and params.dtype == torch.float64 and params.shape == (n, 6)
+    assert aug.dtype == torch.int32 and aug.numel() == n and noise.dtype == torch.float32 and noise.shape == patches_u8.shape
+    for t in (patches_u8, params, aug, noise):
+        assert t.is_cuda and t.is_contiguous()
+    dev = patches_u8.device
+    im_noisy = torch.empty(n, c, p, p, device=dev, dtype=torch.float32)
+    im_gt = torch.empty_like(im_noisy)
+    sigma_gt = torch.empty(n, 1, p, p, device=dev, dtype=torch.float32)
+    with _Prof("synth_denoise"):
+        _l.check(_l.load().vk_synth_denoise(_ptr(patches_u8), _ptr(params), _ptr(aug), _ptr(noise), n, p, c, int(clip),
+                                            _ptr(im_noisy), _ptr(im_gt), _ptr(sigma_gt), _stream()), "vk_synth_denoise")
+    return im_noisy, im_gt, sigma_gt
