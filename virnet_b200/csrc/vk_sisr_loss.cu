@@ -128,43 +128,96 @@ sisr_blur_kernel(const float* __restrict__ in, const float* __restrict__ noise, 
     tile[r * TP + c] = v;
   }
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int i = 0; i < K; ++i)
-    for (int j = 0; j < K; ++j) {
-      const float kv = ks[i * K + j];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = fmaf(kv, tile[(ty + 8 * r + i) * TP + tx + j], acc[r]);
+  // each thread owns 4 consecutive columns of one row: a tap row is a sliding window over K + 3 staged values, so
+  // a step costs 2 shared loads (one value, one broadcast weight) for 4 FMAs; lanes of a warp touch 32 distinct banks
+  const int cg = threadIdx.x & 7, ty = threadIdx.x >> 3;      // 8 column groups x 32 rows
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int i = 0; i < K; ++i) {
+    const float* T = tile + (ty + i) * TP + cg * 4;
+    const float* kr = ks + i * K;
+    float v0 = T[0], v1 = T[1], v2 = T[2], v3;
+    int j = 0;
+    for (; j + 3 < K; j += 4) {
+      float k;
+      v3 = T[j + 3], k = kr[j];
+      a0 = fmaf(k, v0, a0), a1 = fmaf(k, v1, a1), a2 = fmaf(k, v2, a2), a3 = fmaf(k, v3, a3);
+      v0 = T[j + 4], k = kr[j + 1];
+      a0 = fmaf(k, v1, a0), a1 = fmaf(k, v2, a1), a2 = fmaf(k, v3, a2), a3 = fmaf(k, v0, a3);
+      v1 = T[j + 5], k = kr[j + 2];
+      a0 = fmaf(k, v2, a0), a1 = fmaf(k, v3, a1), a2 = fmaf(k, v0, a2), a3 = fmaf(k, v1, a3);
+      v2 = T[j + 6], k = kr[j + 3];
+      a0 = fmaf(k, v3, a0), a1 = fmaf(k, v0, a1), a2 = fmaf(k, v1, a2), a3 = fmaf(k, v2, a3);
     }
+    for (; j < K; ++j) {
+      v3 = T[j + 3];
+      const float k = kr[j];
+      a0 = fmaf(k, v0, a0), a1 = fmaf(k, v1, a1), a2 = fmaf(k, v2, a2), a3 = fmaf(k, v3, a3);
+      v0 = v1, v1 = v2, v2 = v3;
+    }
+  }
   float* op = out + static_cast<long long>(p) * Hout * Wout;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int y = oy0 + ty + 8 * r, x = ox0 + tx;
-    if (y < Hout && x < Wout) op[y * Wout + x] = acc[r];
+  const int y = oy0 + ty, x = ox0 + cg * 4;
+  if (y < Hout) {
+    if (x < Wout) op[y * Wout + x] = a0;
+    if (x + 1 < Wout) op[y * Wout + x + 1] = a1;
+    if (x + 2 < Wout) op[y * Wout + x + 2] = a2;
+    if (x + 3 < Wout) op[y * Wout + x + 3] = a3;
   }
 }
 
 // ---- 3,4,6,7: C[p] (M x N) = A (M x Kd) * B (Kd x N), either operand shared by all planes (plane stride 0) ----
+// 64 x 64 block tile, 4 x 4 outputs per thread, K step 16; operands are addressed through (row, column) strides so the
+// same kernel applies the down-sampling operator and its transpose from either side.
 __global__ void __launch_bounds__(256)
 sisr_plane_gemm_kernel(const float* __restrict__ A, long long a_plane, int a_rs, int a_cs, const float* __restrict__ B,
                        long long b_plane, int b_rs, int b_cs, float* __restrict__ Cm, long long c_plane, int M, int N,
                        int Kd) {
-  __shared__ float as[16][17], bs[16][17];
+  __shared__ __align__(16) float as[16][68], bs[16][68];
   const int p = blockIdx.z;
   const float* a = A + a_plane * p;
   const float* b = B + b_plane * p;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
-  float acc = 0.f;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
   for (int k0 = 0; k0 < Kd; k0 += 16) {
-    as[ty][tx] = (row < M && k0 + tx < Kd) ? a[static_cast<long long>(row) * a_rs + static_cast<long long>(k0 + tx) * a_cs] : 0.f;
-    bs[ty][tx] = (k0 + ty < Kd && col < N) ? b[static_cast<long long>(k0 + ty) * b_rs + static_cast<long long>(col) * b_cs] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      {  // A tile: consecutive threads walk k (contiguous for row-major A) unless A is accessed transposed
+        const int m = a_cs == 1 ? e >> 4 : e & 63, k = a_cs == 1 ? e & 15 : e >> 6;
+        as[k][m] = (m0 + m < M && k0 + k < Kd)
+                       ? a[static_cast<long long>(m0 + m) * a_rs + static_cast<long long>(k0 + k) * a_cs] : 0.f;
+      }
+      {
+        const int k = b_cs == 1 ? e >> 6 : e & 15, nn = b_cs == 1 ? e & 63 : e >> 4;
+        bs[k][nn] = (k0 + k < Kd && n0 + nn < N)
+                        ? b[static_cast<long long>(k0 + k) * b_rs + static_cast<long long>(n0 + nn) * b_cs] : 0.f;
+      }
+    }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc = fmaf(as[ty][k], bs[k][tx], acc);
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&as[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&bs[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
     __syncthreads();
   }
-  if (row < M && col < N) Cm[c_plane * p + static_cast<long long>(row) * N + col] = acc;
+  float* c = Cm + c_plane * p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col < N) c[static_cast<long long>(row) * N + col] = acc[i][j];
+    }
+  }
 }
 
 // ---- 5: likelihood residual (ELBO_simple.py:58): O -> gO in place, per-sample sum of squares ----
@@ -250,18 +303,28 @@ sisr_kernel_wgrad_kernel(const float* __restrict__ mu, const float* __restrict__
     const int y = oy0 + t / kBlurTile, x = ox0 + t % kBlurTile;
     gs[t] = (y < H && x < W) ? gp[y * W + x] : 0.f;
   }
+  for (int t = threadIdx.x; t < TW; t += 256) tile[t * TP + TW] = 0.f;
   __syncthreads();
-  const int KK = K * K;
-  for (int tap = threadIdx.x; tap < KK; tap += 256) {
-    const int i = tap / K, j = tap % K;
-    float acc = 0.f;
+  // a thread accumulates two horizontally adjacent taps (i, 2jj) and (i, 2jj + 1): they read the same staged row
+  // shifted by one, so a step is 2 shared loads (one broadcast gradient, one value) for 2 FMAs
+  const int KK = K * K, KH = (K + 1) / 2;
+  for (int w = threadIdx.x; w < K * KH; w += 256) {
+    const int i = w / KH, j = (w - i * KH) * 2;
+    float acc0 = 0.f, acc1 = 0.f;
     for (int y = 0; y < kBlurTile; ++y) {
       const float* trow = tile + (y + i) * TP + j;
       const float* grow = gs + y * kBlurTile;
+      float t0 = trow[0];
 #pragma unroll 8
-      for (int x = 0; x < kBlurTile; ++x) acc = fmaf(grow[x], trow[x], acc);
+      for (int x = 0; x < kBlurTile; ++x) {
+        const float t1 = trow[x + 1], gv = grow[x];          // column TW of the last pair is the (finite) row padding
+        acc0 = fmaf(gv, t0, acc0);
+        acc1 = fmaf(gv, t1, acc1);
+        t0 = t1;
+      }
     }
-    atomicAdd(gk + n * KK + tap, acc);
+    atomicAdd(gk + n * KK + i * K + j, acc0);
+    if (j + 1 < K) atomicAdd(gk + n * KK + i * K + j + 1, acc1);
   }
 }
 
@@ -424,7 +487,7 @@ extern "C" int vk_elbo_sisr(const vk_elbo_sisr_args* a, void* stream_) {
   // 3: T[p] (H x w) = B[p] (H x W) * Rw^T     4: O[p] (h x w) = Rh (h x H) * T[p]
   auto gemm = [&](const float* A_, long long ap, int ars, int acs, const float* B_, long long bp, int brs, int bcs,
                   float* C_, long long cpl, int M, int Nn, int Kd) {
-    sisr_plane_gemm_kernel<<<dim3((Nn + 15) / 16, (M + 15) / 16, P), 256, 0, st>>>(A_, ap, ars, acs, B_, bp, brs, bcs, C_,
+    sisr_plane_gemm_kernel<<<dim3((Nn + 63) / 64, (M + 63) / 64, P), 256, 0, st>>>(A_, ap, ars, acs, B_, bp, brs, bcs, C_,
                                                                                  cpl, M, Nn, Kd);
     ++launches;
   };
