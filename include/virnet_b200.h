@@ -177,6 +177,20 @@ int vk_sft_mlp_bwd(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask,
                    float* gw1, float* gb1, float* gw2, float* gb2, float* gwm, float* gbm, float* gwa, float* gba,
                    float* d_extra, void* stream);
 
+/* Every AttLayer of the network in one launch (forward: fills mul/add; backward: consumes dmul/dadd, accumulates the
+ * parameter gradients and d_extra).  descs_dev: device array of vk_sft_desc, one per layer; requires c1 + c2 <= c. */
+typedef struct vk_sft_desc {
+  const float *w1, *b1, *w2, *b2, *wm, *bm, *wa, *ba;      /* conv1, conv2, mul_conv, add_conv of the AttLayer */
+  float *gw1, *gb1, *gw2, *gb2, *gwm, *gbm, *gwa, *gba;    /* their gradients (accumulated) */
+  float *mul, *add, *dmul, *dadd;                          /* [n][c] each */
+  int32_t c1, c2, c, pad_;
+} vk_sft_desc;
+int vk_sft_mlp_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra, int32_t n, int32_t e,
+                       uint32_t sqrt_mask, float alpha, void* stream);
+int vk_sft_mlp_bwd_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra, int32_t n,
+                           int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra, void* stream);
+uint32_t vk_sizeof_sft_desc(void);
+
 /* CALayer + skip backward: df = g * s + dy / npix (the skip gradient is g); parameter gradients accumulated. */
 int vk_ca_layer_bwd(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1, const float* w2,
                     const float* b2, void* df, float* gw1, float* gb1, float* gw2, float* gb2, int32_t n, int32_t npix,

@@ -143,7 +143,7 @@ __global__ void gap_head_kernel(const float* __restrict__ x, int hw, int C, unsi
 //   f1 = LReLU(W1 e + b1); f2 = LReLU(W2 f1 + b2); mul = sigmoid(Wm f2 + bm); add = Wa f2 + ba
 // e[n][k] = sqrt(extra[n][k]) for k in sqrt_mask (the noise variance), extra[n][k] otherwise.
 // ---------------------------------------------------------------------------
-__global__ void sft_mlp_kernel(const float* __restrict__ extra, int E, unsigned sqrt_mask, const float* __restrict__ w1,
+__device__ __forceinline__ void sft_mlp_body(int n, const float* __restrict__ extra, int E, unsigned sqrt_mask, const float* __restrict__ w1,
                                const float* __restrict__ b1, int C1, const float* __restrict__ w2,
                                const float* __restrict__ b2, int C2, const float* __restrict__ wm,
                                const float* __restrict__ bm, const float* __restrict__ wa,
@@ -153,7 +153,6 @@ __global__ void sft_mlp_kernel(const float* __restrict__ extra, int E, unsigned 
   float* e = sm;
   float* f1 = e + E;
   float* f2 = f1 + C1;
-  const int n = blockIdx.x;
   if (threadIdx.x < E) {
     float v = extra[n * E + threadIdx.x];
     e[threadIdx.x] = (sqrt_mask & (1u << threadIdx.x)) ? sqrtf(v) : v;
@@ -180,6 +179,30 @@ __global__ void sft_mlp_kernel(const float* __restrict__ extra, int E, unsigned 
     mul[n * C + i] = 1.f / (1.f + expf(-tm));
     add[n * C + i] = ta;
   }
+}
+
+__global__ void sft_mlp_kernel(const float* __restrict__ extra, int E, unsigned sqrt_mask, const float* __restrict__ w1,
+                               const float* __restrict__ b1, int C1, const float* __restrict__ w2,
+                               const float* __restrict__ b2, int C2, const float* __restrict__ wm,
+                               const float* __restrict__ bm, const float* __restrict__ wa,
+                               const float* __restrict__ ba, int C, float alpha, float* __restrict__ mul,
+                               float* __restrict__ add) {
+  sft_mlp_body(blockIdx.x, extra, E, sqrt_mask, w1, b1, C1, w2, b2, C2, wm, bm, wa, ba, C, alpha, mul, add);
+}
+
+// every AttLayer of the network in one launch: blockIdx.y selects the layer's descriptor (mirror of vk_sft_desc)
+struct SftDesc {
+  const float *w1, *b1, *w2, *b2, *wm, *bm, *wa, *ba;
+  float *gw1, *gb1, *gw2, *gb2, *gwm, *gbm, *gwa, *gba;
+  float *mul, *add, *dmul, *dadd;
+  int c1, c2, c, pad;
+};
+
+__global__ void sft_mlp_batched_kernel(const SftDesc* __restrict__ descs, const float* __restrict__ extra, int E,
+                                       unsigned sqrt_mask, float alpha) {
+  const SftDesc d = descs[blockIdx.y];
+  sft_mlp_body(blockIdx.x, extra, E, sqrt_mask, d.w1, d.b1, d.c1, d.w2, d.b2, d.c2, d.wm, d.bm, d.wa, d.ba, d.c, alpha,
+               d.mul, d.add);
 }
 
 // F.interpolate(x, scale_factor=sf, mode='nearest') on NCHW fp32 (networks/VIRNet.py:83): the global residual of RNet
@@ -298,7 +321,7 @@ sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* 
 // AttLayer MLP backward, one block per sample (parameter gradients by atomicAdd over samples):
 // recomputes the forward of sft_mlp_kernel, then back-propagates (dmul, dadd) to the four 1x1 convs and to the
 // conditioning values.  d_extra[n][e] += dL/d(raw extra) (the sqrt of the masked entries is chained here).
-__global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E, unsigned sqrt_mask,
+__device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict__ extra, int E, unsigned sqrt_mask,
                                    const float* __restrict__ w1, const float* __restrict__ b1, int C1,
                                    const float* __restrict__ w2, const float* __restrict__ b2, int C2,
                                    const float* __restrict__ wm, const float* __restrict__ bm,
@@ -319,7 +342,6 @@ __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E
   float* gf1 = gf2 + C2;
   const int T = blockDim.x, t = threadIdx.x;
   {
-    const int n = blockIdx.x;
     if (t < E) {
       const float v = extra[n * E + t];
       e[t] = (sqrt_mask & (1u << t)) ? sqrtf(v) : v;
@@ -369,9 +391,29 @@ __global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E
       float a = 0.f;
       for (int j = 0; j < C1; ++j) a = fmaf(w1[j * E + t], gf1[j], a);
       if (sqrt_mask & (1u << t)) a *= 0.5f / fmaxf(e[t], 1e-20f);
-      d_extra[n * E + t] += a;
+      atomicAdd(d_extra + n * E + t, a);
     }
   }
+}
+
+__global__ void sft_mlp_bwd_kernel(const float* __restrict__ extra, int N, int E, unsigned sqrt_mask,
+                                   const float* __restrict__ w1, const float* __restrict__ b1, int C1,
+                                   const float* __restrict__ w2, const float* __restrict__ b2, int C2,
+                                   const float* __restrict__ wm, const float* __restrict__ bm,
+                                   const float* __restrict__ wa, const float* __restrict__ ba, int C, float alpha,
+                                   const float* __restrict__ dmul, const float* __restrict__ dadd, float* __restrict__ gw1,
+                                   float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2,
+                                   float* __restrict__ gwm, float* __restrict__ gbm, float* __restrict__ gwa,
+                                   float* __restrict__ gba, float* __restrict__ d_extra) {
+  sft_mlp_bwd_body(blockIdx.x, extra, E, sqrt_mask, w1, b1, C1, w2, b2, C2, wm, bm, wa, ba, C, alpha, dmul, dadd, gw1, gb1,
+                   gw2, gb2, gwm, gbm, gwa, gba, d_extra);
+}
+
+__global__ void sft_mlp_bwd_batched_kernel(const SftDesc* __restrict__ descs, const float* __restrict__ extra, int E,
+                                           unsigned sqrt_mask, float alpha, float* __restrict__ d_extra) {
+  const SftDesc d = descs[blockIdx.y];
+  sft_mlp_bwd_body(blockIdx.x, extra, E, sqrt_mask, d.w1, d.b1, d.c1, d.w2, d.b2, d.c2, d.wm, d.bm, d.wa, d.ba, d.c, alpha,
+                   d.dmul, d.dadd, d.gw1, d.gb1, d.gw2, d.gb2, d.gwm, d.gbm, d.gwa, d.gba, d_extra);
 }
 
 // CALayer + skip backward (autograd of out = f * s(mean f) + skip), one CTA per sample:
@@ -562,6 +604,27 @@ extern "C" int vk_sft_mlp(const float* extra, int32_t n, int32_t e, uint32_t sqr
                                                  mul, add);
   VK_LAUNCHED();
 }
+
+extern "C" int vk_sft_mlp_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra, int32_t n,
+                                  int32_t e, uint32_t sqrt_mask, float alpha, void* stream) {
+  if (!descs_dev || !extra || n_layers <= 0 || n <= 0 || e <= 0 || e > 32 || max_c <= 0) return VK_E_BADARG;
+  const size_t smem = size_t(e + max_c) * sizeof(float);               // c1 + c2 <= c / 8 + c / 4 < max_c
+  sft_mlp_batched_kernel<<<dim3(n, n_layers), 128, smem, VK_ST(stream)>>>(reinterpret_cast<const SftDesc*>(descs_dev),
+                                                                         extra, e, sqrt_mask, alpha);
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_sft_mlp_bwd_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra,
+                                      int32_t n, int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra,
+                                      void* stream) {
+  if (!descs_dev || !extra || !d_extra || n_layers <= 0 || n <= 0 || e <= 0 || e > 32 || max_c <= 0) return VK_E_BADARG;
+  const size_t smem = size_t(e + 5 * max_c) * sizeof(float);           // 3 c1 + 3 c2 + 2 c <= 5 c
+  sft_mlp_bwd_batched_kernel<<<dim3(n, n_layers), 128, smem, VK_ST(stream)>>>(
+      reinterpret_cast<const SftDesc*>(descs_dev), extra, e, sqrt_mask, alpha, d_extra);
+  VK_LAUNCHED();
+}
+
+extern "C" uint32_t vk_sizeof_sft_desc(void) { return uint32_t(sizeof(SftDesc)); }
 
 extern "C" int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
                                    void* stream) {

@@ -471,6 +471,42 @@ class DenoiseEngine:
     # ------------------------------------------------------------------
     # super-resolution network (networks/VIRNet.py:80-97): forward, and backward w.r.t. every parameter
     # ------------------------------------------------------------------
+    def _sft_tables(self, N):
+        """(mul, add) buffers of every AttLayer, their gradient accumulators (one flat buffer, zeroed per backward) and
+        the device descriptor table of the batched SFT-MLP kernels; cached per batch size."""
+        key = ("sft_tables", N, self._flat_key)
+        hit = self._bufs.get(key)
+        if hit is not None:
+            return hit[:4]
+        rnet, nfeat, dev, f32 = self.net.RNet, self.n_feat, self.flat_params.device, torch.float32
+        layers = [(ii, b, which, getattr(rb, which)) for ii, blk in enumerate(rnet.down_path)
+                  for b, rb in enumerate(blk.body) for which in ("sft1", "sft2")]
+        total = sum(N * nfeat[ii] for ii, _, _, _ in layers)
+        vals = torch.empty(2 * total, device=dev, dtype=f32)       # mul | add
+        grads = torch.zeros(2 * total, device=dev, dtype=f32)      # dmul | dadd
+        sft, dmd, descs, o = {}, {}, [], 0
+        for ii, b, which, att in layers:
+            c = nfeat[ii]
+            mul, add = vals[o:o + N * c].view(N, c), vals[total + o:total + o + N * c].view(N, c)
+            dm, dd = grads[o:o + N * c].view(N, c), grads[total + o:total + o + N * c].view(N, c)
+            o += N * c
+            sft[(ii, b, which)], dmd[(ii, b, which)] = (mul, add), (dm, dd)
+            d = _l.vk_sft_desc()
+            ps = (att.conv1.weight, att.conv1.bias, att.conv2.weight, att.conv2.bias, att.mul_conv.weight,
+                  att.mul_conv.bias, att.add_conv.weight, att.add_conv.bias)
+            for nm, p_ in zip(("w1", "b1", "w2", "b2", "wm", "bm", "wa", "ba"), ps):
+                setattr(d, nm, p_.data_ptr())
+                setattr(d, "g" + nm, self.grad_view(p_).data_ptr())
+            d.mul, d.add, d.dmul, d.dadd = mul.data_ptr(), add.data_ptr(), dm.data_ptr(), dd.data_ptr()
+            d.c1, d.c2, d.c = att.conv1.out_channels, att.conv2.out_channels, c
+            assert d.c1 + d.c2 <= c
+            descs.append(d)
+        arr = (_l.vk_sft_desc * len(descs))(*descs)
+        table = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
+        out = (sft, table, len(descs), max(nfeat), dmd, grads, vals)
+        self._bufs[key] = out
+        return out[:4]
+
     def forward_sr(self, x: torch.Tensor, sf: int, save: bool = False):
         """x: LR image NCHW fp32 -> (mu [N,C,H*sf,W*sf], kinfo [N,3], sigma [N,1,1,1])."""
         net = self.net
@@ -535,14 +571,8 @@ class DenoiseEngine:
         sqrt_mask = ((1 << self.sigma_chn) - 1) << kc
         nfeat = self.n_feat
         rnet = net.RNet
-        sft = {}
-        for ii, blk in enumerate(rnet.down_path):
-            for b, rb in enumerate(blk.body):
-                for which in ("sft1", "sft2"):
-                    mul = self._buf(f"sr.sft.{ii}.{b}.{which}.m", (N, nfeat[ii]), f32)
-                    add = self._buf(f"sr.sft.{ii}.{b}.{which}.a", (N, nfeat[ii]), f32)
-                    ops.sft_mlp(extra, getattr(rb, which), mul, add, sqrt_mask=sqrt_mask)
-                    sft[(ii, b, which)] = (mul, add)
+        sft, sft_descs, sft_n, sft_maxc = self._sft_tables(N)
+        ops.sft_mlp_batched(sft_descs, sft_n, sft_maxc, extra, sqrt_mask=sqrt_mask)
 
         # ---- RNet on the nearest-upsampled image (VIRNet.py:83; AttResUNet.py:141-175, extra_mode 'Both') ----
         Hh, Ww = h * sf, w * sf
@@ -679,10 +709,11 @@ class DenoiseEngine:
                 gXl = self._buf(f"g.sr.u{k}.low", (N, hl, wl, nf[lvl + 1]))
                 self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
                 gX = gXl
-            dm, dd = {}, {}
-            for key, (mul, _) in S["sft"].items():
-                dm[key] = torch.zeros_like(mul)
-                dd[key] = torch.zeros_like(mul)
+            tables = self._bufs[("sft_tables", N, self._flat_key)]
+            sft_descs, sft_n, sft_maxc, dmd, sft_grads = tables[1], tables[2], tables[3], tables[4], tables[5]
+            sft_grads.zero_()
+            dm = {k: v[0] for k, v in dmd.items()}
+            dd = {k: v[1] for k, v in dmd.items()}
             for ii in reversed(range(self.depth)):
                 res, ds = self.down[ii]
                 c = nf[ii]
@@ -701,12 +732,8 @@ class DenoiseEngine:
             self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
             hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
             ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
-            # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values
-            rnet = net.RNet
-            for (ii, b, which), _ in S["sft"].items():
-                att = getattr(rnet.down_path[ii].body[b], which)
-                ops.sft_mlp_bwd(S["extra"], att, dm[(ii, b, which)], dd[(ii, b, which)], self.grad_view, d_extra,
-                                sqrt_mask=sqrt_mask)
+            # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values, every AttLayer in one launch
+            ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, S["extra"], d_extra, sqrt_mask=sqrt_mask)
             # the head saw [kinfo, sqrt(sigma)] as constant planes: chain the sqrt for the variance channels
             hext = hsum[:, C:C + E].clone()
             hext[:, kc:] = hext[:, kc:] * 0.5 / S["extra"][:, kc:].sqrt().clamp_min(1e-20)

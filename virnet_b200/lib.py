@@ -67,6 +67,12 @@ class vk_elbo_sisr_args(C.Structure):
                 [(k, C.c_float) for k in ("center", "alpha0", "digamma_am1", "kappa0", "r2", "eps2", "pk0", "pk1")])
 
 
+class vk_sft_desc(C.Structure):
+    _fields_ = ([(k, C.c_void_p) for k in ("w1", "b1", "w2", "b2", "wm", "bm", "wa", "ba", "gw1", "gb1", "gw2", "gb2",
+                                           "gwm", "gbm", "gwa", "gba", "mul", "add", "dmul", "dadd")] +
+                [(k, C.c_int32) for k in ("c1", "c2", "c", "pad_")])
+
+
 class vk_pack_desc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
                 ("dim0", C.c_int32), ("dim1", C.c_int32), ("taps", C.c_int32),
@@ -119,6 +125,11 @@ _SIGNATURES = {
                                   C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "vk_knet_head_wgrad": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vk_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
+    "vk_sft_mlp_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
+                                     C.c_float, C.c_void_p]),
+    "vk_sft_mlp_bwd_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
+                                         C.c_float, C.c_void_p, C.c_void_p]),
+    "vk_sizeof_sft_desc": (C.c_uint32, []),
     "vk_synth_denoise": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 4),
     "vk_noise_estimate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_float, C.c_void_p]),
@@ -152,7 +163,8 @@ def load():
         fn.argtypes = args
     if (lib.vk_sizeof_conv_args() != C.sizeof(vk_conv_args)
             or lib.vk_sizeof_wgrad_args() != C.sizeof(vk_wgrad_args)
-            or lib.vk_sizeof_elbo_sisr_args() != C.sizeof(vk_elbo_sisr_args)):
+            or lib.vk_sizeof_elbo_sisr_args() != C.sizeof(vk_elbo_sisr_args)
+            or lib.vk_sizeof_sft_desc() != C.sizeof(vk_sft_desc)):
         raise VkError("argument struct layout mismatch between lib.py and the built library; rebuild")
     _lib = lib
     return lib

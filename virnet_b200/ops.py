@@ -499,3 +499,17 @@ def synth_denoise(patches_u8, params, aug, noise, *, clip=False):
         _l.check(_l.load().vk_synth_denoise(_ptr(patches_u8), _ptr(params), _ptr(aug), _ptr(noise), n, p, c, int(clip),
                                             _ptr(im_noisy), _ptr(im_gt), _ptr(sigma_gt), _stream()), "vk_synth_denoise")
     return im_noisy, im_gt, sigma_gt
+
+
+def sft_mlp_batched(descs_dev, n_layers, max_c, extra, *, sqrt_mask=0, alpha=0.2):
+    n, e = extra.shape
+    with _Prof("sft_mlp"):
+        _l.check(_l.load().vk_sft_mlp_batched(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask, alpha,
+                                              _stream()), "vk_sft_mlp_batched")
+
+
+def sft_mlp_bwd_batched(descs_dev, n_layers, max_c, extra, d_extra, *, sqrt_mask=0, alpha=0.2):
+    n, e = extra.shape
+    with _Prof("sft_mlp_bwd"):
+        _l.check(_l.load().vk_sft_mlp_bwd_batched(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask, alpha,
+                                                  _ptr(d_extra), _stream()), "vk_sft_mlp_bwd_batched")
