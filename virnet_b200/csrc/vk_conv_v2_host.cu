@@ -391,6 +391,15 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
             prm.nb, prm.a_stages, prm.a_slot_bytes, prm.b_stages, prm.b_slot_bytes, epi_warp_bytes, ecb, prm.tmem_cols,
             smem_bytes, int(pair), prm.b_resident);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // residual-block convolutions (bf16, pairs, slab mode, 64-byte staging rows, one of the four tensor combinations a
+  // training step uses): kernels specialised on the epilogue combination; VK_V2_NO_HOT=1 forces the generic kernel
+  static const bool no_hot = std::getenv("VK_V2_NO_HOT") != nullptr;
+  if (a->dtype == VK_BF16 && pair && !prm.full_k && a->epi == VK_EPI_STD && ecb == 64 && a->sft_mul == nullptr &&
+      prm.timing == nullptr && !no_hot) {
+    const int mode = prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3);
+    const int r = v2_launch_bf16_pair_hot(chunk, nt, mode, ta, tb, em, prm, grid, smem_bytes, st);
+    if (r != VK_E_UNSUPPORTED) return r;
+  }
   if (a->dtype == VK_BF16)
     return pair ? v2_launch_bf16_pair(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st)
                 : v2_launch_bf16_single(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st);

@@ -12,4 +12,7 @@ VK_V2_DECL(v2_launch_bf16_pair)
 VK_V2_DECL(v2_launch_tf32_single)
 VK_V2_DECL(v2_launch_tf32_pair)
 #undef VK_V2_DECL
+// bf16 CTA-pair slab kernels specialised on the epilogue tensor combination `mode` (vk_conv_v2_inst_bf16_pair_hot.cu)
+int v2_launch_bf16_pair_hot(int chunk, int nt, int mode, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
+                            const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st);
 }  // namespace vk
