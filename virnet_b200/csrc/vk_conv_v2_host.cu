@@ -218,7 +218,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
 
   // ---- CTA pairs (cta_group::2): M = 256 per MMA, each CTA stages half of the weight rows ----
   // force_impl: 0/2 automatic, 3 single CTAs, 4 pairs
-  bool pair = a->force_impl == 4 || (a->force_impl != 3 && n_cta % 32 == 0 && n_cta >= 96);
+  bool pair = a->force_impl == 4 || (a->force_impl != 3 && n_cta % 32 == 0 && n_cta >= 64);
   if (n_cta % 32) pair = false;                 // each half must be a multiple of 16 rows (N % 16, swizzle atoms)
   const int b_rows = pair ? n_cta / 2 : n_cta;  // weight rows staged per CTA
   const int epi_groups = v2_epi_groups(pair);
@@ -386,15 +386,16 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   if (debug)
     fprintf(stderr,
             "vk v2: kind=%d n=%d %dx%d ldx=%d wrows=%d | tile %dx%d tiles=%d P=%d n_cta=%d jobs=%d grid=%d | chunk=%d nt=%d "
-            "nb=%d a_stages=%d(%d B) b_stages=%d(%d B) epi=%d B/warp ecb=%d tmem=%d smem=%d pair=%d resident=%d\n",
+            "nb=%d a_stages=%d(%d B) b_stages=%d(%d B) epi=%d B/warp ecb=%d tmem=%d smem=%d pair=%d resident=%d fullk=%d mode=%d\n",
             a->kind, a->n, a->ih, a->iw, a->ldx, a->wrows, tw, th, prm.n_tiles, P, n_cta, prm.n_jobs, grid, chunk, nt,
             prm.nb, prm.a_stages, prm.a_slot_bytes, prm.b_stages, prm.b_slot_bytes, epi_warp_bytes, ecb, prm.tmem_cols,
-            smem_bytes, int(pair), prm.b_resident);
+            smem_bytes, int(pair), prm.b_resident, prm.full_k,
+            a->epi == VK_EPI_STD ? (prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3)) : -1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // residual-block convolutions (bf16, pairs, slab mode, 64-byte staging rows, one of the four tensor combinations a
   // training step uses): kernels specialised on the epilogue combination; VK_V2_NO_HOT=1 forces the generic kernel
   static const bool no_hot = std::getenv("VK_V2_NO_HOT") != nullptr;
-  if (a->dtype == VK_BF16 && pair && !prm.full_k && a->epi == VK_EPI_STD && ecb == 64 && a->sft_mul == nullptr &&
+  if (a->dtype == VK_BF16 && pair && a->epi == VK_EPI_STD && ecb == 64 && a->sft_mul == nullptr &&
       prm.timing == nullptr && !no_hot) {
     const int mode = prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3);
     const int r = v2_launch_bf16_pair_hot(chunk, nt, mode, ta, tb, em, prm, grid, smem_bytes, st);

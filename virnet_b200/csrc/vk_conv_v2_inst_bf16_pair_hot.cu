@@ -1,5 +1,5 @@
-// conv_v2_kernel instantiations specialised on the epilogue tensor combination (kEpi = 5, 7, 8, 14): bf16, CTA pairs,
-// slab mode — the residual-block convolutions of a training step (conv1 / conv2, forward and dgrad).
+// conv_v2_kernel instantiations specialised on the epilogue tensor combination (kEpi): bf16, CTA pairs — every
+// (kernel configuration, combination) a denoising training step launches at its large layers (tools/v2_config_census.py).
 #include <mutex>
 
 #include "../../include/virnet_b200.h"
@@ -9,12 +9,12 @@
 namespace vk {
 namespace {
 
-template <int kChunk, int kNT, int kEpi>
+template <int kChunk, int kNT, bool kFullK, int kEpi>
 int launch_hot(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em, const ConvV2Params& prm, int grid,
                int smem_bytes, cudaStream_t st) {
   static int cur = 0;
   static std::mutex mu;
-  auto kern = conv_v2_kernel<__nv_bfloat16, kChunk, kNT, true, false, kEpi>;
+  auto kern = conv_v2_kernel<__nv_bfloat16, kChunk, kNT, true, kFullK, kEpi>;
   {
     std::lock_guard<std::mutex> g(mu);
     if (smem_bytes > cur) {
@@ -40,11 +40,17 @@ int launch_hot(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& e
 int v2_launch_bf16_pair_hot(int chunk, int nt, int mode, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
                             const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st) {
 #define VK_HOT(C, T, M) \
-  if (chunk == C && nt == T && mode == M) return launch_hot<C, T, M>(ta, tb, em, prm, grid, smem_bytes, st);
-#define VK_HOT_MODES(C, T) VK_HOT(C, T, 5) VK_HOT(C, T, 7) VK_HOT(C, T, 8) VK_HOT(C, T, 14)
+  if (chunk == C && nt == T && mode == M && !prm.full_k) return launch_hot<C, T, false, M>(ta, tb, em, prm, grid, smem_bytes, st);
+#define VK_HOT_MODES(C, T) VK_HOT(C, T, 5) VK_HOT(C, T, 6) VK_HOT(C, T, 7) VK_HOT(C, T, 8) VK_HOT(C, T, 14)
   VK_HOT_MODES(64, 9) VK_HOT_MODES(128, 9) VK_HOT_MODES(64, 3) VK_HOT_MODES(128, 3)
 #undef VK_HOT_MODES
 #undef VK_HOT
+  // strided / transposed kinds (full-K mode): stride-2 conv (out1 + out2), ConvT (resid + out1 + out2), their dgrads
+#define VK_HOT_FK(C, M) \
+  if (chunk == C && mode == M && prm.full_k) return launch_hot<C, 1, true, M>(ta, tb, em, prm, grid, smem_bytes, st);
+  VK_HOT_FK(64, 4) VK_HOT_FK(64, 6) VK_HOT_FK(64, 12) VK_HOT_FK(64, 14)
+  VK_HOT_FK(128, 4) VK_HOT_FK(128, 6) VK_HOT_FK(128, 12) VK_HOT_FK(128, 14)
+#undef VK_HOT_FK
   return VK_E_UNSUPPORTED;
 }
 
