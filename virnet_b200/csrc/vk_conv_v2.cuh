@@ -305,9 +305,9 @@ __device__ __forceinline__ void epi_item_math_sft(const uint32_t (&acc)[2][16], 
   }
 }
 
-// kEpi: -1 = every epilogue tensor combination behind a run-time switch; 5 / 7 / 8 / 14 = only that combination
-// (mask=1, resid=2, out1=4, out2=8; 64-byte staging rows, no SFT, no stall counters) — the four combinations the
-// residual blocks of a training step use.  The generic kernel's per-item epilogue walks ~460 instructions scattered
+// kEpi: -1 = every epilogue tensor combination behind a run-time switch; >= 0 = only that combination
+// (mask=1, resid=2, out1=4, out2=8, +16 = SFT modulation of out2; 64-byte staging rows, no stall counters) — the
+// combinations the large layers of a training step use.  The generic kernel's per-item epilogue walks ~460 instructions scattered
 // over 40 KB of SASS (ncu: 41 % of the epilogue warps' stall samples are instruction fetch); the specialised ones keep
 // that loop contiguous.
 template <typename DT, int kChunkBytes, int kNT, bool kPair, bool kFullK, int kEpi = -1>
@@ -722,7 +722,14 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           // ---- fused epilogue maths, specialised at compile time on the tensors present ----
           const uint32_t a_o1 = row_base + off_o1, a_o2 = row_base + off_o2;
-          if constexpr (kEpi >= 0) {
+          if constexpr (kEpi >= 16) {             // SFT epilogue (super-resolution forward): out2 = lrelu(v * mul + add)
+            const bool rnd = kTF32 && prm.round_out2;
+            const int c0 = cq0 + kc * ecols;
+            epi_item_math_sft<DT>(acc, rraw, 4, (kEpi & 2) != 0, (kEpi & 4) != 0,
+                                  prm.sft_mul + static_cast<long long>(t_img) * prm.sft_ld + c0,
+                                  prm.sft_add + static_cast<long long>(t_img) * prm.sft_ld + c0, prm.cout - c0, alpha,
+                                  rnd, a_o1, a_o2, swz);
+          } else if constexpr (kEpi >= 0) {
             const bool rnd = kTF32 && prm.round_out2;
             epi_item_math<DT, (kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, (kEpi & 8) != 0, 64>(acc, rraw, kraw, alpha,
                                                                                                   rnd, a_o1, a_o2, swz);

@@ -395,9 +395,9 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   // residual-block convolutions (bf16, pairs, slab mode, 64-byte staging rows, one of the four tensor combinations a
   // training step uses): kernels specialised on the epilogue combination; VK_V2_NO_HOT=1 forces the generic kernel
   static const bool no_hot = std::getenv("VK_V2_NO_HOT") != nullptr;
-  if (a->dtype == VK_BF16 && pair && a->epi == VK_EPI_STD && ecb == 64 && a->sft_mul == nullptr &&
-      prm.timing == nullptr && !no_hot) {
-    const int mode = prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3);
+  if (a->dtype == VK_BF16 && pair && a->epi == VK_EPI_STD && ecb == 64 && prm.timing == nullptr && !no_hot) {
+    const int mode = (prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3)) +
+                     (a->sft_mul != nullptr ? 16 : 0);
     const int r = v2_launch_bf16_pair_hot(chunk, nt, mode, ta, tb, em, prm, grid, smem_bytes, st);
     if (r != VK_E_UNSUPPORTED) return r;
   }
