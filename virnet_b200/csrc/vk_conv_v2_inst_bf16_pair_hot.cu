@@ -43,6 +43,8 @@ int v2_launch_bf16_pair_hot(int chunk, int nt, int mode, const CUtensorMap& ta, 
   if (chunk == C && nt == T && mode == M && !prm.full_k) return launch_hot<C, T, false, M>(ta, tb, em, prm, grid, smem_bytes, st);
 #define VK_HOT_MODES(C, T) VK_HOT(C, T, 5) VK_HOT(C, T, 6) VK_HOT(C, T, 7) VK_HOT(C, T, 8) VK_HOT(C, T, 14)
   VK_HOT_MODES(64, 9) VK_HOT_MODES(128, 9) VK_HOT_MODES(64, 3) VK_HOT_MODES(128, 3)
+  // 16-channel-input layers (network heads, padded 3/4-channel images): SNet conv1, RNet head, tail dgrad
+  VK_HOT(32, 9, 4) VK_HOT(32, 9, 5) VK_HOT(32, 9, 8) VK_HOT(32, 9, 12)
   // SFT-modulated residual blocks of the super-resolution network (mode + 16)
   VK_HOT(64, 9, 24) VK_HOT(64, 9, 28) VK_HOT(64, 9, 30) VK_HOT(64, 3, 24) VK_HOT(64, 3, 28) VK_HOT(64, 3, 30)
 #undef VK_HOT_MODES

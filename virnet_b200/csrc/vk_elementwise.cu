@@ -296,6 +296,48 @@ __global__ void channel_sum_kernel(const DT* __restrict__ x, long long npix, int
   }
 }
 
+// 16-byte-vector form for ld % (16 / sizeof(DT)) == 0: a thread keeps the sums of one vector of channels over its
+// pixels in registers; lanes are reduced through shared memory, one atomicAdd per (block, channel).
+template <typename DT>
+__global__ void __launch_bounds__(256)
+channel_sum_vec_kernel(const DT* __restrict__ x, long long npix, int ld, int C, float* __restrict__ out) {
+  constexpr int V = 16 / int(sizeof(DT));
+  extern __shared__ float cs_sm[];           // [lanes][ld]
+  x += static_cast<long long>(blockIdx.y) * npix * ld;
+  out += static_cast<long long>(blockIdx.y) * C;
+  const int groups = ld / V, lanes = 256 / groups;
+  const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float s[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = 0.f;
+  if (pl < lanes)
+    for (long long p = blockIdx.x * static_cast<long long>(lanes) + pl; p < npix; p += static_cast<long long>(gridDim.x) * lanes) {
+      const uint4 r = *reinterpret_cast<const uint4*>(x + p * ld + cg * V);
+      if constexpr (sizeof(DT) == 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          s[2 * i] += f.x, s[2 * i + 1] += f.y;
+        }
+      } else {
+        const float* f = reinterpret_cast<const float*>(&r);
+#pragma unroll
+        for (int i = 0; i < V; ++i) s[i] += f[i];
+      }
+    }
+  if (pl < lanes) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) cs_sm[pl * ld + cg * V + i] = s[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += cs_sm[l * ld + c];
+    atomicAdd(out + c, t);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Gradient norm -> clip -> Adam over flat fp32 buffers, grouped by sub-network
 // (train_denoising_syn.py:182-184: clip_grad_norm_ per sub-net, optim.Adam.step)
@@ -337,15 +379,34 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   const float coef = fminf(gr.max_norm / (total + 1e-6f), 1.f) * gscale;   // clip_grad_norm_ semantics
   if (norms_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) norms_out[gi] = total;
   const float step = lr / bc1;
+  auto upd = [&](float gv, float& pv, float& mv, float& vv_) {
+    const float gg = gv * coef;
+    const float mm = beta1 * mv + (1.f - beta1) * gg;
+    const float vv = beta2 * vv_ + (1.f - beta2) * gg * gg;
+    mv = mm, vv_ = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv -= step * mm / denom;
+  };
+  if (((gr.begin | gr.end) & 3) == 0) {
+    // every tensor of the flat buffers is padded to 4 elements: 16-byte vectors (7 streams, 28 B per parameter)
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = (gr.begin >> 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < (gr.end >> 2);
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const float4 gv = g4[i];
+      float4 pv = p4[i], mv = m4[i], vv = v4[i];
+      upd(gv.x, pv.x, mv.x, vv.x), upd(gv.y, pv.y, mv.y, vv.y), upd(gv.z, pv.z, mv.z, vv.z), upd(gv.w, pv.w, mv.w, vv.w);
+      m4[i] = mv, v4[i] = vv, p4[i] = pv;
+    }
+    return;
+  }
   for (long long i = gr.begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < gr.end;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gg = g[i] * coef;
-    const float mm = beta1 * m[i] + (1.f - beta1) * gg;
-    const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
-    m[i] = mm;
-    v[i] = vv;
-    const float denom = sqrtf(vv) / bc2_sqrt + eps;
-    p[i] -= step * mm / denom;
+    float pv = p[i], mv = m[i], vv = v[i];
+    upd(g[i], pv, mv, vv);
+    m[i] = mv, v[i] = vv, p[i] = pv;
   }
 }
 
@@ -462,6 +523,23 @@ extern "C" int vk_pack_weights(int32_t dtype, const void* descs_dev, int32_t nde
 extern "C" int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_t ld, int32_t c, float* out,
                               void* stream) {
   if (x == nullptr || out == nullptr || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
+  {
+    const int vec = dtype == VK_BF16 ? 8 : 4;
+    if ((dtype == VK_BF16 || dtype == VK_TF32) && ld % vec == 0 && ld / vec <= 256 && npix >= 4096) {
+      const int lanes = 256 / (ld / vec);
+      const size_t smem = size_t(lanes) * ld * sizeof(float);
+      if (smem <= 48 * 1024) {
+        const int vgrid = int(std::min<long long>((npix + lanes - 1) / lanes, kSMs * 4));
+        if (dtype == VK_BF16)
+          channel_sum_vec_kernel<__nv_bfloat16><<<vgrid, 256, smem, VK_ST(stream)>>>(
+              reinterpret_cast<const __nv_bfloat16*>(x), npix, ld, c, out);
+        else
+          channel_sum_vec_kernel<float><<<vgrid, 256, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c,
+                                                                            out);
+        VK_LAUNCHED();
+      }
+    }
+  }
   const int grid = int(std::min<long long>((npix + 7) / 8, kSMs * 4));
   if (dtype == VK_BF16)
     channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
