@@ -246,26 +246,28 @@ struct PackDesc {
 template <typename DT>
 __global__ void pack_weights_kernel(const PackDesc* __restrict__ descs, int round_tf32_flag) {
   const PackDesc d = descs[blockIdx.y];
-  const long long total = static_cast<long long>(d.dst_taps) * d.rows * d.ld;
+  // one thread per (row, k) element, looping over the destination taps: the taps of one (Co, Ci) pair are contiguous
+  // in the OIHW source (36 B for a 3x3 filter), so every fetched sector is fully used; writes are coalesced along k
+  const unsigned rk = unsigned(d.rows) * unsigned(d.ld);
   DT* dst = reinterpret_cast<DT*>(d.dst);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = int(i % d.ld);
-    const int r = int((i / d.ld) % d.rows);
-    const int t = int(i / (static_cast<long long>(d.ld) * d.rows));
-    float v = 0.f;
-    int i0 = -1, i1 = -1, it = 0;
-    switch (d.mode) {
-      case 0: i0 = r, i1 = k, it = t; break;
-      case 1: i0 = k, i1 = r, it = d.taps - 1 - t; break;
-      case 2: i0 = k, i1 = r % d.dim1, it = r / d.dim1; break;
-      case 3: i0 = r, i1 = k, it = t; break;
-      default: i0 = k, i1 = r, it = t; break;   // mode 4: transpose Ci/Co without rotation
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < rk; i += gridDim.x * blockDim.x) {
+    const int k = int(i % unsigned(d.ld));
+    const int r = int(i / unsigned(d.ld));
+    for (int t = 0; t < d.dst_taps; ++t) {
+      float v = 0.f;
+      int i0 = -1, i1 = -1, it = 0;
+      switch (d.mode) {
+        case 0: i0 = r, i1 = k, it = t; break;
+        case 1: i0 = k, i1 = r, it = d.taps - 1 - t; break;
+        case 2: i0 = k, i1 = r % d.dim1, it = r / d.dim1; break;
+        case 3: i0 = r, i1 = k, it = t; break;
+        default: i0 = k, i1 = r, it = t; break;   // mode 4: transpose Ci/Co without rotation
+      }
+      if (i0 >= 0 && i0 < d.dim0 && i1 >= 0 && i1 < d.dim1 && it < d.taps)
+        v = __ldg(d.src + (static_cast<long long>(i0) * d.dim1 + i1) * d.taps + it);
+      if (round_tf32_flag) v = round_tf32(v);
+      dst[static_cast<long long>(t) * rk + i] = cvt_out<DT>(v);
     }
-    if (i0 >= 0 && i0 < d.dim0 && i1 >= 0 && i1 < d.dim1 && it < d.taps)
-      v = __ldg(d.src + (static_cast<long long>(i0) * d.dim1 + i1) * d.taps + it);
-    if (round_tf32_flag) v = round_tf32(v);
-    dst[i] = cvt_out<DT>(v);
   }
 }
 
@@ -508,7 +510,7 @@ extern "C" int vk_elbo_denoise(const float* mu, const float* sigma, const float*
 extern "C" int vk_pack_weights(int32_t dtype, const void* descs_dev, int32_t ndesc, int64_t max_elems,
                                int32_t round_tf32_flag, void* stream) {
   if (descs_dev == nullptr || ndesc <= 0) return VK_E_BADARG;
-  dim3 grid(grid_for(max_elems, 256, 2), ndesc);
+  dim3 grid(grid_for((max_elems + 8) / 9, 256, 2), ndesc);     // ~one thread per (row, k) of the largest 3x3 layer
   if (dtype == VK_BF16)
     pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(
         reinterpret_cast<const PackDesc*>(descs_dev), 0);
