@@ -272,6 +272,15 @@ int64_t vk_elbo_sisr_ws_bytes(int32_t n, int32_t c, int32_t H, int32_t W, int32_
 uint32_t vk_sizeof_elbo_sisr_args(void);
 int vk_elbo_sisr(const vk_elbo_sisr_args* args, void* stream);
 
+/* Device-side synthesis of SISR training pairs: datasets/SISRDatasets.py:86-104 (GeneralTrainFloder.__getitem__ after
+ * the crop / augmentation, Gaussian-noise branch): im_blur = down(clip(conv(im_hr, kernel[n]), 0, 1)) with
+ * scipy.ndimage.convolve(mode='reflect') semantics and the rh / rw down-sampling operators (Direct or ResizeRight
+ * bicubic), im_lr = clip(im_blur + noise * std[n], 0, 1).  NCHW fp32; kernels [n][k*k]; noise [n][c][h][w]. */
+int64_t vk_sisr_degrade_ws_bytes(int32_t n, int32_t c, int32_t H, int32_t W, int32_t w);
+int vk_sisr_degrade(const float* im_hr, const float* kernels, int32_t k_size, const float* rh, const float* rw,
+                    const float* noise, const float* std, float* im_blur, float* im_lr, void* ws, int64_t ws_bytes,
+                    int32_t n, int32_t c, int32_t H, int32_t W, int32_t h, int32_t w, void* stream);
+
 /* ---- HBM-bound kernels ------------------------------------------------- */
 
 /* NCHW fp32 image (+ conditioning channels) -> NHWC `dtype`, reflect-padded bottom/right

@@ -477,6 +477,34 @@ def synth_denoise_sample(patch_u8, params, aug_flag: int, noise, clip: bool = Fa
 
 
 # --------------------------------------------------------------------------------------
+# SISR training-pair synthesis (datasets/SISRDatasets.py:86-104, utils/util_sisr.py:60-93,108-125) — numpy
+# --------------------------------------------------------------------------------------
+def sisr_degrade_sample(im_hr, kernel, sf: int, downsampler: str, noise, std: float):
+    """One sample, HWC float32: scipy.ndimage.convolve(mode='reflect') restated as a correlation with the flipped
+    kernel on np.pad(mode='symmetric'), clip, Direct / ResizeRight-bicubic down-sampling (the numpy path of ResizeRight
+    computes in float64), Gaussian noise, clip.  Returns (im_blur, im_lr) HWC float32."""
+    import numpy as np
+    k = kernel.shape[0]
+    r = k // 2
+    H, W, C = im_hr.shape
+    pad = np.pad(im_hr.astype(np.float64), ((r, r), (r, r), (0, 0)), mode="symmetric")
+    kf = kernel[::-1, ::-1].astype(np.float64)
+    blur = np.zeros((H, W, C), dtype=np.float64)
+    for i in range(k):
+        for j in range(k):
+            blur += kf[i, j] * pad[i:i + H, j:j + W]
+    blur = np.clip(blur.astype(np.float32), 0.0, 1.0)
+    if downsampler.lower() == "direct":
+        im_blur = blur[::sf, ::sf]
+    else:
+        mh = resize_matrix(H, sf, "bicubic").double().numpy()
+        mw = resize_matrix(W, sf, "bicubic").double().numpy()
+        im_blur = np.einsum("yh,hwc,xw->yxc", mh, blur.astype(np.float64), mw).astype(np.float32)
+    im_lr = np.clip(im_blur + np.asarray(noise, dtype=np.float32) * np.float32(std), 0.0, 1.0).astype(np.float32)
+    return im_blur.astype(np.float32), im_lr
+
+
+# --------------------------------------------------------------------------------------
 # one reference training step (train_denoising_syn.py:175-184), used as the CPU baseline
 # --------------------------------------------------------------------------------------
 def clip_grad_norm_(params: List[Tensor], max_norm: float) -> Tensor:

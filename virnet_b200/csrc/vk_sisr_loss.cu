@@ -101,7 +101,7 @@ template <bool kReflect>
 __global__ void __launch_bounds__(256)
 sisr_blur_kernel(const float* __restrict__ in, const float* __restrict__ noise, float nscale,
                  const float* __restrict__ kern, float* __restrict__ out, int C, int Hin, int Win, int Hout, int Wout,
-                 int off, int K, int flip) {
+                 int off, int K, int flip, int flags = 0) {      // flags: 1 = half-sample symmetric padding, 2 = clip to [0, 1]
   extern __shared__ float sm[];
   const int TW = kBlurTile + K - 1, TP = TW + 1;
   float* tile = sm;                      // [TW][TP]
@@ -118,8 +118,14 @@ sisr_blur_kernel(const float* __restrict__ in, const float* __restrict__ noise, 
     float v = 0.f;
     if (kReflect) {
       // rows/cols beyond the last output tile's needs may reflect twice on tiny images: clamp after reflecting
-      gy = min(max(reflect_idx(gy, Hin), 0), Hin - 1);
-      gx = min(max(reflect_idx(gx, Win), 0), Win - 1);
+      if (flags & 1) {              // scipy.ndimage 'reflect' (d c b a | a b c d): the edge sample is repeated
+        gy = gy < 0 ? -gy - 1 : (gy >= Hin ? 2 * Hin - 1 - gy : gy);
+        gx = gx < 0 ? -gx - 1 : (gx >= Win ? 2 * Win - 1 - gx : gx);
+        gy = min(max(gy, 0), Hin - 1), gx = min(max(gx, 0), Win - 1);
+      } else {
+        gy = min(max(reflect_idx(gy, Hin), 0), Hin - 1);
+        gx = min(max(reflect_idx(gx, Win), 0), Win - 1);
+      }
       v = ip[gy * Win + gx];
       if (np) v = fmaf(nscale, np[gy * Win + gx], v);
     } else if (gy >= 0 && gy < Hin && gx >= 0 && gx < Win) {
@@ -157,6 +163,8 @@ sisr_blur_kernel(const float* __restrict__ in, const float* __restrict__ noise, 
   }
   float* op = out + static_cast<long long>(p) * Hout * Wout;
   const int y = oy0 + ty, x = ox0 + cg * 4;
+  if (flags & 2) a0 = fminf(fmaxf(a0, 0.f), 1.f), a1 = fminf(fmaxf(a1, 0.f), 1.f), a2 = fminf(fmaxf(a2, 0.f), 1.f),
+                 a3 = fminf(fmaxf(a3, 0.f), 1.f);
   if (y < Hout) {
     if (x < Wout) op[y * Wout + x] = a0;
     if (x + 1 < Wout) op[y * Wout + x + 1] = a1;
@@ -408,6 +416,16 @@ __global__ void sisr_finalize_kernel(const double* __restrict__ acc, int N, doub
   terms[5] = float(k0), terms[6] = float(k1), terms[7] = float(k2);
 }
 
+// im_lr = clip(im_blur + noise * std[n], 0, 1) (datasets/SISRDatasets.py:100-104)
+__global__ void sisr_add_noise_kernel(const float* __restrict__ blur, const float* __restrict__ noise,
+                                      const float* __restrict__ std, float* __restrict__ out, int per_sample, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = __fadd_rn(blur[i], __fmul_rn(noise[i], std[i / per_sample]));
+    out[i] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+
 }  // namespace vk
 
 using namespace vk;
@@ -523,5 +541,44 @@ extern "C" int vk_elbo_sisr(const vk_elbo_sisr_args* a, void* stream_) {
   sisr_finalize_kernel<<<1, 1, 0, st>>>(acc, N, hr_count, a->eps2, a->r2, a->pk0, a->pk1, a->terms);
   launches += 2;
   g_launch_count.fetch_add(launches, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+// ---- device-side synthesis of SISR training pairs (datasets/SISRDatasets.py:86-104 after the crop / augmentation) ----
+extern "C" int64_t vk_sisr_degrade_ws_bytes(int32_t n, int32_t c, int32_t H, int32_t W, int32_t w) {
+  if (n <= 0 || c <= 0 || H <= 0 || W <= 0 || w <= 0) return -1;
+  return int64_t(n) * c * H * (int64_t(W) + w) * 4 + 512;
+}
+
+extern "C" int vk_sisr_degrade(const float* im_hr, const float* kernels, int32_t k_size, const float* rh, const float* rw,
+                               const float* noise, const float* std, float* im_blur, float* im_lr, void* ws,
+                               int64_t ws_bytes, int32_t n, int32_t c, int32_t H, int32_t W, int32_t h, int32_t w,
+                               void* stream_) {
+  if (!im_hr || !kernels || !rh || !rw || !noise || !std || !im_blur || !im_lr || !ws) return VK_E_BADARG;
+  if (n <= 0 || c <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0 || k_size < 1 || k_size > kMaxK || (k_size & 1) == 0)
+    return VK_E_BADARG;
+  if (k_size / 2 >= H || k_size / 2 >= W || ws_bytes < vk_sisr_degrade_ws_bytes(n, c, H, W, w)) return VK_E_BADARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  float* Bf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
+  float* Tf = Bf + static_cast<long long>(n) * c * H * W;
+  const int P = n * c, K = k_size, TW = kBlurTile + K - 1;
+  const size_t blur_smem = (size_t(TW) * (TW + 1) + size_t(K) * K) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(sisr_blur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_done = true;
+  }
+  auto tiles = [](int v) { return (v + kBlurTile - 1) / kBlurTile; };
+  // scipy.ndimage.convolve(mode='reflect') = correlation with the flipped kernel on symmetric padding; then clip
+  sisr_blur_kernel<true><<<dim3(tiles(W), tiles(H), P), 256, blur_smem, st>>>(im_hr, nullptr, 0.f, kernels, Bf, c, H, W, H, W,
+                                                                             K / 2, K, 1, 3);
+  sisr_plane_gemm_kernel<<<dim3((w + 63) / 64, (H + 63) / 64, P), 256, 0, st>>>(Bf, (long long)H * W, W, 1, rw, 0, 1, W, Tf,
+                                                                               (long long)H * w, H, w, W);
+  sisr_plane_gemm_kernel<<<dim3((w + 63) / 64, (h + 63) / 64, P), 256, 0, st>>>(rh, 0, H, 1, Tf, (long long)H * w, w, 1,
+                                                                               im_blur, (long long)h * w, h, w, H);
+  const long long total = static_cast<long long>(P) * h * w;
+  sisr_add_noise_kernel<<<int(std::min<long long>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(im_blur, noise, std, im_lr,
+                                                                                             c * h * w, total);
+  g_launch_count.fetch_add(4, std::memory_order_relaxed);
   return int(cudaGetLastError());
 }

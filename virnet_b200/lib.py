@@ -134,6 +134,9 @@ _SIGNATURES = {
     "vk_noise_estimate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_float, C.c_void_p]),
     "vk_mixup": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int64, C.c_void_p]),
+    "vk_sisr_degrade_ws_bytes": (C.c_int64, [C.c_int32] * 5),
+    "vk_sisr_degrade": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_int32] * 6 +
+                        [C.c_void_p]),
     "vk_elbo_sisr_ws_bytes": (C.c_int64, [C.c_int32] * 7),
     "vk_sizeof_elbo_sisr_args": (C.c_uint32, []),
     "vk_elbo_sisr": (C.c_int, [C.c_void_p, C.c_void_p]),

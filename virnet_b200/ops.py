@@ -513,3 +513,24 @@ def sft_mlp_bwd_batched(descs_dev, n_layers, max_c, extra, d_extra, *, sqrt_mask
     with _Prof("sft_mlp_bwd"):
         _l.check(_l.load().vk_sft_mlp_bwd_batched(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask, alpha,
                                                   _ptr(d_extra), _stream()), "vk_sft_mlp_bwd_batched")
+
+
+def sisr_degrade(im_hr, kernels, rh, rw, noise, std):
+    """im_hr [n, c, H, W], kernels [n, k, k], rh [h, H], rw [w, W], noise [n, c, h, w], std [n] (fp32 CUDA contiguous).
+    Returns (im_blur, im_lr) [n, c, h, w]."""
+    n, c, H, W = im_hr.shape
+    h, w, k = rh.shape[0], rw.shape[0], kernels.shape[-1]
+    for t in (im_hr, kernels, rh, rw, noise, std):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+    assert kernels.shape == (n, k, k) and rh.shape == (h, H) and rw.shape == (w, W) and noise.shape == (n, c, h, w)
+    assert std.numel() == n
+    lib = _l.load()
+    need = lib.vk_sisr_degrade_ws_bytes(n, c, H, W, w)
+    ws = torch.empty(need, dtype=torch.uint8, device=im_hr.device)
+    im_blur = torch.empty(n, c, h, w, device=im_hr.device, dtype=torch.float32)
+    im_lr = torch.empty_like(im_blur)
+    with _Prof("sisr_degrade"):
+        _l.check(lib.vk_sisr_degrade(_ptr(im_hr), _ptr(kernels), k, _ptr(rh), _ptr(rw), _ptr(noise), _ptr(std),
+                                     _ptr(im_blur), _ptr(im_lr), _ptr(ws), need, n, c, H, W, h, w, _stream()),
+                 "vk_sisr_degrade")
+    return im_blur, im_lr
