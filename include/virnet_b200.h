@@ -352,6 +352,12 @@ int vk_adam_clip_step(float* params, const float* grads, float* exp_avg, float* 
                       int32_t ngroups, int64_t max_group_elems, double* sq_ws, float grad_scale, float lr,
                       float beta1, float beta2, float eps, int32_t step, float* norms_out, void* stream);
 
+/* Same, with the per-step scalars read from device memory: hyper_dev = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}.
+ * A training step captured in a CUDA graph replays with fresh values written by the host before each launch. */
+int vk_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const void* groups_dev,
+                          int32_t ngroups, int64_t max_group_elems, double* sq_ws, float grad_scale, float beta1,
+                          float beta2, float eps, const float* hyper_dev, float* norms_out, void* stream);
+
 /* sizeof(vk_conv_args) as compiled into the library (binding self-check). */
 uint32_t vk_sizeof_conv_args(void);
 

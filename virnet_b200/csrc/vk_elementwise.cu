@@ -374,7 +374,9 @@ __global__ void grad_sqnorm_kernel(const float* __restrict__ g, const AdamGroup*
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, const AdamGroup* __restrict__ groups, int ngroups,
                                  const double* __restrict__ sq, float gscale, float lr, float beta1, float beta2,
-                                 float eps, float bc1, float bc2_sqrt, float* __restrict__ norms_out) {
+                                 float eps, float bc1, float bc2_sqrt, float* __restrict__ norms_out,
+                                 const float* __restrict__ hyper) {
+  if (hyper != nullptr) lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];     // CUDA-graph replay: per-step values
   const int gi = blockIdx.y;
   const AdamGroup gr = groups[gi];
   const float total = static_cast<float>(sqrt(sq[gi]));
@@ -583,6 +585,23 @@ extern "C" int vk_adam_clip_step(float* params, const float* grads, float* exp_a
   const float bc1 = 1.f - powf(beta1, float(step));
   const float bc2 = 1.f - powf(beta2, float(step));
   adam_clip_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, groups, ngroups, sq_ws, grad_scale, lr,
-                                         beta1, beta2, eps, bc1, sqrtf(bc2), norms_out);
+                                         beta1, beta2, eps, bc1, sqrtf(bc2), norms_out, nullptr);
+  VK_LAUNCHED();
+}
+
+extern "C" int vk_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                     const void* groups_dev, int32_t ngroups, int64_t max_group_elems, double* sq_ws,
+                                     float grad_scale, float beta1, float beta2, float eps, const float* hyper_dev,
+                                     float* norms_out, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !groups_dev || !sq_ws || !hyper_dev || ngroups <= 0) return VK_E_BADARG;
+  cudaStream_t st = VK_ST(stream);
+  cudaError_t e = cudaMemsetAsync(sq_ws, 0, ngroups * sizeof(double), st);
+  if (e != cudaSuccess) return int(e);
+  const AdamGroup* groups = reinterpret_cast<const AdamGroup*>(groups_dev);
+  dim3 grid(grid_for(max_group_elems, 256, 4), ngroups);
+  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(grads, groups, ngroups, grad_scale, sq_ws);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  adam_clip_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, groups, ngroups, sq_ws, grad_scale, 0.f, beta1,
+                                         beta2, eps, 1.f, 1.f, norms_out, hyper_dev);
   VK_LAUNCHED();
 }

@@ -109,6 +109,8 @@ _SIGNATURES = {
                                          C.c_void_p]),
     "vk_adam_clip_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p] + [C.c_float] * 5
                           + [C.c_int32, C.c_void_p, C.c_void_p]),
+    "vk_adam_clip_step_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p] + [C.c_float] * 4
+                              + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vk_knet_head": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vk_ca_layer": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
     "vk_gap_head": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_float, C.c_float,

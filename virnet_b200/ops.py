@@ -296,6 +296,16 @@ def adam_clip_step(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_
                                              step, _ptr(norms_out), _stream()), "vk_adam_clip_step")
 
 
+def adam_clip_step_dev(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_group_elems, sq_ws, hyper_dev, *,
+                       grad_scale, beta1, beta2, eps, norms_out=None):
+    """hyper_dev: fp32 [3] on the device = (lr, 1 - beta1^step, sqrt(1 - beta2^step))."""
+    with _Prof("adam_clip"):
+        _l.check(_l.load().vk_adam_clip_step_dev(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                                 _ptr(groups_dev), ngroups, max_group_elems, _ptr(sq_ws), grad_scale,
+                                                 beta1, beta2, eps, _ptr(hyper_dev), _ptr(norms_out), _stream()),
+                 "vk_adam_clip_step_dev")
+
+
 # ---------------------------------------------------------------------------
 # super-resolution forward path: small per-sample kernels
 # ---------------------------------------------------------------------------

@@ -88,6 +88,10 @@ class DenoiseTrainer:
         self._copy_stream, self._ev = None, None
         self._pf_free = self._pf_ready = self._pf_used = self._pf_key = None
         self._pf_next = 0
+        self._graph = self._graph_key = self._g_in = None
+        self._hyper = torch.zeros(3, device=dev, dtype=torch.float32)
+        self._hyper_ring = [(torch.zeros(3, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+        self._hyper_used = [False] * 8
 
     # -- host -> device staging (pinned host buffers are the caller's) --------------------------------------
     # The copies run on a side stream: the noisy patches are needed first (the weight packing of this step
@@ -164,6 +168,15 @@ class DenoiseTrainer:
             main.wait_event(self._ev[0])
         else:
             x, gt, sg = im_noisy, im_gt, sigma_gt
+        self.step_count += 1
+        self._device_step(x, gt, sg, ev_late, pf_set, self.lr if lr is None else lr, None)
+        return self.losses
+
+    def _device_step(self, x, gt, sg, ev_late, pf_set, lr, hyper_dev):
+        """Everything of a step that runs on the device, for inputs already resident: shared by the eager path and by the
+        CUDA-graph capture (hyper_dev: per-step Adam scalars in device memory instead of kernel arguments)."""
+        eng = self.engine
+        main = torch.cuda.current_stream()
         mu, sigma = eng.forward(x, save=True)
         if self._d_mu is None or self._d_mu.shape != mu.shape:
             self._d_mu, self._d_sigma = torch.empty_like(mu), torch.empty_like(sigma)
@@ -178,13 +191,63 @@ class DenoiseTrainer:
             self._pf_used[pf_set] = True
         eng.backward(self._d_mu, self._d_sigma)
         grad_scale = dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
-        self.step_count += 1
-        ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
-                           self._ngroups, self._max_group, self._sq_ws, grad_scale=grad_scale,
-                           lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1],
-                           eps=self.adam_eps, step=self.step_count, norms_out=self.grad_norms)
+        if hyper_dev is None:
+            ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
+                               self._ngroups, self._max_group, self._sq_ws, grad_scale=grad_scale, lr=lr,
+                               beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps, step=self.step_count,
+                               norms_out=self.grad_norms)
+        else:
+            ops.adam_clip_step_dev(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
+                                   self._ngroups, self._max_group, self._sq_ws, hyper_dev, grad_scale=grad_scale,
+                                   beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps, norms_out=self.grad_norms)
         eng.mark_params_dirty()
         self.last_mu, self.last_sigma = mu, sigma
+
+    # -- CUDA-graph replay of the whole step ---------------------------------------------------------------------
+    # At the reference's own batch (16 patches over 8 GPUs = 2 per GPU) a step is ~190 kernel launches of a few
+    # microseconds each and the Python / driver enqueue (about 3 ms) is the bound; one graph launch removes it.
+    def _capture(self, shapes):
+        eng = self.engine
+        dev = eng.flat_params.device
+        self._g_in = [torch.zeros(s, device=dev, dtype=torch.float32) for s in shapes]
+        state = [t.clone() for t in (eng.flat_params, self.exp_avg, self.exp_avg_sq)]
+        self._hyper.copy_(torch.tensor([0.0, 1.0, 1.0]))     # warm-up / capture run with lr = 0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up outside capture (lazy allocations, attributes)
+            for _ in range(2):
+                eng.mark_params_dirty()
+                self._device_step(*self._g_in, None, None, 0.0, self._hyper)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        eng.mark_params_dirty()                             # the captured step always re-packs the weights
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._device_step(*self._g_in, None, None, 0.0, self._hyper)
+        for t, sv in zip((eng.flat_params, self.exp_avg, self.exp_avg_sq), state):
+            t.copy_(sv)                                     # warm-up steps must not count as training
+        self._graph, self._graph_key = graph, tuple(shapes)
+
+    def step_graph(self, im_noisy, im_gt, sigma_gt, lr: Optional[float] = None):
+        """step() as ONE CUDA-graph launch: inputs (host or device) are copied into static buffers, the per-step Adam
+        scalars into device memory, then the captured forward + ELBO + backward (+ all-reduce) + clip + Adam replays."""
+        shapes = (tuple(im_noisy.shape), tuple(im_gt.shape), tuple(sigma_gt.shape))
+        if self._graph is None or self._graph_key != shapes:
+            self._capture(shapes)
+        for dst, src in zip(self._g_in, (im_noisy, im_gt, sigma_gt)):
+            dst.copy_(src, non_blocking=True)
+        self.step_count += 1
+        k = self.step_count % len(self._hyper_ring)
+        host, ev = self._hyper_ring[k]
+        if self._hyper_used[k]:
+            ev.synchronize()                                # its previous copy has been consumed (8 steps ago)
+        host[0] = self.lr if lr is None else lr
+        host[1] = 1.0 - self.betas[0] ** self.step_count
+        host[2] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
+        self._hyper.copy_(host, non_blocking=True)
+        ev.record()
+        self._hyper_used[k] = True
+        self._graph.replay()
         return self.losses
 
 
