@@ -189,3 +189,27 @@ def test_sisr_autograd_path_equals_trainer_path():
     g_fused = torch.cat([eng.grad_view(p).flatten() for p in net.parameters()])
     assert abs(terms[0].item() - loss.item()) < 1e-5 * abs(loss.item())
     assert rel(g_fused, g_autograd) < 1e-5
+
+
+def test_sisr_cuda_graph_step_matches_eager_step():
+    """SISRTrainer.step_graph (one CUDA-graph launch; the loss's draws made outside the graph) follows the eager step."""
+    from virnet_b200.loss.ELBO_simple import sisr_draws
+    from virnet_b200.trainer import SISRTrainer
+    sf, n, h, w = 4, 2, 16, 16
+    batch = [t.cuda() for t in _sisr_batch(n, h, w, sf)]
+    net_a, _ = make_sr("tf32", n_feat=(32, 64, 96), n_res=1, dep_K=2)
+    net_b, _ = make_sr("tf32", n_feat=(32, 64, 96), n_res=1, dep_K=2)
+    net_a.train(), net_b.train()
+    tr_a, tr_b = SISRTrainer(net_a, sf, lr=1e-4), SISRTrainer(net_b, sf, lr=1e-4)
+    torch.manual_seed(3)
+    for it in range(4):
+        draws = sisr_draws(batch[2], batch[0], 50.0)
+        la = tr_a.step(*batch, lr=1e-4 * (1 + it), draws=draws).clone()
+        lb = tr_b.step_graph(*batch, lr=1e-4 * (1 + it), draws=draws).clone()
+        tol = 2e-4 if it == 0 else 2e-2
+        torch.testing.assert_close(la, lb, rtol=tol, atol=1e-3)
+    torch.manual_seed(4)
+    first = tr_b.step_graph(*batch)[0].item()       # internal draws
+    for _ in range(20):
+        last = tr_b.step_graph(*batch)[0].item()
+    assert last < first

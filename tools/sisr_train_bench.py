@@ -14,9 +14,10 @@ import virnet_b200  # noqa: E402
 from virnet_b200 import ops  # noqa: E402
 from virnet_b200.trainer import SISRTrainer  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
-lr_sz = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+B = int(_pos[0]) if len(_pos) > 0 else 16
+prec = _pos[1] if len(_pos) > 1 else "bf16"
+lr_sz = int(_pos[2]) if len(_pos) > 2 else 64
 sf = 4
 dev = torch.device("cuda", 0)
 torch.manual_seed(1234)
@@ -43,6 +44,19 @@ torch.cuda.synchronize()
 ms = s.elapsed_time(e) / iters
 print(json.dumps(dict(workload=f"train_SISR x{sf} {lr_sz}->{lr_sz * sf} b={B} {prec}", ms_per_step=round(ms, 3),
                       patches_per_s=round(B / ms * 1e3, 1), loss=terms[0].item())))
+if "--graph" in sys.argv:
+    for _ in range(3):
+        tr.step_graph(im_hr, im_lr, kinfo_gt, nlevel)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        terms = tr.step_graph(im_hr, im_lr, kinfo_gt, nlevel)
+    e.record()
+    torch.cuda.synchronize()
+    msg = s.elapsed_time(e) / iters
+    print(json.dumps(dict(workload=f"train_SISR x{sf} {lr_sz}->{lr_sz * sf} b={B} {prec} CUDA graph", ms_per_step=round(msg, 3),
+                          patches_per_s=round(B / msg * 1e3, 1), loss=terms[0].item())))
+    sys.exit(0)
 tr.engine.wgrad_side_stream = False
 tr.step(im_hr, im_lr, kinfo_gt, nlevel)
 ops.start_profile()

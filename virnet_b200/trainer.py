@@ -289,14 +289,23 @@ class SISRTrainer:
 
     def step(self, im_hr, im_lr, kinfo_gt, sigma_prior, lr: Optional[float] = None, draws=None):
         """One optimisation step; returns the device tensor [loss, lh, kl_rnet, kl_snet, kl_knet, kl_k0, kl_k1, kl_k2]."""
-        eng = self.engine
-        dev = eng.flat_params.device
+        dev = self.engine.flat_params.device
         im_hr, im_lr, kinfo_gt, sigma_prior = [t if t.is_cuda else t.to(dev, non_blocking=True)
                                                for t in (im_hr, im_lr, kinfo_gt, sigma_prior)]
+        if draws is None:
+            draws = self._draw(im_hr)
+        self.step_count += 1
+        return self._device_step(im_hr, im_lr, kinfo_gt, sigma_prior, draws, self.lr if lr is None else lr, None)
+
+    def _draw(self, im_hr):
+        """The loss's random draws (shapes are known before the forward pass: mu has the shape of im_hr)."""
+        return sisr_draws(im_hr[:, 0, 0, :1], im_hr, self.kappa0)
+
+    def _device_step(self, im_hr, im_lr, kinfo_gt, sigma_prior, draws, lr, hyper_dev):
+        eng = self.engine
+        dev = eng.flat_params.device
         n = im_lr.shape[0]
         mu, kinfo, sigma = eng.forward_sr(im_lr, self.sf, save=True)
-        if draws is None:
-            draws = sisr_draws(kinfo, mu, self.kappa0)
         H, W = mu.shape[2], mu.shape[3]
         rh = downsample_matrix(H, self.sf, self.downsampler, dev)
         rw = downsample_matrix(W, self.sf, self.downsampler, dev)
@@ -310,12 +319,67 @@ class SISRTrainer:
             pk0=float(self.penalty_K[0]), pk1=float(self.penalty_K[1]))
         eng.backward_sr(d_mu, d_kinfo, d_sigma)
         grad_scale = dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
-        self.step_count += 1
-        ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
-                           self._ngroups, self._max_group, self._sq_ws, grad_scale=grad_scale,
-                           lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1],
-                           eps=self.adam_eps, step=self.step_count, norms_out=self.grad_norms)
+        if hyper_dev is None:
+            ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
+                               self._ngroups, self._max_group, self._sq_ws, grad_scale=grad_scale, lr=lr,
+                               beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps, step=self.step_count,
+                               norms_out=self.grad_norms)
+        else:
+            ops.adam_clip_step_dev(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
+                                   self._ngroups, self._max_group, self._sq_ws, hyper_dev, grad_scale=grad_scale,
+                                   beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps, norms_out=self.grad_norms)
         eng.mark_params_dirty()
         self.losses, self.last_kernel = terms, kernel
         self.last_mu, self.last_kinfo, self.last_sigma = mu, kinfo, sigma
         return terms
+
+    # -- CUDA-graph replay (see DenoiseTrainer.step_graph); the loss's random draws are made OUTSIDE the graph ------
+    def step_graph(self, im_hr, im_lr, kinfo_gt, sigma_prior, lr: Optional[float] = None, draws=None):
+        eng = self.engine
+        dev = eng.flat_params.device
+        ins = (im_hr, im_lr, kinfo_gt, sigma_prior)
+        shapes = tuple(tuple(t.shape) for t in ins)
+        if getattr(self, "_graph", None) is None or self._graph_key != shapes:
+            self._g_in = [torch.zeros(sh, device=dev, dtype=torch.float32) for sh in shapes]
+            self._g_in[2][:, :2] = 1.0                       # kernel variances must be positive during the dry runs
+            self._g_in[3].fill_(1e-3)
+            self._g_draws = [torch.ones(im_hr.shape[0], 2, device=dev), torch.zeros(im_hr.shape[0], 1, device=dev),
+                             torch.zeros(tuple(im_hr.shape), device=dev)]
+            self._hyper = torch.tensor([0.0, 1.0, 1.0], device=dev)
+            self._hyper_ring = [(torch.zeros(3).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+            self._hyper_used = [False] * 8
+            state = [t.clone() for t in (eng.flat_params, self.exp_avg, self.exp_avg_sq)]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    eng.mark_params_dirty()
+                    self._device_step(*self._g_in, self._g_draws, 0.0, self._hyper)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            eng.mark_params_dirty()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._g_out = self._device_step(*self._g_in, self._g_draws, 0.0, self._hyper)
+            for t, sv in zip((eng.flat_params, self.exp_avg, self.exp_avg_sq), state):
+                t.copy_(sv)
+            self._graph, self._graph_key = graph, shapes
+        for dst, src in zip(self._g_in, ins):
+            dst.copy_(src, non_blocking=True)
+        if draws is None:
+            draws = self._draw(self._g_in[0])
+        for dst, src in zip(self._g_draws, draws):
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+        self.step_count += 1
+        k = self.step_count % len(self._hyper_ring)
+        host, ev = self._hyper_ring[k]
+        if self._hyper_used[k]:
+            ev.synchronize()
+        host[0] = self.lr if lr is None else lr
+        host[1] = 1.0 - self.betas[0] ** self.step_count
+        host[2] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
+        self._hyper.copy_(host, non_blocking=True)
+        ev.record()
+        self._hyper_used[k] = True
+        self._graph.replay()
+        return self._g_out
