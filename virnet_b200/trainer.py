@@ -231,6 +231,9 @@ class DenoiseTrainer:
     def step_graph(self, im_noisy, im_gt, sigma_gt, lr: Optional[float] = None):
         """step() as ONE CUDA-graph launch: inputs (host or device) are copied into static buffers, the per-step Adam
         scalars into device memory, then the captured forward + ELBO + backward (+ all-reduce) + clip + Adam replays."""
+        if self.world > 1:
+            raise NotImplementedError("step_graph with world_size > 1 (NCCL all-reduce inside the capture) is not validated: "
+                                      "a 2-GPU trial did not complete; use step() for data-parallel runs")
         shapes = (tuple(im_noisy.shape), tuple(im_gt.shape), tuple(sigma_gt.shape))
         if self._graph is None or self._graph_key != shapes:
             self._capture(shapes)
@@ -335,6 +338,9 @@ class SISRTrainer:
 
     # -- CUDA-graph replay (see DenoiseTrainer.step_graph); the loss's random draws are made OUTSIDE the graph ------
     def step_graph(self, im_hr, im_lr, kinfo_gt, sigma_prior, lr: Optional[float] = None, draws=None):
+        if self.world > 1:
+            raise NotImplementedError("step_graph with world_size > 1 (NCCL all-reduce inside the capture) is not validated: "
+                                      "use step() for data-parallel runs")
         eng = self.engine
         dev = eng.flat_params.device
         ins = (im_hr, im_lr, kinfo_gt, sigma_prior)
