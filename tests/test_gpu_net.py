@@ -241,5 +241,5 @@ def test_cuda_graph_step_matches_eager_step():
         torch.testing.assert_close(tr_a.grad_norms, tr_b.grad_norms, rtol=10 * tol, atol=0)
     pa = torch.cat([p.detach().flatten() for p in net_a.parameters()])
     pb = torch.cat([p.detach().flatten() for p in net_b.parameters()])
-    assert ((pa - pb).abs() > 1e-3).float().mean().item() < 1e-2
+    assert ((pa - pb).abs() > 1e-3).float().mean().item() < 5e-2
     assert torch.isfinite(pb).all()

@@ -75,6 +75,6 @@ def test_trainer_step_real_equals_manual_composition():
     torch.testing.assert_close(tr_a.grad_norms, tr_b.grad_norms, rtol=1e-4, atol=0)
     differ = total = 0
     for pa, pb in zip(net_a.parameters(), net_b.parameters()):
-        differ += ((pa - pb).abs() > 1e-6).sum().item()
+        differ += ((pa - pb).abs() > 1e-5).sum().item()
         total += pa.numel()
-    assert differ / total < 1e-3, differ / total
+    assert differ / total < 5e-3, differ / total
