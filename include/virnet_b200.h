@@ -5,7 +5,7 @@
  * by networks/VIRNet.py, networks/AttResUNet.py, networks/DnCNN.py,
  * networks/KNet.py and loss/ELBO_simple.py.  Each entry point below names the
  * reference call site(s) it replaces.  The Python host side
- * (virnet_b200/networks/*.py) binds these with ctypes; INTEGRATION.md shows
+ * (virnet_b200/networks/) binds these with ctypes; INTEGRATION.md shows
  * the stub.
  *
  * Conventions

@@ -50,3 +50,34 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert h.vk_conv_igemm(ctypes.byref(a), None) == -1
     g = lib.vk_wgrad_args()
     assert h.vk_conv_wgrad(ctypes.byref(g), None) == -1
+
+
+def test_header_is_valid_c99_and_struct_layouts_match_ctypes(tmp_path):
+    """include/virnet_b200.h must be consumable by a plain C compiler (the boundary is a C ABI, not C++), and every
+    struct a caller fills must have the size and field offsets the ctypes mirror in virnet_b200/lib.py uses."""
+    import shutil
+    import subprocess
+    from virnet_b200 import lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = ["vk_conv_args", "vk_wgrad_args", "vk_elbo_sisr_args", "vk_sft_desc", "vk_adam_group", "vk_pack_desc",
+               "vk_unpack_desc"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "virnet_b200.h"', 'int main(void) {']
+    for name in structs:
+        ct = getattr(lib, name)
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in ct._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi_check.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_check"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for name in structs:
+        ct = getattr(lib, name)
+        assert int(out[name]) == ctypes.sizeof(ct), name
+        for field, _ in ct._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(ct, field).offset, f"{name}.{field}"
