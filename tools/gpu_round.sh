@@ -1,12 +1,16 @@
 #!/bin/bash
-# One GPU call: parity tests, bench (both arms), ncu launch list, one full capture of the conv kernel.
+# One GPU call that re-establishes the measured state of the repo: parity tests, smoke, both bench arms, the SISR /
+# inference / graph side benches, and the ncu evidence pass (tools/gpu_final.sh).  ~8 GPU-minutes.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-tail -c 3000 gpurun_out/bench.json
+tail -c 2500 gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
-   python tools/profile_step.py --steps 3 > gpurun_out/launches.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_v2 -s 60 -c 6 -f -o gpurun_out/prof_conv \
-   python tools/profile_step.py --steps 2 > gpurun_out/prof_conv.log 2>&1; echo "ncu full rc=$?"
+timeout 300 python tools/sisr_train_bench.py 16 bf16 > gpurun_out/sisr_step.txt 2>&1; head -1 gpurun_out/sisr_step.txt
+timeout 300 python tools/infer_bench.py > gpurun_out/infer.jsonl 2>&1; tail -4 gpurun_out/infer.jsonl
+timeout 300 python tools/graph_bench.py 2 4 16 > gpurun_out/graph.jsonl 2>&1; tail -3 gpurun_out/graph.jsonl
+timeout 300 python tools/aux_kernels_bench.py > gpurun_out/aux.jsonl 2>&1; tail -6 gpurun_out/aux.jsonl
+bash tools/gpu_final.sh
