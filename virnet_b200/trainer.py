@@ -16,6 +16,7 @@ with the world size.  There is no host synchronisation inside a step.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -222,7 +223,8 @@ class DenoiseTrainer:
         torch.cuda.synchronize(dev)
         eng.mark_params_dirty()                             # the captured step always re-packs the weights
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        mode = "thread_local" if self.world > 1 else "global"
+        with torch.cuda.graph(graph, capture_error_mode=mode):
             self._device_step(*self._g_in, None, None, 0.0, self._hyper)
         for t, sv in zip((eng.flat_params, self.exp_avg, self.exp_avg_sq), state):
             t.copy_(sv)                                     # warm-up steps must not count as training
@@ -231,7 +233,9 @@ class DenoiseTrainer:
     def step_graph(self, im_noisy, im_gt, sigma_gt, lr: Optional[float] = None):
         """step() as ONE CUDA-graph launch: inputs (host or device) are copied into static buffers, the per-step Adam
         scalars into device memory, then the captured forward + ELBO + backward (+ all-reduce) + clip + Adam replays."""
-        if self.world > 1:
+        if self.world > 1 and os.environ.get("VIRNET_B200_GRAPH_DDP") != "1":
+            # EXPERIMENTAL opt-in (VIRNET_B200_GRAPH_DDP=1): capture with capture_error_mode="thread_local" so that the NCCL
+            # watchdog thread's CUDA calls do not invalidate the capture; unvalidated — the default is to refuse.
             raise NotImplementedError("step_graph with world_size > 1 (NCCL all-reduce inside the capture) is not validated: "
                                       "a 2-GPU trial did not complete; use step() for data-parallel runs")
         shapes = (tuple(im_noisy.shape), tuple(im_gt.shape), tuple(sigma_gt.shape))
