@@ -111,53 +111,37 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# the reference's CPU path (oracle port), timed on the host cores
+# the reference's CPU path, timed on the host cores (baseline/comparator.py: the unmodified reference when
+# /root/reference or its staged copy baseline/_ref is importable, else the oracle port)
 # --------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, b):
-    import torch
-    from oracle import virnet_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = O.NetCfg(n_feat=tuple(N_FEAT), n_resblocks=N_RES, dep_S=DEP_S)
-    torch.manual_seed(1234)
-    sd = O.build_state_dict(cfg)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
-    pR = [v for k, v in params.items() if "rnet" in k.lower()]
-    pS = [v for k, v in params.items() if "snet" in k.lower()]
-    im_noisy, im_gt, sigma_gt = synth_batch(b, 0, None)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        mu, sigma = O.vir_denoise_forward(params, im_noisy, cfg)
-        loss, *_ = O.elbo_denoising_simple(mu, sigma, im_noisy, im_gt, EPS2, ALPHA0, ALPHA0 * sigma_gt)
-        loss.backward()
-        O.clip_grad_norm_(pR, 1e3)
-        O.clip_grad_norm_(pS, 1e2)
-        opt.step()
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return b / sec, sec, cores
+def cpu_reference_steps(steps, warmup, b, budget_s=None):
+    """(patches/s, s/step, cores, kind, steps actually timed, (min, median, max) s/step)."""
+    from baseline import comparator as Cmp
+    batch = synth_batch(b, 0, None)
+    return Cmp.cpu_train(batch, b, steps, warmup, budget_s=budget_s)
 
 
 def run_reference(args):
+    """`--impl reference`: the same workload (same batch per step, same --steps / --warmup) on the host cores.  A step
+    of 32 patches takes seconds on a CPU, so a wall-clock budget may end the run early (never below 5 timed steps);
+    `steps` in the line is what was timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    b = 2
-    steps, warmup = min(args.steps, 10), min(args.warmup, 2)
-    v, sec, cores = cpu_reference_steps(steps, warmup, b)
+    b = args.batch
+    v, sec, cores, kind, steps, spread = cpu_reference_steps(args.steps, args.warmup, b, budget_s=args.ref_budget_s)
+    what = ("the UNMODIFIED reference modules (networks/VIRNet.py + loss/ELBO_simple.py), torch CPU" if kind == "reference"
+            else "oracle/virnet_oracle.py (functional port of the reference's ops), torch CPU")
     line = {
         "impl": "reference", "metric": "denoising-syn 128x128 training patches/s (whole job)", "value": v,
-        "unit": "patches/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+        "unit": "patches/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "train_denoising_syn.py step (fwd+ELBO+bwd+clip+Adam), VIRAttResUNet "
-                               "n_feat=[96,192,288] n_resblocks=3 dep_S=5, 128x128x3 patches", "batch_per_step": b},
-        "cpu_baseline": {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps of batch {b} (oracle/virnet_oracle.py = reference ops on torch CPU, "
-                                   f"{cores} threads)"},
+                               "n_feat=[96,192,288] n_resblocks=3 dep_S=5, 128x128x3 patches (configs[2])",
+                   "batch_per_gpu": b, "global_batch": b, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "patches/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} timed steps of batch {b} after {args.warmup} warm-up: {what}, {cores} threads; "
+                                   f"s/step min/median/max = {spread[0]:.3f}/{spread[1]:.3f}/{spread[2]:.3f}"},
         "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -168,6 +152,188 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def _gpu_timed(fn, steps, warmup):
+    """ms per call, CUDA events on the current stream, after warm-up, synchronised on both sides."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
+
+
+def _with_clocks(local_rank, fn):
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    t0 = time.time()
+    out = fn()
+    t1 = time.time()
+    return out, sampler.stop(t0, t1)
+
+
+SISR_TRAIN_GFLOP = 3 * 180.16        # fwd + dgrad + wgrad per 64x64 -> 256x256 sample (BASELINE.md §2; + ~0.2 loss)
+SISR_FWD_GFLOP_LR64 = 180.16
+
+
+def gpu_comparator(dev, b, steps=30, warmup=10):
+    """The kernel to beat: the reference module in eager PyTorch / cuDNN on this GPU, full training
+    step at the same batch, fp32 NCHW (PyTorch default: TF32 convolutions) and bf16 autocast + channels_last."""
+    import torch
+    from baseline import comparator as Cmp
+    batch = synth_batch(b, 0, None)
+    out = {}
+    for mode in ("fp32_tf32conv_nchw", "bf16_autocast_channels_last"):
+        try:
+            out[mode] = Cmp.gpu_train(dev, batch, b, steps, warmup, mode)
+        except Exception as e:  # noqa: BLE001
+            out[mode] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    out["what"] = ("train_denoising_syn.py:175-184 step with stock torch ops (cuDNN convs, cudnn.benchmark=True, "
+                   "torch.optim.Adam, nn.utils.clip_grad_norm_), same network / batch / inputs, CUDA events")
+    return out
+
+
+def extra_configs(args, dev, local_rank, peaks):
+    """The other BASELINE.json configs and regimes, each timed like the headline (CUDA events, W >= 3 warm-up,
+    clocks sampled during the timed region) and placed under `extra` of the one JSON line."""
+    import torch
+    import virnet_b200
+    from baseline import comparator as Cmp
+    from virnet_b200.trainer import DenoiseTrainer, SISRTrainer
+    peak_bf16 = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    out = []
+
+    def add(name, fn):
+        try:
+            torch.cuda.empty_cache()
+            rec, clocks = _with_clocks(local_rank, fn)
+            rec["name"], rec["clocks"] = name, clocks
+        except Exception as e:  # noqa: BLE001
+            rec = {"name": name, "error": repr(e)[:300]}
+        out.append(rec)
+
+    def den_net(prec):
+        torch.manual_seed(1234)
+        return virnet_b200.VIRAttResUNet(im_chn=3, sigma_chn=1, n_feat=N_FEAT, dep_S=DEP_S, n_resblocks=N_RES,
+                                         noise_cond=True, extra_mode="Input", noise_avg=False, precision=prec).to(dev)
+
+    def sr_net(prec):
+        torch.manual_seed(1234)
+        return virnet_b200.VIRAttResUNetSR(im_chn=3, sigma_chn=1, kernel_chn=3, n_feat=[96, 160, 224], dep_S=5, dep_K=8,
+                                           noise_cond=True, kernel_cond=True, n_resblocks=2, extra_mode="Both",
+                                           noise_avg=True, precision=prec).to(dev)
+
+    # ---- denoising-syn training in the 1e-3-parity precision (tf32 operands, fp32 storage) ----
+    def train_tf32():
+        tr = DenoiseTrainer(den_net("tf32"), lr=1e-4, clip_grad_R=1e3, clip_grad_S=1e2, alpha0=ALPHA0, eps2=EPS2)
+        batch = synth_batch(args.batch, 0, dev)
+        ms = _gpu_timed(lambda: tr.step(*batch), args.steps, args.warmup)
+        v = args.batch / ms * 1e3
+        return {"workload": f"configs[2] training step, precision tf32 (the mode held to 1e-3 / 0.01 dB), b={args.batch}",
+                "value": v, "unit": "patches/s", "ms_per_step": ms, "dtype": "tf32",
+                "roofline_frac_whole_step": v * TRAIN_GFLOP_PER_PATCH / 1e3 / (peak_bf16 * 0.5),
+                "peak": peak_bf16 * 0.5, "peak_source": "bf16_tflops_sustained x0.5"}
+    add("train_denoise_tf32", train_tf32)
+
+    # ---- the reference's own batch regime: global batch 16 (train_denoising_syn.py:133), i.e. 16 patches on one GPU
+    # and 2 patches per GPU on an 8-GPU node; eager launches and the CUDA-graph replay of the same step ----
+    def train_small():
+        res = {"workload": "configs[2] training step at the reference's global batch (16 on 1 GPU; 2 = its per-GPU share on 8 GPUs)",
+               "unit": "patches/s", "dtype": "bf16"}
+        for b in (16, 2):
+            tr = DenoiseTrainer(den_net("bf16"), lr=1e-4, clip_grad_R=1e3, clip_grad_S=1e2, alpha0=ALPHA0, eps2=EPS2)
+            batch = synth_batch(b, 0, dev)
+            ms_e = _gpu_timed(lambda: tr.step(*batch), args.steps, args.warmup)
+            ms_g = _gpu_timed(lambda: tr.step_graph(*batch), args.steps, args.warmup)
+            res[f"b{b}"] = {"eager": b / ms_e * 1e3, "eager_ms": ms_e, "cuda_graph": b / ms_g * 1e3, "cuda_graph_ms": ms_g}
+            del tr
+        res["value"] = res["b16"]["cuda_graph"]
+        return res
+    add("train_denoise_reference_batch", train_small)
+
+    # ---- configs[1]: denoising-syn inference 256x256, batch 32 ----
+    def infer_256():
+        x = synth_batch_infer(32, 256, dev)
+        res = {"workload": "configs[1] denoising-syn inference 256x256 niid-Gaussian, batch 32, eval/no_grad through the nn.Module",
+               "unit": "img/s"}
+        for prec in ("bf16", "tf32"):
+            net = den_net(prec).eval()
+            with torch.no_grad():
+                ms = _gpu_timed(lambda: net(x), args.steps, args.warmup)
+            v = 32 / ms * 1e3
+            pk = peak_bf16 * (0.5 if prec == "tf32" else 1.0)
+            res[prec] = {"value": v, "ms_per_batch": ms, "roofline_frac": v * 326.94 / 1e3 / pk, "peak": pk}
+            del net
+        res["value"], res["dtype"] = res["bf16"]["value"], "bf16"
+        if not args.no_comparator:
+            res["gpu_comparator"] = {m: Cmp.gpu_infer(dev, x, 10, 3, m) for m in
+                                     ("fp32_tf32conv_nchw", "bf16_autocast_channels_last")}
+        return res
+    add("infer_denoise_256_b32", infer_256)
+
+    # ---- configs[3]: x4 super-resolution inference on the Set5 shapes (HR 512^2, 288^2, 256^2, 280^2, 344x228), nlevel 2.55 ----
+    def infer_sr():
+        g = torch.Generator(device=dev).manual_seed(5)
+        shapes = [(128, 128), (72, 72), (64, 64), (70, 70), (86, 57)]
+        lrs = [torch.rand(1, 3, h, w, device=dev, generator=g) + 0.01 * torch.randn(1, 3, h, w, device=dev, generator=g)
+               for h, w in shapes]
+        lr16 = torch.rand(16, 3, 64, 64, device=dev, generator=g)
+        res = {"workload": "configs[3] sisr_x4 inference: the five Set5 image shapes one by one (batch 1), and LR 64x64 batch 16",
+               "unit": "img/s"}
+        for prec in ("bf16", "tf32"):
+            net = sr_net(prec).eval()
+            with torch.no_grad():
+                ms5 = _gpu_timed(lambda: [net(t, 4) for t in lrs], args.steps, args.warmup)
+                ms16 = _gpu_timed(lambda: net(lr16, 4), args.steps, args.warmup)
+            pk = peak_bf16 * (0.5 if prec == "tf32" else 1.0)
+            res[prec] = {"set5_img_per_s": 5 / ms5 * 1e3, "set5_ms_per_pass": ms5, "b16_img_per_s": 16 / ms16 * 1e3,
+                         "b16_ms": ms16, "b16_roofline_frac": 16 / ms16 * SISR_FWD_GFLOP_LR64 / pk}
+            del net
+        res["value"], res["dtype"] = res["bf16"]["set5_img_per_s"], "bf16"
+        if not args.no_comparator:
+            res["gpu_comparator"] = {m: Cmp.gpu_infer(dev, lr16, 10, 3, m, sr_sf=4) for m in
+                                     ("fp32_tf32conv_nchw", "bf16_autocast_channels_last")}
+        return res
+    add("infer_sisr_x4", infer_sr)
+
+    # ---- configs[4]: train_SISR x4, 64x64 -> 256x256 patches, batch 16 per GPU, KNet branch + SISR ELBO ----
+    def train_sr():
+        B, lr_sz, sf = 16, 64, 4
+        net = sr_net("bf16").train()
+        g = torch.Generator(device=dev).manual_seed(0)
+        im_hr = torch.rand(B, 3, lr_sz * sf, lr_sz * sf, device=dev, generator=g)
+        im_lr = torch.nn.functional.avg_pool2d(im_hr, sf) + 0.01 * torch.randn(B, 3, lr_sz, lr_sz, device=dev, generator=g)
+        kinfo_gt = torch.stack([0.5 + 3 * torch.rand(B, device=dev, generator=g),
+                                0.5 + 3 * torch.rand(B, device=dev, generator=g),
+                                torch.rand(B, device=dev, generator=g) - 0.5], dim=1)
+        nlevel = torch.full((B, 1, 1, 1), (2.55 / 255) ** 2, device=dev)
+        tr = SISRTrainer(net, sf)
+        ms = _gpu_timed(lambda: tr.step(im_hr, im_lr, kinfo_gt, nlevel), args.steps, args.warmup)
+        v = B / ms * 1e3
+        return {"workload": "configs[4] train_SISR.py step x4, 64x64 -> 256x256 patches, batch 16 (fwd SNet+KNet+SFT RNet, "
+                            "elbo_sisr, bwd, clip x3, Adam)", "value": v, "unit": "patches/s", "ms_per_step": ms, "dtype": "bf16",
+                "roofline_frac_whole_step": v * SISR_TRAIN_GFLOP / 1e3 / peak_bf16, "peak": peak_bf16}
+    add("train_sisr_x4_b16", train_sr)
+    return out
+
+
+def synth_batch_infer(b, size, dev):
+    """configs[1] input: U[0,1) image + niid Gaussian noise (sigma bump map), fp32 NCHW on the device."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(7)
+    gt = torch.rand(b, 3, size, size, device=dev, generator=g)
+    ii = torch.arange(size, device=dev, dtype=torch.float32)
+    bump = torch.exp(-((ii[:, None] - size / 2) ** 2 + (ii[None, :] - size / 2) ** 2) / (2 * (size / 3) ** 2))
+    sig = (10 + 65 * bump) / 255
+    return gt + torch.randn(b, 3, size, size, device=dev, generator=g) * sig
+
+
 class _StdoutToStderr:
     """Native libraries (NCCL prints its version banner) write to file descriptor 1; the driver wants exactly ONE
     JSON line on stdout, so fd 1 points at stderr while the benchmark runs and is restored for the final print."""
@@ -305,11 +471,22 @@ def _run_ours(args):
 
     value = world * b * args.steps / (ms * 1e-3)
     e2e = world * b * args.steps / (ms_e2e * 1e-3)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_reference_steps(2, 1, 2)
-        cpu = {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
-               "sample": f"2 timed steps of batch 2 after 1 warm-up (oracle port of the reference, torch CPU, {cores} threads)"}
+    cpu = comparator = extra = None
+    if rank == 0 and world == 1:
+        # free the headline trainer's activations before the side measurements
+        trainer.engine._bufs.clear()
+        trainer.engine.saved = None
+        torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            cb, cs, cw = 16, 5, 1                       # bounded sample: ~10-30 s of host work
+            v, sec, cores, kind, n, spread = cpu_reference_steps(cs, cw, cb)
+            cpu = {"value": v, "unit": "patches/s", "cores": cores, "kind": kind,
+                   "sample": f"{n} timed steps of batch {cb} after {cw} warm-up ({'unmodified reference modules' if kind == 'reference' else 'oracle port of the reference'}, "
+                             f"torch CPU fp32, {cores} threads); s/step min/median/max = {spread[0]:.3f}/{spread[1]:.3f}/{spread[2]:.3f}"}
+        if not args.no_comparator:
+            comparator = gpu_comparator(dev, b)
+        if not args.no_extra:
+            extra = extra_configs(args, dev, local_rank, peaks)
     if rank == 0:
         line = {
             "metric": "denoising-syn 128x128 training patches/s (whole job)", "value": value, "unit": "patches/s",
@@ -333,6 +510,8 @@ def _run_ours(args):
                          "families_ms_per_step": {k: round(v["ms"] / 2.0, 4) for k, v in fam.items()},
                          "whole_step_tflops": value * TRAIN_GFLOP_PER_PATCH / 1e3 / world},
             "cpu_baseline": cpu,
+            "gpu_comparator": comparator,
+            "extra": extra,
         }
     else:
         line = None
@@ -351,6 +530,10 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-comparator", action="store_true", help="skip the eager PyTorch/cuDNN comparator on the GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (`extra` list)")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="--impl reference: stop timing early after this many seconds (>= 5 timed steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -10,7 +10,19 @@ import sys
 import types
 from pathlib import Path
 
-REF_ROOT = Path("/root/reference")
+_CANDIDATES = (Path("/root/reference"), Path(__file__).resolve().parents[1] / "baseline" / "_ref")
+
+
+def _find_root() -> Path:
+    for c in _CANDIDATES:
+        if (c / "networks" / "VIRNet.py").exists():
+            return c
+    return _CANDIDATES[0]
+
+
+# /root/reference in the build container; the staged copy baseline/_ref (baseline/install_ref.py, git-ignored)
+# on the GPU box, where it is only ever used as the timed comparator of bench.py
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
@@ -34,7 +46,7 @@ def _stub(name: str, **attrs):
 def import_reference():
     """Returns (networks.VIRNet module, loss.ELBO_simple module)."""
     if not available():
-        raise RuntimeError("/root/reference is not present")
+        raise RuntimeError("the reference is not present (/root/reference or baseline/_ref)")
     _stub("thop", profile=lambda *a, **k: (0, 0))
     _stub("lpips")
     _stub("matplotlib")
