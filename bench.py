@@ -474,8 +474,7 @@ def _run_ours(args):
     cpu = comparator = extra = None
     if rank == 0 and world == 1:
         # free the headline trainer's activations before the side measurements
-        trainer.engine._bufs.clear()
-        trainer.engine.saved = None
+        trainer.engine.release_buffers()
         torch.cuda.empty_cache()
         if not args.no_cpu_baseline:
             cb, cs, cw = 16, 5, 1                       # bounded sample: ~10-30 s of host work

@@ -243,3 +243,83 @@ def test_cuda_graph_step_matches_eager_step():
     pb = torch.cat([p.detach().flatten() for p in net_b.parameters()])
     assert ((pa - pb).abs() > 1e-3).float().mean().item() < 5e-2
     assert torch.isfinite(pb).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# buffer ownership of the engine (several live autograd graphs, eval forwards between forward and backward,
+# validation sweeps over many image sizes)
+# ------------------------------------------------------------------------------------------------------------------
+def _loss_of(net, batch):
+    from virnet_b200.loss.ELBO_simple import elbo_denoising_simple
+    im_noisy, im_gt, sigma_gt = [t.cuda() for t in batch]
+    mu, sigma = net(im_noisy)
+    return elbo_denoising_simple(mu, sigma, im_noisy, im_gt, EPS2, ALPHA0, ALPHA0 * sigma_gt)[0]
+
+
+def _grads(net):
+    return {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+
+
+def test_two_live_graphs_and_eval_forward_between_forward_and_backward():
+    """Two differentiable forwards of the SAME shape before either backward, plus a no_grad forward in between:
+    every backward must see its own activations (the reference's nn.Modules allow this; gradient accumulation)."""
+    net, _ = make_net((32, 64, 96), 2, "tf32")
+    b1, b2 = den_inputs(2, 32, 32, seed=1), den_inputs(2, 32, 32, seed=2)
+    want = []
+    for b in (b1, b2):
+        net.zero_grad(set_to_none=True)
+        _loss_of(net, b).backward()
+        want.append(_grads(net))
+    net.zero_grad(set_to_none=True)
+    l1 = _loss_of(net, b1)
+    with torch.no_grad():
+        net(b2[0].cuda())                       # eval-style forward while graph 1 is alive
+    l2 = _loss_of(net, b2)
+    l2.backward()
+    got2 = _grads(net)
+    net.zero_grad(set_to_none=True)
+    l1.backward()
+    got1 = _grads(net)
+    for k in want[0]:
+        assert rel(got1[k], want[0][k]) < 1e-5, k
+        assert rel(got2[k], want[1][k]) < 1e-5, k
+    # a second backward through the same graph has nothing to read: loud error, not silent garbage
+    l3 = _loss_of(net, b1)
+    l3.backward()
+    from virnet_b200.lib import VkError
+    with pytest.raises((VkError, RuntimeError)):
+        l3.backward()
+
+
+def test_inference_over_many_shapes_does_not_pin_memory():
+    """Validation loops run batch 1 over images of many sizes (Set5 / Set14 / CBSD68): eval forwards keep no
+    per-shape buffers, and training-shape buffer sets are bounded by an LRU."""
+    net, _ = make_net((32, 64, 96), 2, "bf16")
+    net.eval()
+    with torch.no_grad():
+        net(torch.rand(1, 3, 40, 40).cuda())
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        for i in range(12):
+            net(torch.rand(1, 3, 33 + 7 * i, 41 + 5 * i).cuda())
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() - base < 1 << 20
+    eng = net.engine()
+    net.train()
+    for i in range(5):
+        _loss_of(net, den_inputs(1, 32 + 4 * i, 32)).backward()
+    assert len(eng._sets) <= eng.max_cached_shapes
+
+
+def test_data_writes_need_mark_params_dirty():
+    net, _ = make_net((32, 64, 96), 2, "tf32")
+    x = den_inputs(1, 32, 32)[0].cuda()
+    with torch.no_grad():
+        mu0, _ = net(x)
+        for p in net.parameters():
+            p.data.mul_(1.5)                   # does not bump the version counter of the Parameter
+        net.mark_params_dirty()
+        mu1, _ = net(x)
+    assert rel(mu1, mu0) > 1e-3

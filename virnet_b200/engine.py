@@ -19,6 +19,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional
 
 import torch
@@ -61,7 +62,23 @@ class _Layer:
         return self.mod.bias
 
 
+class _NoSave(dict):
+    """Activation table of a forward that nobody will differentiate: drops what is put in, so every tensor dies with
+    its last Python reference and torch's caching allocator recycles the block for a later layer."""
+
+    def __setitem__(self, k, v):
+        pass
+
+
 class DenoiseEngine:
+    """Buffer ownership.  A forward that saves for backward (`save=True`) writes its activations into a named buffer
+    SET keyed by the input shape; sets live in a small LRU (`max_cached_shapes`, default 2) so that a validation loop
+    over many image sizes cannot pin memory without bound.  A set in use by a forward whose backward has not run yet is
+    never handed to another forward (a second differentiable forward of the same shape gets its own set), and each
+    saved forward carries a generation number that `backward` checks.  Forwards with `save=False` (eval / no_grad)
+    use no named buffers at all: every activation is a fresh allocation that is released as soon as the next layer
+    has consumed it, so inference needs the live set only (a few tensors), and never touches saved activations."""
+
     def __init__(self, net: nn.Module, precision: str = "tf32", sr: bool = False):
         self.net = net
         self.sr = sr
@@ -131,8 +148,14 @@ class DenoiseEngine:
         self._wg_stream, self._wg_events, self._wg_i = None, [], 0
         self._flat_key = None
         self._packed_version = None
-        self._bufs: Dict = {}
-        self.saved = None
+        self._sets: "OrderedDict" = OrderedDict()      # (signature, slot) -> {"bufs": {...}, "owner": generation or None}
+        self._cur: Optional[Dict] = None               # buffer set of the running forward / backward
+        self._transient = False                        # True while a save=False forward runs
+        self._tables: Dict = {}                        # per-batch-size SFT tables (small)
+        self.max_cached_shapes = int(os.environ.get("VIRNET_B200_MAX_CACHED_SHAPES", "2"))
+        self._gen = 0
+        self._pending: Dict[int, Dict] = {}            # generation -> saved activations awaiting their backward
+        self.saved = None                              # most recent saved forward (what the fused trainers consume)
 
     # ------------------------------------------------------------------
     # parameters: one flat fp32 buffer (params) + one for grads + wgrad workspace
@@ -163,7 +186,7 @@ class DenoiseEngine:
         self._flat_key = (dev, tuple(p.data_ptr() for p in params))
         self._build_packing(dev)
         self._packed_version = None
-        self._bufs = {}
+        self.release_buffers()
 
     def grad_view(self, p: torch.Tensor) -> torch.Tensor:
         i = self.param_index[id(p)]
@@ -233,12 +256,77 @@ class DenoiseEngine:
     # ------------------------------------------------------------------
     # buffers
     # ------------------------------------------------------------------
+    def release_buffers(self):
+        """Drop every cached activation / gradient buffer (pending backwards are invalidated)."""
+        self._sets.clear()
+        self._tables = {}
+        self._pending.clear()
+        self._cur, self.saved = None, None
+
+    def _begin(self, sig, save: bool):
+        """Select the buffer set of a forward with input signature `sig`; returns the table the forward records its
+        activations in."""
+        self._transient = not save
+        if not save:
+            self._cur = None
+            return _NoSave()
+        slot = 0
+        while True:
+            key = (sig, slot)
+            st = self._sets.get(key)
+            if st is None:
+                st = self._sets[key] = {"bufs": {}, "owner": None}
+                break
+            if st["owner"] is None or st["owner"] not in self._pending:
+                break
+            slot += 1                                   # its backward is still pending: leave it alone
+        self._sets.move_to_end(key)
+        for k in [k for k, v in self._sets.items() if v["owner"] is None or v["owner"] not in self._pending]:
+            if len(self._sets) <= self.max_cached_shapes:
+                break
+            if k != key:
+                del self._sets[k]
+        self._gen += 1
+        st["owner"] = self._gen
+        self._cur = st
+        A: Dict = {"gen": self._gen, "set": st}
+        return A
+
+    def _commit(self, A):
+        """Register the saved activations of a differentiable forward; returns its generation number."""
+        self._pending[A["gen"]] = A
+        # forwards whose outputs were dropped without a backward would otherwise pin their sets forever
+        while len(self._pending) > 8:
+            self._pending.pop(next(iter(self._pending)))
+        self.saved = A
+        return A["gen"]
+
+    def _take_saved(self, gen):
+        if gen is None:
+            A = self.saved
+            if A is None:
+                raise _l.VkError("backward called without a saved forward")
+            gen = A["gen"]
+        A = self._pending.pop(gen, None)
+        if A is None:
+            raise _l.VkError("backward of a forward whose saved activations are gone: it was already back-propagated, or "
+                             "more than 8 differentiable forwards were pending (retain_graph / double backward are not supported)")
+        if A["set"]["owner"] != gen:
+            raise _l.VkError("stale saved activations: their buffers were reused by a later forward")
+        if self.saved is A:
+            self.saved = None
+        self._cur, self._transient = A["set"], False
+        return A
+
     def _buf(self, name, shape, dtype=None):
-        key = (name, tuple(shape), dtype or self.tdt)
-        b = self._bufs.get(key)
+        dtype = dtype or self.tdt
+        if self._transient:
+            return torch.empty(shape, device=self.flat_params.device, dtype=dtype)
+        bufs = self._cur["bufs"]
+        key = (name, tuple(shape), dtype)
+        b = bufs.get(key)
         if b is None:
-            b = torch.empty(shape, device=self.flat_params.device, dtype=dtype or self.tdt)
-            self._bufs[key] = b
+            b = bufs[key] = torch.empty(shape, device=self.flat_params.device, dtype=dtype)
         return b
 
     # ------------------------------------------------------------------
@@ -265,7 +353,7 @@ class DenoiseEngine:
         Hp, Wp = (H + mod - 1) // mod * mod, (W + mod - 1) // mod * mod
         if Hp > 2 * H - 1 or Wp > 2 * W - 1:
             raise _l.VkError("image too small for reflect padding")
-        A: Dict[str, torch.Tensor] = {}
+        A = self._begin(("den", N, H, W), save)
 
         # ---- SNet ----
         xs = self._buf("xs", (N, H, W, cp(C)))
@@ -342,7 +430,7 @@ class DenoiseEngine:
         if save:
             A["sigma"] = sigma
             A["shape"] = (N, C, H, W, Hp, Wp, dims)
-            self.saved = A
+            self._commit(A)
         return mu, sigma
 
     # ------------------------------------------------------------------
@@ -371,7 +459,7 @@ class DenoiseEngine:
         ops.conv_igemm(g, ly.wd, dtype=self.dtype, kind=kind, cout=cout, bias=None, **kw)
 
     def _resblock_bwd(self, tag, c1, c2, gX, shape):
-        A = self.saved
+        A = self._saved_A
         N, h, w, c = shape
         a, bt = A[tag + ".a"], A[tag + ".b"]
         self._wgrad(c2, gX, bt, VK_CONV3X3_S1)
@@ -382,11 +470,10 @@ class DenoiseEngine:
         self._dgrad(gF, c1, VK_CONV3X3_S1, c, ldo=c, mask=a, resid=gX, out1=gXp, alpha=0.2)
         return gXp
 
-    def backward(self, g_mu: Optional[torch.Tensor], g_sigma: Optional[torch.Tensor]):
-        """Accumulates parameter gradients into self.flat_grads (zeroed here first)."""
-        A = self.saved
-        if A is None:
-            raise _l.VkError("backward called without a saved forward")
+    def backward(self, g_mu: Optional[torch.Tensor], g_sigma: Optional[torch.Tensor], gen: Optional[int] = None):
+        """Accumulates parameter gradients into self.flat_grads (zeroed here first).  `gen`: generation of the forward to
+        differentiate (default: the most recent saved one)."""
+        A = self._saved_A = self._take_saved(gen)
         N, C, H, W, Hp, Wp, dims = A["shape"]
         dt = self.dtype
         cp = lambda c: ops.chan_pad(c, dt)
@@ -465,8 +552,8 @@ class DenoiseEngine:
         if self._wg_stream is not None:
             torch.cuda.current_stream().wait_stream(self._wg_stream)
         ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
-        self.saved = None
-
+        self._saved_A = None
+        A["set"]["owner"] = None
 
     # ------------------------------------------------------------------
     # super-resolution network (networks/VIRNet.py:80-97): forward, and backward w.r.t. every parameter
@@ -475,7 +562,7 @@ class DenoiseEngine:
         """(mul, add) buffers of every AttLayer, their gradient accumulators (one flat buffer, zeroed per backward) and
         the device descriptor table of the batched SFT-MLP kernels; cached per batch size."""
         key = ("sft_tables", N, self._flat_key)
-        hit = self._bufs.get(key)
+        hit = self._tables.get(key)
         if hit is not None:
             return hit[:4]
         rnet, nfeat, dev, f32 = self.net.RNet, self.n_feat, self.flat_params.device, torch.float32
@@ -504,7 +591,7 @@ class DenoiseEngine:
         arr = (_l.vk_sft_desc * len(descs))(*descs)
         table = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
         out = (sft, table, len(descs), max(nfeat), dmd, grads, vals)
-        self._bufs[key] = out
+        self._tables[key] = out
         return out[:4]
 
     def forward_sr(self, x: torch.Tensor, sf: int, save: bool = False):
@@ -523,7 +610,7 @@ class DenoiseEngine:
         dt, dev = self.dtype, x.device
         cp = lambda c: ops.chan_pad(c, dt)
         f32 = torch.float32
-        S: Dict[str, torch.Tensor] = {}
+        S = self._begin(("sr", N, h, w, int(sf)), save)
 
         # ---- SNet with global average of the log-variance (DnCNN.py:30-33,42; VIRNet.py:81) ----
         xs = self._buf("sr.xs", (N, h, w, cp(C)))
@@ -645,12 +732,12 @@ class DenoiseEngine:
         if save:
             S["x"], S["sigma"], S["kinfo"], S["extra"], S["sft"] = x, sigma, kinfo, extra, sft
             S["shape"] = (N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask)
-            self.saved = S
+            self._commit(S)
         return mu, kinfo, sigma
 
     def _sft_block_bwd(self, ii, b, c1, c2, gX, shape, dm, dd):
         """Backward of one SFT-modulated AttResBlock (AttResUNet.py:48-60); returns the gradient w.r.t. its input."""
-        S = self.saved
+        S = self._saved_A
         N, hh, ww, c = shape
         tag = f"d{ii}.{b}"
         m1 = S["sft"][(ii, b, "sft1")][0]
@@ -667,10 +754,10 @@ class DenoiseEngine:
         ops.sft_bwd(G1, S[tag + ".x"], m1, gXp, dm[(ii, b, "sft1")], dd[(ii, b, "sft1")], dtype=self.dtype, c=c, resid=gX)
         return gXp
 
-    def backward_sr(self, g_mu, g_kinfo, g_sigma):
+    def backward_sr(self, g_mu, g_kinfo, g_sigma, gen: Optional[int] = None):
         """Accumulates the gradients of every parameter (SNet, KNet, RNet incl. the SFT MLPs) into flat_grads."""
-        S = self.saved
-        if S is None or "sft" not in S:
+        S = self._saved_A = self._take_saved(gen)
+        if "sft" not in S:
             raise _l.VkError("backward_sr called without a saved super-resolution forward")
         N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask = S["shape"]
         dt, dev, f32 = self.dtype, S["x"].device, torch.float32
@@ -709,7 +796,7 @@ class DenoiseEngine:
                 gXl = self._buf(f"g.sr.u{k}.low", (N, hl, wl, nf[lvl + 1]))
                 self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
                 gX = gXl
-            tables = self._bufs[("sft_tables", N, self._flat_key)]
+            tables = self._tables[("sft_tables", N, self._flat_key)]
             sft_descs, sft_n, sft_maxc, dmd, sft_grads = tables[1], tables[2], tables[3], tables[4], tables[5]
             sft_grads.zero_()
             dm = {k: v[0] for k, v in dmd.items()}
@@ -782,4 +869,5 @@ class DenoiseEngine:
         if self._wg_stream is not None:
             torch.cuda.current_stream().wait_stream(self._wg_stream)
         ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
-        self.saved = None
+        self._saved_A = None
+        S["set"]["owner"] = None

@@ -25,6 +25,34 @@ def _default_precision():
     return os.environ.get("VIRNET_B200_PRECISION", "tf32").lower()
 
 
+def _param_grads(eng, params):
+    """Per-parameter gradients for autograd: views into ONE private copy of the engine's flat gradient buffer (a single
+    copy kernel; the engine's own buffer is overwritten by the next backward, and autograd may keep what it is given)."""
+    flat = eng.flat_grads.clone()
+    out = []
+    for p in params:
+        if not p.requires_grad:
+            out.append(None)
+            continue
+        o = eng.flat_offsets[eng.param_index[id(p)]]
+        out.append(flat[o:o + p.numel()].view_as(p))
+    return tuple(out)
+
+
+class _EngineMixin:
+    def mark_params_dirty(self):
+        """Call after writing parameters through `.data` (EMA, manual re-initialisation, `p.data.copy_`): such writes do
+        not bump the tensors' version counters, so the packed tensor-core operands would otherwise stay stale.
+        Optimizer steps, `load_state_dict` and in-place ops on the parameters themselves are detected automatically."""
+        if self._engine is not None:
+            self._engine.mark_params_dirty()
+
+    def release_buffers(self):
+        """Free every cached activation buffer of the engine (e.g. after a validation sweep over many image sizes)."""
+        if self._engine is not None:
+            self._engine.release_buffers()
+
+
 class _WholeNetFn(torch.autograd.Function):
     """One autograd node for SNet + RNet: forward saves activations inside the engine,
     backward returns the parameter gradients computed by the dgrad / wgrad kernels."""
@@ -35,16 +63,15 @@ class _WholeNetFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[2:])
         mu, sigma = engine.forward(x, save=need_grad)
         ctx.engine = engine
-        ctx.n_params = len(params)
+        ctx.gen = engine.saved["gen"] if need_grad else None
         ctx.params = params
         return mu, sigma
 
     @staticmethod
     def backward(ctx, g_mu, g_sigma):
         eng = ctx.engine
-        eng.backward(g_mu, g_sigma)
-        grads = tuple(eng.grad_view(p).clone() if p.requires_grad else None for p in ctx.params)
-        return (None, None) + grads
+        eng.backward(g_mu, g_sigma, gen=ctx.gen)
+        return (None, None) + _param_grads(eng, ctx.params)
 
 
 class _SRNetFn(torch.autograd.Function):
@@ -56,17 +83,17 @@ class _SRNetFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[3:])
         mu, kinfo, sigma = engine.forward_sr(x, sf, save=need_grad)
         ctx.engine, ctx.params = engine, params
+        ctx.gen = engine.saved["gen"] if need_grad else None
         return mu, kinfo, sigma
 
     @staticmethod
     def backward(ctx, g_mu, g_kinfo, g_sigma):
         eng = ctx.engine
-        eng.backward_sr(g_mu, g_kinfo, g_sigma)
-        grads = tuple(eng.grad_view(p).clone() if p.requires_grad else None for p in ctx.params)
-        return (None, None, None) + grads
+        eng.backward_sr(g_mu, g_kinfo, g_sigma, gen=ctx.gen)
+        return (None, None, None) + _param_grads(eng, ctx.params)
 
 
-class VIRAttResUNet(nn.Module):
+class VIRAttResUNet(_EngineMixin, nn.Module):
     """Denoising: sigma = exp(clamp(SNet(x))), mu = RNet(x, sqrt(sigma)); returns (mu, sigma)."""
 
     def __init__(self, im_chn, sigma_chn=3, n_feat=[64, 128, 192], dep_S=5, n_resblocks=2, noise_cond=True,
@@ -93,7 +120,7 @@ class VIRAttResUNet(nn.Module):
         return mu, sigma
 
 
-class VIRAttResUNetSR(nn.Module):
+class VIRAttResUNetSR(_EngineMixin, nn.Module):
     """Super-resolution variant (SNet + KNet + SFT-modulated RNet); returns (mu, kinfo, sigma)."""
 
     def __init__(self, im_chn, sigma_chn=1, kernel_chn=3, n_feat=[64, 128, 192], dep_S=5, dep_K=8,

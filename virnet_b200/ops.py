@@ -255,6 +255,10 @@ def elbo_denoise(mu, sigma, noisy, gt, beta0, *, eps2, alpha0, digamma_am1, beta
     sc = sigma.shape[1]
     for t in (mu, sigma, noisy, gt, beta0):
         assert t.dtype == torch.float32 and t.is_contiguous()
+    # the kernel indexes the prior with sigma's channel layout (the reference broadcasts beta0 against beta,
+    # loss/ELBO_simple.py:38-40; callers expand a 1-channel prior before coming here)
+    assert beta0.shape == sigma.shape, f"beta0 {tuple(beta0.shape)} must have sigma's shape {tuple(sigma.shape)}"
+    assert noisy.shape == mu.shape and gt.shape == mu.shape and sigma.shape[0] == n and sigma.shape[2:] == (h, w)
     if acc3 is None:
         acc3 = torch.empty(3, device=mu.device, dtype=torch.float64)
     if out4 is None:
@@ -418,12 +422,14 @@ def knet_head_wgrad(x, g, gw, *, dtype):
 # ---------------------------------------------------------------------------
 # super-resolution negative ELBO (forward value + gradients in one call)
 # ---------------------------------------------------------------------------
-_SISR_WS = {}
-
-
 def elbo_sisr(mu, im_hr, im_lr, sigma_est, kinfo_est, kinfo_gt, prior_mean, prior_logmean, gamma_draw, rho_draw,
-              z_draw, rh, rw, *, k_size, center, alpha0, digamma_am1, kappa0, r2, eps2, pk0, pk1):
-    """All tensors fp32 contiguous CUDA.  Returns (terms[8], kernel [n,1,k,k], d_mu, d_sigma [n], d_kinfo [n,3])."""
+              z_draw, rh, rw, *, k_size, center, alpha0, digamma_am1, kappa0, r2, eps2, pk0, pk1, ws_cache=None):
+    """All tensors fp32 contiguous CUDA.  Returns (terms[8], kernel [n,1,k,k], d_mu, d_sigma [n], d_kinfo [n,3]).
+
+    Scratch memory belongs to the CALLER: `ws_cache` is a dict the caller keeps alive (one per trainer); buffers put in
+    it are never freed here, so a CUDA graph that captured their addresses stays valid whatever other shapes are
+    evaluated later.  Without a cache every call allocates its own scratch buffer from torch's caching allocator
+    (stream-ordered, and from the graph's private pool during a capture)."""
     n, c, H, W = mu.shape
     h, w = im_lr.shape[2], im_lr.shape[3]
     for t in (mu, im_hr, im_lr, sigma_est, kinfo_est, kinfo_gt, prior_mean, prior_logmean, gamma_draw, rho_draw,
@@ -437,12 +443,13 @@ def elbo_sisr(mu, im_hr, im_lr, sigma_est, kinfo_est, kinfo_gt, prior_mean, prio
     need = lib.vk_elbo_sisr_ws_bytes(n, c, H, W, h, w, k_size)
     if need < 0:
         raise _l.VkError("vk_elbo_sisr_ws_bytes: bad shape")
-    key = (mu.device, need)
-    ws = _SISR_WS.get(key)
-    if ws is None:
-        _SISR_WS.clear()
+    if ws_cache is None:
         ws = torch.empty(need, dtype=torch.uint8, device=mu.device)
-        _SISR_WS[key] = ws
+    else:
+        key = (mu.device, need, torch.cuda.current_stream(mu.device).cuda_stream)
+        ws = ws_cache.get(key)
+        if ws is None:
+            ws = ws_cache[key] = torch.empty(need, dtype=torch.uint8, device=mu.device)
     dev = mu.device
     d_mu = torch.empty_like(mu)
     d_sigma = torch.empty(n, device=dev, dtype=torch.float32)

@@ -288,6 +288,7 @@ class SISRTrainer:
         self.exp_avg = torch.zeros_like(eng.flat_params)
         self.exp_avg_sq = torch.zeros_like(eng.flat_params)
         self.group_names = ["RNet", "SNet", "KNet"]
+        self._loss_ws = {}                 # scratch of vk_elbo_sisr, owned by this trainer (never freed: graphs capture it)
         self._groups_dev, self._ngroups, self._max_group = _clip_groups(
             net, eng, (("rnet", clip_grad_R), ("snet", clip_grad_S), ("knet", clip_grad_K)))
         self._sq_ws = torch.zeros(self._ngroups, device=dev, dtype=torch.float64)
@@ -323,7 +324,7 @@ class SISRTrainer:
             sp.mean(1).contiguous(), sp.log().mean(1).contiguous(), draws[0].contiguous(),
             draws[1].reshape(n).contiguous(), draws[2].contiguous(), rh, rw, k_size=self.k_size, center=float(center),
             alpha0=self.alpha0, digamma_am1=_digamma(self.alpha0 - 1.0), kappa0=self.kappa0, r2=self.r2, eps2=self.eps2,
-            pk0=float(self.penalty_K[0]), pk1=float(self.penalty_K[1]))
+            pk0=float(self.penalty_K[0]), pk1=float(self.penalty_K[1]), ws_cache=self._loss_ws)
         eng.backward_sr(d_mu, d_kinfo, d_sigma)
         grad_scale = dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
         if hyper_dev is None:
