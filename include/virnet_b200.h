@@ -191,6 +191,43 @@ int vk_sft_mlp_bwd_batched(const void* descs_dev, int32_t n_layers, int32_t max_
                            int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra, void* stream);
 uint32_t vk_sizeof_sft_desc(void);
 
+/* ---- SFT modulation with SPATIALLY VARYING conditioning maps (csrc/vk_sft_spatial.cu) ----
+ * Source of the conditioning channels at a pixel of any U-Net level: `ec` per-sample constants cst[n][ec] followed by
+ * `em` map channels map[n][em][eh][ew] that are nearest-upsampled by esf to the un-padded full resolution hh x ww,
+ * reflect-padded (bottom / right) to hp x wp and nearest-resized to the level's grid; sqrt applied to the channels in
+ * sqrt_mask.  Replaces kinfo.repeat / F.interpolate(sigma.sqrt()) / cat (networks/VIRNet.py:87-95),
+ * util_net.pad_input and F.interpolate(extra_maps, size, 'nearest') (networks/AttResUNet.py:147-168). */
+typedef struct vk_extra_src {
+  const float* cst; /* [n][ec] fp32 or NULL */
+  const float* map; /* [n][em][eh][ew] fp32 or NULL */
+  int32_t ec, em, eh, ew, esf;
+  uint32_t sqrt_mask;
+  int32_t hh, ww; /* un-padded full-resolution size */
+  int32_t hp, wp; /* reflect-padded full-resolution size (multiple of every level's grid) */
+} vk_extra_src;
+
+/* out = lrelu(x * mul + add) with (mul, add) = AttLayer(conditioning at that pixel): AttLayer.forward
+ * (networks/AttResUNet.py:27-32) + the modulation of AttResBlock.forward (:54-58) in one pass.
+ * x, out: NHWC `dtype` [n][h][w][ld]; w1 [c1][ec+em], w2 [c2][c1], wm / wa [c][c2] fp32 (the nn.Conv2d 1x1 weights). */
+typedef struct vk_sft_apply_args {
+  int32_t dtype;
+  int32_t n, h, w, c, ld;
+  int32_t c1, c2;
+  const void* x;
+  void* out;
+  const float *w1, *b1, *w2, *b2, *wm, *bm, *wa, *ba;
+  vk_extra_src extra;
+  float alpha;
+  int32_t round_tf32; /* fp32 storage: round the output to TF32 (it feeds a tcgen05 kind::tf32 MMA) */
+} vk_sft_apply_args;
+int vk_sft_apply(const vk_sft_apply_args* args, void* stream);
+uint32_t vk_sizeof_sft_apply_args(void);
+
+/* vk_pack_input with mixed conditioning channels: out NHWC `dtype` [n][hp][wp][ld] =
+ * [img (nearest x sf, reflect padded) | constants | maps | 0 ...]  (networks/VIRNet.py:83-96, AttResUNet.py:147-153) */
+int vk_pack_input_mixed(int32_t dtype, const float* img, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
+                        const vk_extra_src* extra, void* out, int32_t ld, void* stream);
+
 /* CALayer + skip backward: df = g * s + dy / npix (the skip gradient is g); parameter gradients accumulated. */
 int vk_ca_layer_bwd(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1, const float* w2,
                     const float* b2, void* df, float* gw1, float* gb1, float* gw2, float* gb2, int32_t n, int32_t npix,

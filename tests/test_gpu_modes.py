@@ -1,0 +1,95 @@
+"""Drop-in completeness: every constructor-legal configuration of the two wrapper modules
+on the B200 against outputs and gradients of the UNMODIFIED reference (tests/golden/modes.pt,
+tools/gen_golden_modes.py): extra_mode Null / Input / Down (the SR class's own default) / Both, noise_cond /
+kernel_cond switched off, and per-pixel sigma maps (noise_avg=False, JPEG-noise SISR; VIRAttResUNet Down / Both),
+whose AttLayers run per pixel (vk_sft_apply).  Tolerance: 1e-3 relative (tf32 mode), 1e-2 (bf16); gradients 2e-2."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tools"))
+import gen_golden_modes as G  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+SPATIAL_SFT = {"sr_both_sigma_map", "sr_down_sigma_map", "sr_both_sigma_map_noise_only", "den_both", "den_down",
+               "den_both_sigma3"}
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def build(name, precision):
+    import virnet_b200
+    torch.manual_seed(1234)
+    if name in G.SR_CASES:
+        kw, shape, sf = G.SR_CASES[name]
+        net = virnet_b200.VIRAttResUNetSR(**G.sr_kwargs(kw), precision=precision)
+    else:
+        kw, shape = G.DEN_CASES[name]
+        sf = None
+        net = virnet_b200.VIRAttResUNet(**G.den_kwargs(kw), precision=precision)
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(11))
+    return net.cuda(), x.cuda(), sf
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", 1e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("name", list(G.SR_CASES) + list(G.DEN_CASES))
+def test_forward_of_every_configuration_vs_reference(name, precision, tol, golden_dir):
+    fx = torch.load(golden_dir / "modes.pt")[name]
+    net, x, sf = build(name, precision)
+    net.eval()
+    with torch.no_grad():
+        outs = net(x, sf) if sf else net(x)
+    names = ("mu", "kinfo", "sigma") if sf else ("mu", "sigma")
+    for nm, o in zip(names, outs):
+        assert o.shape == fx[nm].shape, nm
+        assert rel(o.cpu(), fx[nm]) < tol, (nm, rel(o.cpu(), fx[nm]))
+
+
+@pytest.mark.parametrize("name", [n for n in list(G.SR_CASES) + list(G.DEN_CASES) if n not in SPATIAL_SFT])
+def test_gradients_of_every_trainable_configuration_vs_reference(name, golden_dir):
+    fx = torch.load(golden_dir / "modes.pt")[name]
+    net, x, sf = build(name, "tf32")
+    net.train()
+    outs = net(x, sf) if sf else net(x)
+    G.functional([o.cpu() for o in outs], 17)            # same seeds -> same functional weights
+    g = torch.Generator().manual_seed(17)
+    tot = 0.0
+    for o in outs:
+        tot = tot + (o * (torch.randn(o.shape, generator=g) / o.numel() ** 0.5).cuda()).sum()
+    tot.backward()
+    got = {k: p.grad for k, p in net.named_parameters()}
+    for k, gn in fx["grad_norm"].items():
+        assert got[k] is not None, k
+        n = float(got[k].norm())
+        assert abs(n - gn) <= 2e-2 * max(gn, 1e-6) + 1e-6, (k, n, gn)
+    for k, gref in fx["grads"].items():
+        if float(gref.norm()) > 1e-6:
+            assert rel(got[k].cpu(), gref) < 2e-2, (k, rel(got[k].cpu(), gref))
+    # branches the reference never touches (e.g. SFT-less conditioning) receive zero gradient
+    for k, p in net.named_parameters():
+        if k not in fx["grad_norm"]:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+
+
+@pytest.mark.parametrize("name", sorted(SPATIAL_SFT))
+def test_training_with_per_pixel_sft_maps_fails_loudly(name):
+    net, x, sf = build(name, "tf32")
+    net.train()
+    outs = net(x, sf) if sf else net(x)
+    with pytest.raises(NotImplementedError):
+        outs[0].sum().backward()
+
+
+def test_extra_mode_without_conditioning_is_rejected_like_the_reference():
+    import virnet_b200
+    from virnet_b200.lib import VkError
+    net = virnet_b200.VIRAttResUNetSR(im_chn=3, n_feat=[32, 64, 96], dep_K=2, noise_cond=False, kernel_cond=False,
+                                      extra_mode="Both", precision="tf32").cuda()
+    with pytest.raises((VkError, TypeError, ValueError)):
+        net(torch.rand(1, 3, 12, 12).cuda(), 2)

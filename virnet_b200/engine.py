@@ -90,14 +90,21 @@ class DenoiseEngine:
         self.sigma_chn = snet.conv_last.out_channels
         self.noise_cond = bool(net.noise_cond)
         self.extra_mode = rnet.extra_mode
-        if not sr:
-            if self.extra_mode in ("down", "both"):
-                raise NotImplementedError("extra_mode 'Down'/'Both' (SFT modulation) belongs to the SISR engine")
-            if snet.noise_avg:
-                raise NotImplementedError("noise_avg=True belongs to the SISR engine")
-            self.head_extra = self.sigma_chn if (self.noise_cond and self.extra_mode == "input") else 0
-        else:
-            self.head_extra = rnet.extra_chn if self.extra_mode in ("input", "both") else 0
+        # conditioning channels of RNet (networks/VIRNet.py:36-40, 66-75): [kernel code (SISR, kernel_cond)] + [sigma]
+        self.kernel_cond = bool(getattr(net, "kernel_cond", False)) if sr else False
+        self.kc = net.KNet.tail[0].out_channels if self.kernel_cond else 0
+        self.sc_extra = self.sigma_chn if self.noise_cond else 0
+        self.n_extra = self.kc + self.sc_extra
+        self.noise_avg = bool(snet.noise_avg)
+        if rnet.extra_chn != self.n_extra:
+            raise ValueError("RNet.extra_chn does not match the conditioning channels of the wrapper module")
+        if not sr and self.noise_avg:
+            # the reference itself cannot run this: RNet reflect-pads the 1x1 sigma "map" (utils/util_net.py:20-25)
+            raise NotImplementedError("VIRAttResUNet(noise_avg=True): the reference's RNet cannot pad a 1x1 sigma map either")
+        # per-pixel sigma map (noise_avg=False) -> the SFT layers see spatially varying conditioning
+        self.spatial_extra = self.sc_extra > 0 and not self.noise_avg
+        self.head_extra = self.n_extra if self.extra_mode in ("input", "both") else 0
+        self.use_sft = self.extra_mode in ("down", "both") and self.n_extra > 0
         self.depth, self.n_feat, self.n_res = rnet.depth, rnet.n_feat, rnet.n_resblocks
 
         # ---- layer table (forward order) ----
@@ -370,6 +377,19 @@ class DenoiseEngine:
                    clamp=(SNET_LOG_MIN, SNET_LOG_MAX))
 
         # ---- RNet ----
+        if self.extra_mode != "null" and self.n_extra == 0:
+            raise _l.VkError("extra_mode != 'Null' needs conditioning maps (noise_cond=True): the reference fails on "
+                             "pad_input(None) here as well (networks/AttResUNet.py:147-149)")
+        if self.use_sft:
+            # extra_mode 'Down' / 'Both': the per-pixel sigma map modulates the down path through the AttLayers
+            src = ops.ExtraSource(None, sigma, 1, (1 << self.sigma_chn) - 1, H, W, Hp, Wp)
+            mu = self._rnet_forward(A, x, 1, None, src, save)
+            if save:
+                A["sigma"] = sigma
+                A["shape"] = (N, C, H, W, Hp, Wp, None)
+                A["sft_spatial"] = True
+                self._commit(A)
+            return mu, sigma
         cin0 = C + self.head_extra
         r0 = self._buf("r0", (N, Hp, Wp, cp(cin0)))
         if self.head_extra:
@@ -474,6 +494,9 @@ class DenoiseEngine:
         """Accumulates parameter gradients into self.flat_grads (zeroed here first).  `gen`: generation of the forward to
         differentiate (default: the most recent saved one)."""
         A = self._saved_A = self._take_saved(gen)
+        if A.get("sft_spatial"):
+            raise NotImplementedError("training VIRAttResUNet with extra_mode 'Down' / 'Both' (per-pixel SFT maps) is not "
+                                      "built: the forward / inference path of this configuration is")
         N, C, H, W, Hp, Wp, dims = A["shape"]
         dt = self.dtype
         cp = lambda c: ops.chan_pad(c, dt)
@@ -594,115 +617,102 @@ class DenoiseEngine:
         self._tables[key] = out
         return out[:4]
 
-    def forward_sr(self, x: torch.Tensor, sf: int, save: bool = False):
-        """x: LR image NCHW fp32 -> (mu [N,C,H*sf,W*sf], kinfo [N,3], sigma [N,1,1,1])."""
-        net = self.net
-        if not (net.noise_cond and net.kernel_cond and net.noise_avg and self.extra_mode == "both"):
-            raise NotImplementedError(
-                "the SISR engine implements the shipped configuration (noise_cond, kernel_cond, noise_avg=True, "
-                "extra_mode='Both'): the SFT maps are then per-sample constants; spatially varying maps are not built")
-        self._ensure_flat()
-        self._ensure_packed()
-        if x.dtype != torch.float32 or not x.is_cuda:
-            raise _l.VkError("input must be a CUDA fp32 NCHW tensor")
-        x = x.contiguous()
-        N, C, h, w = x.shape
-        dt, dev = self.dtype, x.device
+    def _rnet_forward(self, S, x, sf, extra_cst, src, save, sqrt_mask=0):
+        """AttResUNet.forward (networks/AttResUNet.py:141-175) for every extra_mode.  x: NCHW fp32 (the LR image when
+        sf > 1: the nearest up-sampling is fused into the packing); extra_cst [N, E] fp32: per-sample constant
+        conditioning values (SFT by conv epilogue); src: ops.ExtraSource when a conditioning channel varies per pixel
+        (SFT by vk_sft_apply).  Records what the backward needs in S; returns mu (NCHW fp32, caller-owned)."""
+        dt, dev, f32 = self.dtype, x.device, torch.float32
         cp = lambda c: ops.chan_pad(c, dt)
-        f32 = torch.float32
-        S = self._begin(("sr", N, h, w, int(sf)), save)
-
-        # ---- SNet with global average of the log-variance (DnCNN.py:30-33,42; VIRNet.py:81) ----
-        xs = self._buf("sr.xs", (N, h, w, cp(C)))
-        ops.pack_input(x, xs, dtype=dt)
-        S["xs"] = xs
-        cur = xs
-        for i, ly in enumerate(self.s_layers[:-1]):
-            o = self._buf(f"sr.s{i}", (N, h, w, cp(ly.cout)))
-            self._conv(cur, ly, VK_CONV3X3_S1, ldo=cp(ly.cout), out2=o, alpha=0.25)
-            S[f"s{i}"] = o
-            cur = o
-        logvar = self._buf("sr.logvar", (N, self.sigma_chn, h, w), f32)
-        self._conv(cur, self.s_layers[-1], VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=logvar)
-        sigma = torch.empty(N, self.sigma_chn, 1, 1, device=dev, dtype=f32)
-        ops.gap_head(logvar, sigma, exp_mask=(1 << self.sigma_chn) - 1, lo=SNET_LOG_MIN, hi=SNET_LOG_MAX)
-
-        # ---- KNet (KNet.py:52-59) ----
-        knet = net.KNet
-        nfk = knet.head.out_channels
-        kh, kw = (h - 1) // 4 + 1, (w - 1) // 4 + 1
-        H = self._buf("sr.k.h0", (N, kh, kw, cp(nfk)))
-        ops.knet_head(x, knet.head.weight, H, dtype=dt)
-        for b, (c1, c2, ca) in enumerate(self.k_blocks):
-            A = self._buf(f"sr.k{b}.a", (N, kh, kw, cp(nfk)))
-            self._conv(H, c1, VK_CONV3X3_S1, ldo=cp(nfk), out2=A, alpha=0.2)
-            F_ = self._buf(f"sr.k{b}.f", (N, kh, kw, cp(nfk)))
-            self._conv(A, c2, VK_CONV3X3_S1, ldo=cp(nfk), out1=F_)
-            Hn = self._buf(f"sr.k.h{b + 1}", (N, kh, kw, cp(nfk)))
-            ops.ca_layer(F_, H, ca.body[0].weight, ca.body[0].bias, ca.body[2].weight, ca.body[2].bias, Hn, dtype=dt,
-                         c=nfk, alpha=0.2)
-            S[f"k{b}.h"], S[f"k{b}.a"], S[f"k{b}.f"] = H, A, F_
-            H = Hn
-        S["k.hlast"] = H
-        kc = self.k_tail.cout
-        kraw = self._buf("sr.k.raw", (N, kc, kh, kw), f32)
-        self._conv(H, self.k_tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=kraw)
-        kinfo = torch.empty(N, kc, device=dev, dtype=f32)
-        ops.gap_head(kraw, kinfo, exp_mask=0b011, tanh_mask=1 << (kc - 1), lo=KNET_LOG_MIN, hi=KNET_LOG_MAX)
-
-        # ---- conditioning values per sample: [kinfo (3), sigma (1)]; sqrt of the variance at use (VIRNet.py:89-92) ----
-        E = kc + self.sigma_chn
-        extra = self._buf("sr.extra", (N, E), f32)
-        extra[:, :kc].copy_(kinfo)
-        extra[:, kc:].copy_(sigma.view(N, self.sigma_chn))
-        sqrt_mask = ((1 << self.sigma_chn) - 1) << kc
-        nfeat = self.n_feat
-        rnet = net.RNet
-        sft, sft_descs, sft_n, sft_maxc = self._sft_tables(N)
-        ops.sft_mlp_batched(sft_descs, sft_n, sft_maxc, extra, sqrt_mask=sqrt_mask)
-
-        # ---- RNet on the nearest-upsampled image (VIRNet.py:83; AttResUNet.py:141-175, extra_mode 'Both') ----
+        N, C, h, w = x.shape
         Hh, Ww = h * sf, w * sf
         mod = 2 ** (self.depth - 1)
         Hp, Wp = (Hh + mod - 1) // mod * mod, (Ww + mod - 1) // mod * mod
         if Hp > 2 * Hh - 1 or Wp > 2 * Ww - 1:
             raise _l.VkError("image too small for reflect padding")
+        nfeat, rnet = self.n_feat, self.net.RNet
+        sft_const = self.use_sft and src is None
+        sft_spatial = self.use_sft and src is not None
+        rnd = dt == VK_TF32
+        sft = None
+        if sft_const:
+            sft, sft_descs, sft_n, sft_maxc = self._sft_tables(N)
+            ops.sft_mlp_batched(sft_descs, sft_n, sft_maxc, extra_cst, sqrt_mask=sqrt_mask)
         cin0 = C + self.head_extra
         r0 = self._buf("sr.r0", (N, Hp, Wp, cp(cin0)))
-        ops.pack_input(x, r0, dtype=dt, sf=sf, extra=extra, extra_is_map=False, extra_sqrt_mask=sqrt_mask)
+        if self.head_extra and src is not None:
+            ops.pack_input_mixed(x, r0, src, dtype=dt, sf=sf)
+        elif self.head_extra:
+            ops.pack_input(x, r0, dtype=dt, sf=sf, extra=extra_cst, extra_is_map=False, extra_sqrt_mask=sqrt_mask)
+        else:
+            ops.pack_input(x, r0, dtype=dt, sf=sf)
         S["r0"] = r0
         hh, ww = Hp, Wp
+
+        def att(ii, b, which):
+            return getattr(rnet.down_path[ii].body[b], which)
+
+        def modulated(name, X, ii, b, which, c):
+            """lrelu(X * mul + add) with the AttLayer evaluated per pixel (spatially varying conditioning)."""
+            out = self._buf(name, tuple(X.shape))
+            ops.sft_apply(X, out, att(ii, b, which), src, dtype=dt, c=c, alpha=0.2, round_tf32=rnd)
+            return out
+
         X = self._buf("sr.X.head", (N, hh, ww, nfeat[0]))
-        Act = self._buf("sr.A.head", (N, hh, ww, nfeat[0]))
-        self._conv(r0, self.head, VK_CONV3X3_S1, ldo=nfeat[0], out1=X, out2=Act, alpha=0.2, sft=sft[(0, 0, "sft1")])
+        if sft_spatial:
+            self._conv(r0, self.head, VK_CONV3X3_S1, ldo=nfeat[0], out1=X)
+            Act = modulated("sr.A.head", X, 0, 0, "sft1", nfeat[0])
+        else:
+            Act = self._buf("sr.A.head", (N, hh, ww, nfeat[0]))
+            self._conv(r0, self.head, VK_CONV3X3_S1, ldo=nfeat[0], out1=X, out2=Act, alpha=0.2,
+                       sft=sft[(0, 0, "sft1")] if sft_const else None)
         bridges, dims = [], [(hh, ww)]
         for ii, (res, ds) in enumerate(self.down):
             c = nfeat[ii]
             for b, (c1, c2) in enumerate(res):
                 tag = f"d{ii}.{b}"
-                Bt = self._buf(f"sr.{tag}.B", (N, hh, ww, c))
-                F1 = self._buf(f"sr.{tag}.F1", (N, hh, ww, c)) if save else None
-                # conv1 emits a2 = lrelu(fea1 * mul2 + add2); training also keeps fea1 (needed for d mul2)
-                self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out1=F1, out2=Bt, alpha=0.2, sft=sft[(ii, b, "sft2")])
-                S[tag + ".x"], S[tag + ".a"], S[tag + ".f1"], S[tag + ".b"] = X, Act, F1, Bt
+                last = b == len(res) - 1
                 Xn = self._buf(f"sr.{tag}.X", (N, hh, ww, c))
-                if b == len(res) - 1:
+                if sft_spatial:
+                    F1 = self._buf(f"sr.{tag}.F1", (N, hh, ww, c))
+                    self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out1=F1)
+                    Bt = modulated(f"sr.{tag}.B", F1, ii, b, "sft2", c)
+                    S[tag + ".x"], S[tag + ".a"], S[tag + ".f1"], S[tag + ".b"] = X, Act, F1, Bt
+                    self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn)
+                    X, Act = Xn, (None if last else modulated(f"sr.{tag}.A", Xn, ii, b + 1, "sft1", c))
+                    continue
+                Bt = self._buf(f"sr.{tag}.B", (N, hh, ww, c))
+                if sft_const:
+                    F1 = self._buf(f"sr.{tag}.F1", (N, hh, ww, c)) if save else None
+                    # conv1 emits a2 = lrelu(fea1 * mul2 + add2); training also keeps fea1 (needed for d mul2)
+                    self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out1=F1, out2=Bt, alpha=0.2, sft=sft[(ii, b, "sft2")])
+                    S[tag + ".x"], S[tag + ".f1"] = X, F1
+                else:
+                    self._conv(Act, c1, VK_CONV3X3_S1, ldo=c, out2=Bt, alpha=0.2)
+                S[tag + ".a"], S[tag + ".b"] = Act, Bt
+                if last:
                     self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn)
                     X, Act = Xn, None
                 else:
                     An = self._buf(f"sr.{tag}.A", (N, hh, ww, c))
                     self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2,
-                               sft=sft[(ii, b + 1, "sft1")])
+                               sft=sft[(ii, b + 1, "sft1")] if sft_const else None)
                     X, Act = Xn, An
             if ds is not None:
                 bridges.append(X)
                 S[f"d{ii}.xlast"] = X
                 h2, w2 = (hh + 1) // 2, (ww + 1) // 2
                 Xd = self._buf(f"sr.d{ii}.ds.X", (N, h2, w2, nfeat[ii + 1]))
-                Ad = self._buf(f"sr.d{ii}.ds.A", (N, h2, w2, nfeat[ii + 1]))
-                self._conv(X, ds, VK_CONV3X3_S2, ldo=nfeat[ii + 1], out1=Xd, out2=Ad, alpha=0.2,
-                           sft=sft[(ii + 1, 0, "sft1")])
-                X, Act, hh, ww = Xd, Ad, h2, w2
+                if sft_spatial:
+                    self._conv(X, ds, VK_CONV3X3_S2, ldo=nfeat[ii + 1], out1=Xd)
+                    hh, ww = h2, w2
+                    Ad = modulated(f"sr.d{ii}.ds.A", Xd, ii + 1, 0, "sft1", nfeat[ii + 1])
+                else:
+                    Ad = self._buf(f"sr.d{ii}.ds.A", (N, h2, w2, nfeat[ii + 1]))
+                    self._conv(X, ds, VK_CONV3X3_S2, ldo=nfeat[ii + 1], out1=Xd, out2=Ad, alpha=0.2,
+                               sft=sft[(ii + 1, 0, "sft1")] if sft_const else None)
+                    hh, ww = h2, w2
+                X, Act = Xd, Ad
                 dims.append((hh, ww))
         for k, (us, res) in enumerate(self.up):
             lvl = self.depth - 2 - k
@@ -724,13 +734,104 @@ class DenoiseEngine:
                 self._conv(Bt, c2, VK_CONV3X3_S1, ldo=c, resid=X, out1=Xn, out2=An, alpha=0.2)
                 X, Act = Xn, An
         S["tail.x"] = X
-        # tail: + bias, crop, + x_up (the nearest-upsampled LR image, AttResUNet.py:173) -> NCHW fp32
-        x_up = self._buf("sr.xup", (N, C, Hh, Ww), f32)
-        ops.upsample_nearest_nchw(x, x_up, sf)
+        # tail: + bias, crop, + x_in (for SISR the nearest-upsampled LR image, AttResUNet.py:173) -> NCHW fp32
+        if sf > 1:
+            x_res = self._buf("sr.xup", (N, C, Hh, Ww), f32)
+            ops.upsample_nearest_nchw(x, x_res, sf)
+        else:
+            x_res = x
         mu = torch.empty(N, C, Hh, Ww, device=dev, dtype=f32)
-        self._conv(X, self.tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, resid=x_up, out1=mu, crop=(Hh, Ww))
+        self._conv(X, self.tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, resid=x_res, out1=mu, crop=(Hh, Ww))
+        S["rnet_dims"] = (Hh, Ww, Hp, Wp, dims)
+        S["sft"] = sft
+        return mu
+
+    def forward_sr(self, x: torch.Tensor, sf: int, save: bool = False):
+        """x: LR image NCHW fp32 -> (mu [N,C,H*sf,W*sf], kinfo [N,3], sigma [N,1,1,1] or, with noise_avg=False, the
+        per-pixel variance map [N,sigma_chn,H,W]) — networks/VIRNet.py:80-97 for every constructor configuration."""
+        net = self.net
+        if self.extra_mode != "null" and self.n_extra == 0:
+            raise _l.VkError("extra_mode != 'Null' needs conditioning maps (noise_cond or kernel_cond): the reference "
+                             "fails on pad_input(None) here as well (networks/AttResUNet.py:147-149)")
+        self._ensure_flat()
+        self._ensure_packed()
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise _l.VkError("input must be a CUDA fp32 NCHW tensor")
+        x = x.contiguous()
+        N, C, h, w = x.shape
+        sf = int(sf)
+        dt, dev = self.dtype, x.device
+        cp = lambda c: ops.chan_pad(c, dt)
+        f32 = torch.float32
+        S = self._begin(("sr", N, h, w, sf), save)
+
+        # ---- SNet (DnCNN.py:37-44): global average of the log-variance (noise_avg) or a per-pixel map ----
+        xs = self._buf("sr.xs", (N, h, w, cp(C)))
+        ops.pack_input(x, xs, dtype=dt)
+        S["xs"] = xs
+        cur = xs
+        for i, ly in enumerate(self.s_layers[:-1]):
+            o = self._buf(f"sr.s{i}", (N, h, w, cp(ly.cout)))
+            self._conv(cur, ly, VK_CONV3X3_S1, ldo=cp(ly.cout), out2=o, alpha=0.25)
+            S[f"s{i}"] = o
+            cur = o
+        sc = self.sigma_chn
+        if self.noise_avg:
+            logvar = self._buf("sr.logvar", (N, sc, h, w), f32)
+            self._conv(cur, self.s_layers[-1], VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=logvar)
+            sigma = torch.empty(N, sc, 1, 1, device=dev, dtype=f32)
+            ops.gap_head(logvar, sigma, exp_mask=(1 << sc) - 1, lo=SNET_LOG_MIN, hi=SNET_LOG_MAX)
+        else:
+            sigma = torch.empty(N, sc, h, w, device=dev, dtype=f32)
+            self._conv(cur, self.s_layers[-1], VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=sigma, act_expclamp=True,
+                       clamp=(SNET_LOG_MIN, SNET_LOG_MAX))
+
+        # ---- KNet (KNet.py:52-59) ----
+        knet = net.KNet
+        nfk = knet.head.out_channels
+        kh, kw = (h - 1) // 4 + 1, (w - 1) // 4 + 1
+        H = self._buf("sr.k.h0", (N, kh, kw, cp(nfk)))
+        ops.knet_head(x, knet.head.weight, H, dtype=dt)
+        for b, (c1, c2, ca) in enumerate(self.k_blocks):
+            A = self._buf(f"sr.k{b}.a", (N, kh, kw, cp(nfk)))
+            self._conv(H, c1, VK_CONV3X3_S1, ldo=cp(nfk), out2=A, alpha=0.2)
+            F_ = self._buf(f"sr.k{b}.f", (N, kh, kw, cp(nfk)))
+            self._conv(A, c2, VK_CONV3X3_S1, ldo=cp(nfk), out1=F_)
+            Hn = self._buf(f"sr.k.h{b + 1}", (N, kh, kw, cp(nfk)))
+            ops.ca_layer(F_, H, ca.body[0].weight, ca.body[0].bias, ca.body[2].weight, ca.body[2].bias, Hn, dtype=dt,
+                         c=nfk, alpha=0.2)
+            S[f"k{b}.h"], S[f"k{b}.a"], S[f"k{b}.f"] = H, A, F_
+            H = Hn
+        S["k.hlast"] = H
+        kcn = self.k_tail.cout
+        kraw = self._buf("sr.k.raw", (N, kcn, kh, kw), f32)
+        self._conv(H, self.k_tail, VK_CONV3X3_S1, epi=VK_EPI_NCHW_F32, out1=kraw)
+        kinfo = torch.empty(N, kcn, device=dev, dtype=f32)
+        ops.gap_head(kraw, kinfo, exp_mask=0b011, tanh_mask=1 << (kcn - 1), lo=KNET_LOG_MIN, hi=KNET_LOG_MAX)
+
+        # ---- conditioning (VIRNet.py:84-95): [kinfo if kernel_cond] + [sqrt(sigma) if noise_cond], constants per
+        # sample except the sigma map of noise_avg=False ----
+        kc = self.kc
+        n_cst = kc + (self.sc_extra if self.noise_avg else 0)
+        extra = None
+        if n_cst:
+            extra = self._buf("sr.extra", (N, n_cst), f32)
+            if kc:
+                extra[:, :kc].copy_(kinfo)
+            if n_cst > kc:
+                extra[:, kc:].copy_(sigma.view(N, sc))
+        sqrt_mask = (((1 << self.sc_extra) - 1) << kc) if self.sc_extra else 0
+        src = None
+        if self.spatial_extra and self.extra_mode != "null":
+            Hh, Ww = h * sf, w * sf
+            mod = 2 ** (self.depth - 1)
+            src = ops.ExtraSource(extra, sigma, sf, sqrt_mask, Hh, Ww, (Hh + mod - 1) // mod * mod,
+                                  (Ww + mod - 1) // mod * mod)
+        mu = self._rnet_forward(S, x, sf, extra, src, save, sqrt_mask)
         if save:
-            S["x"], S["sigma"], S["kinfo"], S["extra"], S["sft"] = x, sigma, kinfo, extra, sft
+            Hh, Ww, Hp, Wp, dims = S["rnet_dims"]
+            S["x"], S["sigma"], S["kinfo"], S["extra"] = x, sigma, kinfo, extra
+            S["sft_spatial"] = src is not None
             S["shape"] = (N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask)
             self._commit(S)
         return mu, kinfo, sigma
@@ -757,15 +858,19 @@ class DenoiseEngine:
     def backward_sr(self, g_mu, g_kinfo, g_sigma, gen: Optional[int] = None):
         """Accumulates the gradients of every parameter (SNet, KNet, RNet incl. the SFT MLPs) into flat_grads."""
         S = self._saved_A = self._take_saved(gen)
-        if "sft" not in S:
+        if "kinfo" not in S:
             raise _l.VkError("backward_sr called without a saved super-resolution forward")
+        if S.get("sft_spatial"):
+            raise NotImplementedError("training with per-pixel conditioning maps (noise_avg=False) is not built: the "
+                                      "forward / inference path of this configuration is")
         N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask = S["shape"]
         dt, dev, f32 = self.dtype, S["x"].device, torch.float32
         cp = lambda c: ops.chan_pad(c, dt)
         nf = self.n_feat
         net = self.net
-        kc, sc = self.k_tail.cout, self.sigma_chn
-        E = kc + sc
+        kcn, sc = self.k_tail.cout, self.sigma_chn         # outputs of KNet / SNet (always produced, VIRNet.py:81-82)
+        kc = self.kc                                       # conditioning channels taken from kinfo (0 without kernel_cond)
+        E = self.n_extra                                   # all constants here (the sigma-map case returned above)
         self.flat_grads.zero_()
         self.flat_ws.zero_()
         if self.wgrad_side_stream and self._wg_stream is None:
@@ -773,7 +878,7 @@ class DenoiseEngine:
             self._wg_events = [torch.cuda.Event() for _ in range(8)]
         if not self.wgrad_side_stream:
             self._wg_stream = None
-        d_extra = torch.zeros(N, E, device=dev, dtype=f32)
+        d_extra = torch.zeros(N, max(E, 1), device=dev, dtype=f32)
         if g_mu is not None:
             G = self._buf("g.sr.mu", (N, Hp, Wp, cp(C)))
             ops.pack_grad(g_mu.contiguous().float(), G, dtype=dt)
@@ -796,11 +901,13 @@ class DenoiseEngine:
                 gXl = self._buf(f"g.sr.u{k}.low", (N, hl, wl, nf[lvl + 1]))
                 self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
                 gX = gXl
-            tables = self._tables[("sft_tables", N, self._flat_key)]
-            sft_descs, sft_n, sft_maxc, dmd, sft_grads = tables[1], tables[2], tables[3], tables[4], tables[5]
-            sft_grads.zero_()
-            dm = {k: v[0] for k, v in dmd.items()}
-            dd = {k: v[1] for k, v in dmd.items()}
+            dm = dd = None
+            if self.use_sft:
+                tables = self._tables[("sft_tables", N, self._flat_key)]
+                sft_descs, sft_n, sft_maxc, dmd, sft_grads = tables[1], tables[2], tables[3], tables[4], tables[5]
+                sft_grads.zero_()
+                dm = {k: v[0] for k, v in dmd.items()}
+                dd = {k: v[1] for k, v in dmd.items()}
             for ii in reversed(range(self.depth)):
                 res, ds = self.down[ii]
                 c = nf[ii]
@@ -811,31 +918,41 @@ class DenoiseEngine:
                     self._dgrad(gX, ds, VK_CONV3X3_S2_DGRAD, c, ldo=c, resid=g_bridge[ii], out1=gXf, out_hw=(hh, ww))
                     gX = gXf
                 for b in reversed(range(len(res))):
-                    gX = self._sft_block_bwd(ii, b, res[b][0], res[b][1], gX, (N, hh, ww, c), dm, dd)
+                    if self.use_sft:
+                        gX = self._sft_block_bwd(ii, b, res[b][0], res[b][1], gX, (N, hh, ww, c), dm, dd)
+                    else:
+                        gX = self._resblock_bwd(f"d{ii}.{b}", res[b][0], res[b][1], gX, (N, hh, ww, c))
             # head conv: weight gradient, and the gradient w.r.t. its (per-sample constant) conditioning channels
             self._wgrad(self.head, gX, S["r0"], VK_CONV3X3_S1)
-            cin0 = C + self.head_extra
-            gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))
-            self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
-            hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
-            ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
-            # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values, every AttLayer in one launch
-            ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, S["extra"], d_extra, sqrt_mask=sqrt_mask)
-            # the head saw [kinfo, sqrt(sigma)] as constant planes: chain the sqrt for the variance channels
-            hext = hsum[:, C:C + E].clone()
-            hext[:, kc:] = hext[:, kc:] * 0.5 / S["extra"][:, kc:].sqrt().clamp_min(1e-20)
-            d_extra += hext
-        gk = d_extra[:, :kc].clone()
+            if self.use_sft:
+                # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values, every AttLayer in one launch
+                ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, S["extra"], d_extra, sqrt_mask=sqrt_mask)
+            if self.head_extra:
+                cin0 = C + self.head_extra
+                gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))
+                self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
+                hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
+                ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
+                # the head saw [kinfo, sqrt(sigma)] as constant planes: chain the sqrt for the variance channels
+                hext = hsum[:, C:C + E].clone()
+                if E > kc:
+                    hext[:, kc:] = hext[:, kc:] * 0.5 / S["extra"][:, kc:].sqrt().clamp_min(1e-20)
+                d_extra[:, :E] += hext
+        gk = torch.zeros(N, kcn, device=dev, dtype=f32)
+        if kc:
+            gk += d_extra[:, :kc]
         if g_kinfo is not None:
-            gk += g_kinfo.reshape(N, kc).float()
-        gs = d_extra[:, kc:].clone()
+            gk += g_kinfo.reshape(N, kcn).float()
+        gs = torch.zeros(N, sc, device=dev, dtype=f32)
+        if E > kc:
+            gs += d_extra[:, kc:E]
         if g_sigma is not None:
             gs += g_sigma.reshape(N, sc).float()
         # ---- KNet ----
         knet = net.KNet
         nfk = knet.head.out_channels
-        Gt = self._buf("g.sr.k.tail", (N, kh, kw, cp(kc)))
-        ops.gap_head_bwd(gk.contiguous(), S["kinfo"], Gt, dtype=dt, c=kc, exp_mask=0b011, tanh_mask=1 << (kc - 1),
+        Gt = self._buf("g.sr.k.tail", (N, kh, kw, cp(kcn)))
+        ops.gap_head_bwd(gk.contiguous(), S["kinfo"], Gt, dtype=dt, c=kcn, exp_mask=0b011, tanh_mask=1 << (kcn - 1),
                          lo=KNET_LOG_MIN, hi=KNET_LOG_MAX)
         self._wgrad(self.k_tail, Gt, S["k.hlast"], VK_CONV3X3_S1)
         gH = self._buf("g.sr.k.h", (N, kh, kw, cp(nfk)))

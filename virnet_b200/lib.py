@@ -73,6 +73,19 @@ class vk_sft_desc(C.Structure):
                 [(k, C.c_int32) for k in ("c1", "c2", "c", "pad_")])
 
 
+class vk_extra_src(C.Structure):
+    _fields_ = [("cst", C.c_void_p), ("map", C.c_void_p),
+                ("ec", C.c_int32), ("em", C.c_int32), ("eh", C.c_int32), ("ew", C.c_int32), ("esf", C.c_int32),
+                ("sqrt_mask", C.c_uint32),
+                ("hh", C.c_int32), ("ww", C.c_int32), ("hp", C.c_int32), ("wp", C.c_int32)]
+
+
+class vk_sft_apply_args(C.Structure):
+    _fields_ = ([(k, C.c_int32) for k in ("dtype", "n", "h", "w", "c", "ld", "c1", "c2")] +
+                [(k, C.c_void_p) for k in ("x", "out", "w1", "b1", "w2", "b2", "wm", "bm", "wa", "ba")] +
+                [("extra", vk_extra_src), ("alpha", C.c_float), ("round_tf32", C.c_int32)])
+
+
 class vk_pack_desc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
                 ("dim0", C.c_int32), ("dim1", C.c_int32), ("taps", C.c_int32),
@@ -132,6 +145,10 @@ _SIGNATURES = {
     "vk_sft_mlp_bwd_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
                                          C.c_float, C.c_void_p, C.c_void_p]),
     "vk_sizeof_sft_desc": (C.c_uint32, []),
+    "vk_sft_apply": (C.c_int, [C.POINTER(vk_sft_apply_args), C.c_void_p]),
+    "vk_sizeof_sft_apply_args": (C.c_uint32, []),
+    "vk_pack_input_mixed": (C.c_int, [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.POINTER(vk_extra_src), C.c_void_p,
+                                                                                  C.c_int32, C.c_void_p]),
     "vk_synth_denoise": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 4),
     "vk_noise_estimate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_float, C.c_void_p]),
@@ -169,7 +186,8 @@ def load():
     if (lib.vk_sizeof_conv_args() != C.sizeof(vk_conv_args)
             or lib.vk_sizeof_wgrad_args() != C.sizeof(vk_wgrad_args)
             or lib.vk_sizeof_elbo_sisr_args() != C.sizeof(vk_elbo_sisr_args)
-            or lib.vk_sizeof_sft_desc() != C.sizeof(vk_sft_desc)):
+            or lib.vk_sizeof_sft_desc() != C.sizeof(vk_sft_desc)
+            or lib.vk_sizeof_sft_apply_args() != C.sizeof(vk_sft_apply_args)):
         raise VkError("argument struct layout mismatch between lib.py and the built library; rebuild")
     _lib = lib
     return lib

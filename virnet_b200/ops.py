@@ -551,3 +551,50 @@ def sisr_degrade(im_hr, kernels, rh, rw, noise, std):
                                      _ptr(im_blur), _ptr(im_lr), _ptr(ws), need, n, c, H, W, h, w, _stream()),
                  "vk_sisr_degrade")
     return im_blur, im_lr
+
+
+# ---------------------------------------------------------------------------
+# spatially varying conditioning maps (csrc/vk_sft_spatial.cu)
+# ---------------------------------------------------------------------------
+class ExtraSource:
+    """Where the conditioning channels of a pixel come from: per-sample constants `cst` [n, ec] and / or maps `map`
+    [n, em, eh, ew] (nearest-upsampled by esf to hh x ww, reflect padded to hp x wp).  Keeps the tensors alive."""
+
+    def __init__(self, cst, map_, esf, sqrt_mask, hh, ww, hp, wp):
+        for t in (cst, map_):
+            assert t is None or (t.dtype == torch.float32 and t.is_cuda and t.is_contiguous())
+        self.cst, self.map = cst, map_
+        s = _l.vk_extra_src()
+        s.cst, s.map = _ptr(cst), _ptr(map_)
+        s.ec = 0 if cst is None else cst.shape[1]
+        s.em, s.eh, s.ew = (0, 0, 0) if map_ is None else (map_.shape[1], map_.shape[2], map_.shape[3])
+        s.esf, s.sqrt_mask, s.hh, s.ww, s.hp, s.wp = int(esf), int(sqrt_mask), hh, ww, hp, wp
+        self.c = s
+        self.e = s.ec + s.em
+
+
+def pack_input_mixed(img, out, src: ExtraSource, *, dtype, sf=1):
+    n, c, h, w = img.shape
+    assert img.dtype == torch.float32 and img.is_contiguous() and out.is_contiguous()
+    assert out.shape[:3] == (n, src.c.hp, src.c.wp)
+    with _Prof("pack_input"):
+        _l.check(_l.load().vk_pack_input_mixed(dtype, _ptr(img), n, c, h, w, sf, C.byref(src.c), _ptr(out), out.shape[-1],
+                                               _stream()), "vk_pack_input_mixed")
+
+
+def sft_apply(x, out, att, src: ExtraSource, *, dtype, c, alpha=0.2, round_tf32=False):
+    """out = lrelu(x * mul + add), (mul, add) = AttLayer `att` evaluated per pixel on the conditioning source."""
+    n, h, w, ld = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape
+    a = _l.vk_sft_apply_args()
+    a.dtype, a.n, a.h, a.w, a.c, a.ld = dtype, n, h, w, c, ld
+    a.c1, a.c2 = att.conv1.out_channels, att.conv2.out_channels
+    a.x, a.out = _ptr(x), _ptr(out)
+    for nm, p_ in (("w1", att.conv1.weight), ("b1", att.conv1.bias), ("w2", att.conv2.weight), ("b2", att.conv2.bias),
+                   ("wm", att.mul_conv.weight), ("bm", att.mul_conv.bias), ("wa", att.add_conv.weight),
+                   ("ba", att.add_conv.bias)):
+        setattr(a, nm, p_.data_ptr())
+    a.extra = src.c
+    a.alpha, a.round_tf32 = alpha, int(round_tf32)
+    with _Prof("sft_apply"):
+        _l.check(_l.load().vk_sft_apply(C.byref(a), _stream()), "vk_sft_apply")
