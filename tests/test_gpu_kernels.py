@@ -153,3 +153,29 @@ def test_pack_input_reflect_sqrt_concat():
         assert torch.isfinite(got).all()
         torch.testing.assert_close(got[..., :4].permute(0, 3, 1, 2), want, rtol=tol, atol=tol)
         assert (got[..., 4:] == 0).all()
+
+
+def test_elbo_list_form_of_mu_matches_the_reference_formula():
+    """Deep-supervision list form (loss/ELBO_simple.py:30-36,44-49): lh and kl_gauss averaged over the list, kl_Igamma
+    shared; value and gradients against the oracle's per-element restatement (fp32, 1e-5)."""
+    from oracle import virnet_oracle as O
+    from virnet_b200.loss.ELBO_simple import elbo_denoising_simple
+    g = torch.Generator().manual_seed(3)
+    mus = [torch.rand(2, 3, 16, 16, generator=g).requires_grad_(True) for _ in range(3)]
+    sg = (torch.rand(2, 1, 16, 16, generator=g) * 0.05 + 1e-3).requires_grad_(True)
+    y, gt = torch.rand(2, 3, 16, 16, generator=g), torch.rand(2, 3, 16, 16, generator=g)
+    b0 = 24.5 * (torch.rand(2, 1, 16, 16, generator=g) * 0.05 + 1e-3)
+    parts = [O.elbo_denoising_simple(m, sg, y, gt, 1e-6, 24.5, b0) for m in mus]
+    lh = sum(p[1] for p in parts) / 3
+    kg = sum(p[2] for p in parts) / 3
+    want = lh + kg + parts[0][3]
+    want.backward()
+    mus_c = [m.detach().cuda().requires_grad_(True) for m in mus]
+    sg_c = sg.detach().cuda().requires_grad_(True)
+    loss, lh_c, kg_c, ig_c = elbo_denoising_simple(mus_c, sg_c, y.cuda(), gt.cuda(), 1e-6, 24.5, b0.cuda())
+    loss.backward()
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert abs(lh_c.item() - lh.item()) <= 1e-5 * abs(lh.item()) and abs(ig_c.item() - parts[0][3].item()) <= 1e-5 * abs(parts[0][3].item())
+    for a, b in zip(mus_c, mus):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sg_c.grad.cpu(), sg.grad, rtol=1e-5, atol=1e-5)

@@ -44,9 +44,10 @@ class _ElboDenoiseFn(torch.autograd.Function):
 
 def elbo_denoising_simple(mu, sigma_est, im_noisy, im_gt, eps2, alpha0, beta0):
     if isinstance(mu, (list, tuple)):
-        if len(mu) != 1:
-            raise NotImplementedError("deep-supervision list form is unused by the shipped networks")
-        mu = mu[0]
+        # deep-supervision form (loss/ELBO_simple.py:30-36,44-49): lh and kl_gauss are averaged over the list, the
+        # inverse-Gamma KL is shared -> the mean of the per-element fused losses, term by term
+        outs = [elbo_denoising_simple(m, sigma_est, im_noisy, im_gt, eps2, alpha0, beta0) for m in mu]
+        return tuple(sum(o[i] for o in outs) / len(outs) for i in range(4))
     alpha0_f = float(alpha0.item() if torch.is_tensor(alpha0) else alpha0)
     eps2_f = float(eps2)
     if not torch.is_tensor(beta0):
@@ -101,9 +102,18 @@ def elbo_sisr(mu, sigma_est, kinfo_est, im_hr, im_lr, sigma_prior, alpha0, kinfo
     kl_knet1, kl_knet2, kernel]).  `draws` (extra, optional): (gamma_draw [N,2], rho_draw [N,1], z_draw like mu)
     to replace the internal random draws — used by the parity tests."""
     if isinstance(mu, (list, tuple)):
-        if len(mu) != 1:
-            raise NotImplementedError("deep-supervision list form is unused by the shipped networks")
-        mu = mu[0]
+        # deep-supervision form (loss/ELBO_simple.py:105-110,128-133): ONE kernel re-parameterisation, one z draw per
+        # list element (the reference's generator order), lh and kl_rnet averaged, the other terms shared
+        if draws is None:
+            g_draw, r_draw, z0 = sisr_draws(kinfo_est, mu[0], _f(kappa0))
+            zs = [z0] + [torch.randn_like(m, dtype=torch.float32) for m in mu[1:]]
+        else:
+            g_draw, r_draw, zs = draws[0], draws[1], list(draws[2])
+        outs = [elbo_sisr(m, sigma_est, kinfo_est, im_hr, im_lr, sigma_prior, alpha0, kinfo_gt, kappa0, r2, eps2, sf, k_size,
+                          penalty_K, shift, downsampler, draws=(g_draw, r_draw, z)) for m, z in zip(mu, zs)]
+        loss = sum(o[0] for o in outs) / len(outs)
+        detail = [sum(o[1][i] for o in outs) / len(outs) for i in range(7)] + [outs[0][1][7]]
+        return loss, detail
     if sigma_est.numel() != mu.shape[0]:
         raise NotImplementedError("elbo_sisr expects the per-image noise variance of noise_avg=True (N x 1 x 1 x 1)")
     n, _, H, W = mu.shape
