@@ -253,6 +253,30 @@ int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_
 int vk_noise_estimate(const float* noisy, const float* gt, const float* window, int32_t k_size, float* out,
                       int32_t planes, int32_t h, int32_t w, float floor_, void* stream);
 
+/* ---- evaluation-side kernels (csrc/vk_eval.cu) ----
+ * 8-fold flip / rotate self-ensemble (scripts/denoising_virnet_real_sidd.py:120-136,
+ * dnd_submission_py/pytorch_wrapper.py:17-32; utils/util_image.py:391-466 data_aug_np / inverse_data_aug_np):
+ * vk_aug8 gathers the 8 augmentations of `planes` = N*C fp32 planes [h][w] into out_a [4][planes][h][w] (modes 0, 1,
+ * 4, 5) and out_b [4][planes][w][h] (modes 2, 3, 6, 7) for ONE batched forward (two when h != w); vk_aug8_merge
+ * averages the inversely augmented network outputs (accumulation order 0..7, x 1/8; clip01: DND's final clip). */
+int vk_aug8(const float* in, float* out_a, float* out_b, int64_t planes, int32_t h, int32_t w, void* stream);
+int vk_aug8_merge(const float* in_a, const float* in_b, float* out, int64_t planes, int32_t h, int32_t w,
+                  int32_t clip01, void* stream);
+
+/* skimage.img_as_ubyte(clamp(x, 0, 1)) of the eval scripts: NCHW fp32 -> [n][h][w][c] uint8, rint(x * 255) in fp32. */
+int vk_to_u8(const float* in, uint8_t* out, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+
+/* utils/util_image.py:68-89 calculate_psnr on uint8 HWC images (device pointers): *ssd_out = exact sum of squared
+ * differences over the border-cropped region, on RGB (all c channels) or on the rounded Y channel of MATLAB's
+ * rgb2ycbcr (:129-153) when ycbcr != 0.  PSNR = 20 log10(255 / sqrt(ssd / count)) is formed by the caller. */
+int vk_psnr_u8(const uint8_t* a, const uint8_t* b, int32_t h, int32_t w, int32_t c, int32_t border, int32_t ycbcr,
+               uint64_t* ssd_out, void* stream);
+
+/* utils/util_image.py:16-66 calculate_ssim: sums_out[ch] = sum of the SSIM map over the valid (h-2b-10) x (w-2b-10)
+ * region per channel (one entry when ycbcr), fp64; window121_host = the 11x11 Gaussian window (HOST pointer). */
+int vk_ssim_u8(const uint8_t* a, const uint8_t* b, int32_t h, int32_t w, int32_t c, int32_t border, int32_t ycbcr,
+               const double* window121_host, double* sums_out, void* stream);
+
 /* datasets/data_tools.py:21-30 (MixUp_AUG.aug): out_x[i] = lam[i] * x[i] + (1 - lam[i]) * x[perm[i]] for x in {a, b};
  * [n][per_sample] fp32, per_sample a multiple of 4; perm int64 [n], lam fp32 [n] on the device; out must not alias in. */
 int vk_mixup(const float* a, const float* b, const int64_t* perm, const float* lam, float* out_a, float* out_b, int32_t n,

@@ -152,6 +152,11 @@ _SIGNATURES = {
     "vk_synth_denoise": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 4),
     "vk_noise_estimate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_float, C.c_void_p]),
+    "vk_aug8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "vk_aug8_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vk_to_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]),
+    "vk_psnr_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p]),
+    "vk_ssim_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vk_mixup": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int64, C.c_void_p]),
     "vk_sisr_degrade_ws_bytes": (C.c_int64, [C.c_int32] * 5),
     "vk_sisr_degrade": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_int32] * 6 +
