@@ -76,7 +76,7 @@ def test_self_ensemble_is_one_batched_forward_and_matches_the_reference_loop(sha
         l1 = lib.launch_count()
         net(x)
         one_forward = lib.launch_count() - l1
-    assert launches <= (1 if shape[2] == shape[3] else 2) * one_forward + 2
+    assert launches <= (1 if shape[2] == shape[3] else 2) * one_forward + 4, (launches, one_forward)   # not 8 forwards
     # the reference loop: eight separate forwards, numpy flips, float32 accumulation, / 8
 
     def fn(im_hwc):

@@ -102,13 +102,14 @@ __global__ void to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__
   }
 }
 
-// Y of MATLAB's rgb2ycbcr on a uint8 pixel: round(dot([r g b], [65.481 128.553 24.966] / 255) + 16), fp64, no FMA
-// contraction, round-half-even (np.round) — utils/util_image.py:129-153
+// Y of MATLAB's rgb2ycbcr on a uint8 pixel (utils/util_image.py:129-153): the reference rounds (half to even)
+// np.dot([r g b], [65.481 128.553 24.966] / 255) + 16, and numpy's dot is OpenBLAS' dgemv = the fused chain
+// fma(b, c2, fma(g, c1, r * c0)) on x86 — about one pixel in 250 000 is an exact tie, so the chain must be the same.
 __device__ __forceinline__ int y_of_rgb_u8(int r, int g, int b) {
   const double c0 = 65.481 / 255.0, c1 = 128.553 / 255.0, c2 = 24.966 / 255.0;
   double s = __dmul_rn(double(r), c0);
-  s = __dadd_rn(s, __dmul_rn(double(g), c1));
-  s = __dadd_rn(s, __dmul_rn(double(b), c2));
+  s = __fma_rn(double(g), c1, s);
+  s = __fma_rn(double(b), c2, s);
   s = __dadd_rn(s, 16.0);
   return int(rint(s));
 }
