@@ -10,7 +10,9 @@ fp32, PSNR within 0.01 dB on test_data/Set5"), VERDICT r1 item 3:
   initialisation on crops of the same images (model_zoo is empty and a 42 MB checkpoint cannot be committed; random-init
   nets output ~11 dB garbage, the trained ones denoise), loaded into both implementations with load_state_dict;
 * reference side: the CPU oracle (bit-identical to the reference, tests/test_oracle_eval.py) evaluated live;
-* bars: tf32 mode — rel-L2(mu) <= 1e-3, |dPSNR| <= 0.01 dB, |dSSIM| <= 1e-3 per image; bf16 mode (the benchmarked
+* bars: tf32 mode — rel-L2(mu) <= 1e-3, |dPSNR| <= 0.01 dB, |dSSIM| <= 1e-3 per image, and the variance output held
+  to 1e-3 where the network computes it, in the log domain (sigma = exp(clamp(SNet(x))): a trained SNet emits
+  log-variances around -10, so a relative error of 3e-4 of the raw output is 3e-3 of sigma itself); bf16 mode (the benchmarked
   dtype) — |dPSNR| <= 0.05 dB and rel-L2 <= 1e-2, with the measured values written to gpurun_out/psnr_protocol.json.
   PSNR / SSIM of our outputs are computed ON THE DEVICE (virnet_b200.utils.util_image)."""
 import json
@@ -34,6 +36,10 @@ REPORT = {}
 
 def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rel_log(a, b):
+    return rel(a.clamp_min(1e-30).log(), b.clamp_min(1e-30).log())
 
 
 def _report(key, rows):
@@ -136,14 +142,17 @@ def test_cbsd68_full_size_protocol(weights, K):
                 mu, sig = net(xt.cuda())
             d8 = U.img_as_ubyte(mu)[0]
             row[prec] = {"rel_mu": rel(mu.cpu(), mu_o), "rel_sigma": rel(sig.cpu(), sig_o),
+                         "rel_log_sigma": rel_log(sig.cpu(), sig_o),
                          "psnr": U.calculate_psnr(d8, g8), "ssim": U.calculate_ssim(d8, g8)}
             row[prec]["dpsnr"] = row[prec]["psnr"] - psnr_o
         rows.append(row)
         t, b = row["tf32"], row["bf16"]
-        assert t["rel_mu"] <= 1e-3 and t["rel_sigma"] <= 1e-3, row
-        assert abs(t["dpsnr"]) <= 0.01 and abs(t["ssim"] - ssim_o) <= 1e-3, row
-        assert b["rel_mu"] <= 1e-2 and abs(b["dpsnr"]) <= 0.05, row
     _report(f"cbsd68_{weights}", rows)
+    for row in rows:
+        t, b = row["tf32"], row["bf16"]
+        assert t["rel_mu"] <= 1e-3 and t["rel_log_sigma"] <= 1e-3 and t["rel_sigma"] <= 1e-2, row
+        assert abs(t["dpsnr"]) <= 0.01 and abs(t["ssim"] - row["ssim_ref"]) <= 1e-3, row
+        assert b["rel_mu"] <= 1e-2 and abs(b["dpsnr"]) <= 0.05, row
     if weights == "short_trained":                     # the checkpoint must actually denoise (the point of using it)
         assert np.mean([r["psnr_ref"] for r in rows]) > 20.0, rows
 
@@ -185,12 +194,14 @@ def test_set5_x4_full_protocol(weights, K):
                 mu, kinfo, sig = net(xt.cuda(), sf)
             s8 = U.img_as_ubyte(mu)[0]
             row[prec] = {"rel_mu": rel(mu.cpu(), mu_o), "rel_kinfo": rel(kinfo.cpu(), kinfo_o),
-                         "rel_sigma": rel(sig.cpu(), sig_o), "psnr_y": U.calculate_psnr(s8, g8, sf ** 2, True),
+                         "rel_sigma": rel(sig.cpu(), sig_o), "rel_log_sigma": rel_log(sig.cpu(), sig_o),
+                         "psnr_y": U.calculate_psnr(s8, g8, sf ** 2, True),
                          "ssim_y": U.calculate_ssim(s8, g8, sf ** 2, True)}
             row[prec]["dpsnr"] = row[prec]["psnr_y"] - psnr_o
         rows.append(row)
-        t, b = row["tf32"], row["bf16"]
-        assert t["rel_mu"] <= 1e-3 and t["rel_kinfo"] <= 1e-3 and t["rel_sigma"] <= 1e-3, row
-        assert abs(t["dpsnr"]) <= 0.01 and abs(t["ssim_y"] - ssim_o) <= 1e-3, row
-        assert b["rel_mu"] <= 1e-2 and abs(b["dpsnr"]) <= 0.05, row
     _report(f"set5_x4_{weights}", rows)
+    for row in rows:
+        t, b = row["tf32"], row["bf16"]
+        assert t["rel_mu"] <= 1e-3 and t["rel_kinfo"] <= 1e-3 and t["rel_log_sigma"] <= 1e-3 and t["rel_sigma"] <= 1e-2, row
+        assert abs(t["dpsnr"]) <= 0.01 and abs(t["ssim_y"] - row["ssim_y_ref"]) <= 1e-3, row
+        assert b["rel_mu"] <= 1e-2 and abs(b["dpsnr"]) <= 0.05, row

@@ -152,6 +152,7 @@ class DenoiseEngine:
         self.layers = L
 
         self.wgrad_side_stream = os.environ.get("VIRNET_B200_WGRAD_STREAM", "1") != "0"
+        self.grad_sync = None          # dp.BucketedGradSync when the trainer overlaps the gradient all-reduce (world > 1)
         self._wg_stream, self._wg_events, self._wg_i = None, [], 0
         self._flat_key = None
         self._packed_version = None
@@ -475,6 +476,26 @@ class DenoiseEngine:
         with torch.cuda.stream(ws):
             ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias)
 
+    def _bucket_done(self, first_layer: _Layer):
+        """Every layer from `first_layer` (forward order) to the end of the previous bucket has had its weight-gradient
+        kernels issued: hand that range of the flat gradient buffer to the overlapped all-reduce (dp.BucketedGradSync)."""
+        if self.grad_sync is not None:
+            self.grad_sync.bucket_ready(self.layers.index(first_layer), self._wg_stream)
+
+    def unpack_range(self, i0: int, i1: int):
+        """Workspace -> parameter layout for layers [i0, i1) (a sub-range of the batched descriptor table)."""
+        sz = C.sizeof(_l.vk_unpack_desc)
+        descs = self._unpack_descs[i0 * sz:i1 * sz]
+        ops.wgrad_unpack_batched(descs, i1 - i0, self._unpack_max, accumulate=False)
+
+    def layer_flat_range(self, i0: int, i1: int):
+        """[begin, end) of the flat parameter / gradient buffer covered by layers [i0, i1) (weights and biases)."""
+        def first_off(ly):
+            return self.flat_offsets[self.param_index[id(ly.weight)]]
+        begin = first_off(self.layers[i0])
+        end = first_off(self.layers[i1]) if i1 < len(self.layers) else self.flat_total
+        return begin, end
+
     def _dgrad(self, g, ly: _Layer, kind, cout, **kw):
         ops.conv_igemm(g, ly.wd, dtype=self.dtype, kind=kind, cout=cout, bias=None, **kw)
 
@@ -503,6 +524,8 @@ class DenoiseEngine:
         nf = self.n_feat
         self.flat_grads.zero_()
         self.flat_ws.zero_()
+        if self.grad_sync is not None:
+            self.grad_sync.begin()
         if self.wgrad_side_stream and self._wg_stream is None:
             self._wg_stream = torch.cuda.Stream(device=self.flat_params.device)
             self._wg_events = [torch.cuda.Event() for _ in range(8)]
@@ -531,6 +554,7 @@ class DenoiseEngine:
                 xlow = A[f"u{k}.x"]
                 self._wgrad(us, xlow, gX, VK_CONVT2X2_S2)
                 ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt)
+                self._bucket_done(us)            # everything from this up block to the tail has its gradient
                 hl, wl = dims[lvl + 1]
                 gXl = self._buf(f"g.u{k}.low", (N, hl, wl, nf[lvl + 1]))
                 self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
@@ -548,6 +572,8 @@ class DenoiseEngine:
                     gX = gXf
                 for b in reversed(range(len(res))):
                     gX = self._resblock_bwd(f"d{ii}.{b}", res[b][0], res[b][1], gX, (N, h, w, c))
+                if ii > 0:
+                    self._bucket_done(res[0][0])     # this level of the down path (and its down-sampler) is complete
             # head
             self._wgrad(self.head, gX, A["r0"], VK_CONV3X3_S1)
             if self.head_extra:
@@ -572,9 +598,13 @@ class DenoiseEngine:
                     self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
                     g = gn
         # ---- workspace -> parameter-layout gradients ----
-        if self._wg_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._wg_stream)
-        ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
+        if self.grad_sync is not None:
+            self._bucket_done(self.layers[0])    # the rest: down level 0, head, SNet
+            self.grad_sync.finish()
+        else:
+            if self._wg_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._wg_stream)
+            ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
         self._saved_A = None
         A["set"]["owner"] = None
 

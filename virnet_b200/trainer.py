@@ -93,6 +93,12 @@ class DenoiseTrainer:
         self._hyper = torch.zeros(3, device=dev, dtype=torch.float32)
         self._hyper_ring = [(torch.zeros(3, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
         self._hyper_used = [False] * 8
+        # world > 1: the gradient all-reduce runs bucket by bucket on a side stream, overlapped with the rest of the
+        # backward pass (dp.BucketedGradSync); VIRNET_B200_OVERLAP_ALLREDUCE=0 restores the single
+        # blocking all-reduce after the backward
+        self._sync = None
+        if self.world > 1 and os.environ.get("VIRNET_B200_OVERLAP_ALLREDUCE", "1") != "0" and dev.type == "cuda":
+            self._sync = dp.BucketedGradSync(eng, process_group)
 
     # -- host -> device staging (pinned host buffers are the caller's) --------------------------------------
     # The copies run on a side stream: the noisy patches are needed first (the weight packing of this step
@@ -176,6 +182,12 @@ class DenoiseTrainer:
     def _device_step(self, x, gt, sg, ev_late, pf_set, lr, hyper_dev):
         """Everything of a step that runs on the device, for inputs already resident: shared by the eager path and by the
         CUDA-graph capture (hyper_dev: per-step Adam scalars in device memory instead of kernel arguments)."""
+        self._device_fwd_bwd(x, gt, sg, ev_late, pf_set, overlap=True)
+        self._device_update(lr, hyper_dev, reduced=self._sync is not None)
+
+    def _device_fwd_bwd(self, x, gt, sg, ev_late, pf_set, overlap):
+        """forward + fused ELBO + backward; with `overlap` (and world > 1) the gradient buckets are all-reduced on the
+        side stream while the backward is still running, and are complete when this returns (in stream order)."""
         eng = self.engine
         main = torch.cuda.current_stream()
         mu, sigma = eng.forward(x, save=True)
@@ -190,8 +202,17 @@ class DenoiseTrainer:
         if pf_set is not None:
             self._pf_free[pf_set].record(main)   # inputs are not read after the loss kernel
             self._pf_used[pf_set] = True
-        eng.backward(self._d_mu, self._d_sigma)
-        grad_scale = dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
+        eng.grad_sync = self._sync if overlap else None
+        try:
+            eng.backward(self._d_mu, self._d_sigma)
+        finally:
+            eng.grad_sync = None
+        self.last_mu, self.last_sigma = mu, sigma
+
+    def _device_update(self, lr, hyper_dev, reduced):
+        """[all-reduce unless the buckets were reduced during the backward] -> per-sub-network norm, clip, Adam."""
+        eng = self.engine
+        grad_scale = 1.0 / self.world if reduced else dp.all_reduce_flat_grads(eng.flat_grads, self.pg)
         if hyper_dev is None:
             ops.adam_clip_step(eng.flat_params, eng.flat_grads, self.exp_avg, self.exp_avg_sq, self._groups_dev,
                                self._ngroups, self._max_group, self._sq_ws, grad_scale=grad_scale, lr=lr,
@@ -202,48 +223,60 @@ class DenoiseTrainer:
                                    self._ngroups, self._max_group, self._sq_ws, hyper_dev, grad_scale=grad_scale,
                                    beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps, norms_out=self.grad_norms)
         eng.mark_params_dirty()
-        self.last_mu, self.last_sigma = mu, sigma
 
     # -- CUDA-graph replay of the whole step ---------------------------------------------------------------------
     # At the reference's own batch (16 patches over 8 GPUs = 2 per GPU) a step is ~190 kernel launches of a few
     # microseconds each and the Python / driver enqueue (about 3 ms) is the bound; one graph launch removes it.
     def _capture(self, shapes):
+        """world == 1: the whole step is one graph.  world > 1: forward + ELBO + backward (ending with the workspace ->
+        parameter-layout conversion) is the graph; the NCCL all-reduce and the clip + Adam launch stay outside it —
+        three enqueues per step instead of ~190 (NCCL inside a capture did not complete in a 2-GPU trial)."""
         eng = self.engine
         dev = eng.flat_params.device
+        multi = self.world > 1
         self._g_in = [torch.zeros(s, device=dev, dtype=torch.float32) for s in shapes]
         state = [t.clone() for t in (eng.flat_params, self.exp_avg, self.exp_avg_sq)]
         self._hyper.copy_(torch.tensor([0.0, 1.0, 1.0]))     # warm-up / capture run with lr = 0
+
+        def body():
+            if multi:
+                self._device_fwd_bwd(*self._g_in, None, None, overlap=False)
+            else:
+                self._device_fwd_bwd(*self._g_in, None, None, overlap=False)
+                self._device_update(0.0, self._hyper, reduced=False)
+
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                       # warm-up outside capture (lazy allocations, attributes)
             for _ in range(2):
                 eng.mark_params_dirty()
-                self._device_step(*self._g_in, None, None, 0.0, self._hyper)
+                body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         eng.mark_params_dirty()                             # the captured step always re-packs the weights
         graph = torch.cuda.CUDAGraph()
-        mode = "thread_local" if self.world > 1 else "global"
-        with torch.cuda.graph(graph, capture_error_mode=mode):
-            self._device_step(*self._g_in, None, None, 0.0, self._hyper)
+        with torch.cuda.graph(graph, capture_error_mode="thread_local" if multi else "global"):
+            body()
         for t, sv in zip((eng.flat_params, self.exp_avg, self.exp_avg_sq), state):
             t.copy_(sv)                                     # warm-up steps must not count as training
         self._graph, self._graph_key = graph, tuple(shapes)
 
     def step_graph(self, im_noisy, im_gt, sigma_gt, lr: Optional[float] = None):
-        """step() as ONE CUDA-graph launch: inputs (host or device) are copied into static buffers, the per-step Adam
-        scalars into device memory, then the captured forward + ELBO + backward (+ all-reduce) + clip + Adam replays."""
-        if self.world > 1 and os.environ.get("VIRNET_B200_GRAPH_DDP") != "1":
-            # EXPERIMENTAL opt-in (VIRNET_B200_GRAPH_DDP=1): capture with capture_error_mode="thread_local" so that the NCCL
-            # watchdog thread's CUDA calls do not invalidate the capture; unvalidated — the default is to refuse.
-            raise NotImplementedError("step_graph with world_size > 1 (NCCL all-reduce inside the capture) is not validated: "
-                                      "a 2-GPU trial did not complete; use step() for data-parallel runs")
+        """step() with the device work replayed from a CUDA graph: inputs (host or device) are copied into static
+        buffers, then ONE graph launch replays forward + ELBO + backward (+ clip + Adam when world == 1, with the
+        per-step Adam scalars read from device memory).  With world > 1 the gradient all-reduce and the clip + Adam
+        kernel are enqueued after the graph (see _capture)."""
         shapes = (tuple(im_noisy.shape), tuple(im_gt.shape), tuple(sigma_gt.shape))
         if self._graph is None or self._graph_key != shapes:
             self._capture(shapes)
         for dst, src in zip(self._g_in, (im_noisy, im_gt, sigma_gt)):
             dst.copy_(src, non_blocking=True)
         self.step_count += 1
+        if self.world > 1:
+            self._graph.replay()
+            self._device_update(self.lr if lr is None else lr, None, reduced=False)
+            # the captured forward re-packs the weights unconditionally: nothing else to mark
+            return self.losses
         k = self.step_count % len(self._hyper_ring)
         host, ev = self._hyper_ring[k]
         if self._hyper_used[k]:
