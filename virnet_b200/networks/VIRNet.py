@@ -58,9 +58,9 @@ class _WholeNetFn(torch.autograd.Function):
     backward returns the parameter gradients computed by the dgrad / wgrad kernels."""
 
     @staticmethod
-    def forward(ctx, x, engine, *params):
-        # grad mode is always off inside Function.forward; ask autograd which inputs need gradients
-        need_grad = any(ctx.needs_input_grad[2:])
+    def forward(ctx, x, engine, need_grad, *params):
+        # grad mode is always off inside Function.forward and ctx.needs_input_grad ignores torch.no_grad(): the module
+        # decides before apply() whether this forward will be differentiated (no_grad / eval forwards save nothing)
         mu, sigma = engine.forward(x, save=need_grad)
         ctx.engine = engine
         ctx.gen = engine.saved["gen"] if need_grad else None
@@ -71,7 +71,7 @@ class _WholeNetFn(torch.autograd.Function):
     def backward(ctx, g_mu, g_sigma):
         eng = ctx.engine
         eng.backward(g_mu, g_sigma, gen=ctx.gen)
-        return (None, None) + _param_grads(eng, ctx.params)
+        return (None, None, None) + _param_grads(eng, ctx.params)
 
 
 class _SRNetFn(torch.autograd.Function):
@@ -79,8 +79,7 @@ class _SRNetFn(torch.autograd.Function):
     differentiates w.r.t. the LR image, train_SISR.py)."""
 
     @staticmethod
-    def forward(ctx, x, sf, engine, *params):
-        need_grad = any(ctx.needs_input_grad[3:])
+    def forward(ctx, x, sf, engine, need_grad, *params):
         mu, kinfo, sigma = engine.forward_sr(x, sf, save=need_grad)
         ctx.engine, ctx.params = engine, params
         ctx.gen = engine.saved["gen"] if need_grad else None
@@ -90,7 +89,7 @@ class _SRNetFn(torch.autograd.Function):
     def backward(ctx, g_mu, g_kinfo, g_sigma):
         eng = ctx.engine
         eng.backward_sr(g_mu, g_kinfo, g_sigma, gen=ctx.gen)
-        return (None, None, None) + _param_grads(eng, ctx.params)
+        return (None, None, None, None) + _param_grads(eng, ctx.params)
 
 
 class VIRAttResUNet(_EngineMixin, nn.Module):
@@ -116,7 +115,8 @@ class VIRAttResUNet(_EngineMixin, nn.Module):
     def forward(self, x):
         eng = self.engine()
         params = tuple(self.parameters())
-        mu, sigma = _WholeNetFn.apply(x, eng, *params)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        mu, sigma = _WholeNetFn.apply(x, eng, need_grad, *params)
         return mu, sigma
 
 
@@ -146,4 +146,5 @@ class VIRAttResUNetSR(_EngineMixin, nn.Module):
         """(mu, kinfo_est [N,3], sigma [N,1,1,1]) as networks/VIRNet.py:80-97; differentiable w.r.t. the parameters."""
         eng = self.engine()
         params = tuple(self.parameters())
-        return _SRNetFn.apply(x, int(sf), eng, *params)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _SRNetFn.apply(x, int(sf), eng, need_grad, *params)
