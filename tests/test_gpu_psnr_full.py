@@ -12,8 +12,9 @@ fp32, PSNR within 0.01 dB on test_data/Set5"), VERDICT r1 item 3:
 * reference side: the CPU oracle (bit-identical to the reference, tests/test_oracle_eval.py) evaluated live;
 * bars (SURVEY.md §8d "PSNR parity protocol": mean |dPSNR| <= 0.01 dB and tensor rel-L2 <= 1e-3): tf32 mode — rel-L2(mu)
   <= 1e-3 per image, mean |dPSNR| over the set <= 0.01 dB (and no single image beyond 0.02 dB), |dSSIM| <= 1e-3, and the variance output held
-  to 1e-3 where the network computes it, in the log domain (sigma = exp(clamp(SNet(x))): a trained SNet emits
-  log-variances around -10, so a relative error of 3e-4 of the raw output is 3e-3 of sigma itself); bf16 mode (the benchmarked
+  to 1e-3 either as a value or where the network computes it, in the log domain (sigma = exp(clamp(SNet(x))): a
+  trained SNet emits log-variances around -10, so a relative error of 3e-4 of its raw output is 3e-3 of sigma itself,
+  while for the random-init net log sigma is ~0 and only the value domain is meaningful), and to 1e-2 as a value; bf16 mode (the benchmarked
   dtype) — |dPSNR| <= 0.05 dB and rel-L2 <= 1e-2, with the measured values written to gpurun_out/psnr_protocol.json.
   PSNR / SSIM of our outputs are computed ON THE DEVICE (virnet_b200.utils.util_image)."""
 import json
@@ -151,7 +152,7 @@ def test_cbsd68_full_size_protocol(weights, K):
     _report(f"cbsd68_{weights}", rows)
     for row in rows:
         t, b = row["tf32"], row["bf16"]
-        assert t["rel_mu"] <= 1e-3 and t["rel_log_sigma"] <= 1e-3 and t["rel_sigma"] <= 1e-2, row
+        assert t["rel_mu"] <= 1e-3 and min(t["rel_log_sigma"], t["rel_sigma"]) <= 1e-3 and t["rel_sigma"] <= 1e-2, row
         assert abs(t["dpsnr"]) <= 0.02 and abs(t["ssim"] - row["ssim_ref"]) <= 1e-3, row
         assert b["rel_mu"] <= 1e-2 and abs(b["dpsnr"]) <= 0.05, row
     assert np.mean([abs(r["tf32"]["dpsnr"]) for r in rows]) <= 0.01, rows
@@ -204,7 +205,7 @@ def test_set5_x4_full_protocol(weights, K):
     _report(f"set5_x4_{weights}", rows)
     for row in rows:
         t, b = row["tf32"], row["bf16"]
-        assert t["rel_mu"] <= 1e-3 and t["rel_kinfo"] <= 1e-3 and t["rel_log_sigma"] <= 1e-3 and t["rel_sigma"] <= 1e-2, row
+        assert t["rel_mu"] <= 1e-3 and t["rel_kinfo"] <= 1e-3 and min(t["rel_log_sigma"], t["rel_sigma"]) <= 1e-3 and t["rel_sigma"] <= 1e-2, row
         assert abs(t["dpsnr"]) <= 0.02 and abs(t["ssim_y"] - row["ssim_y_ref"]) <= 1e-3, row
         assert b["rel_mu"] <= 1e-2 and abs(b["dpsnr"]) <= 0.05, row
     assert np.mean([abs(r["tf32"]["dpsnr"]) for r in rows]) <= 0.01, rows
