@@ -804,8 +804,190 @@ static void run_mma_min(int n, int per_commit, int nacc, int mode = 0) {
   cudaFree(cyc);
 }
 
+
+// =====================================================================================
+// tcgen05.mma with the A operand in TENSOR MEMORY (wgrad v2 design question): A [M=128][K] bf16 is written by the four
+// warps with tcgen05.st (lane = row m, 32-bit column j holds K elements 2j, 2j+1), B [K pixels][N channels] is the
+// MN-major SW128 tile a TMA box of an NHWC tensor gives (as in vk_wgrad.cuh).  Checks D = A * B^T-style product
+// against the host, then times M=128 x N x K=16 MMAs with A from TMEM vs A from shared memory.
+// =====================================================================================
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct TsCfg {
+  int n;          // GEMM N (channels of B)
+  int k;          // K (pixel rows), multiple of 16, <= 128
+  int iters;      // timing loop: MMAs issued
+  int mode;       // 0: correctness (TS); 1: timing TS; 2: timing SS (A MN-major from smem)
+};
+
+__global__ void __launch_bounds__(128, 1) tsmma_kernel(const __grid_constant__ CUtensorMap tmb, const uint16_t* __restrict__ a_g,
+                                                       TsCfg c, float* out, long long* cyc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full, done;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk_bytes = c.k * 128;                 // one 64-channel block: K rows of 128 B
+  const int n_blocks = (c.n + 63) / 64;
+  if (threadIdx.x == 0) {
+    mbar_init(&full, 1);
+    mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_a = tmem + 256;              // A: columns [256, 256 + k/2)
+  // ---- A -> TMEM: lane m = row m, column j = (A[m][2j], A[m][2j+1]) ----
+  {
+    const int m = threadIdx.x;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(a_g + size_t(m) * c.k);
+    for (int j0 = 0; j0 < c.k / 2; j0 += 16) {
+      uint32_t r[16];
+      for (int i = 0; i < 16; ++i) r[i] = row[j0 + i];
+      tmem_st16(tmem_a + (uint32_t(warp * 32) << 16) + j0, r);
+    }
+    tmem_st_wait();
+  }
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&full, n_blocks * blk_bytes);
+    for (int j = 0; j < n_blocks; ++j) tma_load_3d(smem + j * blk_bytes, &tmb, &full, j * 64, 0, 0);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (threadIdx.x == 0) {
+    mbar_wait(&full, 0);
+    tc_fence_after_sync();
+    // B: MN-major SW128 (layout 2), LBO = block pitch, SBO = 1024 (8 pixel rows); A from TMEM is K-major by construction
+    const uint32_t idesc_ts = make_idesc(1, 128, c.n, 0, 1);
+    const uint32_t idesc_ss = make_idesc(1, 128, c.n, 1, 1);
+    const uint32_t b0 = smem_u32(smem);
+    const int ksteps = c.k / 16;
+    if (c.mode == 0) {
+      for (int kk = 0; kk < ksteps; ++kk) {
+        const uint64_t bd = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);
+        umma_ts(tmem, tmem_a + kk * 8, bd, idesc_ts, kk > 0);
+      }
+      umma_commit(&done);
+    } else {
+      const long long t0 = clock64();
+      for (int it = 0; it < c.iters; it += ksteps) {
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t bd = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);
+          if (c.mode == 1) {
+            umma_ts(tmem + ((it / ksteps) & 1) * 128, tmem_a + kk * 8, bd, idesc_ts, 1);
+          } else {
+            const uint64_t ad = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);     // any resident tile: timing only
+            umma_ss<false>(tmem + ((it / ksteps) & 1) * 128, ad, bd, idesc_ss, 1);
+          }
+        }
+      }
+      umma_commit(&done);
+      mbar_wait(&done, 0);
+      cyc[0] = clock64() - t0;
+    }
+  }
+  mbar_wait(&done, 0);
+  tc_fence_after_sync();
+  if (c.mode == 0) {
+    for (int jc = 0; jc < c.n; jc += 16) {
+      uint32_t rr[16];
+      __syncwarp();
+      tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + jc, rr);
+      tmem_ld_wait();
+      for (int i = 0; i < 16; ++i) out[(warp * 32 + lane) * c.n + jc + i] = __uint_as_float(rr[i]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static void run_tsmma() {
+  const int K = 128;
+  for (int N : {96, 64, 192}) {
+    std::vector<float> a(size_t(128) * K), b(size_t(K) * N);
+    std::vector<uint16_t> a16(a.size()), b16(b.size());
+    srand(7);
+    for (size_t i = 0; i < a.size(); ++i) a[i] = bf16_round((rand() % 2001 - 1000) / 1000.f), a16[i] = bf16_bits(a[i]);
+    for (size_t i = 0; i < b.size(); ++i) b[i] = bf16_round((rand() % 2001 - 1000) / 1000.f), b16[i] = bf16_bits(b[i]);
+    void *da, *db;
+    float* dout;
+    long long* dcyc;
+    CK(cudaMalloc(&da, a16.size() * 2));
+    CK(cudaMalloc(&db, b16.size() * 2));
+    CK(cudaMalloc(&dout, 128 * N * 4));
+    CK(cudaMalloc(&dcyc, 8));
+    CK(cudaMemcpy(da, a16.data(), a16.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
+    uint64_t dims[3] = {uint64_t(N), uint64_t(K), 1};
+    uint64_t strides[2] = {uint64_t(N) * 2, uint64_t(N) * 2 * K};
+    uint32_t box[3] = {64, uint32_t(K), 1};
+    CUtensorMap tmb = make_map(db, 3, dims, strides, box, 128);
+    CK(cudaFuncSetAttribute(tsmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TsCfg c{N, K, 0, 0};
+    CK(cudaMemset(dout, 0, 128 * N * 4));
+    tsmma_kernel<<<1, 128, 100 * 1024>>>(tmb, reinterpret_cast<const uint16_t*>(da), c, dout, dcyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("tsmma N=%d: CUDA error %s\n", N, cudaGetErrorString(e));
+      exit(1);
+    }
+    std::vector<float> h(128 * N);
+    CK(cudaMemcpy(h.data(), dout, h.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < N; ++n) {
+        double acc = 0;
+        for (int k = 0; k < K; ++k) acc += double(a[size_t(m) * K + k]) * b[size_t(k) * N + n];
+        maxerr = std::max(maxerr, std::fabs(acc - h[m * N + n]));
+      }
+    printf("tsmma (A in TMEM, B MN-major SW128) M=128 N=%3d K=%d : max|err| = %.3e %s\n", N, K, maxerr,
+           maxerr < 1e-3 ? "OK" : "WRONG");
+    for (int mode : {1, 2}) {
+      TsCfg t{N, K, 4096, mode};
+      tsmma_kernel<<<1, 128, 100 * 1024>>>(tmb, reinterpret_cast<const uint16_t*>(da), t, dout, dcyc);
+      CK(cudaDeviceSynchronize());
+      long long cy;
+      CK(cudaMemcpy(&cy, dcyc, 8, cudaMemcpyDeviceToHost));
+      printf("  rate N=%3d %s : %6.1f cyc/MMA (ideal %5.1f)\n", N, mode == 1 ? "A from TMEM  " : "A from smem  ",
+             double(cy) / 4096, N / 2.0);
+    }
+    cudaFree(da), cudaFree(db), cudaFree(dout), cudaFree(dcyc);
+  }
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
+  if (!strcmp(what, "tsmma")) run_tsmma();
   if (!strcmp(what, "shift") || !strcmp(what, "all")) run_shift();
   if (!strcmp(what, "tma") || !strcmp(what, "all")) {
     // L2-resident (16 images of 128x128xC bf16: 50 MB at C=96) and HBM-streaming (64 images at C=192: 400 MB)
