@@ -895,16 +895,25 @@ __global__ void __launch_bounds__(128, 1) tsmma_kernel(const __grid_constant__ C
       }
       umma_commit(&done);
     } else {
+      // descriptors precomputed, issue loop fully unrolled (a run-time loop is issue-bound at ~140 clk per MMA)
+      uint64_t bd[8], ad[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        bd[kk] = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);
+        ad[kk] = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);     // any resident tile: timing only
+      }
       const long long t0 = clock64();
-      for (int it = 0; it < c.iters; it += ksteps) {
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t bd = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);
-          if (c.mode == 1) {
-            umma_ts(tmem + ((it / ksteps) & 1) * 128, tmem_a + kk * 8, bd, idesc_ts, 1);
-          } else {
-            const uint64_t ad = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);     // any resident tile: timing only
-            umma_ss<false>(tmem + ((it / ksteps) & 1) * 128, ad, bd, idesc_ss, 1);
-          }
+      if (c.mode == 1) {
+        for (int it = 0; it < c.iters; it += 8) {
+          const uint32_t d = tmem + ((it >> 3) & 1) * 128;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_ts(d, tmem_a + kk * 8, bd[kk], idesc_ts, 1);
+        }
+      } else {
+        for (int it = 0; it < c.iters; it += 8) {
+          const uint32_t d = tmem + ((it >> 3) & 1) * 128;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_ss<false>(d, ad[kk], bd[kk], idesc_ss, 1);
         }
       }
       umma_commit(&done);

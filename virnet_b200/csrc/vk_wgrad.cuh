@@ -50,6 +50,7 @@ struct WgradParams {
   int total_taps;
   float* dw;                    // [total_taps][m_valid][n_valid] fp32, accumulated
   float* dbias;                 // [m_valid] fp32 accumulated, or null
+  int debug_skip_epi;           // tuning aid (VK_WGRAD_SKIP_EPI=1): leave the accumulators in TMEM, measure the mainloop alone
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -234,7 +235,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after_sync();
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
-    const bool m_ok = (m < prm.m_valid) && (my_tiles > 0);
+    const bool m_ok = (m < prm.m_valid) && (my_tiles > 0) && !prm.debug_skip_epi;
     const bool vec_ok = (prm.n_valid % 4) == 0;
     for (int tp = 0; tp < prm.n_taps; ++tp) {
       const int tap = prm.taps[group][tp].tap;

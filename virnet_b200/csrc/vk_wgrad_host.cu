@@ -1,6 +1,7 @@
 // vk_wgrad_host.cu — host side of vk_conv_wgrad (tiling, split-K, TMA maps, launch).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/virnet_b200.h"
 #include "vk_host.h"
@@ -61,6 +62,10 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   prm.n_valid = a->n_valid;
   prm.dw = a->dw;
   prm.dbias = a->dbias;
+  {
+    static const int skip = getenv("VK_WGRAD_SKIP_EPI") != nullptr;
+    prm.debug_skip_epi = skip;
+  }
 
   bool slab = false;
   switch (a->kind) {
