@@ -223,6 +223,31 @@ typedef struct vk_sft_apply_args {
 int vk_sft_apply(const vk_sft_apply_args* args, void* stream);
 uint32_t vk_sizeof_sft_apply_args(void);
 
+/* Backward of vk_sft_apply (autograd of networks/AttResUNet.py:27-32,54-58).  g = dL/d(x*mul+add) (the producing
+ * dgrad kernel already applied lrelu').  Writes gx = g * mul (+ resid), and the per-pixel operands of the four pixel-K
+ * GEMMs that form the AttLayer's parameter gradients with vk_conv_wgrad(VK_CONV1X1): dm [..][ld] (with g: mul_conv /
+ * add_conv), f2, dq2 [..][ld2] and f1, dq1 [..][ld1] (conv2), ev [..][16] (conv1 input).  The gradient w.r.t. the
+ * conditioning values is accumulated (atomicAdd, zero first) into d_cst [n][ec] and d_map [n][em][eh][ew]. */
+typedef struct vk_sft_apply_bwd_args {
+  int32_t dtype;
+  int32_t n, h, w, c, ld;
+  int32_t c1, c2, ld1, ld2;
+  const void *g, *x, *resid;
+  void *gx, *dm, *f2, *dq2, *f1, *dq1, *ev;
+  const float *w1, *b1, *w2, *b2, *wm, *bm, *wa, *ba;
+  float *d_cst, *d_map;
+  vk_extra_src extra;
+  float alpha;
+  int32_t pad_;
+} vk_sft_apply_bwd_args;
+int vk_sft_apply_bwd(const vk_sft_apply_bwd_args* args, void* stream);
+uint32_t vk_sizeof_sft_apply_bwd_args(void);
+
+/* Gradient of the head convolution's packed input w.r.t. its conditioning channels [c, c + ec + em) (NHWC `dtype`
+ * [n][hp][wp][ld]), folded through reflect padding / nearest up-sampling / sqrt into d_cst and d_map (accumulated). */
+int vk_extra_head_grad(int32_t dtype, const void* g, int32_t n, int32_t ld, int32_t c, const vk_extra_src* extra,
+                       float* d_cst, float* d_map, void* stream);
+
 /* vk_pack_input with mixed conditioning channels: out NHWC `dtype` [n][hp][wp][ld] =
  * [img (nearest x sf, reflect padded) | constants | maps | 0 ...]  (networks/VIRNet.py:83-96, AttResUNet.py:147-153) */
 int vk_pack_input_mixed(int32_t dtype, const float* img, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,

@@ -61,7 +61,7 @@ def test_header_is_valid_c99_and_struct_layouts_match_ctypes(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     structs = ["vk_conv_args", "vk_wgrad_args", "vk_elbo_sisr_args", "vk_sft_desc", "vk_adam_group", "vk_pack_desc",
-               "vk_unpack_desc", "vk_extra_src", "vk_sft_apply_args"]
+               "vk_unpack_desc", "vk_extra_src", "vk_sft_apply_args", "vk_sft_apply_bwd_args"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "virnet_b200.h"', 'int main(void) {']
     for name in structs:
         ct = getattr(lib, name)

@@ -2,7 +2,7 @@
 on the B200 against outputs and gradients of the UNMODIFIED reference (tests/golden/modes.pt,
 tools/gen_golden_modes.py): extra_mode Null / Input / Down (the SR class's own default) / Both, noise_cond /
 kernel_cond switched off, and per-pixel sigma maps (noise_avg=False, JPEG-noise SISR; VIRAttResUNet Down / Both),
-whose AttLayers run per pixel (vk_sft_apply).  Tolerance: 1e-3 relative (tf32 mode), 1e-2 (bf16); gradients 2e-2 on
+whose AttLayers run per pixel (vk_sft_apply / vk_sft_apply_bwd + 1x1 weight-gradient GEMMs).  Tolerance: 1e-3 relative (tf32 mode), 1e-2 (bf16); gradients 2e-2 on
 sub-network norms, 4e-2 on the concatenated small tensors the fixture stores."""
 import sys
 from pathlib import Path
@@ -15,11 +15,6 @@ sys.path.insert(0, str(ROOT / "tools"))
 import gen_golden_modes as G  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-
-# configurations whose conditioning varies per pixel: forward / inference is built, their backward is not (it raises)
-SPATIAL_SFT = {"sr_both_sigma_map", "sr_down_sigma_map", "sr_both_sigma_map_noise_only", "sr_input_sigma_map",
-               "den_both", "den_down", "den_both_sigma3"}
-
 
 def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
@@ -53,8 +48,8 @@ def test_forward_of_every_configuration_vs_reference(name, precision, tol, golde
         assert rel(o.cpu(), fx[nm]) < tol, (nm, rel(o.cpu(), fx[nm]))
 
 
-@pytest.mark.parametrize("name", [n for n in list(G.SR_CASES) + list(G.DEN_CASES) if n not in SPATIAL_SFT])
-def test_gradients_of_every_trainable_configuration_vs_reference(name, golden_dir):
+@pytest.mark.parametrize("name", list(G.SR_CASES) + list(G.DEN_CASES))
+def test_gradients_of_every_configuration_vs_reference(name, golden_dir):
     fx = torch.load(golden_dir / "modes.pt")[name]
     net, x, sf = build(name, "tf32")
     net.train()
@@ -92,15 +87,6 @@ def test_gradients_of_every_trainable_configuration_vs_reference(name, golden_di
     for k, p in net.named_parameters():
         if k not in fx["grad_norm"]:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
-
-
-@pytest.mark.parametrize("name", sorted(SPATIAL_SFT))
-def test_training_with_per_pixel_sft_maps_fails_loudly(name):
-    net, x, sf = build(name, "tf32")
-    net.train()
-    outs = net(x, sf) if sf else net(x)
-    with pytest.raises(NotImplementedError):
-        outs[0].sum().backward()
 
 
 def test_extra_mode_without_conditioning_is_rejected_like_the_reference():

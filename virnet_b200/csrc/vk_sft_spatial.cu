@@ -282,6 +282,201 @@ int dispatch_apply(const vk_sft_apply_args* a, const ExtraSrc& src, const SftW& 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// backward of the per-pixel modulation  a = lrelu(p),  p = x * mul + add,  (mul, add) = AttLayer(e)
+// (autograd of networks/AttResUNet.py:27-32,54-58).  The producing dgrad kernel has already applied lrelu'(p), so
+// g = dL/dp arrives.  One thread per pixel:
+//   gx   = g * mul (+ resid)                                        -> gx   [n][h][w][ld]   (dL/dx)
+//   dm   = g * x * mul * (1 - mul)   (through the sigmoid)          -> dm   [n][h][w][ld]
+//   df2  = Wm^T dm + Wa^T g ; dq2 = df2 * lrelu'(q2)                -> f2, dq2 [n][h][w][ld2]
+//   df1  = W2^T dq2         ; dq1 = df1 * lrelu'(q1)                -> f1, dq1 [n][h][w][ld1]
+//   de   = W1^T dq1                                                 -> scattered (atomicAdd) onto the conditioning
+//          sources: d_cst [n][ec], d_map [n][em][eh][ew] (sqrt chain rule applied), ev [n][h][w][16] = e
+// The parameter gradients are then four pixel-K GEMMs on the tensor cores (vk_conv_wgrad, VK_CONV1X1):
+//   gWm = dm^T f2, gbm = sum dm;  gWa = g^T f2, gba = sum g;  gW2 = dq2^T f1, gb2 = sum dq2;  gW1 = dq1^T ev, gb1 = sum dq1.
+// ---------------------------------------------------------------------------------------------------------
+struct SftBwdOut {
+  void *gx, *dm, *f2, *dq2, *f1, *dq1, *ev;
+  int ld2, ld1;
+  float *d_cst, *d_map;
+};
+
+__device__ __forceinline__ void scatter_extra_grad(const ExtraSrc& s, int n, int Y, int X, const float (&de)[kMaxE],
+                                                   const float (&ex)[kMaxE], float* d_cst, float* d_map) {
+  const int ey = reflect_far(Y, s.hh) / s.esf, exx = reflect_far(X, s.ww) / s.esf;
+#pragma unroll
+  for (int e = 0; e < kMaxE; ++e) {
+    if (e >= s.ec + s.em) break;
+    float g = de[e];
+    if (s.sqrt_mask & (1u << e)) g *= 0.5f / fmaxf(ex[e], 1e-20f);          // ex = sqrt(raw): d sqrt = 1 / (2 sqrt)
+    if (e < s.ec) {
+      if (d_cst != nullptr) atomicAdd(d_cst + static_cast<long long>(n) * s.ec + e, g);
+    } else if (d_map != nullptr) {
+      atomicAdd(d_map + ((static_cast<long long>(n) * s.em + (e - s.ec)) * s.eh + ey) * s.ew + exx, g);
+    }
+  }
+}
+
+template <typename DT>
+__device__ __forceinline__ void store_vec_row(DT* dst, int ld, const float* v, int nvalid) {
+  constexpr int V = 16 / int(sizeof(DT));
+  for (int c0 = 0; c0 < ld; c0 += V) {
+    float t[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) t[i] = (c0 + i < nvalid) ? v[c0 + i] : 0.f;
+    *reinterpret_cast<uint4*>(dst + c0) = pack16<DT>(t);
+  }
+}
+
+template <typename DT, int C2P>
+__global__ void __launch_bounds__(128)
+sft_apply_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const DT* __restrict__ resid, int ld, int N, int h,
+                     int w, ExtraSrc src, SftW wt, float alpha, int rnd, SftBwdOut o) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int E = src.ec + src.em;
+  stage_weights<C2P>(smem_f, wt, E);
+  __syncthreads();
+  constexpr int C1P = C2P / 2;
+  constexpr int V = 16 / int(sizeof(DT));
+  const float* w1 = smem_f;
+  const float* w2 = w1 + C1P * kMaxE + C1P;
+  const float* wm = smem_f + C1P * kMaxE + C1P + C2P * C1P + C2P;
+  const float* bm = wm + wt.c * C2P;
+  const float* wa = bm + wt.c;
+  const long long total = static_cast<long long>(N) * h * w;
+  const int sy = src.hp / h, sx = src.wp / w;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int px = int(p % w), py = int((p / w) % h), n = int(p / (static_cast<long long>(w) * h));
+    float ex[kMaxE], f1[C1P], f2[C2P], df2[C2P];
+    load_extra(src, n, py * sy, px * sx, ex);
+    mlp_hidden<C2P>(smem_f, ex, alpha, f1, f2);
+#pragma unroll
+    for (int j = 0; j < C2P; ++j) df2[j] = 0.f;
+    const DT* gr = g + p * ld;
+    const DT* xr = x + p * ld;
+    DT* gxr = reinterpret_cast<DT*>(o.gx) + p * ld;
+    DT* dmr = reinterpret_cast<DT*>(o.dm) + p * ld;
+    for (int c0 = 0; c0 < ld; c0 += V) {
+      float gv[V], xv[V], rv[V], ogx[V], odm[V];
+      unpack16<DT>(*reinterpret_cast<const uint4*>(gr + c0), gv);
+      unpack16<DT>(*reinterpret_cast<const uint4*>(xr + c0), xv);
+      if (resid != nullptr) unpack16<DT>(*reinterpret_cast<const uint4*>(resid + p * ld + c0), rv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = c0 + i;
+        float vgx = 0.f, vdm = 0.f;
+        if (c < wt.c) {
+          float am = bm[c];
+          const float4* wm4 = reinterpret_cast<const float4*>(wm + c * C2P);
+#pragma unroll
+          for (int j4 = 0; j4 < C2P / 4; ++j4) {
+            const float4 m = wm4[j4];
+            am = fmaf(m.x, f2[4 * j4], am), am = fmaf(m.y, f2[4 * j4 + 1], am);
+            am = fmaf(m.z, f2[4 * j4 + 2], am), am = fmaf(m.w, f2[4 * j4 + 3], am);
+          }
+          const float mul = 1.f / (1.f + __expf(-am));
+          const float gg = gv[i];
+          vgx = gg * mul + (resid != nullptr ? rv[i] : 0.f);
+          vdm = gg * xv[i] * mul * (1.f - mul);
+          // the GEMMs that form the parameter gradients read dm / g in the storage type: back-propagate the same values
+          float dmq = vdm;
+          if (sizeof(DT) == 2) dmq = __bfloat162float(__float2bfloat16_rn(vdm));
+          const float4* wa4 = reinterpret_cast<const float4*>(wa + c * C2P);
+#pragma unroll
+          for (int j4 = 0; j4 < C2P / 4; ++j4) {
+            const float4 m = wm4[j4], a = wa4[j4];
+            df2[4 * j4] = fmaf(m.x, dmq, fmaf(a.x, gg, df2[4 * j4]));
+            df2[4 * j4 + 1] = fmaf(m.y, dmq, fmaf(a.y, gg, df2[4 * j4 + 1]));
+            df2[4 * j4 + 2] = fmaf(m.z, dmq, fmaf(a.z, gg, df2[4 * j4 + 2]));
+            df2[4 * j4 + 3] = fmaf(m.w, dmq, fmaf(a.w, gg, df2[4 * j4 + 3]));
+          }
+        }
+        ogx[i] = vgx, odm[i] = vdm;
+      }
+      *reinterpret_cast<uint4*>(gxr + c0) = pack16<DT>(ogx);
+      *reinterpret_cast<uint4*>(dmr + c0) = pack16<DT>(odm);
+    }
+    // through the two hidden layers
+    float dq1[C1P], de[kMaxE];
+#pragma unroll
+    for (int j = 0; j < C2P; ++j) df2[j] *= (f2[j] > 0.f ? 1.f : alpha);           // dq2
+#pragma unroll
+    for (int i = 0; i < C1P; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < C2P; ++j) a = fmaf(w2[j * C1P + i], df2[j], a);
+      dq1[i] = a * (f1[i] > 0.f ? 1.f : alpha);
+    }
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < C1P; ++i) a = fmaf(w1[i * kMaxE + e], dq1[i], a);
+      de[e] = a;
+    }
+    store_vec_row<DT>(reinterpret_cast<DT*>(o.f2) + p * o.ld2, o.ld2, f2, wt.c2);
+    store_vec_row<DT>(reinterpret_cast<DT*>(o.dq2) + p * o.ld2, o.ld2, df2, wt.c2);
+    store_vec_row<DT>(reinterpret_cast<DT*>(o.f1) + p * o.ld1, o.ld1, f1, wt.c1);
+    store_vec_row<DT>(reinterpret_cast<DT*>(o.dq1) + p * o.ld1, o.ld1, dq1, wt.c1);
+    store_vec_row<DT>(reinterpret_cast<DT*>(o.ev) + p * 16, 16, ex, E);
+    scatter_extra_grad(src, n, py * sy, px * sx, de, ex, o.d_cst, o.d_map);
+  }
+}
+
+// gradient of the head convolution's input w.r.t. its conditioning channels (channels [C, C + E) of the packed input,
+// networks/AttResUNet.py:152-153), folded back through the reflect padding / nearest up-sampling / sqrt
+template <typename DT>
+__global__ void extra_head_grad_kernel(const DT* __restrict__ g, int ld, int C, int N, ExtraSrc src, float* d_cst,
+                                       float* d_map) {
+  const long long total = static_cast<long long>(N) * src.hp * src.wp;
+  const int E = src.ec + src.em;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = int(p % src.wp), y = int((p / src.wp) % src.hp), n = int(p / (static_cast<long long>(src.wp) * src.hp));
+    float ex[kMaxE], de[kMaxE];
+    load_extra(src, n, y, x, ex);
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) de[e] = e < E ? float(g[p * ld + C + e]) : 0.f;
+    scatter_extra_grad(src, n, y, x, de, ex, d_cst, d_map);
+  }
+}
+
+template <typename DT, int C2P>
+int launch_apply_bwd(const vk_sft_apply_bwd_args* a, const ExtraSrc& src, const SftW& wt, cudaStream_t st) {
+  constexpr int C1P = C2P / 2;
+  const int smem = int(sizeof(float)) * (C1P * kMaxE + C1P + C2P * C1P + C2P + 2 * (wt.c * C2P + wt.c));
+  auto kern = sft_apply_bwd_kernel<DT, C2P>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return int(e);
+  }
+  SftBwdOut o{a->gx, a->dm, a->f2, a->dq2, a->f1, a->dq1, a->ev, a->ld2, a->ld1, a->d_cst, a->d_map};
+  const long long total = static_cast<long long>(a->n) * a->h * a->w;
+  kern<<<grid_for_px(total, 128), 128, smem, st>>>(reinterpret_cast<const DT*>(a->g), reinterpret_cast<const DT*>(a->x),
+                                                  reinterpret_cast<const DT*>(a->resid), a->ld, a->n, a->h, a->w, src, wt,
+                                                  a->alpha, 0, o);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+template <typename DT>
+int dispatch_apply_bwd(const vk_sft_apply_bwd_args* a, const ExtraSrc& src, const SftW& wt, cudaStream_t st) {
+  switch ((wt.c2 + 7) / 8 * 8) {
+    case 8: return launch_apply_bwd<DT, 8>(a, src, wt, st);
+    case 16: return launch_apply_bwd<DT, 16>(a, src, wt, st);
+    case 24: return launch_apply_bwd<DT, 24>(a, src, wt, st);
+    case 32: return launch_apply_bwd<DT, 32>(a, src, wt, st);
+    case 40: return launch_apply_bwd<DT, 40>(a, src, wt, st);
+    case 48: return launch_apply_bwd<DT, 48>(a, src, wt, st);
+    case 56: return launch_apply_bwd<DT, 56>(a, src, wt, st);
+    case 64: return launch_apply_bwd<DT, 64>(a, src, wt, st);
+    case 72: return launch_apply_bwd<DT, 72>(a, src, wt, st);
+    default: return VK_E_UNSUPPORTED;
+  }
+}
+
 bool fill_src(const vk_extra_src* e, ExtraSrc* s) {
   if (e->ec < 0 || e->em < 0 || e->ec + e->em > kMaxE) return false;
   if (e->ec > 0 && e->cst == nullptr) return false;
@@ -334,5 +529,45 @@ extern "C" int vk_pack_input_mixed(int32_t dtype, const float* img, int32_t n, i
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
 }
+
+
+extern "C" int vk_sft_apply_bwd(const vk_sft_apply_bwd_args* a, void* stream) {
+  if (a == nullptr || !a->g || !a->x || !a->gx || !a->dm || !a->f2 || !a->dq2 || !a->f1 || !a->dq1 || !a->ev) return VK_E_BADARG;
+  if (a->n <= 0 || a->h <= 0 || a->w <= 0 || a->c <= 0 || a->c > a->ld) return VK_E_BADARG;
+  const int esize = a->dtype == VK_BF16 ? 2 : 4;
+  if ((a->dtype != VK_BF16 && a->dtype != VK_TF32) || (a->ld * esize) % 16 || (a->ld2 * esize) % 16 || (a->ld1 * esize) % 16)
+    return VK_E_BADARG;
+  if (!a->w1 || !a->b1 || !a->w2 || !a->b2 || !a->wm || !a->bm || !a->wa || !a->ba) return VK_E_BADARG;
+  if (a->c1 <= 0 || a->c2 <= 0 || a->c1 > a->ld1 || a->c2 > a->ld2 || 2 * a->c1 > (a->c2 + 7) / 8 * 8) return VK_E_UNSUPPORTED;
+  ExtraSrc src;
+  if (!fill_src(&a->extra, &src)) return VK_E_BADARG;
+  if (src.hp % a->h || src.wp % a->w) return VK_E_BADARG;
+  SftW wt{a->w1, a->b1, a->w2, a->b2, a->wm, a->bm, a->wa, a->ba, a->c1, a->c2, a->c};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == VK_BF16) return dispatch_apply_bwd<__nv_bfloat16>(a, src, wt, st);
+  return dispatch_apply_bwd<float>(a, src, wt, st);
+}
+
+extern "C" int vk_extra_head_grad(int32_t dtype, const void* g, int32_t n, int32_t ld, int32_t c, const vk_extra_src* extra,
+                                  float* d_cst, float* d_map, void* stream) {
+  if (g == nullptr || extra == nullptr || n <= 0 || c < 0) return VK_E_BADARG;
+  ExtraSrc src;
+  if (!fill_src(extra, &src)) return VK_E_BADARG;
+  if (c + src.ec + src.em > ld) return VK_E_BADARG;
+  const long long total = static_cast<long long>(n) * src.hp * src.wp;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == VK_BF16)
+    extra_head_grad_kernel<__nv_bfloat16><<<grid_for_px(total, 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(g), ld, c, n, src, d_cst, d_map);
+  else if (dtype == VK_TF32)
+    extra_head_grad_kernel<float><<<grid_for_px(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(g), ld, c, n, src,
+                                                                          d_cst, d_map);
+  else
+    return VK_E_BADARG;
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+extern "C" uint32_t vk_sizeof_sft_apply_bwd_args(void) { return uint32_t(sizeof(vk_sft_apply_bwd_args)); }
 
 extern "C" uint32_t vk_sizeof_sft_apply_args(void) { return uint32_t(sizeof(vk_sft_apply_args)); }

@@ -386,9 +386,9 @@ class DenoiseEngine:
             src = ops.ExtraSource(None, sigma, 1, (1 << self.sigma_chn) - 1, H, W, Hp, Wp)
             mu = self._rnet_forward(A, x, 1, None, src, save)
             if save:
-                A["sigma"] = sigma
+                A["sigma"], A["src"], A["x"] = sigma, src, x
                 A["shape"] = (N, C, H, W, Hp, Wp, None)
-                A["sft_spatial"] = True
+                A["rnet_general"] = True
                 self._commit(A)
             return mu, sigma
         cin0 = C + self.head_extra
@@ -515,9 +515,8 @@ class DenoiseEngine:
         """Accumulates parameter gradients into self.flat_grads (zeroed here first).  `gen`: generation of the forward to
         differentiate (default: the most recent saved one)."""
         A = self._saved_A = self._take_saved(gen)
-        if A.get("sft_spatial"):
-            raise NotImplementedError("training VIRAttResUNet with extra_mode 'Down' / 'Both' (per-pixel SFT maps) is not "
-                                      "built: the forward / inference path of this configuration is")
+        if A.get("rnet_general"):
+            return self._backward_general_denoise(A, g_mu, g_sigma)
         N, C, H, W, Hp, Wp, dims = A["shape"]
         dt = self.dtype
         cp = lambda c: ops.chan_pad(c, dt)
@@ -861,7 +860,7 @@ class DenoiseEngine:
         if save:
             Hh, Ww, Hp, Wp, dims = S["rnet_dims"]
             S["x"], S["sigma"], S["kinfo"], S["extra"] = x, sigma, kinfo, extra
-            S["sft_spatial"] = src is not None
+            S["src"] = src
             S["shape"] = (N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask)
             self._commit(S)
         return mu, kinfo, sigma
@@ -885,22 +884,128 @@ class DenoiseEngine:
         ops.sft_bwd(G1, S[tag + ".x"], m1, gXp, dm[(ii, b, "sft1")], dd[(ii, b, "sft1")], dtype=self.dtype, c=c, resid=gX)
         return gXp
 
-    def backward_sr(self, g_mu, g_kinfo, g_sigma, gen: Optional[int] = None):
-        """Accumulates the gradients of every parameter (SNet, KNet, RNet incl. the SFT MLPs) into flat_grads."""
-        S = self._saved_A = self._take_saved(gen)
-        if "kinfo" not in S:
-            raise _l.VkError("backward_sr called without a saved super-resolution forward")
-        if S.get("sft_spatial"):
-            raise NotImplementedError("training with per-pixel conditioning maps (noise_avg=False) is not built: the "
-                                      "forward / inference path of this configuration is")
-        N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask = S["shape"]
-        dt, dev, f32 = self.dtype, S["x"].device, torch.float32
+    def _sft_block_bwd_spatial(self, ii, b, c1, c2, gX, shape, src, d_cst, d_map):
+        """Backward of one AttResBlock whose AttLayers run per pixel (vk_sft_apply_bwd + four 1x1 weight-gradient GEMMs
+        per AttLayer); returns the gradient w.r.t. the block input."""
+        S = self._saved_A
+        N, hh, ww, c = shape
+        tag = f"d{ii}.{b}"
+        blk = self.net.RNet.down_path[ii].body[b]
+        self._wgrad(c2, gX, S[tag + ".b"], VK_CONV3X3_S1)
+        G2 = self._buf(f"g.sr.{tag}.G2", (N, hh, ww, c))
+        self._dgrad(gX, c2, VK_CONV3X3_S1, c, ldo=c, mask=S[tag + ".b"], out1=G2, alpha=0.2)
+        gF1 = self._buf(f"g.sr.{tag}.F1", (N, hh, ww, c))
+        ops.sft_apply_bwd(G2, S[tag + ".f1"], gF1, blk.sft2, src, self.grad_view, dtype=self.dtype, c=c, d_cst=d_cst,
+                          d_map=d_map)
+        self._wgrad(c1, gF1, S[tag + ".a"], VK_CONV3X3_S1)
+        G1 = self._buf(f"g.sr.{tag}.G1", (N, hh, ww, c))
+        self._dgrad(gF1, c1, VK_CONV3X3_S1, c, ldo=c, mask=S[tag + ".a"], out1=G1, alpha=0.2)
+        gXp = self._buf(f"g.sr.{tag}.X", (N, hh, ww, c))
+        ops.sft_apply_bwd(G1, S[tag + ".x"], gXp, blk.sft1, src, self.grad_view, dtype=self.dtype, c=c, resid=gX,
+                          d_cst=d_cst, d_map=d_map)
+        return gXp
+
+    def _rnet_backward(self, S, g_mu, N, C, sqrt_mask):
+        """Backward of _rnet_forward for every extra_mode: parameter gradients of RNet (convs through the dgrad / wgrad
+        kernels, AttLayers per sample or per pixel) and the gradient w.r.t. the conditioning values.
+        Returns (d_cst [N, n_cst] fp32 or None, d_map like src.map or None)."""
+        dt, dev, f32 = self.dtype, g_mu.device, torch.float32
         cp = lambda c: ops.chan_pad(c, dt)
         nf = self.n_feat
-        net = self.net
-        kcn, sc = self.k_tail.cout, self.sigma_chn         # outputs of KNet / SNet (always produced, VIRNet.py:81-82)
-        kc = self.kc                                       # conditioning channels taken from kinfo (0 without kernel_cond)
-        E = self.n_extra                                   # all constants here (the sigma-map case returned above)
+        Hh, Ww, Hp, Wp, dims = S["rnet_dims"]
+        src = S.get("src")
+        extra = S.get("extra")
+        n_cst = 0 if extra is None else extra.shape[1]
+        d_cst = torch.zeros(N, n_cst, device=dev, dtype=f32) if n_cst else None
+        d_map = torch.zeros_like(src.map) if (src is not None and src.map is not None) else None
+        sft_const = self.use_sft and src is None
+        sft_spatial = self.use_sft and src is not None
+        G = self._buf("g.sr.mu", (N, Hp, Wp, cp(C)))
+        ops.pack_grad(g_mu.contiguous().float(), G, dtype=dt)
+        self._wgrad(self.tail, G, S["tail.x"], VK_CONV3X3_S1)
+        hh, ww = dims[0]
+        gX = self._buf("g.sr.tail.X", (N, hh, ww, nf[0]))
+        self._dgrad(G, self.tail, VK_CONV3X3_S1, nf[0], ldo=nf[0], out1=gX)
+        g_bridge = {}
+        for k in reversed(range(len(self.up))):
+            us, res = self.up[k]
+            lvl = self.depth - 2 - k
+            c = nf[lvl]
+            hh, ww = dims[lvl]
+            for b in reversed(range(len(res))):
+                gX = self._resblock_bwd(f"u{k}.{b}", res[b][0], res[b][1], gX, (N, hh, ww, c))
+            g_bridge[lvl] = gX
+            self._wgrad(us, S[f"u{k}.x"], gX, VK_CONVT2X2_S2)
+            ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt)
+            hl, wl = dims[lvl + 1]
+            gXl = self._buf(f"g.sr.u{k}.low", (N, hl, wl, nf[lvl + 1]))
+            self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
+            gX = gXl
+        dm = dd = None
+        if sft_const:
+            tables = self._tables[("sft_tables", N, self._flat_key)]
+            sft_descs, sft_n, sft_maxc, dmd, sft_grads = tables[1], tables[2], tables[3], tables[4], tables[5]
+            sft_grads.zero_()
+            dm = {k: v[0] for k, v in dmd.items()}
+            dd = {k: v[1] for k, v in dmd.items()}
+        for ii in reversed(range(self.depth)):
+            res, ds = self.down[ii]
+            c = nf[ii]
+            hh, ww = dims[ii]
+            if ds is not None:
+                self._wgrad(ds, gX, S[f"d{ii}.xlast"], VK_CONV3X3_S2)
+                gXf = self._buf(f"g.sr.d{ii}.ds", (N, hh, ww, c))
+                self._dgrad(gX, ds, VK_CONV3X3_S2_DGRAD, c, ldo=c, resid=g_bridge[ii], out1=gXf, out_hw=(hh, ww))
+                gX = gXf
+            for b in reversed(range(len(res))):
+                if sft_const:
+                    gX = self._sft_block_bwd(ii, b, res[b][0], res[b][1], gX, (N, hh, ww, c), dm, dd)
+                elif sft_spatial:
+                    gX = self._sft_block_bwd_spatial(ii, b, res[b][0], res[b][1], gX, (N, hh, ww, c), src, d_cst, d_map)
+                else:
+                    gX = self._resblock_bwd(f"d{ii}.{b}", res[b][0], res[b][1], gX, (N, hh, ww, c))
+        # head conv: weight gradient, and the gradient w.r.t. its conditioning channels
+        self._wgrad(self.head, gX, S["r0"], VK_CONV3X3_S1)
+        if sft_const:
+            # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values, every AttLayer in one launch
+            ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, extra, d_cst, sqrt_mask=sqrt_mask)
+        if self.head_extra:
+            cin0 = C + self.head_extra
+            gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))
+            self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
+            if src is not None:
+                ops.extra_head_grad(gR0, C, src, dtype=dt, d_cst=d_cst, d_map=d_map)
+            else:
+                E = n_cst
+                kc = self.kc
+                hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
+                ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
+                # the head saw [kinfo, sqrt(sigma)] as constant planes: chain the sqrt for the variance channels
+                hext = hsum[:, C:C + E].clone()
+                if E > kc:
+                    hext[:, kc:] = hext[:, kc:] * 0.5 / extra[:, kc:].sqrt().clamp_min(1e-20)
+                d_cst += hext
+        return d_cst, d_map
+
+    def _snet_backward_map(self, S, g_total, N, h, w, prefix):
+        """SNet backward for a per-pixel variance output sigma = exp(clamp(SNet(x))) (VIRNet.py:42-43,81): g_total is
+        dL/dsigma [N, sc, h, w] fp32 (loss gradient + conditioning gradient)."""
+        dt = self.dtype
+        cp = lambda c: ops.chan_pad(c, dt)
+        sc = self.sigma_chn
+        GS = self._buf(prefix + "g.sig", (N, h, w, cp(sc)))
+        ops.sigma_head_bwd(S["sigma"], g_total.contiguous(), None, 0, GS, dtype=dt, log_lo=SNET_LOG_MIN, log_hi=SNET_LOG_MAX)
+        g = GS
+        for i in reversed(range(len(self.s_layers))):
+            ly = self.s_layers[i]
+            inp = S["xs"] if i == 0 else S[f"s{i - 1}"]
+            self._wgrad(ly, g, inp, VK_CONV3X3_S1)
+            if i > 0:
+                gn = self._buf(f"{prefix}g.s{i - 1}", (N, h, w, cp(ly.cin)))
+                self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
+                g = gn
+
+    def _begin_backward(self, dev):
         self.flat_grads.zero_()
         self.flat_ws.zero_()
         if self.wgrad_side_stream and self._wg_stream is None:
@@ -908,76 +1013,61 @@ class DenoiseEngine:
             self._wg_events = [torch.cuda.Event() for _ in range(8)]
         if not self.wgrad_side_stream:
             self._wg_stream = None
-        d_extra = torch.zeros(N, max(E, 1), device=dev, dtype=f32)
+
+    def _end_backward(self, A):
+        if self._wg_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._wg_stream)
+        ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
+        self._saved_A = None
+        A["set"]["owner"] = None
+
+    def _backward_general_denoise(self, A, g_mu, g_sigma):
+        """VIRAttResUNet with extra_mode 'Down' / 'Both': RNet modulated by the per-pixel sigma map."""
+        N, C, H, W, Hp, Wp, _ = A["shape"]
+        dev = A["x"].device
+        self._begin_backward(dev)
+        g_total = torch.zeros_like(A["sigma"])
+        if g_sigma is not None:
+            g_total += g_sigma.float()
         if g_mu is not None:
-            G = self._buf("g.sr.mu", (N, Hp, Wp, cp(C)))
-            ops.pack_grad(g_mu.contiguous().float(), G, dtype=dt)
-            self._wgrad(self.tail, G, S["tail.x"], VK_CONV3X3_S1)
-            hh, ww = dims[0]
-            gX = self._buf("g.sr.tail.X", (N, hh, ww, nf[0]))
-            self._dgrad(G, self.tail, VK_CONV3X3_S1, nf[0], ldo=nf[0], out1=gX)
-            g_bridge = {}
-            for k in reversed(range(len(self.up))):
-                us, res = self.up[k]
-                lvl = self.depth - 2 - k
-                c = nf[lvl]
-                hh, ww = dims[lvl]
-                for b in reversed(range(len(res))):
-                    gX = self._resblock_bwd(f"u{k}.{b}", res[b][0], res[b][1], gX, (N, hh, ww, c))
-                g_bridge[lvl] = gX
-                self._wgrad(us, S[f"u{k}.x"], gX, VK_CONVT2X2_S2)
-                ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt)
-                hl, wl = dims[lvl + 1]
-                gXl = self._buf(f"g.sr.u{k}.low", (N, hl, wl, nf[lvl + 1]))
-                self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
-                gX = gXl
-            dm = dd = None
-            if self.use_sft:
-                tables = self._tables[("sft_tables", N, self._flat_key)]
-                sft_descs, sft_n, sft_maxc, dmd, sft_grads = tables[1], tables[2], tables[3], tables[4], tables[5]
-                sft_grads.zero_()
-                dm = {k: v[0] for k, v in dmd.items()}
-                dd = {k: v[1] for k, v in dmd.items()}
-            for ii in reversed(range(self.depth)):
-                res, ds = self.down[ii]
-                c = nf[ii]
-                hh, ww = dims[ii]
-                if ds is not None:
-                    self._wgrad(ds, gX, S[f"d{ii}.xlast"], VK_CONV3X3_S2)
-                    gXf = self._buf(f"g.sr.d{ii}.ds", (N, hh, ww, c))
-                    self._dgrad(gX, ds, VK_CONV3X3_S2_DGRAD, c, ldo=c, resid=g_bridge[ii], out1=gXf, out_hw=(hh, ww))
-                    gX = gXf
-                for b in reversed(range(len(res))):
-                    if self.use_sft:
-                        gX = self._sft_block_bwd(ii, b, res[b][0], res[b][1], gX, (N, hh, ww, c), dm, dd)
-                    else:
-                        gX = self._resblock_bwd(f"d{ii}.{b}", res[b][0], res[b][1], gX, (N, hh, ww, c))
-            # head conv: weight gradient, and the gradient w.r.t. its (per-sample constant) conditioning channels
-            self._wgrad(self.head, gX, S["r0"], VK_CONV3X3_S1)
-            if self.use_sft:
-                # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values, every AttLayer in one launch
-                ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, S["extra"], d_extra, sqrt_mask=sqrt_mask)
-            if self.head_extra:
-                cin0 = C + self.head_extra
-                gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))
-                self._dgrad(gX, self.head, VK_CONV3X3_S1, cin0, ldo=cp(cin0), out1=gR0)
-                hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
-                ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
-                # the head saw [kinfo, sqrt(sigma)] as constant planes: chain the sqrt for the variance channels
-                hext = hsum[:, C:C + E].clone()
-                if E > kc:
-                    hext[:, kc:] = hext[:, kc:] * 0.5 / S["extra"][:, kc:].sqrt().clamp_min(1e-20)
-                d_extra[:, :E] += hext
+            _, d_map = self._rnet_backward(A, g_mu, N, C, (1 << self.sigma_chn) - 1)
+            g_total += d_map
+        self._snet_backward_map(A, g_total, N, H, W, "")
+        self._end_backward(A)
+
+    def backward_sr(self, g_mu, g_kinfo, g_sigma, gen: Optional[int] = None):
+        """Accumulates the gradients of every parameter (SNet, KNet, RNet incl. the SFT MLPs) into flat_grads."""
+        S = self._saved_A = self._take_saved(gen)
+        if "kinfo" not in S:
+            raise _l.VkError("backward_sr called without a saved super-resolution forward")
+        N, C, h, w, sf, Hh, Ww, Hp, Wp, dims, kh, kw, sqrt_mask = S["shape"]
+        dt, dev, f32 = self.dtype, S["x"].device, torch.float32
+        cp = lambda c: ops.chan_pad(c, dt)
+        net = self.net
+        kcn, sc = self.k_tail.cout, self.sigma_chn         # outputs of KNet / SNet (always produced, VIRNet.py:81-82)
+        kc = self.kc                                       # conditioning channels taken from kinfo (0 without kernel_cond)
+        spatial = S.get("src") is not None                 # per-pixel sigma map (noise_avg=False)
+        self._begin_backward(dev)
+        d_cst = d_map = None
+        if g_mu is not None:
+            d_cst, d_map = self._rnet_backward(S, g_mu, N, C, sqrt_mask)
         gk = torch.zeros(N, kcn, device=dev, dtype=f32)
-        if kc:
-            gk += d_extra[:, :kc]
+        if kc and d_cst is not None:
+            gk += d_cst[:, :kc]
         if g_kinfo is not None:
             gk += g_kinfo.reshape(N, kcn).float()
-        gs = torch.zeros(N, sc, device=dev, dtype=f32)
-        if E > kc:
-            gs += d_extra[:, kc:E]
-        if g_sigma is not None:
-            gs += g_sigma.reshape(N, sc).float()
+        if spatial:
+            gs_map = torch.zeros_like(S["sigma"])
+            if d_map is not None:
+                gs_map += d_map
+            if g_sigma is not None:
+                gs_map += g_sigma.float()
+        else:
+            gs = torch.zeros(N, sc, device=dev, dtype=f32)
+            if d_cst is not None and d_cst.shape[1] > kc:
+                gs += d_cst[:, kc:]
+            if g_sigma is not None:
+                gs += g_sigma.reshape(N, sc).float()
         # ---- KNet ----
         knet = net.KNet
         nfk = knet.head.out_channels
@@ -999,20 +1089,23 @@ class DenoiseEngine:
             self._dgrad(gA, c1, VK_CONV3X3_S1, nfk, ldo=cp(nfk), resid=gH, out1=gHn)
             gH = gHn
         ops.knet_head_wgrad(S["x"], gH, self.grad_view(knet.head.weight), dtype=dt)
-        # ---- SNet (global average head) ----
-        GS = self._buf("g.sr.sig", (N, h, w, cp(sc)))
-        ops.gap_head_bwd(gs.contiguous(), S["sigma"].reshape(N, sc), GS, dtype=dt, c=sc, exp_mask=(1 << sc) - 1,
-                         lo=SNET_LOG_MIN, hi=SNET_LOG_MAX)
-        g = GS
-        nS = len(self.s_layers)
-        for i in reversed(range(nS)):
-            ly = self.s_layers[i]
-            inp = S["xs"] if i == 0 else S[f"s{i - 1}"]
-            self._wgrad(ly, g, inp, VK_CONV3X3_S1)
-            if i > 0:
-                gn = self._buf(f"g.sr.s{i - 1}", (N, h, w, cp(ly.cin)))
-                self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
-                g = gn
+        # ---- SNet: per-pixel map head, or the global-average head ----
+        if spatial:
+            self._snet_backward_map(S, gs_map, N, h, w, "sr.")
+        else:
+            GS = self._buf("g.sr.sig", (N, h, w, cp(sc)))
+            ops.gap_head_bwd(gs.contiguous(), S["sigma"].reshape(N, sc), GS, dtype=dt, c=sc, exp_mask=(1 << sc) - 1,
+                             lo=SNET_LOG_MIN, hi=SNET_LOG_MAX)
+            g = GS
+            nS = len(self.s_layers)
+            for i in reversed(range(nS)):
+                ly = self.s_layers[i]
+                inp = S["xs"] if i == 0 else S[f"s{i - 1}"]
+                self._wgrad(ly, g, inp, VK_CONV3X3_S1)
+                if i > 0:
+                    gn = self._buf(f"g.sr.s{i - 1}", (N, h, w, cp(ly.cin)))
+                    self._dgrad(g, ly, VK_CONV3X3_S1, ly.cin, ldo=cp(ly.cin), mask=inp, out1=gn, alpha=0.25)
+                    g = gn
         if self._wg_stream is not None:
             torch.cuda.current_stream().wait_stream(self._wg_stream)
         ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)

@@ -86,6 +86,13 @@ class vk_sft_apply_args(C.Structure):
                 [("extra", vk_extra_src), ("alpha", C.c_float), ("round_tf32", C.c_int32)])
 
 
+class vk_sft_apply_bwd_args(C.Structure):
+    _fields_ = ([(k, C.c_int32) for k in ("dtype", "n", "h", "w", "c", "ld", "c1", "c2", "ld1", "ld2")] +
+                [(k, C.c_void_p) for k in ("g", "x", "resid", "gx", "dm", "f2", "dq2", "f1", "dq1", "ev", "w1", "b1", "w2",
+                                           "b2", "wm", "bm", "wa", "ba", "d_cst", "d_map")] +
+                [("extra", vk_extra_src), ("alpha", C.c_float), ("pad_", C.c_int32)])
+
+
 class vk_pack_desc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
                 ("dim0", C.c_int32), ("dim1", C.c_int32), ("taps", C.c_int32),
@@ -147,6 +154,10 @@ _SIGNATURES = {
     "vk_sizeof_sft_desc": (C.c_uint32, []),
     "vk_sft_apply": (C.c_int, [C.POINTER(vk_sft_apply_args), C.c_void_p]),
     "vk_sizeof_sft_apply_args": (C.c_uint32, []),
+    "vk_sft_apply_bwd": (C.c_int, [C.POINTER(vk_sft_apply_bwd_args), C.c_void_p]),
+    "vk_sizeof_sft_apply_bwd_args": (C.c_uint32, []),
+    "vk_extra_head_grad": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vk_extra_src),
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "vk_pack_input_mixed": (C.c_int, [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.POINTER(vk_extra_src), C.c_void_p,
                                                                                   C.c_int32, C.c_void_p]),
     "vk_synth_denoise": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 4),
@@ -192,7 +203,8 @@ def load():
             or lib.vk_sizeof_wgrad_args() != C.sizeof(vk_wgrad_args)
             or lib.vk_sizeof_elbo_sisr_args() != C.sizeof(vk_elbo_sisr_args)
             or lib.vk_sizeof_sft_desc() != C.sizeof(vk_sft_desc)
-            or lib.vk_sizeof_sft_apply_args() != C.sizeof(vk_sft_apply_args)):
+            or lib.vk_sizeof_sft_apply_args() != C.sizeof(vk_sft_apply_args)
+            or lib.vk_sizeof_sft_apply_bwd_args() != C.sizeof(vk_sft_apply_bwd_args)):
         raise VkError("argument struct layout mismatch between lib.py and the built library; rebuild")
     _lib = lib
     return lib

@@ -598,3 +598,51 @@ def sft_apply(x, out, att, src: ExtraSource, *, dtype, c, alpha=0.2, round_tf32=
     a.alpha, a.round_tf32 = alpha, int(round_tf32)
     with _Prof("sft_apply"):
         _l.check(_l.load().vk_sft_apply(C.byref(a), _stream()), "vk_sft_apply")
+
+
+def sft_apply_bwd(g, x, gx, att, src: ExtraSource, grad_view, *, dtype, c, resid=None, d_cst=None, d_map=None, alpha=0.2):
+    """Backward of sft_apply.  g = dL/d(x*mul+add) (lrelu' already applied by the producing dgrad), x = the modulated
+    features; writes gx = g * mul (+ resid), accumulates the AttLayer's parameter gradients into grad_view(param) (four
+    pixel-K tensor-core GEMMs over per-pixel operands) and the conditioning gradients into d_cst / d_map."""
+    n, h, w, ld = x.shape
+    assert g.shape == x.shape and gx.shape == x.shape and g.is_contiguous() and x.is_contiguous() and gx.is_contiguous()
+    tdt = TORCH_DTYPE[dtype]
+    c1, c2 = att.conv1.out_channels, att.conv2.out_channels
+    ld1, ld2 = (c1 + 15) // 16 * 16, (c2 + 15) // 16 * 16
+    dev = x.device
+    dm = torch.empty_like(x)
+    f2, dq2 = torch.empty(n, h, w, ld2, device=dev, dtype=tdt), torch.empty(n, h, w, ld2, device=dev, dtype=tdt)
+    f1, dq1 = torch.empty(n, h, w, ld1, device=dev, dtype=tdt), torch.empty(n, h, w, ld1, device=dev, dtype=tdt)
+    ev = torch.empty(n, h, w, 16, device=dev, dtype=tdt)
+    a = _l.vk_sft_apply_bwd_args()
+    a.dtype, a.n, a.h, a.w, a.c, a.ld = dtype, n, h, w, c, ld
+    a.c1, a.c2, a.ld1, a.ld2 = c1, c2, ld1, ld2
+    a.g, a.x, a.resid, a.gx = _ptr(g), _ptr(x), _ptr(resid), _ptr(gx)
+    a.dm, a.f2, a.dq2, a.f1, a.dq1, a.ev = _ptr(dm), _ptr(f2), _ptr(dq2), _ptr(f1), _ptr(dq1), _ptr(ev)
+    for nm, p_ in (("w1", att.conv1.weight), ("b1", att.conv1.bias), ("w2", att.conv2.weight), ("b2", att.conv2.bias),
+                   ("wm", att.mul_conv.weight), ("bm", att.mul_conv.bias), ("wa", att.add_conv.weight),
+                   ("ba", att.add_conv.bias)):
+        setattr(a, nm, p_.data_ptr())
+    a.d_cst, a.d_map = _ptr(d_cst), _ptr(d_map)
+    a.extra = src.c
+    a.alpha = alpha
+    with _Prof("sft_apply_bwd"):
+        _l.check(_l.load().vk_sft_apply_bwd(C.byref(a), _stream()), "vk_sft_apply_bwd")
+    e = src.e
+
+    def gemm(m_op, n_op, conv, m_valid, n_valid):
+        conv_wgrad(m_op, n_op, grad_view(conv.weight).view(1, m_valid, n_valid), dtype=dtype, kind=VK_CONV1X1,
+                   m_valid=m_valid, n_valid=n_valid, dbias=grad_view(conv.bias))
+
+    gemm(dm, f2, att.mul_conv, c, c2)
+    gemm(g, f2, att.add_conv, c, c2)
+    gemm(dq2, f1, att.conv2, c2, c1)
+    gemm(dq1, ev, att.conv1, c1, e)
+
+
+def extra_head_grad(g_r0, c, src: ExtraSource, *, dtype, d_cst=None, d_map=None):
+    """Conditioning-channel gradient of the head conv's packed input g_r0 [n, hp, wp, ld] -> d_cst / d_map (accumulated)."""
+    n, hp, wp, ld = g_r0.shape
+    with _Prof("extra_head_grad"):
+        _l.check(_l.load().vk_extra_head_grad(dtype, _ptr(g_r0), n, ld, c, C.byref(src.c), _ptr(d_cst), _ptr(d_map),
+                                              _stream()), "vk_extra_head_grad")
