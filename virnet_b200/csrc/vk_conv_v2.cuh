@@ -92,6 +92,10 @@ struct ConvV2Params {
   int off_r, off_k, off_o1, off_o2;
   int epi_base;              // byte offset of the staging region in dynamic smem
   int b_base;                // byte offset of the B ring
+  // fast epilogue of the specialised slab kernels: residual / mask rows are read straight from global memory
+  const void* mask_ptr;      // NHWC [n][oh][ow][ldo_e] (same layout as the outputs)
+  int ldo_e;                 // channel pitch (elements) of the epilogue tensors
+  int fast_epi;              // 1: staging area = 2 x (out1, out2) buffers per group, no input staging
   // EPI_NCHW_F32 (direct stores)
   void* out1_ptr;
   const void* resid_ptr;
@@ -134,6 +138,20 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -621,6 +639,8 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool lead = lane == 0;
     long long w_tf = 0, w_in = 0, w_rd = 0, w_ld = 0, w_math = 0, w_sync = 0, w_st = 0, w_misc = 0, w_fence = 0;
     long long tq = 0;
+    uint32_t fast_cnt = 0;                     // items this group has staged so far (selects the output buffer)
+    (void)fast_cnt;
     auto lap = [&](long long& acc) {
       if (prof) {
         const long long now = clock64();
@@ -639,6 +659,101 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int nvalid = max(0, min(P, prm.n_tiles - tile0));
       const uint32_t acc0 = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(as * P) * prm.acc_stride;
 
+      if constexpr (kEpi >= 0 && !kFullK) {
+        // ---------------- fast epilogue of the specialised slab kernels ----------------
+        // * residual / mask rows come straight from global memory into registers (64 B per thread and tensor), after an
+        //   L2 prefetch (TMA prefetch, no smem, no barrier) issued two items ahead — no input staging, no wait on a
+        //   staging barrier, nothing to protect with a group barrier;
+        // * the output staging is double-buffered: the only barrier per item is the one that publishes the staged
+        //   tile to the thread that issues the TMA stores, and the store it has to wait for is one item old.
+        const int n_items = P * n_ech;
+        const int g_items = nvalid > 0 && half < n_items ? (n_items - half + kGroups - 1) / kGroups : 0;
+        int tc_img[2], tc_x[2], tc_y[2];
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          const int t = tile0 + pp;
+          tc_img[pp] = t / tiles_per_img;
+          const int r = t - tc_img[pp] * tiles_per_img;
+          const int ty = r / prm.tiles_x, tx = r - ty * prm.tiles_x;
+          tc_x[pp] = tx << prm.tw_log2, tc_y[pp] = ty * prm.th;
+        }
+        constexpr bool kIn = (kEpi & 3) != 0;
+        auto prefetch_item = [&](int g) {            // one thread: pull the item's residual / mask tiles into L2
+          const int idx = half + g * kGroups;
+          const int pp = idx & (P - 1);
+          const int c0 = cq0 + (idx >> prm.p_log2) * ecols;
+          const int x = pp ? tc_x[1] : tc_x[0], y = pp ? tc_y[1] : tc_y[0], img = pp ? tc_img[1] : tc_img[0];
+          if (e_resid) tma_prefetch_l2_4d(&emaps.resid[0], c0, x, y, img);
+          if (e_mask) tma_prefetch_l2_4d(&emaps.mask, c0, x, y, img);
+        };
+        if (kIn && glead) {
+          if (g_items > 0) prefetch_item(0);
+          if (g_items > 1) prefetch_item(1);
+        }
+        mbar_wait(&tmem_full[as], phacc);
+        tc_fence_after_sync();
+        for (int g = 0; g < g_items; ++g) {
+          const int idx = half + g * kGroups;
+          const int p = idx & (P - 1);
+          const int kc = idx >> prm.p_log2;
+          const int t_x = p ? tc_x[1] : tc_x[0], t_y = p ? tc_y[1] : tc_y[0], t_img = p ? tc_img[1] : tc_img[0];
+          const uint32_t taddr = acc0 + uint32_t(p) * prm.acc_stride + uint32_t(kc * ecols);
+          const int c0 = cq0 + kc * ecols;
+          // ---- inputs: this thread's pixel row, 4 x 16 B per tensor, issued before the accumulator load ----
+          uint4 rraw[4], kraw[4];
+          if constexpr (kIn) {
+            if (g + 2 < g_items && glead) prefetch_item(g + 2);
+            const int py = t_y + tyy, px = t_x + txx;
+            const bool ok = t_img < prm.n_img && py < prm.oh && px < prm.ow;
+            const long long off = ((static_cast<long long>(t_img) * prm.oh + py) * prm.ow + px) * prm.ldo_e + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (e_resid)
+                rraw[j] = ok ? ldg_nc_v4(reinterpret_cast<const DT*>(prm.resid_ptr) + off + j * (16 / kElemBytes))
+                             : make_uint4(0u, 0u, 0u, 0u);
+              if (e_mask)
+                kraw[j] = ok ? ldg_nc_v4(reinterpret_cast<const DT*>(prm.mask_ptr) + off + j * (16 / kElemBytes))
+                             : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          uint32_t acc[2][16];
+          __syncwarp();
+          tmem_ld16(taddr, acc[0]);
+          if constexpr (kElemBytes == 2) tmem_ld16(taddr + 16, acc[1]);
+          tmem_ld_wait();
+          if (prm.bias != nullptr) {              // bias: 16-byte broadcast loads, added in place
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + n0 + kc * ecols);
+#pragma unroll
+            for (int i4 = 0; i4 < 16 / kElemBytes; ++i4) {
+              const float4 b = bp[i4];
+              uint32_t* a4 = &acc[(i4 * 4) >> 4][(i4 * 4) & 15];
+              a4[0] = __float_as_uint(__uint_as_float(a4[0]) + b.x), a4[1] = __float_as_uint(__uint_as_float(a4[1]) + b.y);
+              a4[2] = __float_as_uint(__uint_as_float(a4[2]) + b.z), a4[3] = __float_as_uint(__uint_as_float(a4[3]) + b.w);
+            }
+          }
+          const uint32_t obuf = uint32_t(fast_cnt & 1) * uint32_t(prm.epi_warp_bytes >> 1);
+          const uint32_t a_o1 = row_base + obuf + off_o1, a_o2 = row_base + obuf + off_o2;
+          const bool rnd = kTF32 && prm.round_out2;
+          if constexpr (kEpi >= 16) {
+            epi_item_math_sft<DT>(acc, rraw, 4, (kEpi & 2) != 0, (kEpi & 4) != 0,
+                                  prm.sft_mul + static_cast<long long>(t_img) * prm.sft_ld + c0,
+                                  prm.sft_add + static_cast<long long>(t_img) * prm.sft_ld + c0, prm.cout - c0, alpha,
+                                  rnd, a_o1, a_o2, swz);
+          } else {
+            epi_item_math<DT, (kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, (kEpi & 8) != 0, 64>(acc, rraw, kraw, alpha,
+                                                                                                  rnd, a_o1, a_o2, swz);
+          }
+          fence_proxy_async_smem();
+          if (slead) bulk_wait_read0();           // the store that last read the OTHER buffer (one item old) is done
+          group_sync();                           // the whole 128-pixel item is staged
+          if (slead) {
+            if (e_out1) tma_store_4d(&emaps.out1[0], stg_p + obuf + prm.off_o1, c0, t_x, t_y, t_img);
+            if (e_out2) tma_store_4d(&emaps.out2[0], stg_p + obuf + prm.off_o2, c0, t_x, t_y, t_img);
+            bulk_commit();
+          }
+          ++fast_cnt;
+        }
+      } else
       if (prm.epi == EPI_STD) {
         // Items of a job are (channel chunk kc, tile p), p fastest (P is 1 or 2), dealt round-robin to the
         // kGroups groups: group `half` takes items half, half + kGroups, ...  Tiles past the end of the image

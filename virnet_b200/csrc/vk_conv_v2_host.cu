@@ -222,6 +222,27 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   if (n_cta % 32) pair = false;                 // each half must be a multiple of 16 rows (N % 16, swizzle atoms)
   const int b_rows = pair ? n_cta / 2 : n_cta;  // weight rows staged per CTA
   const int epi_groups = v2_epi_groups(pair);
+  // fast epilogue (specialised bf16 pair slab kernels, vk_conv_v2.cuh): inputs come from global memory into registers,
+  // the staging area holds two sets of output buffers; only when a specialised kernel exists for every (chunk, nt)
+  // the planner may pick below (nt is restricted accordingly)
+  static const bool no_hot_env = std::getenv("VK_V2_NO_HOT") != nullptr;
+  static const bool no_fast_env = std::getenv("VK_V2_NO_FAST_EPI") != nullptr;
+  const int epi_mode = (prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3)) +
+                       (a->sft_mul != nullptr ? 16 : 0);
+  const bool fast_epi = a->dtype == VK_BF16 && pair && a->epi == VK_EPI_STD && ecb == 64 && a->cta_timing == nullptr &&
+                        !no_hot_env && !no_fast_env && slab && v2_hot_slab_exists(chunk, 9, epi_mode) && !a->force_nt;
+  prm.fast_epi = fast_epi ? 1 : 0;
+  prm.mask_ptr = a->mask;
+  prm.ldo_e = a->ldo;
+  if (fast_epi) {
+    const int unit = 128 * ecb;
+    int off = 0;
+    prm.off_r = prm.off_k = 0;
+    prm.off_o1 = off; if (prm.has_out1) off += unit;
+    prm.off_o2 = off; if (prm.has_out2) off += unit;
+    epi_warp_bytes = 2 * round_up(std::max(off, unit), 1024);
+    prm.epi_warp_bytes = epi_warp_bytes;
+  }
   const int epi_bytes = epi_groups * epi_warp_bytes;   // one staging area per epilogue group (4 warps)
 
   // ---- P, NT and ring depths ----
@@ -260,6 +281,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
       const int nt = slab ? nt_opts[i] : 1;
       const int kg = slab ? 1 : kg_fixed;
       if (a->force_nt && slab && nt != a->force_nt) continue;
+      if (fast_epi && !v2_hot_slab_exists(chunk, nt, epi_mode)) continue;   // the staging layout needs the fast kernel
       const int n_sub = kg;                                      // boxes per tile per A item
       const int n_kgroups = slab ? prm.k_chunks : (prm.k_chunks + kg - 1) / kg;
       const int a_slot = P * n_sub * prm.a_box_bytes;
