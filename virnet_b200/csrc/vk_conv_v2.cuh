@@ -659,8 +659,11 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int nvalid = max(0, min(P, prm.n_tiles - tile0));
       const uint32_t acc0 = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(as * P) * prm.acc_stride;
 
-      if constexpr (kEpi >= 0 && !kFullK) {
-        // ---------------- fast epilogue of the specialised slab kernels ----------------
+      if constexpr (kEpi >= 0 && !kFullK && (kEpi & 3) == 0) {
+        // ---------------- fast epilogue of the specialised slab kernels WITHOUT input tensors ----------------
+        // (measured, profiles/r02_epilogue_experiments.txt: reading residual / mask rows straight from global memory into
+        //  registers, or storing results straight from registers, both LOSE to the TMA-staged path — 64-byte rows with a
+        //  192-byte pitch make every warp access 32 partial sectors; only the double-buffered output staging below pays)
         // * residual / mask rows come straight from global memory into registers (64 B per thread and tensor), after an
         //   L2 prefetch (TMA prefetch, no smem, no barrier) issued two items ahead — no input staging, no wait on a
         //   staging barrier, nothing to protect with a group barrier;
@@ -781,7 +784,18 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (e_mask)
             tma_load_4d(reinterpret_cast<void*>(stg_p + prm.off_k), &emaps.mask, my_bar, c0, x, y, img);
         };
-        if (has_in && g_items > 0 && glead) issue_in(0);
+        auto prefetch_in = [&](int g) {
+          const int idx = half + g * kGroups;
+          const int pp = idx & (P - 1);
+          const int c0 = cq0 + (idx >> prm.p_log2) * ecols;
+          const int x = pp ? tc_x[1] : tc_x[0], y = pp ? tc_y[1] : tc_y[0], img = pp ? tc_img[1] : tc_img[0];
+          if (e_resid) tma_prefetch_l2_4d(&emaps.resid[qi], c0, x, y, img);
+          if (e_mask) tma_prefetch_l2_4d(&emaps.mask, c0, x, y, img);
+        };
+        if (has_in && g_items > 0 && glead) {
+          issue_in(0);
+          if (g_items > 1) prefetch_in(1);
+        }
         mbar_wait_t(&tmem_full[as], phacc, prof, w_tf);
         tc_fence_after_sync();
         for (int g = 0; g < g_items; ++g) {
@@ -809,6 +823,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           group_sync();                           // inputs consumed by all 4 warps, out buffers free
           lap(w_sync);
           if (has_in && g + 1 < g_items && glead) issue_in(g + 1);
+          if (has_in && g + 2 < g_items && glead) prefetch_in(g + 2);   // pull the item after next into L2
           // ---- accumulators ----
           uint32_t acc[2][16];
           __syncwarp();

@@ -230,7 +230,8 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   const int epi_mode = (prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3)) +
                        (a->sft_mul != nullptr ? 16 : 0);
   const bool fast_epi = a->dtype == VK_BF16 && pair && a->epi == VK_EPI_STD && ecb == 64 && a->cta_timing == nullptr &&
-                        !no_hot_env && !no_fast_env && slab && v2_hot_slab_exists(chunk, 9, epi_mode) && !a->force_nt;
+                        !no_hot_env && !no_fast_env && slab && !prm.has_mask && !prm.has_resid &&
+                        v2_hot_slab_exists(chunk, 9, epi_mode) && !a->force_nt;
   prm.fast_epi = fast_epi ? 1 : 0;
   prm.mask_ptr = a->mask;
   prm.ldo_e = a->ldo;
