@@ -833,6 +833,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct TsCfg {
+  int shift;      // correctness mode: the B view starts `shift` pixel rows into the loaded tile (unaligned to the 8-row atom)
   int n;          // GEMM N (channels of B)
   int k;          // K (pixel rows), multiple of 16, <= 128
   int iters;      // timing loop: MMAs issued
@@ -846,7 +847,7 @@ __global__ void __launch_bounds__(128, 1) tsmma_kernel(const __grid_constant__ C
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int blk_bytes = c.k * 128;                 // one 64-channel block: K rows of 128 B
+  const int blk_bytes = (c.k + 24) * 128;          // one 64-channel block: K + 24 rows of 128 B (room for shifted views)
   const int n_blocks = (c.n + 63) / 64;
   if (threadIdx.x == 0) {
     mbar_init(&full, 1);
@@ -890,7 +891,7 @@ __global__ void __launch_bounds__(128, 1) tsmma_kernel(const __grid_constant__ C
     const int ksteps = c.k / 16;
     if (c.mode == 0) {
       for (int kk = 0; kk < ksteps; ++kk) {
-        const uint64_t bd = make_smem_desc(b0 + kk * 2048, blk_bytes, 1024, 2);
+        const uint64_t bd = make_smem_desc(b0 + c.shift * 128 + kk * 2048, blk_bytes, 1024, 2);
         umma_ts(tmem, tmem_a + kk * 8, bd, idesc_ts, kk > 0);
       }
       umma_commit(&done);
@@ -943,7 +944,8 @@ __global__ void __launch_bounds__(128, 1) tsmma_kernel(const __grid_constant__ C
 static void run_tsmma() {
   const int K = 128;
   for (int N : {96, 64, 192}) {
-    std::vector<float> a(size_t(128) * K), b(size_t(K) * N);
+    const int KB = K + 24;
+    std::vector<float> a(size_t(128) * K), b(size_t(KB) * N);
     std::vector<uint16_t> a16(a.size()), b16(b.size());
     srand(7);
     for (size_t i = 0; i < a.size(); ++i) a[i] = bf16_round((rand() % 2001 - 1000) / 1000.f), a16[i] = bf16_bits(a[i]);
@@ -957,12 +959,13 @@ static void run_tsmma() {
     CK(cudaMalloc(&dcyc, 8));
     CK(cudaMemcpy(da, a16.data(), a16.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db, b16.data(), b16.size() * 2, cudaMemcpyHostToDevice));
-    uint64_t dims[3] = {uint64_t(N), uint64_t(K), 1};
-    uint64_t strides[2] = {uint64_t(N) * 2, uint64_t(N) * 2 * K};
-    uint32_t box[3] = {64, uint32_t(K), 1};
+    uint64_t dims[3] = {uint64_t(N), uint64_t(KB), 1};
+    uint64_t strides[2] = {uint64_t(N) * 2, uint64_t(N) * 2 * KB};
+    uint32_t box[3] = {64, uint32_t(KB), 1};
     CUtensorMap tmb = make_map(db, 3, dims, strides, box, 128);
     CK(cudaFuncSetAttribute(tsmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    TsCfg c{N, K, 0, 0};
+    for (int shift : {0, 1, 2, 3, 8, 17, 18, 19}) {
+    TsCfg c{shift, N, K, 0, 0};
     CK(cudaMemset(dout, 0, 128 * N * 4));
     tsmma_kernel<<<1, 128, 100 * 1024>>>(tmb, reinterpret_cast<const uint16_t*>(da), c, dout, dcyc);
     cudaError_t e = cudaDeviceSynchronize();
@@ -976,13 +979,14 @@ static void run_tsmma() {
     for (int m = 0; m < 128; ++m)
       for (int n = 0; n < N; ++n) {
         double acc = 0;
-        for (int k = 0; k < K; ++k) acc += double(a[size_t(m) * K + k]) * b[size_t(k) * N + n];
+        for (int k = 0; k < K; ++k) acc += double(a[size_t(m) * K + k]) * b[size_t(k + shift) * N + n];
         maxerr = std::max(maxerr, std::fabs(acc - h[m * N + n]));
       }
-    printf("tsmma (A in TMEM, B MN-major SW128) M=128 N=%3d K=%d : max|err| = %.3e %s\n", N, K, maxerr,
-           maxerr < 1e-3 ? "OK" : "WRONG");
+    printf("tsmma (A in TMEM, B MN-major SW128 view shifted by %2d pixel rows) M=128 N=%3d K=%d : max|err| = %.3e %s\n", shift, N, K,
+           maxerr, maxerr < 1e-3 ? "OK" : "WRONG");
+    }
     for (int mode : {1, 2}) {
-      TsCfg t{N, K, 4096, mode};
+      TsCfg t{0, N, K, 4096, mode};
       tsmma_kernel<<<1, 128, 100 * 1024>>>(tmb, reinterpret_cast<const uint16_t*>(da), t, dout, dcyc);
       CK(cudaDeviceSynchronize());
       long long cy;
@@ -994,9 +998,72 @@ static void run_tsmma() {
   }
 }
 
+
+// =====================================================================================
+// Register <-> (lane, column) mapping of tcgen05.st.16x256b.x1 (4 registers per thread), read back with the
+// 32x32b shape whose mapping is known (thread = lane, register = column).
+// =====================================================================================
+__global__ void __launch_bounds__(128, 1) stmap_kernel(uint32_t* out) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 32);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  // every warp writes its lane quarter: two 16-lane halves, value = (warp << 24) | (half << 20) | (lane << 8) | reg
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t r[4];
+    for (int i = 0; i < 4; ++i) r[i] = (uint32_t(warp) << 24) | (uint32_t(hf) << 20) | (uint32_t(lane) << 8) | uint32_t(i);
+    const uint32_t taddr = tmem + (uint32_t(warp * 32 + hf * 16) << 16);
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t v[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(tmem + (uint32_t(warp * 32) << 16)));
+  tmem_ld_wait();
+  for (int i = 0; i < 8; ++i) out[threadIdx.x * 8 + i] = v[i];
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, 32);
+  }
+}
+
+static void run_stmap() {
+  uint32_t* d;
+  CK(cudaMalloc(&d, 128 * 8 * 4));
+  stmap_kernel<<<1, 128>>>(d);
+  CK(cudaDeviceSynchronize());
+  std::vector<uint32_t> h(128 * 8);
+  CK(cudaMemcpy(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost));
+  printf("tcgen05.st.16x256b.x1: TMEM (lane, column) <- (warp, half, thread, register)\n");
+  for (int l = 0; l < 40; ++l) {
+    printf("lane %3d:", l);
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t v = h[l * 8 + c];
+      printf("  w%u h%u t%2u r%u", v >> 24, (v >> 20) & 15, (v >> 8) & 255, v & 255);
+    }
+    printf("\n");
+  }
+  cudaFree(d);
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
   if (!strcmp(what, "tsmma")) run_tsmma();
+  if (!strcmp(what, "stmap")) run_stmap();
   if (!strcmp(what, "shift") || !strcmp(what, "all")) run_shift();
   if (!strcmp(what, "tma") || !strcmp(what, "all")) {
     // L2-resident (16 images of 128x128xC bf16: 50 MB at C=96) and HBM-streaming (64 images at C=192: 400 MB)

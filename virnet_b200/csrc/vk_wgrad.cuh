@@ -15,6 +15,14 @@
 // to the fp32 gradient workspace with red.global.add.v4.f32.
 //
 // Bias gradient: one extra N=16 MMA per K step against a tile of ones.
+//
+// kTS variant (bf16): the M operand is fed to the MMA from TENSOR MEMORY instead of shared memory.  An M=128 x N=96
+// SS-MMA reads 7 KB of operands per 48-clock slot, more than shared memory delivers (measured 56 clk / MMA, tools/probe
+// `tsmma`); with A in TMEM only the 3 KB of B come from shared memory and the MMA runs at its 48-clock rate.  The four
+// epilogue warps (idle during the mainloop otherwise) transpose each dY tile on the fly: ldmatrix.trans pulls 8x8 blocks
+// out of the SW128 tile as (pixel pair, channel) fragments, which is exactly the register layout tcgen05.st.16x256b
+// wants for "lane = channel, 32-bit column = two consecutive pixels" (mapping verified by tools/probe `stmap`).  The
+// same threads sum the tile for the bias gradient, so the ones-MMA disappears.
 #pragma once
 #include "vk_common.cuh"
 #include "vk_conv_igemm.cuh"   // DTraits
@@ -41,7 +49,9 @@ struct WgradParams {
   int n_loads, n_taps;          // per tap group
   int n_groups;                 // tap groups (blockIdx.z = group)
   WgradLoad loads[3][3];        // [group][load]
-  WgradTap taps[3][3];          // [group][tap]
+  WgradTap taps[3][5];          // [group][tap]
+  int b_kstep_rows;             // N-operand pixel rows between consecutive K steps (tile width, or slab width for halo slabs)
+  int shared_tap;               // >= 0: tap slot computed by group g only on K tiles with (tile ^ g) even (split between 2 groups)
   int n_cta;                    // GEMM N per CTA (multiple of 16)
   int n_blocks_n;               // N blocks (blockIdx.y = m_block * n_blocks_n + n_block)
   int acc_stride, tmem_cols;
@@ -50,6 +60,7 @@ struct WgradParams {
   int total_taps;
   float* dw;                    // [total_taps][m_valid][n_valid] fp32, accumulated
   float* dbias;                 // [m_valid] fp32 accumulated, or null
+  int prefetch_dist;            // K tiles of L2 prefetch lookahead (0 = off)
   int debug_skip_epi;           // tuning aid (VK_WGRAD_SKIP_EPI=1): leave the accumulators in TMEM, measure the mainloop alone
 };
 
@@ -60,17 +71,50 @@ __device__ __forceinline__ void red_add(float* p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
+__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_4d_w(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void tmem_st_16x256b(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float bf16x2_sum(uint32_t v) { return __uint_as_float(v << 16) + __uint_as_float(v & 0xFFFF0000u); }
+
 constexpr int kWgradThreads = 288;   // warps 0, 6-8: TMA producers; 1: MMA; 2-5: epilogue
 constexpr int kWgradProducers = 4;
 
 // kRows = pixels per K tile (compile time: the MMA issue loop is fully unrolled with immediate descriptor
 // offsets — with a run-time trip count the issuing thread spends ~87 clk per MMA on R2UR / address arithmetic,
 // which is what bounded this kernel; tools/probe `mma`)
-template <typename DT, int kRows>
+template <typename DT, int kRows, bool kTS = false>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ WgradParams prm) {
   constexpr bool kTF32 = DTraits<DT>::kTF32;
+  static_assert(!kTS || (!kTF32 && kRows % 16 == 0), "the TMEM-A variant is bf16 only");
+  constexpr int kACols = kRows / 2;                        // TMEM columns of one transposed A tile (2 pixels per column)
   constexpr int kBlockElems = 128 / int(sizeof(DT));       // channels per 128-byte block
   constexpr int kRowsPerMma = 32 / int(sizeof(DT));        // pixels (K) per UMMA
   constexpr int kAdvance = kRowsPerMma * 128;              // bytes between consecutive K steps
@@ -83,6 +127,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t a_ready[2], a_free[2];    // kTS: transposed A tile written / consumed
   __shared__ uint32_t tmem_base_slot;
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -114,6 +159,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&a_ready[i], 4), mbar_init(&a_free[i], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -153,6 +199,25 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         uint8_t* a_s = smem + s * stage_bytes;
         uint8_t* b_s = a_s + a_bytes;
         if (pw == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        // L2 prefetch of the tile `prefetch_dist` steps ahead (no shared memory, no barrier): the three (two) CTAs that
+        // share a K tile all miss L2 on its first touch, and with 2-3 stages of 70+ KB the ring alone cannot cover a
+        // DRAM round trip under load
+        if (prm.prefetch_dist > 0 && it + prm.prefetch_dist < my_tiles) {
+          const int tp_ = blockIdx.x + (it + prm.prefetch_dist) * prm.ksplit;
+          const int pimg = tp_ / tiles_per_img;
+          const int pr = tp_ - pimg * tiles_per_img;
+          const int pty = pr / prm.tiles_x, ptx = pr - pty * prm.tiles_x;
+          const int px0 = ptx << prm.tw_log2, py0 = pty * prm.th;
+          int pop = 0;
+          for (int j = 0; j < prm.n_a_blocks; ++j, ++pop)
+            if (pop % kWgradProducers == pw && group == 0)
+              tma_prefetch_l2_4d_w(&tmap_a, m0 + j * kBlockElems, px0, py0, pimg);
+          for (int l = 0; l < prm.n_loads; ++l)
+            for (int j = 0; j < prm.n_b_blocks; ++j, ++pop)
+              if (pop % kWgradProducers == pw)
+                tma_prefetch_l2_4d_w(&tmap_b, n0 + j * kBlockElems, px0 * prm.b_stride + prm.loads[group][l].dx,
+                                     py0 * prm.b_stride + prm.loads[group][l].dy, pimg);
+        }
         for (int j = 0; j < prm.n_a_blocks; ++j, ++op) {
           if (op % kWgradProducers != pw) continue;
           tma_load_4d(a_s + j * a_block_bytes, &tmap_a, &full_bar[s], m0 + j * kBlockElems, x0, y0, img);
@@ -184,33 +249,50 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       constexpr uint32_t kAdv16 = uint32_t(kAdvance) >> 4;
       constexpr int ksteps = kRows / kRowsPerMma;
       const int n_taps = prm.n_taps;
-      uint32_t tap_off[3];
+      uint32_t tap_off[5];
 #pragma unroll
-      for (int tp = 0; tp < 3; ++tp)
+      for (int tp = 0; tp < 5; ++tp)
         tap_off[tp] = (uint32_t(prm.taps[group][tp].load * b_bytes + prm.taps[group][tp].rowoff * 128) >> 4);
+      // B advances by one tile row of the (possibly wider) N-operand buffer per K step; A tiles are dense
+      // (b_kstep_rows differs from the tile width only for bf16 halo slabs of 16-pixel-wide tiles: one K step = one slab row)
+      const uint32_t b_adv16 = prm.b_kstep_rows == (1 << prm.tw_log2) ? kAdv16 : (uint32_t(prm.b_kstep_rows) * 128u) >> 4;
+      const int shared_tap = prm.shared_tap;
+      uint32_t shared_accum = 0;
       const uint32_t acc_stride = prm.acc_stride;
       uint32_t accum = 0, bias_accum = 0;
       int s = 0;
       uint32_t ph = 0;
+      // kTS: A K-major from TMEM (columns [a_col0 + buf * kACols, ...)), B MN-major from shared memory
+      const uint32_t idesc_ts = make_idesc(DTraits<DT>::kFmt, 128, prm.n_cta, 0, 1);
+      const uint32_t a_col0 = uint32_t(n_taps) * acc_stride;
       for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(&full_bar[s], ph);
+        if constexpr (kTS) mbar_wait(&a_ready[it & 1], uint32_t(it >> 1) & 1u);
         tc_fence_after_sync();
         const uint32_t a_lo = (smem16 + uint32_t(s) * stage16) | a_lbo;
         const uint32_t b_lo = (smem16 + uint32_t(s) * stage16 + a16) | b_lbo;
         if (leader) {
 #pragma unroll
-          for (int tp = 0; tp < 3; ++tp) {
-            if (tp < n_taps) {
+          for (int tp = 0; tp < 5; ++tp) {
+            const bool is_shared = tp == shared_tap;
+            if (tp < n_taps && (!is_shared || (((it ^ group) & 1) == 0))) {
               uint32_t ad = a_lo, bd = b_lo + tap_off[tp];
-              uint32_t acc = accum;
+              uint32_t acc = is_shared ? shared_accum : accum;
+              if (is_shared) shared_accum = 1;
 #pragma unroll
               for (int kk = 0; kk < ksteps; ++kk) {
-                umma_ss<kTF32>(tmem_base + tp * acc_stride, desc_hi | (ad + kk * kAdv16), desc_hi | (bd + kk * kAdv16),
-                               idesc, kk == 0 ? acc : 1u);
+                if constexpr (kTS) {
+                  umma_ts_bf16(tmem_base + tp * acc_stride, tmem_base + a_col0 + uint32_t(it & 1) * kACols + kk * 8,
+                               desc_hi | (bd + kk * b_adv16), idesc_ts, kk == 0 ? acc : 1u);
+                } else {
+                  umma_ss<kTF32>(tmem_base + tp * acc_stride, desc_hi | (ad + kk * kAdv16), desc_hi | (bd + kk * b_adv16),
+                                 idesc, kk == 0 ? acc : 1u);
+                }
               }
             }
           }
-          if (bias_en && (it % prm.n_groups) == group) {
+          if constexpr (kTS) umma_commit(&a_free[it & 1]);
+          if (!kTS && bias_en && (it % prm.n_groups) == group) {
             uint32_t ad = a_lo;
             uint32_t acc = bias_accum;
             bias_accum = 1;
@@ -232,12 +314,56 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // ===================== epilogue: TMEM -> fp32 red.add =====================
     const int q4 = warp & 3;
     const int m = m0 + q4 * 32 + lane;
+    float bias_part[4] = {0.f, 0.f, 0.f, 0.f};   // kTS: column sums of dY for channels q4*32 + {0, 8, 16, 24} + lane/4
+    if constexpr (kTS) {
+      // ---- transposer: dY tile [pixel][channel] (SW128 blocks) -> TMEM [channel lane][pixel-pair column] ----
+      // thread L supplies the row address of 8x8 block (L / 8), row (L % 8): blocks 0/1 = pixel rows {0,1,4,5,..} /
+      // {2,3,6,7,..} of the first 8 channels, blocks 2/3 the same rows of the next 8 channels, so that after the
+      // transposing load register i of thread T is (channel T/4 + 8*(i/2), pixels 4*(T%4) + 2*(i%2) + {0,1}) —
+      // the (lane, column) fragment of tcgen05.st.16x256b
+      const int blk = lane >> 3, rr8 = lane & 7;
+      const int px_in_step = 4 * (rr8 >> 1) + 2 * (blk & 1) + (rr8 & 1);
+      const bool lanes_valid = (m0 + q4 * 32) < prm.m_valid;     // a quarter of padding channels has nothing to move
+      const uint32_t a_col0 = uint32_t(prm.n_taps) * prm.acc_stride;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        if (it >= 2) mbar_wait(&a_free[it & 1], uint32_t((it - 2) >> 1) & 1u);
+        tc_fence_after_sync();
+        if (lanes_valid) {
+          const uint32_t a_s = smem_u32(smem + s * stage_bytes);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int ch = q4 * 32 + hf * 16 + 8 * (blk >> 1);        // first channel of this thread's 8x8 block
+            const uint32_t blk_base = a_s + uint32_t(ch >> 6) * uint32_t(a_block_bytes);
+            const uint32_t chunk = uint32_t(ch & 63) >> 3;            // 16-byte chunk inside the 128-byte row
+#pragma unroll
+            for (int kk = 0; kk < kRows / 16; ++kk) {
+              const int px = kk * 16 + px_in_step;
+              uint32_t r[4];
+              ldsm_x4_trans(blk_base + uint32_t(px) * 128u + ((chunk ^ uint32_t(px & 7)) << 4), r);
+              tmem_st_16x256b(tmem_base + (uint32_t(q4 * 32 + hf * 16) << 16) + a_col0 + uint32_t(it & 1) * kACols + kk * 8, r);
+              bias_part[2 * hf] += bf16x2_sum(r[0]) + bf16x2_sum(r[1]);
+              bias_part[2 * hf + 1] += bf16x2_sum(r[2]) + bf16x2_sum(r[3]);
+            }
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[it & 1]);
+        if (++s == prm.stages) s = 0, ph ^= 1;
+      }
+    }
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after_sync();
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
     const bool m_ok = (m < prm.m_valid) && (my_tiles > 0) && !prm.debug_skip_epi;
     const bool vec_ok = (prm.n_valid % 4) == 0;
     for (int tp = 0; tp < prm.n_taps; ++tp) {
+      // the split tap was accumulated only if this CTA saw a K tile of its parity (tiles it = 0, 1, ...: it ^ group even)
+      if (tp == prm.shared_tap && my_tiles <= (group & 1)) continue;
       const int tap = prm.taps[group][tp].tap;
       float* row = prm.dw + (static_cast<long long>(tap) * prm.m_valid + m) * prm.n_valid;
       for (int jc = 0; jc < prm.n_cta; jc += 16) {
@@ -260,7 +386,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
       }
     }
-    if (bias_en && group < my_tiles) {
+    if constexpr (kTS) {
+      // the four threads that share a channel hold partial sums over different pixel pairs
+      if (bias_en && group == 0 && !prm.debug_skip_epi) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = bias_part[i];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          const int c = m0 + q4 * 32 + (i >> 1) * 16 + (i & 1) * 8 + (lane >> 2);
+          if ((lane & 3) == 0 && c < prm.m_valid && my_tiles > 0) red_add(prm.dbias + c, v);
+        }
+      }
+    } else if (bias_en && group < my_tiles) {
       uint32_t rr[16];
       __syncwarp();
       tmem_ld16(lane_addr + prm.n_taps * prm.acc_stride, rr);

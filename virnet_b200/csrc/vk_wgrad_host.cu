@@ -18,11 +18,11 @@ inline int next_pow2_cols(int x) {
 }
 constexpr int kWgradSmemBudget = 216 * 1024;
 
-template <typename DT, int kRows>
+template <typename DT, int kRows, bool kTS = false>
 int launch_wgrad_k(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
                    cudaStream_t st) {
   static int cur = 0;
-  auto kern = wgrad_kernel<DT, kRows>;
+  auto kern = wgrad_kernel<DT, kRows, kTS>;
   if (smem_bytes > cur) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return int(e);
@@ -31,6 +31,17 @@ int launch_wgrad_k(const CUtensorMap& ta, const CUtensorMap& tb, const WgradPara
   kern<<<grid, kWgradThreads, smem_bytes, st>>>(ta, tb, prm);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
+}
+// bf16 with the M operand transposed into tensor memory by the epilogue warps (vk_wgrad.cuh, kTS)
+int launch_wgrad_ts(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
+                    cudaStream_t st) {
+  switch (prm.k_rows) {
+    case 128: return launch_wgrad_k<__nv_bfloat16, 128, true>(ta, tb, prm, grid, smem_bytes, st);
+    case 64: return launch_wgrad_k<__nv_bfloat16, 64, true>(ta, tb, prm, grid, smem_bytes, st);
+    case 32: return launch_wgrad_k<__nv_bfloat16, 32, true>(ta, tb, prm, grid, smem_bytes, st);
+    case 16: return launch_wgrad_k<__nv_bfloat16, 16, true>(ta, tb, prm, grid, smem_bytes, st);
+    default: return VK_E_UNSUPPORTED;
+  }
 }
 template <typename DT>
 int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
@@ -65,13 +76,24 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   {
     static const int skip = getenv("VK_WGRAD_SKIP_EPI") != nullptr;
     prm.debug_skip_epi = skip;
+    static const int pf = getenv("VK_WGRAD_PREFETCH") ? atoi(getenv("VK_WGRAD_PREFETCH")) : 0;   // measured: slower
+    prm.prefetch_dist = pf;
   }
 
   bool slab = false;
+  prm.shared_tap = -1;
+  // 3x3 stride 1: ONE halo slab of the N operand ((tw+2) x (th+2) pixels) serves all nine taps through descriptors whose
+  // start is shifted by r * (tw+2) + s pixel rows (the swizzle is a function of the absolute address also for MN-major
+  // operands: tools/probe `tsmma`, shifts 1..19).  Two tap groups of 4 taps + the centre tap, which the two CTAs of a
+  // K slice compute on alternating K tiles: each operand byte is fetched from L2 by 2 CTAs instead of 3 and every CTA
+  // issues 4.5 taps per tile.  Opt-in with VK_WGRAD_SLAB9=1 (default: three tap groups of three vertical taps, one slab per horizontal shift).
+  static const bool slab3 = getenv("VK_WGRAD_SLAB9") == nullptr;   // measured: no faster (profiles/r02_wgrad_experiments.txt): opt-in
+  bool slab9 = false;
   switch (a->kind) {
     case VK_CONV3X3_S1:
       slab = true;
       prm.b_stride = 1, prm.n_groups = 3, prm.n_loads = 1, prm.n_taps = 3, prm.total_taps = 9;
+      if (!slab3 && a->dtype == VK_BF16) slab9 = true, prm.n_groups = 2, prm.n_taps = 5, prm.shared_tap = 4;
       break;
     case VK_CONV3X3_S2:
       prm.b_stride = 2, prm.n_groups = 3, prm.n_loads = 3, prm.n_taps = 3, prm.total_taps = 9;
@@ -97,15 +119,19 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
     default: return VK_E_BADARG;
   }
 
-  // ---- N split under the TMEM budget: n_taps * round32(n_cta) + 32 (bias) <= 512 ----
+  // ---- N split under the TMEM budget: n_taps * round32(n_cta) + 32 (bias) <= 512; the TMEM-A variant (bf16) keeps
+  // two transposed M tiles of k_rows / 2 columns there instead of the bias accumulator ----
+  // (the TMEM-A variant leaves room for 4 accumulators of 96 columns only: it stays with the three-group layout)
+  static const bool no_ts = getenv("VK_WGRAD_TS") == nullptr;          // opt-in: same speed on the big layers (power-bound)
+  const bool ts = a->dtype == VK_BF16 && !no_ts && !slab9;
   const int n_pad = round_up(a->n_valid, 16);
-  const int max_n = std::min(256, ((512 - 32) / prm.n_taps) / 32 * 32);
+  const int max_n = std::min(256, ((512 - (ts ? 128 : 32)) / prm.n_taps) / 32 * 32);
   const int parts = (n_pad + max_n - 1) / max_n;
   const int n_cta = round_up((n_pad + parts - 1) / parts, 16);
   prm.n_cta = n_cta;
   prm.n_blocks_n = parts;
   prm.acc_stride = round_up(n_cta, 32);
-  prm.tmem_cols = next_pow2_cols(prm.n_taps * prm.acc_stride + 32);
+  prm.tmem_cols = next_pow2_cols(prm.n_taps * prm.acc_stride + (ts ? 128 : 32));
   if (prm.tmem_cols > 512) return VK_E_UNSUPPORTED;
   prm.n_a_blocks = 128 / block_elems;
   prm.n_b_blocks = (n_cta + block_elems - 1) / block_elems;
@@ -119,10 +145,11 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
       const int k_rows = cand[i][0] * cand[i][1];
       if (a->force_k_rows && a->force_k_rows != k_rows) continue;
       if (k_rows * esize < 32 * 8 / 8 * 8) { /* at least one UMMA K step */ }
-      const int box_rows = slab ? (cand[i][1] + 2) * cand[i][0] : k_rows;
+      const int box_rows = slab9 ? (cand[i][1] + 2) * (cand[i][0] + 2) : slab ? (cand[i][1] + 2) * cand[i][0] : k_rows;
       const int stage = prm.n_a_blocks * k_rows * 128 + prm.n_loads * prm.n_b_blocks * box_rows * 128;
       int st = std::min(8, kWgradSmemBudget / stage);
       if (a->force_stages) st = std::min(st, a->force_stages);
+      if (slab9 && cand[i][0] != 16) continue;           // a K step (16 pixels) must be one contiguous slab row
       if (st >= want) tw = cand[i][0], th = cand[i][1], stages = st;
     }
   }
@@ -130,9 +157,19 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   prm.tw_log2 = 31 - __builtin_clz(tw);
   prm.th = th;
   prm.k_rows = tw * th;
-  prm.box_rows = slab ? (th + 2) * tw : tw * th;
+  prm.box_rows = slab9 ? (th + 2) * (tw + 2) : slab ? (th + 2) * tw : tw * th;
+  prm.b_kstep_rows = slab9 ? tw + 2 : tw;
   prm.stages = stages;
-  if (slab) {
+  if (slab9) {
+    // group 0: taps 0..3 + centre (4) on even K tiles; group 1: taps 5..8 + centre on odd K tiles
+    for (int g = 0; g < 2; ++g) {
+      prm.loads[g][0].dx = -1, prm.loads[g][0].dy = -1;
+      for (int i = 0; i < 5; ++i) {
+        const int tap = i == 4 ? 4 : (g == 0 ? i : 5 + i);
+        prm.taps[g][i].load = 0, prm.taps[g][i].rowoff = (tap / 3) * (tw + 2) + (tap % 3), prm.taps[g][i].tap = tap;
+      }
+    }
+  } else if (slab) {
     for (int s = 0; s < 3; ++s) {
       prm.loads[s][0].dx = s - 1, prm.loads[s][0].dy = -1;
       for (int r = 0; r < 3; ++r)
@@ -174,7 +211,8 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
     const uint64_t strides[3] = {rb, rb * a->bw, rb * a->bw * a->bh};
     const uint32_t s = prm.b_stride;
     const uint32_t box_h = slab ? th + 2 : th;
-    const uint32_t box[4] = {uint32_t(block_elems), uint32_t(tw) * s, box_h * s, 1u};
+    const uint32_t box_w = slab9 ? tw + 2 : tw;
+    const uint32_t box[4] = {uint32_t(block_elems), box_w * s, box_h * s, 1u};
     const uint32_t es[4] = {1u, s, s, 1u};
     int r = make_tensor_map(&tb, a->dtype, 4, a->b, dims, strides, box, es, sw_code);
     if (r) return r;
@@ -184,6 +222,7 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   const int smem_bytes = stages * stage_bytes + 2048 + 1024;
   dim3 grid(ksplit, m_blocks * parts, prm.n_groups);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ts) return launch_wgrad_ts(ta, tb, prm, grid, smem_bytes, st);
   if (a->dtype == VK_BF16) return launch_wgrad<__nv_bfloat16>(ta, tb, prm, grid, smem_bytes, st);
   return launch_wgrad<float>(ta, tb, prm, grid, smem_bytes, st);
 }
