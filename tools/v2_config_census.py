@@ -16,7 +16,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     dev = torch.device("cuda", 0)
     torch.manual_seed(1234)
     net = virnet_b200.VIRAttResUNet(im_chn=3, sigma_chn=1, n_feat=bench.N_FEAT, dep_S=bench.DEP_S, n_resblocks=bench.N_RES,
-                                    noise_cond=True, extra_mode="Input", noise_avg=False, precision="bf16").to(dev)
+                                    noise_cond=True, extra_mode="Input", noise_avg=False, precision=(sys.argv[3] if len(sys.argv) > 3 else "bf16")).to(dev)
     tr = DenoiseTrainer(net)
     batch = bench.synth_batch(int(sys.argv[2]), 0, dev)
     tr.step(*batch)
@@ -27,7 +27,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sys.exit(0)
 
 b = sys.argv[1] if len(sys.argv) > 1 else "32"
-out = subprocess.run([sys.executable, __file__, "--child", b], capture_output=True, text=True).stderr
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+out = subprocess.run([sys.executable, __file__, "--child", b, prec], capture_output=True, text=True).stderr
 out = out.split("CENSUS-START")[-1]
 cnt = Counter()
 for line in out.splitlines():

@@ -229,9 +229,11 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   static const bool no_fast_env = std::getenv("VK_V2_NO_FAST_EPI") != nullptr;
   const int epi_mode = (prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3)) +
                        (a->sft_mul != nullptr ? 16 : 0);
-  const bool fast_epi = a->dtype == VK_BF16 && pair && a->epi == VK_EPI_STD && ecb == 64 && a->cta_timing == nullptr &&
-                        !no_hot_env && !no_fast_env && slab && !prm.has_mask && !prm.has_resid &&
-                        v2_hot_slab_exists(chunk, 9, epi_mode) && !a->force_nt;
+  auto hot_exists = [&](int nt_) {
+    return a->dtype == VK_BF16 ? v2_hot_slab_exists(chunk, nt_, epi_mode) : v2_hot_slab_exists_tf32(chunk, nt_, epi_mode);
+  };
+  const bool fast_epi = pair && a->epi == VK_EPI_STD && ecb == 64 && a->cta_timing == nullptr && !no_hot_env &&
+                        !no_fast_env && slab && !prm.has_mask && !prm.has_resid && hot_exists(9) && !a->force_nt;
   prm.fast_epi = fast_epi ? 1 : 0;
   prm.mask_ptr = a->mask;
   prm.ldo_e = a->ldo;
@@ -282,7 +284,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
       const int nt = slab ? nt_opts[i] : 1;
       const int kg = slab ? 1 : kg_fixed;
       if (a->force_nt && slab && nt != a->force_nt) continue;
-      if (fast_epi && !v2_hot_slab_exists(chunk, nt, epi_mode)) continue;   // the staging layout needs the fast kernel
+      if (fast_epi && !hot_exists(nt)) continue;        // the staging layout needs the fast kernel
       const int n_sub = kg;                                      // boxes per tile per A item
       const int n_kgroups = slab ? prm.k_chunks : (prm.k_chunks + kg - 1) / kg;
       const int a_slot = P * n_sub * prm.a_box_bytes;
@@ -418,11 +420,16 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   // residual-block convolutions (bf16, pairs, slab mode, 64-byte staging rows, one of the four tensor combinations a
   // training step uses): kernels specialised on the epilogue combination; VK_V2_NO_HOT=1 forces the generic kernel
   static const bool no_hot = std::getenv("VK_V2_NO_HOT") != nullptr;
-  if (a->dtype == VK_BF16 && pair && a->epi == VK_EPI_STD && ecb == 64 && prm.timing == nullptr && !no_hot) {
+  if (pair && a->epi == VK_EPI_STD && ecb == 64 && prm.timing == nullptr && !no_hot) {
     const int mode = (prm.has_mask | (prm.has_resid << 1) | (prm.has_out1 << 2) | (prm.has_out2 << 3)) +
                      (a->sft_mul != nullptr ? 16 : 0);
-    const int r = v2_launch_bf16_pair_hot(chunk, nt, mode, ta, tb, em, prm, grid, smem_bytes, st);
-    if (r != VK_E_UNSUPPORTED) return r;
+    // the specialised slab kernels without input tensors run the double-buffered-staging epilogue: only with its layout
+    const bool layout_ok = prm.full_k || ((mode & 3) != 0) || prm.fast_epi;
+    if (layout_ok) {
+      const int r = a->dtype == VK_BF16 ? v2_launch_bf16_pair_hot(chunk, nt, mode, ta, tb, em, prm, grid, smem_bytes, st)
+                                        : v2_launch_tf32_pair_hot(chunk, nt, mode, ta, tb, em, prm, grid, smem_bytes, st);
+      if (r != VK_E_UNSUPPORTED) return r;
+    }
   }
   if (a->dtype == VK_BF16)
     return pair ? v2_launch_bf16_pair(chunk, nt, ta, tb, em, prm, grid, smem_bytes, st)

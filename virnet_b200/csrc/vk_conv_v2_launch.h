@@ -22,7 +22,17 @@ constexpr bool v2_hot_slab_exists(int chunk, int nt, int mode) {
   if (chunk == 64 && (nt == 9 || nt == 3) && sft_modes) return true;
   return false;
 }
+// the same for the tf32 (fp32 storage) CTA-pair slab kernels of vk_conv_v2_inst_tf32_pair_hot.cu: what a tf32 training
+// step launches (tools/v2_config_census.py 32 tf32)
+constexpr bool v2_hot_slab_exists_tf32(int chunk, int nt, int mode) {
+  const bool main_modes = mode == 5 || mode == 6 || mode == 7 || mode == 8 || mode == 14;
+  if (chunk == 128 && (nt == 9 || nt == 3) && main_modes) return true;
+  if (chunk == 32 && nt == 9 && (mode == 4 || mode == 5 || mode == 8 || mode == 12)) return true;
+  return false;
+}
 // bf16 CTA-pair slab kernels specialised on the epilogue tensor combination `mode` (vk_conv_v2_inst_bf16_pair_hot.cu)
 int v2_launch_bf16_pair_hot(int chunk, int nt, int mode, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
+                            const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st);
+int v2_launch_tf32_pair_hot(int chunk, int nt, int mode, const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& em,
                             const ConvV2Params& prm, int grid, int smem_bytes, cudaStream_t st);
 }  // namespace vk
