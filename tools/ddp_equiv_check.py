@@ -111,7 +111,7 @@ os.environ["VIRNET_B200_OVERLAP_ALLREDUCE"] = "1"
 # split-K weight gradients are accumulated with fp32 atomics (order-dependent in the last bits), Adam amplifies the sign
 # of tiny gradients: compare the parameter UPDATE direction statistically
 d = (params["overlap"] - params["blocking"]).abs()
-say(check="overlap_vs_blocking", max_abs_diff=d.max().item(), frac_gt_1e-4=(d > 1e-4).float().mean().item())
+say(check="overlap_vs_blocking", max_abs_diff=d.max().item(), frac_gt_1e_4=(d > 1e-4).float().mean().item())
 assert (d > 1e-3).float().mean().item() < 1e-3
 
 # ---- 3. step_graph at world > 1 ----
@@ -123,7 +123,7 @@ for it in range(4):
 torch.cuda.synchronize()
 d = (tr_a.engine.flat_params - tr_b.engine.flat_params).abs()
 say(check="graph_vs_eager_world>1", loss_eager=la[0].item(), loss_graph=lb[0].item(),
-    frac_gt_1e-3=(d > 1e-3).float().mean().item())
+    frac_gt_1e_3=(d > 1e-3).float().mean().item())
 assert abs(la[0].item() - lb[0].item()) <= 2e-2 * abs(la[0].item()) and (d > 1e-3).float().mean().item() < 0.05
 del tr_a, tr_b, net_a, net_b
 torch.cuda.empty_cache()
