@@ -67,7 +67,7 @@ def timed(fn, steps=20, warmup=5):
 
 # ---- 1. torch DDP == flat-bucket all-reduce ----
 net = make("tf32", [32, 64, 96], 2)
-batch = bench.synth_batch(4, rank, dev)
+batch = bench.synth_batch(8, rank, dev)
 x, gt, sg = batch
 
 
