@@ -241,6 +241,44 @@ def extra_configs(args, dev, local_rank, peaks):
                 "peak": peak_bf16 * 0.5, "peak_source": "bf16_tflops_sustained x0.5"}
     add("train_denoise_tf32", train_tf32)
 
+    # ---- the same step with deterministic=True (ordered split-K reduction: run-to-run bit-identical training) ----
+    def train_det():
+        tr = DenoiseTrainer(den_net("bf16"), lr=1e-4, clip_grad_R=1e3, clip_grad_S=1e2, alpha0=ALPHA0, eps2=EPS2,
+                            deterministic=True)
+        batch = synth_batch(args.batch, 0, dev)
+        ms = _gpu_timed(lambda: tr.step(*batch), args.steps, args.warmup)
+        v = args.batch / ms * 1e3
+        return {"workload": f"configs[2] training step, bf16, b={args.batch}, DenoiseTrainer(deterministic=True): no fp32 atomics "
+                            "anywhere on the step", "value": v, "unit": "patches/s", "ms_per_step": ms, "dtype": "bf16",
+                "roofline_frac_whole_step": v * TRAIN_GFLOP_PER_PATCH / 1e3 / peak_bf16, "peak": peak_bf16}
+    add("train_denoise_deterministic", train_det)
+
+    # ---- the drop-in as the reference's own loop uses it (train_denoising_syn.py:169-184 with the import swapped):
+    # net(x) -> elbo_denoising_simple -> loss.backward() -> clip_grad_norm_ x2 -> torch.optim.Adam.step ----
+    def train_dropin():
+        from virnet_b200.loss.ELBO_simple import elbo_denoising_simple
+        net = den_net("bf16").train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        p_s = [p for n, p in net.named_parameters() if "snet" in n.lower()]
+        p_r = [p for n, p in net.named_parameters() if "rnet" in n.lower()]
+        x, gt, sg = synth_batch(args.batch, 0, dev)
+
+        def step():
+            opt.zero_grad()
+            mu, sigma = net(x)
+            loss, _, _, _ = elbo_denoising_simple(mu, sigma, x, gt, EPS2, ALPHA0, ALPHA0 * sg)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(p_r, 1e3)
+            torch.nn.utils.clip_grad_norm_(p_s, 1e2)
+            opt.step()
+        ms = _gpu_timed(step, args.steps, args.warmup)
+        v = args.batch / ms * 1e3
+        return {"workload": f"configs[2] training step through the nn.Module autograd node with torch.optim.Adam and "
+                            f"clip_grad_norm_ (the reference's loop, import swapped), bf16, b={args.batch}", "value": v,
+                "unit": "patches/s", "ms_per_step": ms, "dtype": "bf16",
+                "roofline_frac_whole_step": v * TRAIN_GFLOP_PER_PATCH / 1e3 / peak_bf16, "peak": peak_bf16}
+    add("train_denoise_dropin_autograd", train_dropin)
+
     # ---- the reference's own batch regime: global batch 16 (train_denoising_syn.py:133), i.e. 16 patches on one GPU
     # and 2 patches per GPU on an 8-GPU node; eager launches and the CUDA-graph replay of the same step ----
     def train_small():
@@ -472,6 +510,35 @@ def _run_ours(args):
     value = world * b * args.steps / (ms * 1e-3)
     e2e = world * b * args.steps / (ms_e2e * 1e-3)
     cpu = comparator = extra = None
+    if world > 1 and not args.no_extra:
+        # the reference's own regime on this many GPUs: global batch 16 (train_denoising_syn.py:133 batch_size // num_gpus)
+        # -> max(1, 16 // world) patches per GPU; eager launches and the CUDA-graph replay (forward + backward captured,
+        # NCCL all-reduce and clip + Adam outside), every rank timed, max over ranks
+        trainer.engine.release_buffers()
+        torch.cuda.empty_cache()
+        bs = max(1, 16 // world)
+        torch.manual_seed(1234)
+        net_s = virnet_b200.VIRAttResUNet(im_chn=3, sigma_chn=1, n_feat=N_FEAT, dep_S=DEP_S, n_resblocks=N_RES,
+                                          noise_cond=True, extra_mode="Input", noise_avg=False,
+                                          precision=args.precision).to(dev)
+        tr_s = DenoiseTrainer(net_s, lr=1e-4, clip_grad_R=1e3, clip_grad_S=1e2, alpha0=ALPHA0, eps2=EPS2)
+        small = [t.to(dev) for t in synth_batch(bs, rank, None)]
+        rec = {"name": f"train_denoise_reference_batch_dp{world}", "unit": "patches/s", "dtype": args.precision,
+               "workload": f"configs[2] training step at the reference's global batch: {bs} patches per GPU x {world} GPUs",
+               "batch_per_gpu": bs, "global_batch": bs * world}
+        for label, fn in (("eager", lambda: tr_s.step(*small)), ("cuda_graph", lambda: tr_s.step_graph(*small))):
+            try:
+                for _ in range(max(args.warmup, 3)):
+                    fn()
+                ms_s = timed(fn, args.steps)
+                rec[label] = world * bs * args.steps / (ms_s * 1e-3)
+                rec[label + "_ms"] = ms_s / args.steps
+            except Exception as ex:  # noqa: BLE001
+                rec[label] = None
+                rec[label + "_error"] = repr(ex)[:200]
+        rec["value"] = rec.get("cuda_graph") or rec.get("eager")
+        extra = [rec]
+        del tr_s, net_s
     if rank == 0 and world == 1:
         # free the headline trainer's activations before the side measurements
         trainer.engine.release_buffers()

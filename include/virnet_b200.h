@@ -116,11 +116,23 @@ typedef struct vk_wgrad_args {
   int32_t force_ksplit;
   int32_t force_k_rows;
   int32_t force_stages;
+  /* Deterministic split-K (run-to-run bit-identical gradients).  partials != NULL: K slice s stores its partial sums
+   * with plain stores into partials[s][taps][m_valid][n_valid] (and dbias_partials[slot][m_valid], slot <
+   * bias_slots of vk_conv_wgrad_plan) instead of adding atomically into dw / dbias, which are then not touched;
+   * vk_wgrad_unpack_batched sums the slices in order.  max_slices = slabs the buffer holds (the split is clamped to
+   * it; a whole SM wave needs at most one slab per SM). */
+  int32_t max_slices;
+  float* partials;
+  float* dbias_partials;
 } vk_wgrad_args;
 
 /* Weight (and bias) gradient: autograd of F.conv2d / F.conv_transpose2d w.r.t.
  * weight and bias (train_denoising_syn.py:179 loss.backward()). */
 int vk_conv_wgrad(const vk_wgrad_args* args, void* stream);
+
+/* The split vk_conv_wgrad will use for these arguments (pointers may be NULL; max_slices > 0 selects the
+ * deterministic layout): *slices = K slices = partial slabs written, *bias_slots = rows of dbias_partials written. */
+int vk_conv_wgrad_plan(const vk_wgrad_args* args, int32_t* slices, int32_t* bias_slots);
 
 /* dW workspace [taps][M][N] -> parameter layout [M][N][taps] (OIHW for Conv2d,
  * [Cin][Cout][kh][kw] for ConvTranspose2d); accumulate != 0 adds into `out`. */
@@ -129,9 +141,12 @@ int vk_wgrad_unpack(const float* ws, float* out, int32_t taps, int32_t m, int32_
 
 /* The same for every layer of a network in ONE launch.  descs_dev: device array of vk_unpack_desc. */
 typedef struct vk_unpack_desc {
-  const float* ws; /* [taps][mn] */
+  const float* ws; /* [taps][mn]; nslices > 1: [nslices] such slabs, slice_stride elements apart */
   float* out;      /* [mn][taps] */
   int32_t taps, mn;
+  int32_t nslices; /* 0 / 1: one slab; > 1: the slabs are summed in slice order (deterministic split-K reduction) */
+  int32_t pad_;
+  int64_t slice_stride;
 } vk_unpack_desc;
 int vk_wgrad_unpack_batched(const void* descs_dev, int32_t ndesc, int64_t max_mn, int32_t accumulate, void* stream);
 
@@ -396,12 +411,15 @@ int vk_sigma_head_bwd(int32_t dtype, const float* sigma, const float* g_sigma, c
 /* elbo_denoising_simple (loss/ELBO_simple.py:23-53), forward and gradient in one pass.
  * All tensors NCHW fp32; sigma / beta0 have sc (1 or c) channels; the prior parameter used is
  * beta0[i] * beta0_scale (pass sigma_gt and alpha0 to fuse train_denoising_syn.py:172).  out4 = {loss, lh, kl_gauss,
- * kl_Igamma}; d_mu / d_sigma (may be NULL) receive grad_scale * dloss/d(.).  acc3: 3 doubles of
- * scratch.  digamma_alpha0_m1 = digamma(alpha0 - 1), computed by the caller. */
+ * kl_Igamma}; d_mu / d_sigma (may be NULL) receive grad_scale * dloss/d(.).  acc_ws: scratch of acc_ws_doubles
+ * doubles (3 * VK_REDUCE_MAX_BLOCKS always suffices): one slot per thread block, summed in a fixed order (no
+ * atomics: the loss value is run-to-run bit-identical).  digamma_alpha0_m1 = digamma(alpha0 - 1), computed by the
+ * caller. */
+#define VK_REDUCE_MAX_BLOCKS 592 /* largest grid of the two-pass reductions below (4 blocks per SM) */
 int vk_elbo_denoise(const float* mu, const float* sigma, const float* noisy, const float* gt, const float* beta0,
                     float beta0_scale, int32_t n, int32_t c, int32_t sc, int32_t h, int32_t w, float eps2, float alpha0,
-                    float digamma_alpha0_m1, float grad_scale, float* d_mu, float* d_sigma, double* acc3,
-                    float* out4, void* stream);
+                    float digamma_alpha0_m1, float grad_scale, float* d_mu, float* d_sigma, double* acc_ws,
+                    int32_t acc_ws_doubles, float* out4, void* stream);
 
 /* One launch packs every layer's fp32 parameters into the K-major GEMM operands.
  * descs_dev: device array of vk_pack_desc; max_elems = largest dst element count. */
@@ -418,8 +436,11 @@ typedef struct vk_pack_desc {
 int vk_pack_weights(int32_t dtype, const void* descs_dev, int32_t ndesc, int64_t max_elems, int32_t round_tf32,
                     void* stream);
 
-/* out[c] += sum over pixels of x[p][c] (NHWC `dtype`, pitch ld): ConvTranspose2d bias gradient. */
-int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_t ld, int32_t c, float* out, void* stream);
+/* out[c] += sum over pixels of x[p][c] (NHWC `dtype`, pitch ld): ConvTranspose2d bias gradient.
+ * ws != NULL (ws_floats >= VK_REDUCE_MAX_BLOCKS * c): per-block partial sums go to ws and a second launch adds them
+ * in block order (bit-reproducible); ws == NULL: one atomicAdd per (block, channel). */
+int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_t ld, int32_t c, float* out, float* ws,
+                   int64_t ws_floats, void* stream);
 
 /* Per-sample form: out[s][c] += sum over the npix pixels of sample s (x is [n][npix][ld]). */
 int vk_channel_sum_batched(int32_t dtype, const void* x, int32_t n, int64_t npix, int32_t ld, int32_t c, float* out,
@@ -427,22 +448,25 @@ int vk_channel_sum_batched(int32_t dtype, const void* x, int32_t n, int64_t npix
 
 /* Per-sub-network gradient L2 norm -> clip coefficient -> Adam update over flat fp32 buffers, no
  * host synchronisation (train_denoising_syn.py:182-184).  groups_dev: device array of
- * vk_adam_group; sq_ws: ngroups doubles of scratch; grads are first multiplied by grad_scale
- * (1/world_size after a sum all-reduce); norms_out (may be NULL) receives the pre-clip norms. */
+ * vk_adam_group; sq_ws: scratch of sq_ws_doubles doubles (ngroups * VK_REDUCE_MAX_BLOCKS always suffices: one
+ * slot per (group, thread block), summed in a fixed order by the update kernel — no atomics, the step is
+ * bit-reproducible); grads are first multiplied by grad_scale (1/world_size after a sum all-reduce); norms_out
+ * (may be NULL) receives the pre-clip norms. */
 typedef struct vk_adam_group {
   int64_t begin, end; /* element range in the flat buffers */
   float max_norm;
   int32_t pad_;
 } vk_adam_group;
 int vk_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const void* groups_dev,
-                      int32_t ngroups, int64_t max_group_elems, double* sq_ws, float grad_scale, float lr,
-                      float beta1, float beta2, float eps, int32_t step, float* norms_out, void* stream);
+                      int32_t ngroups, int64_t max_group_elems, double* sq_ws, int32_t sq_ws_doubles, float grad_scale,
+                      float lr, float beta1, float beta2, float eps, int32_t step, float* norms_out, void* stream);
 
 /* Same, with the per-step scalars read from device memory: hyper_dev = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}.
  * A training step captured in a CUDA graph replays with fresh values written by the host before each launch. */
 int vk_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const void* groups_dev,
-                          int32_t ngroups, int64_t max_group_elems, double* sq_ws, float grad_scale, float beta1,
-                          float beta2, float eps, const float* hyper_dev, float* norms_out, void* stream);
+                          int32_t ngroups, int64_t max_group_elems, double* sq_ws, int32_t sq_ws_doubles,
+                          float grad_scale, float beta1, float beta2, float eps, const float* hyper_dev,
+                          float* norms_out, void* stream);
 
 /* sizeof(vk_conv_args) as compiled into the library (binding self-check). */
 uint32_t vk_sizeof_conv_args(void);

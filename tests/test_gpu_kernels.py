@@ -122,7 +122,7 @@ def test_adam_clip_step_matches_torch():
     arr[0].begin, arr[0].end, arr[0].max_norm = 0, n1, 1e2
     arr[1].begin, arr[1].end, arr[1].max_norm = n1, n1 + n2, 1e3
     groups = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).cuda()
-    sq = torch.zeros(2, dtype=torch.float64, device="cuda")
+    sq = ops.adam_ws(2, "cuda")
     norms = torch.zeros(2, device="cuda")
     for step in range(1, 4):
         # group 0 gets clipped (norm >> 1e2), group 1 does not (norm << 1e3); world-size-2 style sum + 0.5 scale

@@ -23,6 +23,12 @@ def run(c, h, n, tune=None, dt=ops.VK_BF16):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":
+        # python tools/wgrad_bench.py --one N K_ROWS   (K_ROWS 0 = planner's choice); used with VK_WGRAD_* variants
+        n, kr = int(sys.argv[2]), int(sys.argv[3])
+        for c, h in ((96, 128), (192, 64), (288, 32), (64, 128)):
+            run(c, h, n, dict(k_rows=kr) if kr else None)
+        sys.exit(0)
     n = 16
     for c, h in ((96, 128), (192, 64), (288, 32), (64, 128)):
         run(c, h, n)

@@ -347,6 +347,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __shared__ __align__(8) uint64_t in_bar[8];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[1024];
+  __shared__ uint32_t lds_sink[128 * kGroups];   // see "inputs consumed" in the staged-input epilogue
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
@@ -811,12 +812,19 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait_t(my_bar, in_ph, prof, w_in);
             in_ph ^= 1;
 #pragma unroll
+            uint32_t sink = 0;
             for (int j = 0; j < 4; ++j) {
               if (j < (ecb >> 4)) {
-                if (e_resid) rraw[j] = lds128(row_base + off_r + ((j ^ swz) << 4));
-                if (e_mask) kraw[j] = lds128(row_base + off_k + ((j ^ swz) << 4));
+                if (e_resid) rraw[j] = lds128(row_base + off_r + ((j ^ swz) << 4)), sink ^= rraw[j].x ^ rraw[j].w;
+                if (e_mask) kraw[j] = lds128(row_base + off_k + ((j ^ swz) << 4)), sink ^= kraw[j].x ^ kraw[j].w;
               }
             }
+            // The TMA load of the NEXT item overwrites this staging area right after the group barrier below.  The barrier
+            // orders generic-proxy accesses among the four warps, but a shared-memory load that is still queued in the
+            // memory pipe when its warp arrives can be overtaken by that async-proxy write (seen as a rare stale
+            // 16-byte mask chunk in one quarter-warp of the latest warp; tools/det_check.py).  A store that consumes
+            // every loaded register cannot issue before the loads have returned and cannot move across the barrier.
+            asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&lds_sink[half * 128 + row])), "r"(sink) : "memory");
           }
           if (slead) bulk_wait_read0();           // previous stores have finished reading the out buffers
           lap(w_misc);

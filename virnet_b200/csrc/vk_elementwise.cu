@@ -209,20 +209,43 @@ __global__ void elbo_denoise_kernel(const float* __restrict__ mu, const float* _
     const int nw = blockDim.x >> 5;
     float a = lid < nw ? red[0][lid] : 0.f, b = lid < nw ? red[1][lid] : 0.f, c = lid < nw ? red[2][lid] : 0.f;
     a = warp_sum(a), b = warp_sum(b), c = warp_sum(c);
+    // one slot per block, no atomics: the sums below are taken in a fixed order, so the loss is bit-reproducible
     if (lid == 0) {
-      atomicAdd(acc + 0, static_cast<double>(a));
-      atomicAdd(acc + 1, static_cast<double>(b));
-      atomicAdd(acc + 2, static_cast<double>(c));
+      acc[3 * blockIdx.x + 0] = static_cast<double>(a);
+      acc[3 * blockIdx.x + 1] = static_cast<double>(b);
+      acc[3 * blockIdx.x + 2] = static_cast<double>(c);
     }
   }
 }
 
-__global__ void elbo_finalize_kernel(const double* __restrict__ acc, double m3, double ms, float* __restrict__ out) {
-  const double lh = acc[0] / m3, kg = acc[1] / m3, ig = acc[2] / ms;
-  out[0] = static_cast<float>(lh + kg + ig);
-  out[1] = static_cast<float>(lh);
-  out[2] = static_cast<float>(kg);
-  out[3] = static_cast<float>(ig);
+// Fixed-order sum of `n` doubles spaced `stride` apart by one 256-thread block: thread t adds elements t, t + 256, ...
+// in that order, then a shared-memory tree combines the 256 partial sums.  Every thread returns the total.
+__device__ __forceinline__ double block_ordered_sum(const double* __restrict__ v, int n, int stride, double* sm) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += v[static_cast<long long>(i) * stride];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (int(threadIdx.x) < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double total = sm[0];
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(256)
+elbo_finalize_kernel(const double* __restrict__ acc, int nblocks, double m3, double ms, float* __restrict__ out) {
+  __shared__ double sm[256];
+  const double lh = block_ordered_sum(acc + 0, nblocks, 3, sm) / m3;
+  const double kg = block_ordered_sum(acc + 1, nblocks, 3, sm) / m3;
+  const double ig = block_ordered_sum(acc + 2, nblocks, 3, sm) / ms;
+  if (threadIdx.x == 0) {
+    out[0] = static_cast<float>(lh + kg + ig);
+    out[1] = static_cast<float>(lh);
+    out[2] = static_cast<float>(kg);
+    out[3] = static_cast<float>(ig);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -275,7 +298,8 @@ __global__ void pack_weights_kernel(const PackDesc* __restrict__ descs, int roun
 // channel_sum: out[c] += sum over pixels of x[p][c]  (ConvTranspose2d bias gradient)
 // ---------------------------------------------------------------------------
 template <typename DT>
-__global__ void channel_sum_kernel(const DT* __restrict__ x, long long npix, int ld, int C, float* __restrict__ out) {
+__global__ void channel_sum_kernel(const DT* __restrict__ x, long long npix, int ld, int C, float* __restrict__ out,
+                                   float* __restrict__ ws) {
   // block = 256 threads = 8 pixel lanes x 32 channel lanes; blockIdx.y = sample (batched form: per-sample sums)
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   x += static_cast<long long>(blockIdx.y) * npix * ld;
@@ -292,7 +316,8 @@ __global__ void channel_sum_kernel(const DT* __restrict__ x, long long npix, int
       float t = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) t += part[j][cl];
-      atomicAdd(out + c, t);
+      if (ws != nullptr) ws[static_cast<long long>(blockIdx.x) * C + c] = t;   // summed in block order by the finalize pass
+      else atomicAdd(out + c, t);
     }
     __syncthreads();
   }
@@ -302,7 +327,8 @@ __global__ void channel_sum_kernel(const DT* __restrict__ x, long long npix, int
 // pixels in registers; lanes are reduced through shared memory, one atomicAdd per (block, channel).
 template <typename DT>
 __global__ void __launch_bounds__(256)
-channel_sum_vec_kernel(const DT* __restrict__ x, long long npix, int ld, int C, float* __restrict__ out) {
+channel_sum_vec_kernel(const DT* __restrict__ x, long long npix, int ld, int C, float* __restrict__ out,
+                       float* __restrict__ ws) {
   constexpr int V = 16 / int(sizeof(DT));
   extern __shared__ float cs_sm[];           // [lanes][ld]
   x += static_cast<long long>(blockIdx.y) * npix * ld;
@@ -336,7 +362,29 @@ channel_sum_vec_kernel(const DT* __restrict__ x, long long npix, int ld, int C, 
   for (int c = threadIdx.x; c < C; c += 256) {
     float t = 0.f;
     for (int l = 0; l < lanes; ++l) t += cs_sm[l * ld + c];
-    atomicAdd(out + c, t);
+    if (ws != nullptr) ws[static_cast<long long>(blockIdx.x) * C + c] = t;
+    else atomicAdd(out + c, t);
+  }
+}
+
+// out[c] += sum over the nblocks per-block partial sums, in block order (no atomics: bit-reproducible)
+// block = 32 channels x 8 lanes; lane l adds the partials of blocks l, l + 8, ... in that order, then the 8 lane sums are
+// added in lane order: a fixed summation tree
+__global__ void __launch_bounds__(256)
+channel_sum_finalize_kernel(const float* __restrict__ ws, int nblocks, int C, float* __restrict__ out) {
+  const int cl = threadIdx.x & 31, l = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  __shared__ float part[8][33];
+  float t = 0.f;
+  if (c < C)
+    for (int b = l; b < nblocks; b += 8) t += ws[static_cast<long long>(b) * C + c];
+  part[l][cl] = t;
+  __syncthreads();
+  if (l == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][cl];
+    out[c] += s;
   }
 }
 
@@ -367,7 +415,7 @@ __global__ void grad_sqnorm_kernel(const float* __restrict__ g, const AdamGroup*
   if (threadIdx.x < 32) {
     float a = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     a = warp_sum(a);
-    if (threadIdx.x == 0) atomicAdd(sq + gi, static_cast<double>(a));
+    if (threadIdx.x == 0) sq[static_cast<long long>(gi) * gridDim.x + blockIdx.x] = static_cast<double>(a);   // per-block slot
   }
 }
 
@@ -379,7 +427,10 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   if (hyper != nullptr) lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];     // CUDA-graph replay: per-step values
   const int gi = blockIdx.y;
   const AdamGroup gr = groups[gi];
-  const float total = static_cast<float>(sqrt(sq[gi]));
+  // squared norm of the group = the per-block partials of grad_sqnorm_kernel (same grid) summed in a fixed order by
+  // every block: no atomics, so the clip coefficient and with it the whole update are bit-reproducible
+  __shared__ double sq_sm[256];
+  const float total = static_cast<float>(sqrt(block_ordered_sum(sq + static_cast<long long>(gi) * gridDim.x, int(gridDim.x), 1, sq_sm)));
   const float coef = fminf(gr.max_norm / (total + 1e-6f), 1.f) * gscale;   // clip_grad_norm_ semantics
   if (norms_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) norms_out[gi] = total;
   const float step = lr / bc1;
@@ -494,18 +545,18 @@ extern "C" int vk_sigma_head_bwd(int32_t dtype, const float* sigma, const float*
 extern "C" int vk_elbo_denoise(const float* mu, const float* sigma, const float* noisy, const float* gt,
                                const float* beta0, float beta0_scale, int32_t n, int32_t c, int32_t sc, int32_t h,
                                int32_t w, float eps2, float alpha0, float digamma_alpha0_m1, float grad_scale, float* d_mu,
-                               float* d_sigma, double* acc3, float* out4, void* stream) {
-  if (!mu || !sigma || !noisy || !gt || !beta0 || !acc3 || !out4) return VK_E_BADARG;
+                               float* d_sigma, double* acc_ws, int32_t acc_ws_doubles, float* out4, void* stream) {
+  if (!mu || !sigma || !noisy || !gt || !beta0 || !acc_ws || !out4) return VK_E_BADARG;
   if (n <= 0 || c <= 0 || (sc != 1 && sc != c)) return VK_E_BADARG;
   cudaStream_t st = VK_ST(stream);
-  cudaError_t e = cudaMemsetAsync(acc3, 0, 3 * sizeof(double), st);
-  if (e != cudaSuccess) return int(e);
   const long long hw = static_cast<long long>(h) * w;
   const int grid = grid_for(static_cast<long long>(n) * hw, 256, 4);
+  static_assert(kSMs * 4 <= VK_REDUCE_MAX_BLOCKS, "scratch sizing");
+  if (acc_ws_doubles < 3 * grid) return VK_E_BADARG;
   elbo_denoise_kernel<<<grid, 256, 0, st>>>(mu, sigma, noisy, gt, beta0, beta0_scale, n, c, sc, hw, eps2, alpha0,
-                                            digamma_alpha0_m1, grad_scale, d_mu, d_sigma, acc3);
+                                            digamma_alpha0_m1, grad_scale, d_mu, d_sigma, acc_ws);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  elbo_finalize_kernel<<<1, 1, 0, st>>>(acc3, double(n) * c * hw, double(n) * sc * hw, out4);
+  elbo_finalize_kernel<<<1, 256, 0, st>>>(acc_ws, grid, double(n) * c * hw, double(n) * sc * hw, out4);
   VK_LAUNCHED();
 }
 
@@ -525,8 +576,16 @@ extern "C" int vk_pack_weights(int32_t dtype, const void* descs_dev, int32_t nde
 }
 
 extern "C" int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_t ld, int32_t c, float* out,
-                              void* stream) {
+                              float* ws, int64_t ws_floats, void* stream) {
   if (x == nullptr || out == nullptr || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
+  if (dtype != VK_BF16 && dtype != VK_TF32) return VK_E_BADARG;
+  if (ws != nullptr && ws_floats < static_cast<int64_t>(VK_REDUCE_MAX_BLOCKS) * c) return VK_E_BADARG;
+  auto finalize = [&](int nblocks) -> int {
+    if (ws == nullptr) return int(cudaGetLastError());
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    channel_sum_finalize_kernel<<<(c + 31) / 32, 256, 0, VK_ST(stream)>>>(ws, nblocks, c, out);
+    return int(cudaGetLastError());
+  };
   {
     const int vec = dtype == VK_BF16 ? 8 : 4;
     if ((dtype == VK_BF16 || dtype == VK_TF32) && ld % vec == 0 && ld / vec <= 256 && npix >= 4096) {
@@ -536,23 +595,23 @@ extern "C" int vk_channel_sum(int32_t dtype, const void* x, int64_t npix, int32_
         const int vgrid = int(std::min<long long>((npix + lanes - 1) / lanes, kSMs * 4));
         if (dtype == VK_BF16)
           channel_sum_vec_kernel<__nv_bfloat16><<<vgrid, 256, smem, VK_ST(stream)>>>(
-              reinterpret_cast<const __nv_bfloat16*>(x), npix, ld, c, out);
+              reinterpret_cast<const __nv_bfloat16*>(x), npix, ld, c, out, ws);
         else
           channel_sum_vec_kernel<float><<<vgrid, 256, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c,
-                                                                            out);
-        VK_LAUNCHED();
+                                                                            out, ws);
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return finalize(vgrid);
       }
     }
   }
   const int grid = int(std::min<long long>((npix + 7) / 8, kSMs * 4));
   if (dtype == VK_BF16)
     channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                      npix, ld, c, out);
-  else if (dtype == VK_TF32)
-    channel_sum_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c, out);
+                                                                      npix, ld, c, out, ws);
   else
-    return VK_E_BADARG;
-  VK_LAUNCHED();
+    channel_sum_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c, out, ws);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return finalize(grid);
 }
 
 extern "C" int vk_channel_sum_batched(int32_t dtype, const void* x, int32_t n, int64_t npix, int32_t ld, int32_t c,
@@ -561,9 +620,9 @@ extern "C" int vk_channel_sum_batched(int32_t dtype, const void* x, int32_t n, i
   const dim3 grid(unsigned(std::min<long long>((npix + 7) / 8, std::max(1, kSMs * 4 / n))), unsigned(n));
   if (dtype == VK_BF16)
     channel_sum_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                      npix, ld, c, out);
+                                                                      npix, ld, c, out, nullptr);
   else if (dtype == VK_TF32)
-    channel_sum_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c, out);
+    channel_sum_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(reinterpret_cast<const float*>(x), npix, ld, c, out, nullptr);
   else
     return VK_E_BADARG;
   VK_LAUNCHED();
@@ -571,34 +630,34 @@ extern "C" int vk_channel_sum_batched(int32_t dtype, const void* x, int32_t n, i
 
 extern "C" int vk_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                  const void* groups_dev, int32_t ngroups, int64_t max_group_elems, double* sq_ws,
-                                 float grad_scale, float lr, float beta1, float beta2, float eps, int32_t step,
-                                 float* norms_out, void* stream) {
+                                 int32_t sq_ws_doubles, float grad_scale, float lr, float beta1, float beta2, float eps,
+                                 int32_t step, float* norms_out, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !groups_dev || !sq_ws || ngroups <= 0 || step <= 0)
     return VK_E_BADARG;
   cudaStream_t st = VK_ST(stream);
-  cudaError_t e = cudaMemsetAsync(sq_ws, 0, ngroups * sizeof(double), st);
-  if (e != cudaSuccess) return int(e);
   const AdamGroup* groups = reinterpret_cast<const AdamGroup*>(groups_dev);
   dim3 grid(grid_for(max_group_elems, 256, 4), ngroups);
+  if (static_cast<long long>(sq_ws_doubles) < static_cast<long long>(grid.x) * ngroups) return VK_E_BADARG;
   grad_sqnorm_kernel<<<grid, 256, 0, st>>>(grads, groups, ngroups, grad_scale, sq_ws);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  const float bc1 = 1.f - powf(beta1, float(step));
-  const float bc2 = 1.f - powf(beta2, float(step));
+  // bias corrections in double from the fp32 betas — the values a caller of vk_adam_clip_step_dev computes on the host
+  // (virnet_b200/trainer.py), so that the eager and the graph-replayed step are bit-identical
+  const float bc1 = float(1.0 - pow(double(beta1), double(step)));
+  const float bc2_sqrt = float(sqrt(1.0 - pow(double(beta2), double(step))));
   adam_clip_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, groups, ngroups, sq_ws, grad_scale, lr,
-                                         beta1, beta2, eps, bc1, sqrtf(bc2), norms_out, nullptr);
+                                         beta1, beta2, eps, bc1, bc2_sqrt, norms_out, nullptr);
   VK_LAUNCHED();
 }
 
 extern "C" int vk_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                      const void* groups_dev, int32_t ngroups, int64_t max_group_elems, double* sq_ws,
-                                     float grad_scale, float beta1, float beta2, float eps, const float* hyper_dev,
-                                     float* norms_out, void* stream) {
+                                     int32_t sq_ws_doubles, float grad_scale, float beta1, float beta2, float eps,
+                                     const float* hyper_dev, float* norms_out, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !groups_dev || !sq_ws || !hyper_dev || ngroups <= 0) return VK_E_BADARG;
   cudaStream_t st = VK_ST(stream);
-  cudaError_t e = cudaMemsetAsync(sq_ws, 0, ngroups * sizeof(double), st);
-  if (e != cudaSuccess) return int(e);
   const AdamGroup* groups = reinterpret_cast<const AdamGroup*>(groups_dev);
   dim3 grid(grid_for(max_group_elems, 256, 4), ngroups);
+  if (static_cast<long long>(sq_ws_doubles) < static_cast<long long>(grid.x) * ngroups) return VK_E_BADARG;
   grad_sqnorm_kernel<<<grid, 256, 0, st>>>(grads, groups, ngroups, grad_scale, sq_ws);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   adam_clip_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, groups, ngroups, sq_ws, grad_scale, 0.f, beta1,

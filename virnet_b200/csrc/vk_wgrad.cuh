@@ -60,6 +60,12 @@ struct WgradParams {
   int total_taps;
   float* dw;                    // [total_taps][m_valid][n_valid] fp32, accumulated
   float* dbias;                 // [m_valid] fp32 accumulated, or null
+  // deterministic split-K: when `partials` is set every K slice (blockIdx.x) stores its partial sums with plain stores
+  // into its own [total_taps][m_valid][n_valid] slab (slice_elems apart) instead of red.add into dw; the bias partials
+  // go to dbias_partials[(slice * n_groups + group) * m_valid + m].  vk_wgrad_unpack_batched sums the slices in order.
+  float* partials;
+  float* dbias_partials;
+  long long slice_elems;
   int prefetch_dist;            // K tiles of L2 prefetch lookahead (0 = off)
   int debug_skip_epi;           // tuning aid (VK_WGRAD_SKIP_EPI=1): leave the accumulators in TMEM, measure the mainloop alone
 };
@@ -69,6 +75,9 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 __device__ __forceinline__ void red_add(float* p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ void st_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -361,11 +370,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
     const bool m_ok = (m < prm.m_valid) && (my_tiles > 0) && !prm.debug_skip_epi;
     const bool vec_ok = (prm.n_valid % 4) == 0;
+    // deterministic mode: this K slice's own slab, plain stores (every (tap, m, n) has exactly one writer per slice)
+    const bool det = prm.partials != nullptr;
+    float* const out_base = det ? prm.partials + static_cast<long long>(blockIdx.x) * prm.slice_elems : prm.dw;
     for (int tp = 0; tp < prm.n_taps; ++tp) {
       // the split tap was accumulated only if this CTA saw a K tile of its parity (tiles it = 0, 1, ...: it ^ group even)
       if (tp == prm.shared_tap && my_tiles <= (group & 1)) continue;
       const int tap = prm.taps[group][tp].tap;
-      float* row = prm.dw + (static_cast<long long>(tap) * prm.m_valid + m) * prm.n_valid;
+      float* row = out_base + (static_cast<long long>(tap) * prm.m_valid + m) * prm.n_valid;
       for (int jc = 0; jc < prm.n_cta; jc += 16) {
         uint32_t rr[16];
         __syncwarp();
@@ -375,13 +387,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (m_ok && n < prm.n_valid) {
           if (vec_ok && n + 16 <= prm.n_valid) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              red_add_v4(row + n + i, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]),
-                         __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+            for (int i = 0; i < 16; i += 4) {
+              if (det)
+                st_v4(row + n + i, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]), __uint_as_float(rr[i + 2]),
+                      __uint_as_float(rr[i + 3]));
+              else
+                red_add_v4(row + n + i, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]),
+                           __uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (n + i < prm.n_valid) red_add(row + n + i, __uint_as_float(rr[i]));
+              if (n + i < prm.n_valid) {
+                if (det) row[n + i] = __uint_as_float(rr[i]);
+                else red_add(row + n + i, __uint_as_float(rr[i]));
+              }
           }
         }
       }
@@ -398,6 +418,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if ((lane & 3) == 0 && c < prm.m_valid && my_tiles > 0) red_add(prm.dbias + c, v);
         }
       }
+    } else if (bias_en && det) {
+      // one slot per (K slice, tap group); a group that saw no bias tile (fewer K tiles than groups) stores zero
+      float v = 0.f;
+      if (group < my_tiles) {
+        uint32_t rr[16];
+        __syncwarp();
+        tmem_ld16(lane_addr + prm.n_taps * prm.acc_stride, rr);
+        tmem_ld_wait();
+        v = __uint_as_float(rr[0]);
+      }
+      if (m < prm.m_valid && !prm.debug_skip_epi)
+        prm.dbias_partials[(static_cast<long long>(blockIdx.x) * prm.n_groups + group) * prm.m_valid + m] = v;
     } else if (bias_en && group < my_tiles) {
       uint32_t rr[16];
       __syncwarp();
@@ -433,12 +465,25 @@ struct WgradUnpackDesc {
   const float* ws;
   float* out;
   int taps, mn;
+  int nslices, pad;         // > 1: ws holds nslices split-K partial slabs, summed here in slice order (deterministic)
+  long long slice_stride;   // elements between consecutive slabs
 };
 __global__ void wgrad_unpack_batched_kernel(const WgradUnpackDesc* __restrict__ descs, int accumulate) {
   const WgradUnpackDesc d = descs[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.mn; i += gridDim.x * blockDim.x) {
     for (int t = 0; t < d.taps; ++t) {
-      const float v = d.ws[static_cast<long long>(t) * d.mn + i];
+      const float* src = d.ws + static_cast<long long>(t) * d.mn + i;
+      float v = src[0];
+      if (d.nslices > 1) {
+        // fixed summation order 0, 1, 2, ...; four independent loads in flight per step
+        int s = 1;
+        for (; s + 4 <= d.nslices; s += 4) {
+          const float x0 = src[(s + 0) * d.slice_stride], x1 = src[(s + 1) * d.slice_stride];
+          const float x2 = src[(s + 2) * d.slice_stride], x3 = src[(s + 3) * d.slice_stride];
+          v = (((v + x0) + x1) + x2) + x3;
+        }
+        for (; s < d.nslices; ++s) v += src[s * d.slice_stride];
+      }
       float* o = d.out + static_cast<long long>(i) * d.taps + t;
       *o = accumulate ? *o + v : v;
     }

@@ -48,6 +48,8 @@ int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams
                  cudaStream_t st) {
   switch (prm.k_rows) {
     case 128: return launch_wgrad_k<DT, 128>(ta, tb, prm, grid, smem_bytes, st);
+    case 112: return launch_wgrad_k<DT, 112>(ta, tb, prm, grid, smem_bytes, st);
+    case 96: return launch_wgrad_k<DT, 96>(ta, tb, prm, grid, smem_bytes, st);
     case 64: return launch_wgrad_k<DT, 64>(ta, tb, prm, grid, smem_bytes, st);
     case 32: return launch_wgrad_k<DT, 32>(ta, tb, prm, grid, smem_bytes, st);
     case 16: return launch_wgrad_k<DT, 16>(ta, tb, prm, grid, smem_bytes, st);
@@ -56,8 +58,14 @@ int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams
 }
 }  // namespace
 
-extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
-  if (a == nullptr || a->a == nullptr || a->b == nullptr || a->dw == nullptr) return VK_E_BADARG;
+namespace {
+// plan_only: stop after the tiling / split-K decisions and report them (vk_conv_wgrad_plan)
+int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* slices_out, int32_t* bias_slots_out) {
+  if (a == nullptr) return VK_E_BADARG;
+  const bool det = a->partials != nullptr || (plan_only && a->max_slices > 0);
+  if (!plan_only && (a->a == nullptr || a->b == nullptr || (a->dw == nullptr && a->partials == nullptr))) return VK_E_BADARG;
+  if (!plan_only && a->partials != nullptr && (a->max_slices <= 0 || (a->dbias != nullptr && a->dbias_partials == nullptr)))
+    return VK_E_BADARG;
   if (a->dtype != VK_BF16 && a->dtype != VK_TF32) return VK_E_BADARG;
   const int esize = a->dtype == VK_BF16 ? 2 : 4;
   const int block_elems = 128 / esize;
@@ -73,6 +81,8 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   prm.n_valid = a->n_valid;
   prm.dw = a->dw;
   prm.dbias = a->dbias;
+  prm.partials = a->partials;
+  prm.dbias_partials = a->dbias_partials;
   {
     static const int skip = getenv("VK_WGRAD_SKIP_EPI") != nullptr;
     prm.debug_skip_epi = skip;
@@ -93,7 +103,7 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
     case VK_CONV3X3_S1:
       slab = true;
       prm.b_stride = 1, prm.n_groups = 3, prm.n_loads = 1, prm.n_taps = 3, prm.total_taps = 9;
-      if (!slab3 && a->dtype == VK_BF16) slab9 = true, prm.n_groups = 2, prm.n_taps = 5, prm.shared_tap = 4;
+      if (!slab3 && a->dtype == VK_BF16 && !det) slab9 = true, prm.n_groups = 2, prm.n_taps = 5, prm.shared_tap = 4;
       break;
     case VK_CONV3X3_S2:
       prm.b_stride = 2, prm.n_groups = 3, prm.n_loads = 3, prm.n_taps = 3, prm.total_taps = 9;
@@ -123,7 +133,7 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   // two transposed M tiles of k_rows / 2 columns there instead of the bias accumulator ----
   // (the TMEM-A variant leaves room for 4 accumulators of 96 columns only: it stays with the three-group layout)
   static const bool no_ts = getenv("VK_WGRAD_TS") == nullptr;          // opt-in: same speed on the big layers (power-bound)
-  const bool ts = a->dtype == VK_BF16 && !no_ts && !slab9;
+  const bool ts = a->dtype == VK_BF16 && !no_ts && !slab9 && !det;
   const int n_pad = round_up(a->n_valid, 16);
   const int max_n = std::min(256, ((512 - (ts ? 128 : 32)) / prm.n_taps) / 32 * 32);
   const int parts = (n_pad + max_n - 1) / max_n;
@@ -138,12 +148,15 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   const int m_blocks = (a->m_valid + 127) / 128;
 
   // ---- K tile and stages under the smem budget ----
-  static const int cand[4][2] = {{16, 8}, {16, 4}, {8, 4}, {8, 2}};   // (tw, th): 128, 64, 32, 16 pixels
+  // (tw, th): 128, 112, 96, 64, 32, 16 pixels; the 7- and 6-row tiles exist for the 9-tap halo slab only (three ring
+  // stages of A tile + slab fit the shared memory with them, two with 8 rows)
+  static const int cand[6][2] = {{16, 8}, {16, 7}, {16, 6}, {16, 4}, {8, 4}, {8, 2}};
   int tw = 0, th = 0, stages = 0;
   for (int want = 3; want >= 1 && !stages; --want) {
-    for (int i = 0; i < 4 && !stages; ++i) {
+    for (int i = 0; i < 6 && !stages; ++i) {
       const int k_rows = cand[i][0] * cand[i][1];
       if (a->force_k_rows && a->force_k_rows != k_rows) continue;
+      if ((cand[i][1] == 7 || cand[i][1] == 6) && !slab9) continue;
       if (k_rows * esize < 32 * 8 / 8 * 8) { /* at least one UMMA K step */ }
       const int box_rows = slab9 ? (cand[i][1] + 2) * (cand[i][0] + 2) : slab ? (cand[i][1] + 2) * cand[i][0] : k_rows;
       const int stage = prm.n_a_blocks * k_rows * 128 + prm.n_loads * prm.n_b_blocks * box_rows * 128;
@@ -191,7 +204,12 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   int ksplit = std::max(1, n_sm / base_ctas);
   if (a->force_ksplit) ksplit = a->force_ksplit;
   ksplit = std::min(ksplit, prm.n_tiles);
+  if (det) ksplit = std::min(ksplit, a->max_slices);   // one partial slab per K slice
   prm.ksplit = ksplit;
+  prm.slice_elems = static_cast<long long>(prm.total_taps) * a->m_valid * a->n_valid;
+  if (slices_out != nullptr) *slices_out = ksplit;
+  if (bias_slots_out != nullptr) *bias_slots_out = ksplit * prm.n_groups;
+  if (plan_only) return 0;
 
   // ---- tensor maps: 128-byte channel blocks; SWIZZLE_128B (bf16) / 128B_ATOM_32B (fp32, code 129) ----
   const int sw_code = a->dtype == VK_BF16 ? 128 : 129;
@@ -225,6 +243,14 @@ extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) {
   if (ts) return launch_wgrad_ts(ta, tb, prm, grid, smem_bytes, st);
   if (a->dtype == VK_BF16) return launch_wgrad<__nv_bfloat16>(ta, tb, prm, grid, smem_bytes, st);
   return launch_wgrad<float>(ta, tb, prm, grid, smem_bytes, st);
+}
+}  // namespace
+
+extern "C" int vk_conv_wgrad(const vk_wgrad_args* a, void* stream) { return wgrad_impl(a, stream, false, nullptr, nullptr); }
+
+extern "C" int vk_conv_wgrad_plan(const vk_wgrad_args* a, int32_t* slices, int32_t* bias_slots) {
+  if (slices == nullptr || bias_slots == nullptr) return VK_E_BADARG;
+  return wgrad_impl(a, nullptr, true, slices, bias_slots);
 }
 
 extern "C" int vk_wgrad_unpack(const float* ws, float* out, int32_t taps, int32_t m, int32_t n, int32_t accumulate,

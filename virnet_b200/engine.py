@@ -152,6 +152,13 @@ class DenoiseEngine:
         self.layers = L
 
         self.wgrad_side_stream = os.environ.get("VIRNET_B200_WGRAD_STREAM", "1") != "0"
+        # deterministic weight gradients: every split-K slice of vk_conv_wgrad stores its partial sums in its own slab
+        # and the unpack kernel adds the slabs in slice order (no fp32 atomics).  Together with the atomic-free loss /
+        # norm / bias reductions the denoising training step is then run-to-run bit-identical; costs one extra pass
+        # over the partial slabs (about 0.6 GB at batch 32).  Also set by the trainers' `deterministic=True`.
+        self.deterministic = os.environ.get("VIRNET_B200_DETERMINISTIC", "0") == "1"
+        self._det_ran: Dict[int, _Layer] = {}          # layers whose wgrad ran in the current backward (det mode)
+        self._det_tables: Dict = {}
         self.grad_sync = None          # dp.BucketedGradSync when the trainer overlaps the gradient all-reduce (world > 1)
         self._wg_stream, self._wg_events, self._wg_i = None, [], 0
         self._flat_key = None
@@ -250,6 +257,10 @@ class DenoiseEngine:
         arr = (_l.vk_unpack_desc * len(udescs))(*udescs)
         self._unpack_descs = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
         self._unpack_n, self._unpack_max = len(udescs), max(d.mn for d in udescs)
+        self._det_tables = {}
+        for ly in self.layers:
+            ly.det = None
+        self._csum_ws = ops.channel_sum_ws(max(max(ly.cout, ly.cin) for ly in self.layers), dev)
 
     def mark_params_dirty(self):
         self._packed_version = None
@@ -463,9 +474,24 @@ class DenoiseEngine:
         dbias = None
         if ly.bias is not None and ly.kind != "convT":
             dbias = self.grad_view(ly.bias)
+        kw = {}
+        if self.deterministic:
+            key = (tuple(a.shape), tuple(b.shape), kind)
+            ent = ly.det
+            if ent is None or ent["key"] != key:
+                slices, bias_slots = ops.conv_wgrad_plan(a, b, dtype=self.dtype, kind=kind, m_valid=m_valid,
+                                                         n_valid=n_valid, dbias=dbias)
+                dev = self.flat_params.device
+                ent = ly.det = {"key": key, "slices": slices, "bias_slots": bias_slots,
+                                "partials": torch.empty((slices,) + tuple(ly.ws.shape), device=dev, dtype=torch.float32),
+                                "dbias": None if dbias is None else torch.empty(bias_slots, m_valid, device=dev,
+                                                                                dtype=torch.float32)}
+                self._det_tables = {}
+            self._det_ran[id(ly)] = ly
+            kw = dict(partials=ent["partials"], dbias_partials=ent["dbias"])
         ws = self._wg_stream
         if ws is None:
-            ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias)
+            ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias, **kw)
             return
         # weight gradients are leaves of the backward graph: run them on a side stream so their CTAs fill the SMs
         # the persistent dgrad kernels leave idle in their last (partial) round
@@ -474,7 +500,7 @@ class DenoiseEngine:
         ev.record()
         ws.wait_event(ev)
         with torch.cuda.stream(ws):
-            ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias)
+            ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias, **kw)
 
     def _bucket_done(self, first_layer: _Layer):
         """Every layer from `first_layer` (forward order) to the end of the previous bucket has had its weight-gradient
@@ -482,11 +508,59 @@ class DenoiseEngine:
         if self.grad_sync is not None:
             self.grad_sync.bucket_ready(self.layers.index(first_layer), self._wg_stream)
 
+    def _det_table(self):
+        """Descriptor table of the deterministic unpack: per layer the split-K slabs written in this backward (summed in
+        slice order) plus, where the kernel produced them, the bias slots; layers whose wgrad did not run keep their
+        zero workspace.  Cached per set of layers / shapes."""
+        key = tuple((id(ly), ly.det["key"]) for ly in self.layers if id(ly) in self._det_ran)
+        hit = self._det_tables.get(key)
+        if hit is not None:
+            return hit
+        descs, offs = [], []
+        for ly in self.layers:
+            offs.append(len(descs))
+            m_, n_ = (ly.cin, ly.cout) if ly.kind == "convT" else (ly.cout, ly.cin)
+            d = _l.vk_unpack_desc()
+            d.out, d.taps, d.mn = self.grad_view(ly.weight).data_ptr(), ly.taps, m_ * n_
+            if id(ly) in self._det_ran:
+                ent = ly.det
+                d.ws, d.nslices, d.slice_stride = ent["partials"].data_ptr(), ent["slices"], ly.taps * m_ * n_
+                descs.append(d)
+                if ent["dbias"] is not None:
+                    b = _l.vk_unpack_desc()
+                    b.ws, b.out, b.taps, b.mn = ent["dbias"].data_ptr(), self.grad_view(ly.bias).data_ptr(), 1, m_
+                    b.nslices, b.slice_stride = ent["bias_slots"], m_
+                    descs.append(b)
+            else:
+                d.ws, d.nslices, d.slice_stride = ly.ws.data_ptr(), 1, 0
+                descs.append(d)
+        offs.append(len(descs))
+        arr = (_l.vk_unpack_desc * len(descs))(*descs)
+        table = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(self.flat_params.device)
+        hit = self._det_tables[key] = (table, offs, max(d.mn for d in descs))
+        return hit
+
+    def _begin_wgrads(self):
+        """Start of a backward pass: clear the gradient buffers the weight-gradient kernels accumulate into."""
+        self.flat_grads.zero_()
+        if self.deterministic:
+            self._det_ran = {}          # flat_ws is never written in this mode and stays zero
+        else:
+            self.flat_ws.zero_()
+
     def unpack_range(self, i0: int, i1: int):
         """Workspace -> parameter layout for layers [i0, i1) (a sub-range of the batched descriptor table)."""
         sz = C.sizeof(_l.vk_unpack_desc)
+        if self.deterministic:
+            table, offs, max_mn = self._det_table()
+            d0, d1 = offs[i0], offs[i1]
+            ops.wgrad_unpack_batched(table[d0 * sz:d1 * sz], d1 - d0, max_mn, accumulate=False)
+            return
         descs = self._unpack_descs[i0 * sz:i1 * sz]
         ops.wgrad_unpack_batched(descs, i1 - i0, self._unpack_max, accumulate=False)
+
+    def _unpack_all(self):
+        self.unpack_range(0, len(self.layers))
 
     def layer_flat_range(self, i0: int, i1: int):
         """[begin, end) of the flat parameter / gradient buffer covered by layers [i0, i1) (weights and biases)."""
@@ -521,8 +595,7 @@ class DenoiseEngine:
         dt = self.dtype
         cp = lambda c: ops.chan_pad(c, dt)
         nf = self.n_feat
-        self.flat_grads.zero_()
-        self.flat_ws.zero_()
+        self._begin_wgrads()
         if self.grad_sync is not None:
             self.grad_sync.begin()
         if self.wgrad_side_stream and self._wg_stream is None:
@@ -552,7 +625,7 @@ class DenoiseEngine:
                 g_bridge[lvl] = gX
                 xlow = A[f"u{k}.x"]
                 self._wgrad(us, xlow, gX, VK_CONVT2X2_S2)
-                ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt)
+                ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt, ws=self._csum_ws)
                 self._bucket_done(us)            # everything from this up block to the tail has its gradient
                 hl, wl = dims[lvl + 1]
                 gXl = self._buf(f"g.u{k}.low", (N, hl, wl, nf[lvl + 1]))
@@ -603,7 +676,7 @@ class DenoiseEngine:
         else:
             if self._wg_stream is not None:
                 torch.cuda.current_stream().wait_stream(self._wg_stream)
-            ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
+            self._unpack_all()
         self._saved_A = None
         A["set"]["owner"] = None
 
@@ -936,7 +1009,7 @@ class DenoiseEngine:
                 gX = self._resblock_bwd(f"u{k}.{b}", res[b][0], res[b][1], gX, (N, hh, ww, c))
             g_bridge[lvl] = gX
             self._wgrad(us, S[f"u{k}.x"], gX, VK_CONVT2X2_S2)
-            ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt)
+            ops.channel_sum(gX, c, self.grad_view(us.bias), dtype=dt, ws=self._csum_ws)
             hl, wl = dims[lvl + 1]
             gXl = self._buf(f"g.sr.u{k}.low", (N, hl, wl, nf[lvl + 1]))
             self._dgrad(gX, us, VK_CONV2X2_S2, nf[lvl + 1], ldo=nf[lvl + 1], out1=gXl)
@@ -1006,8 +1079,7 @@ class DenoiseEngine:
                 g = gn
 
     def _begin_backward(self, dev):
-        self.flat_grads.zero_()
-        self.flat_ws.zero_()
+        self._begin_wgrads()
         if self.wgrad_side_stream and self._wg_stream is None:
             self._wg_stream = torch.cuda.Stream(device=dev)
             self._wg_events = [torch.cuda.Event() for _ in range(8)]
@@ -1017,7 +1089,7 @@ class DenoiseEngine:
     def _end_backward(self, A):
         if self._wg_stream is not None:
             torch.cuda.current_stream().wait_stream(self._wg_stream)
-        ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
+        self._unpack_all()
         self._saved_A = None
         A["set"]["owner"] = None
 
@@ -1108,6 +1180,6 @@ class DenoiseEngine:
                     g = gn
         if self._wg_stream is not None:
             torch.cuda.current_stream().wait_stream(self._wg_stream)
-        ops.wgrad_unpack_batched(self._unpack_descs, self._unpack_n, self._unpack_max, accumulate=False)
+        self._unpack_all()
         self._saved_A = None
         S["set"]["owner"] = None

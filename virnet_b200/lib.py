@@ -55,6 +55,7 @@ class vk_wgrad_args(C.Structure):
         ("bh", C.c_int32), ("bw", C.c_int32), ("ldb", C.c_int32), ("n_valid", C.c_int32),
         ("dw", C.c_void_p), ("dbias", C.c_void_p),
         ("force_ksplit", C.c_int32), ("force_k_rows", C.c_int32), ("force_stages", C.c_int32),
+        ("max_slices", C.c_int32), ("partials", C.c_void_p), ("dbias_partials", C.c_void_p),
     ]
 
 
@@ -101,7 +102,8 @@ class vk_pack_desc(C.Structure):
 
 
 class vk_unpack_desc(C.Structure):
-    _fields_ = [("ws", C.c_void_p), ("out", C.c_void_p), ("taps", C.c_int32), ("mn", C.c_int32)]
+    _fields_ = [("ws", C.c_void_p), ("out", C.c_void_p), ("taps", C.c_int32), ("mn", C.c_int32),
+                ("nslices", C.c_int32), ("pad_", C.c_int32), ("slice_stride", C.c_int64)]
 
 
 class vk_adam_group(C.Structure):
@@ -114,6 +116,7 @@ _lib = None
 _SIGNATURES = {
     "vk_conv_igemm": (C.c_int, [C.POINTER(vk_conv_args), C.c_void_p]),
     "vk_conv_wgrad": (C.c_int, [C.POINTER(vk_wgrad_args), C.c_void_p]),
+    "vk_conv_wgrad_plan": (C.c_int, [C.POINTER(vk_wgrad_args), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vk_wgrad_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vk_wgrad_unpack_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "vk_sizeof_wgrad_args": (C.c_uint32, []),
@@ -122,14 +125,16 @@ _SIGNATURES = {
     "vk_pack_grad": (C.c_int, [C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p]),
     "vk_sigma_head_bwd": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]
                           + [C.c_int32] * 5 + [C.c_float, C.c_float, C.c_void_p]),
-    "vk_elbo_denoise": (C.c_int, [C.c_void_p] * 5 + [C.c_float] + [C.c_int32] * 5 + [C.c_float] * 4 + [C.c_void_p] * 5),
+    "vk_elbo_denoise": (C.c_int, [C.c_void_p] * 5 + [C.c_float] + [C.c_int32] * 5 + [C.c_float] * 4 + [C.c_void_p] * 3
+                        + [C.c_int32, C.c_void_p, C.c_void_p]),
     "vk_pack_weights": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
-    "vk_channel_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vk_channel_sum": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_void_p]),
     "vk_channel_sum_batched": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p]),
-    "vk_adam_clip_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p] + [C.c_float] * 5
+    "vk_adam_clip_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p, C.c_int32] + [C.c_float] * 5
                           + [C.c_int32, C.c_void_p, C.c_void_p]),
-    "vk_adam_clip_step_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p] + [C.c_float] * 4
+    "vk_adam_clip_step_dev": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p, C.c_int32] + [C.c_float] * 4
                               + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vk_knet_head": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vk_ca_layer": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),

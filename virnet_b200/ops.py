@@ -176,11 +176,7 @@ def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_S
 # ---------------------------------------------------------------------------
 # vk_conv_wgrad
 # ---------------------------------------------------------------------------
-def conv_wgrad(a, b, dw, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None):
-    """a: M operand NHWC (conv: dY; convT: X); b: N operand NHWC (conv: X; convT: dY_up).
-    dw: fp32 [taps, m_valid, n_valid] workspace, accumulated into."""
-    assert a.is_contiguous() and b.is_contiguous() and dw.is_contiguous() and dw.dtype == torch.float32
-    assert a.dtype == TORCH_DTYPE[dtype] and b.dtype == TORCH_DTYPE[dtype]
+def _wgrad_args(a, b, dw, dtype, kind, m_valid, n_valid, dbias, tune):
     g = _l.vk_wgrad_args()
     g.dtype, g.kind = dtype, kind
     g.a, g.n, g.gh, g.gw, g.lda, g.m_valid = _ptr(a), a.shape[0], a.shape[1], a.shape[2], a.shape[3], m_valid
@@ -190,6 +186,33 @@ def conv_wgrad(a, b, dw, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None
         g.force_ksplit = tune.get("ksplit", 0)
         g.force_k_rows = tune.get("k_rows", 0)
         g.force_stages = tune.get("stages", 0)
+    return g
+
+
+WGRAD_MAX_SLICES = 148      # a split-K wave never has more K slices than SMs
+
+
+def conv_wgrad_plan(a, b, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None, max_slices=WGRAD_MAX_SLICES):
+    """(K slices, bias slots) vk_conv_wgrad will write in the deterministic layout for these operands."""
+    g = _wgrad_args(a, b, None, dtype, kind, m_valid, n_valid, dbias, tune)
+    g.max_slices = max_slices
+    sl, bs = C.c_int32(0), C.c_int32(0)
+    _l.check(_l.load().vk_conv_wgrad_plan(C.byref(g), C.byref(sl), C.byref(bs)), "vk_conv_wgrad_plan")
+    return sl.value, bs.value
+
+
+def conv_wgrad(a, b, dw, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None, partials=None, dbias_partials=None):
+    """a: M operand NHWC (conv: dY; convT: X); b: N operand NHWC (conv: X; convT: dY_up).
+    dw: fp32 [taps, m_valid, n_valid] workspace, accumulated into with red.add — or, deterministic form, `partials`
+    fp32 [slices, taps, m_valid, n_valid] (+ `dbias_partials` [bias slots, m_valid]) written with plain stores, one slab
+    per K slice (sizes from conv_wgrad_plan); wgrad_unpack_batched sums the slabs in order."""
+    assert a.is_contiguous() and b.is_contiguous() and dw.is_contiguous() and dw.dtype == torch.float32
+    assert a.dtype == TORCH_DTYPE[dtype] and b.dtype == TORCH_DTYPE[dtype]
+    g = _wgrad_args(a, b, dw, dtype, kind, m_valid, n_valid, dbias, tune)
+    if partials is not None:
+        assert partials.dtype == torch.float32 and partials.is_contiguous() and partials.shape[1:] == dw.shape
+        assert dbias is None or (dbias_partials is not None and dbias_partials.dtype == torch.float32)
+        g.max_slices, g.partials, g.dbias_partials = partials.shape[0], _ptr(partials), _ptr(dbias_partials)
     taps = dw.shape[0]
     with _Prof("conv_wgrad", 2.0 * g.n * g.gh * g.gw * taps * m_valid * n_valid):
         _l.check(_l.load().vk_conv_wgrad(C.byref(g), _stream()), "vk_conv_wgrad")
@@ -249,6 +272,24 @@ def sigma_head_bwd(sigma, g_sigma, g_in, chan, out, *, dtype, log_lo, log_hi):
                                              ld, n, sc, h, w, log_lo, log_hi, _stream()), "vk_sigma_head_bwd")
 
 
+REDUCE_MAX_BLOCKS = 592     # VK_REDUCE_MAX_BLOCKS (include/virnet_b200.h): slots of the atomic-free two-pass reductions
+
+
+def elbo_ws(device):
+    """Scratch of vk_elbo_denoise: one (lh, kl_gauss, kl_Igamma) slot per thread block."""
+    return torch.empty(3 * REDUCE_MAX_BLOCKS, device=device, dtype=torch.float64)
+
+
+def adam_ws(ngroups, device):
+    """Scratch of vk_adam_clip_step(_dev): one squared-norm slot per (parameter group, thread block)."""
+    return torch.empty(ngroups * REDUCE_MAX_BLOCKS, device=device, dtype=torch.float64)
+
+
+def channel_sum_ws(c, device):
+    """Scratch of the atomic-free vk_channel_sum for up to `c` channels."""
+    return torch.empty(REDUCE_MAX_BLOCKS * c, device=device, dtype=torch.float32)
+
+
 def elbo_denoise(mu, sigma, noisy, gt, beta0, *, eps2, alpha0, digamma_am1, beta0_scale=1.0, grad_scale=1.0, d_mu=None, d_sigma=None,
                  acc3=None, out4=None):
     n, c, h, w = mu.shape
@@ -260,13 +301,14 @@ def elbo_denoise(mu, sigma, noisy, gt, beta0, *, eps2, alpha0, digamma_am1, beta
     assert beta0.shape == sigma.shape, f"beta0 {tuple(beta0.shape)} must have sigma's shape {tuple(sigma.shape)}"
     assert noisy.shape == mu.shape and gt.shape == mu.shape and sigma.shape[0] == n and sigma.shape[2:] == (h, w)
     if acc3 is None:
-        acc3 = torch.empty(3, device=mu.device, dtype=torch.float64)
+        acc3 = elbo_ws(mu.device)
+    assert acc3.dtype == torch.float64 and acc3.is_contiguous()
     if out4 is None:
         out4 = torch.empty(4, device=mu.device, dtype=torch.float32)
     with _Prof("elbo_denoise"):
         _l.check(_l.load().vk_elbo_denoise(_ptr(mu), _ptr(sigma), _ptr(noisy), _ptr(gt), _ptr(beta0), beta0_scale, n, c, sc, h, w,
                                            eps2, alpha0, digamma_am1, grad_scale, _ptr(d_mu), _ptr(d_sigma), _ptr(acc3),
-                                           _ptr(out4), _stream()), "vk_elbo_denoise")
+                                           acc3.numel(), _ptr(out4), _stream()), "vk_elbo_denoise")
     return out4
 
 
@@ -276,10 +318,14 @@ def pack_weights(descs_dev, ndesc, max_elems, *, dtype, round_tf32=True):
                  "vk_pack_weights")
 
 
-def channel_sum(x, c, out, *, dtype):
+def channel_sum(x, c, out, *, dtype, ws=None):
+    """out[c] += per-channel sums of x.  ws (channel_sum_ws): per-block partials summed in block order, bit-reproducible;
+    without it one atomicAdd per (block, channel)."""
     npix = x.numel() // x.shape[-1]
+    assert ws is None or (ws.dtype == torch.float32 and ws.is_contiguous())
     with _Prof("channel_sum"):
-        _l.check(_l.load().vk_channel_sum(dtype, _ptr(x), npix, x.shape[-1], c, _ptr(out), _stream()), "vk_channel_sum")
+        _l.check(_l.load().vk_channel_sum(dtype, _ptr(x), npix, x.shape[-1], c, _ptr(out), _ptr(ws),
+                                          0 if ws is None else ws.numel(), _stream()), "vk_channel_sum")
 
 
 def channel_sum_batched(x, c, out, *, dtype):
@@ -296,8 +342,8 @@ def adam_clip_step(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_
                    beta1, beta2, eps, step, norms_out=None):
     with _Prof("adam_clip"):
         _l.check(_l.load().vk_adam_clip_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(groups_dev),
-                                             ngroups, max_group_elems, _ptr(sq_ws), grad_scale, lr, beta1, beta2, eps,
-                                             step, _ptr(norms_out), _stream()), "vk_adam_clip_step")
+                                             ngroups, max_group_elems, _ptr(sq_ws), sq_ws.numel(), grad_scale, lr, beta1,
+                                             beta2, eps, step, _ptr(norms_out), _stream()), "vk_adam_clip_step")
 
 
 def adam_clip_step_dev(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, max_group_elems, sq_ws, hyper_dev, *,
@@ -305,8 +351,8 @@ def adam_clip_step_dev(params, grads, exp_avg, exp_avg_sq, groups_dev, ngroups, 
     """hyper_dev: fp32 [3] on the device = (lr, 1 - beta1^step, sqrt(1 - beta2^step))."""
     with _Prof("adam_clip"):
         _l.check(_l.load().vk_adam_clip_step_dev(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq),
-                                                 _ptr(groups_dev), ngroups, max_group_elems, _ptr(sq_ws), grad_scale,
-                                                 beta1, beta2, eps, _ptr(hyper_dev), _ptr(norms_out), _stream()),
+                                                 _ptr(groups_dev), ngroups, max_group_elems, _ptr(sq_ws), sq_ws.numel(),
+                                                 grad_scale, beta1, beta2, eps, _ptr(hyper_dev), _ptr(norms_out), _stream()),
                  "vk_adam_clip_step_dev")
 
 

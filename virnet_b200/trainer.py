@@ -47,11 +47,24 @@ def _clip_groups(net, eng, spec):
     return table, len(groups), max(e - b for b, e, _ in groups)
 
 
+def _bias_corrections(betas, step):
+    """(1 - beta1^step, sqrt(1 - beta2^step)) exactly as vk_adam_clip_step computes them: double arithmetic on the betas
+    rounded to fp32 (the kernel argument type), so the graph-replayed update equals the eager one bit for bit."""
+    import struct
+    b1, b2 = (struct.unpack("f", struct.pack("f", b))[0] for b in betas)
+    return 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5
+
+
 class DenoiseTrainer:
     def __init__(self, net, lr=1e-4, clip_grad_R=1e3, clip_grad_S=1e2, alpha0=24.5, eps2=1e-6, betas=(0.9, 0.999),
-                 adam_eps=1e-8, process_group=None):
+                 adam_eps=1e-8, process_group=None, deterministic=None):
+        """deterministic=True: split-K weight gradients are reduced in a fixed order (engine.deterministic) — with the
+        atomic-free loss / norm / bias reductions every step is then run-to-run bit-identical, eager or graph-replayed,
+        at the cost of one extra pass over the partial sums (a few % of the step)."""
         self.net = net
         self.engine = net.engine()
+        if deterministic is not None:
+            self.engine.deterministic = bool(deterministic)
         self.engine._ensure_flat()
         eng = self.engine
         dev = eng.flat_params.device
@@ -80,9 +93,9 @@ class DenoiseTrainer:
         self._groups_dev = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
         self._ngroups = len(groups)
         self._max_group = max(e - b for b, e, _ in groups)
-        self._sq_ws = torch.zeros(len(groups), device=dev, dtype=torch.float64)
+        self._sq_ws = ops.adam_ws(len(groups), dev)
         self.grad_norms = torch.zeros(len(groups), device=dev, dtype=torch.float32)
-        self._acc3 = torch.zeros(3, device=dev, dtype=torch.float64)
+        self._acc3 = ops.elbo_ws(dev)
         self.losses = torch.zeros(4, device=dev, dtype=torch.float32)
         self._d_mu = self._d_sigma = None
         self._staging = {}
@@ -286,8 +299,7 @@ class DenoiseTrainer:
         if self._hyper_used[k]:
             ev.synchronize()                                # its previous copy has been consumed (8 steps ago)
         host[0] = self.lr if lr is None else lr
-        host[1] = 1.0 - self.betas[0] ** self.step_count
-        host[2] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
+        host[1], host[2] = _bias_corrections(self.betas, self.step_count)
         self._hyper.copy_(host, non_blocking=True)
         ev.record()
         self._hyper_used[k] = True
@@ -328,7 +340,7 @@ class SISRTrainer:
         self._loss_ws = {}                 # scratch of vk_elbo_sisr, owned by this trainer (never freed: graphs capture it)
         self._groups_dev, self._ngroups, self._max_group = _clip_groups(
             net, eng, (("rnet", clip_grad_R), ("snet", clip_grad_S), ("knet", clip_grad_K)))
-        self._sq_ws = torch.zeros(self._ngroups, device=dev, dtype=torch.float64)
+        self._sq_ws = ops.adam_ws(self._ngroups, dev)
         self.grad_norms = torch.zeros(self._ngroups, device=dev, dtype=torch.float32)
         self.losses = None
 
@@ -424,8 +436,7 @@ class SISRTrainer:
         if self._hyper_used[k]:
             ev.synchronize()
         host[0] = self.lr if lr is None else lr
-        host[1] = 1.0 - self.betas[0] ** self.step_count
-        host[2] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
+        host[1], host[2] = _bias_corrections(self.betas, self.step_count)
         self._hyper.copy_(host, non_blocking=True)
         ev.record()
         self._hyper_used[k] = True
