@@ -56,15 +56,17 @@ def test_sisr_forward_vs_oracle_ragged(shape, sf):
 
 
 @pytest.mark.parametrize("precision,tol", [("tf32", 2e-2), ("bf16", 8e-2)])
-@pytest.mark.parametrize("shape,sf", [((2, 3, 16, 16), 4), ((1, 3, 21, 30), 2)])
-def test_sisr_backward_vs_oracle(precision, tol, shape, sf):
+@pytest.mark.parametrize("shape,sf,n_feat,dep_K", [((2, 3, 16, 16), 4, (32, 64, 96), 3), ((1, 3, 21, 30), 2, (32, 64, 96), 3),
+                                                   ((2, 3, 16, 20), 4, (96, 160, 224), 8)])
+def test_sisr_backward_vs_oracle(precision, tol, shape, sf, n_feat, dep_K):
     """Gradients of every parameter (SNet, KNet incl. the 9x9 head and channel attention, RNet incl. the SFT
     MLPs) of a random linear functional of (mu, kinfo, sigma) against torch autograd through the CPU oracle.
-    Tolerance: relative L2 per sub-network, same bar as the denoising backward tests (tf32 2e-2, bf16 8e-2)."""
+    Tolerance: relative L2 per sub-network, same bar as the denoising backward tests (tf32 2e-2, bf16 8e-2).
+    The last case is the shipped sisr_x4.json width (96 / 160 / 224 features, 8 KNet blocks)."""
     from oracle import virnet_oracle as O
-    net, sd = make_sr(precision, n_feat=(32, 64, 96), n_res=2, dep_K=3)
+    net, sd = make_sr(precision, n_feat=n_feat, n_res=2, dep_K=dep_K)
     net.train()
-    cfg = O.NetCfg(n_feat=(32, 64, 96), n_resblocks=2, extra_mode="Both", noise_avg=True, sisr=True, dep_K=3)
+    cfg = O.NetCfg(n_feat=n_feat, n_resblocks=2, extra_mode="Both", noise_avg=True, sisr=True, dep_K=dep_K)
     g = torch.Generator().manual_seed(5)
     x = torch.rand(*shape, generator=g)
     N, C, h, w = shape

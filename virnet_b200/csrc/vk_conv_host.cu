@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -155,6 +156,14 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase);   // vk_conv_v
 extern "C" int vk_conv_igemm(const vk_conv_args* a, void* stream) {
   if (a == nullptr || a->x == nullptr || a->w == nullptr) return VK_E_BADARG;
   if (a->kind == VK_CONV3X3_S2_DGRAD) {
+    // all four (row, column) parity phases of the fine grid as ONE persistent launch (a job = tile group x phase): dY is
+    // fetched from HBM once instead of four times; shapes it declines (an empty phase, several N blocks) run per phase
+    if (a->force_impl != 1 && std::getenv("VK_S2D_PER_PHASE") == nullptr) {
+      if (a->dtype != VK_BF16 && a->dtype != VK_TF32) return VK_E_BADARG;
+      if (a->n <= 0 || a->ih <= 0 || a->iw <= 0 || a->cout <= 0) return VK_E_BADARG;
+      const int r = conv_v2_impl(a, stream, -1);
+      if (r != VK_E_UNSUPPORTED) return r;
+    }
     for (int phase = 0; phase < 4; ++phase) {
       int r = conv_igemm_impl(a, stream, phase);
       if (r) return r;

@@ -69,6 +69,8 @@ struct ConvV2Params {
   int P;                     // pixel tiles per job (1, 2 or 4; <= epilogue groups)
   int p_log2;
   int n_cta, n_blocks;       // GEMM N per job, N blocks
+  int phase_jobs;            // 1 (merged stride-2 dgrad): the N-block index of a job is a PHASE — it selects the load
+                             // (tap views), the epilogue quadrant maps; the weight rows always start at 0
   int n_jobs;
   int acc_stride;            // TMEM columns between accumulators
   int tmem_cols;
@@ -360,7 +362,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int tiles_per_img = prm.tiles_x * prm.tiles_y;
   // full-K mode: item ai = (load l, chunk group g) -> chunks [c0, c0 + ns); slab mode: item = (load 0, chunk c0), ns = 1
   const int n_kgroups = kFullK ? (prm.k_chunks + prm.kg - 1) / prm.kg : prm.k_chunks;
-  const int n_a_items = prm.n_loads * n_kgroups;
+  const int n_a_items = (prm.phase_jobs ? 1 : prm.n_loads) * n_kgroups;
   const int sub_max = kFullK ? prm.kg : 1;               // A boxes per tile per A item (slot layout)
   auto item_of = [&](int ai, int& l, int& c0, int& ns) {
     l = ai / n_kgroups;
@@ -440,6 +442,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int ai = 0; ai < n_a_items; ++ai) {
           int l, c0, n_sub;
           item_of(ai, l, c0, n_sub);
+          if (prm.phase_jobs) l = job % prm.n_blocks;
           const int dx = prm.loads[l].dx, dy = prm.loads[l].dy;
           mbar_wait_t(&empty_a[sa], ph ^ 1, prof, w_empty);
           uint8_t* dst = smem_a + sa * prm.a_slot_bytes;
@@ -477,10 +480,11 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int job = worker; job < prm.n_jobs; job += n_workers) {
         if (prm.b_resident && job != worker) break;    // weights stay in shared memory after the first job
         // pair mode: this CTA supplies rows [n0, n0 + n_cta / 2) of the job's weight block
-        const int n0 = (job % prm.n_blocks) * prm.n_cta + (kPair ? int(cta_rank) * (prm.n_cta >> 1) : 0);
+        const int n0 = (prm.phase_jobs ? 0 : (job % prm.n_blocks) * prm.n_cta) + (kPair ? int(cta_rank) * (prm.n_cta >> 1) : 0);
         for (int ai = 0; ai < n_a_items; ++ai) {
           int l, c, n_sub;
           item_of(ai, l, c, n_sub);
+          if (prm.phase_jobs) l = job % prm.n_blocks;
           const int nb_l = kFullK ? prm.loads[l].nb : prm.nb;
           for (int bi = 0; bi < nb_l; ++bi) {
             if (turn == pw) {
@@ -549,6 +553,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait_t(&full_a[sa], pha, prof, w_fa);
         int l_, c0_, n_sub;
         item_of(ai, l_, c0_, n_sub);
+        if (prm.phase_jobs) l_ = job % prm.n_blocks;
         const int nb_l = kFullK ? prm.loads[l_].nb : prm.nb;
 #pragma unroll
         for (int bi = 0; bi < 9; ++bi) {
@@ -653,9 +658,9 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int job = worker; job < prm.n_jobs; job += n_workers) {
       const int jgroup = job / prm.n_blocks;
       const int group = kPair ? 2 * jgroup + int(cta_rank) : jgroup;
-      const int n0 = (job - jgroup * prm.n_blocks) * prm.n_cta;
-      const int qi = n0 / prm.cq;
-      const int cq0 = n0 - qi * prm.cq;
+      const int n0 = prm.phase_jobs ? 0 : (job - jgroup * prm.n_blocks) * prm.n_cta;
+      const int qi = prm.phase_jobs ? job - jgroup * prm.n_blocks : n0 / prm.cq;
+      const int cq0 = n0 - (prm.phase_jobs ? 0 : qi * prm.cq);
       const int tile0 = group * P;
       const int nvalid = max(0, min(P, prm.n_tiles - tile0));
       const uint32_t acc0 = tmem_base + (uint32_t(q4 * 32) << 16) + uint32_t(as * P) * prm.acc_stride;

@@ -56,6 +56,13 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
     case VK_CONV3X3_S2_DGRAD: {
       if (a->out_h <= 0 || a->out_w <= 0 || (a->out_h + 1) / 2 != a->ih || (a->out_w + 1) / 2 != a->iw)
         return VK_E_BADARG;
+      if (phase < 0) {
+        // merged phases: the tile grid of phase (0, 0), the largest; the other phases' views clip it (TMA bounds)
+        if (a->out_h < 2 || a->out_w < 2) return VK_E_UNSUPPORTED;      // an empty phase has no tensor map
+        prm.oh = (a->out_h + 1) / 2, prm.ow = (a->out_w + 1) / 2;
+        prm.a_stride = 1, us = 2;
+        break;
+      }
       const int py = phase >> 1, px = phase & 1;
       prm.oh = (a->out_h - py + 1) / 2, prm.ow = (a->out_w - px + 1) / 2;
       prm.a_stride = 1, us = 2;
@@ -66,6 +73,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   }
   const bool is_convT = a->kind == VK_CONVT2X2_S2;
   const bool is_s2d = a->kind == VK_CONV3X3_S2_DGRAD;
+  const bool s2d_merged = is_s2d && phase < 0;
   prm.n_img = a->n;
   prm.cout = a->cout;
   prm.wrows = a->wrows;
@@ -121,6 +129,10 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
   if (a->epi == VK_EPI_NCHW_F32 && a->wrows != n_cta) return VK_E_UNSUPPORTED;
   prm.n_cta = n_cta;
   prm.n_blocks = a->wrows / n_cta;
+  if (s2d_merged) {
+    if (prm.n_blocks != 1) return VK_E_UNSUPPORTED;
+    prm.n_blocks = 4, prm.phase_jobs = 1;       // the "N block" index of a job is its phase
+  }
   prm.acc_stride = round_up(n_cta, 32);
 
   // ---- loads / taps ----
@@ -163,19 +175,22 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
         l.dx = t & 1, l.dy = t >> 1, l.nb = 1, l.tap[0] = t, l.aoff16[0] = 0;
       }
     } else if (is_s2d) {
-      const int py = phase >> 1, px = phase & 1;
-      const int nr = py ? 2 : 1, ns = px ? 2 : 1;
-      const int rr[2] = {py ? 0 : 1, 2}, dyv[2] = {py ? 1 : 0, 0};
-      const int ss[2] = {px ? 0 : 1, 2}, dxv[2] = {px ? 1 : 0, 0};
       box_w = tw + 1, box_h = th + 1;
-      prm.n_loads = 1;
-      ConvV2Load& l = prm.loads[0];
-      for (int i = 0; i < nr; ++i)
-        for (int j = 0; j < ns; ++j) {
-          l.tap[l.nb] = rr[i] * 3 + ss[j];
-          l.aoff16[l.nb] = aoff(dyv[i], dxv[j], box_w);
-          ++l.nb;
-        }
+      prm.n_loads = s2d_merged ? 4 : 1;
+      for (int ph = 0; ph < 4; ++ph) {
+        if (!s2d_merged && ph != phase) continue;
+        const int py = ph >> 1, px = ph & 1;
+        const int nr = py ? 2 : 1, ns = px ? 2 : 1;
+        const int rr[2] = {py ? 0 : 1, 2}, dyv[2] = {py ? 1 : 0, 0};
+        const int ss[2] = {px ? 0 : 1, 2}, dxv[2] = {px ? 1 : 0, 0};
+        ConvV2Load& l = prm.loads[s2d_merged ? ph : 0];
+        for (int i = 0; i < nr; ++i)
+          for (int j = 0; j < ns; ++j) {
+            l.tap[l.nb] = rr[i] * 3 + ss[j];
+            l.aoff16[l.nb] = aoff(dyv[i], dxv[j], box_w);
+            ++l.nb;
+          }
+      }
     } else {
       box_w = tw, box_h = th;
       prm.n_loads = 1;
@@ -292,7 +307,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
       int gen_b_items = 0;
       for (int l = 0; l < prm.n_loads; ++l) gen_b_items += prm.loads[l].nb;
       const int total_b_items = slab ? prm.k_chunks * (9 / nt) : gen_b_items * n_kgroups;
-      const int total_a_items = slab ? prm.k_chunks : prm.n_loads * n_kgroups;
+      const int total_a_items = slab ? prm.k_chunks : (prm.phase_jobs ? 1 : prm.n_loads) * n_kgroups;
       const int avail = kV2SmemBudget - 1024 - epi_bytes;
       // depth: at least 2 of each; B ring as deep as fits (up to 8), A ring 2 (3 when cheap)
       int as = std::min(2, std::max(1, total_a_items)) ;
@@ -391,8 +406,8 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
       const uint32_t es[4] = {1u, 1u, 1u, 1u};
       return make_tensor_map(out, a->dtype, 4, p, dims, strides, box, es, ecb);
     };
-    const int q_lo = is_s2d ? phase : 0;
-    const int nq = is_convT ? 4 : 1;
+    const int q_lo = is_s2d && !s2d_merged ? phase : 0;
+    const int nq = is_convT || s2d_merged ? 4 : 1;
     for (int q = 0; q < nq; ++q) {
       int r = 0;
       if (prm.has_out1) r = make_view(&em.out1[q], a->out1, q_lo + q);

@@ -267,7 +267,10 @@ extern "C" int vk_wgrad_unpack_batched(const void* descs_dev, int32_t ndesc, int
                                        void* stream) {
   if (descs_dev == nullptr || ndesc <= 0 || max_mn <= 0) return VK_E_BADARG;
   static_assert(sizeof(WgradUnpackDesc) == sizeof(vk_unpack_desc), "descriptor layout");
-  const int bx = int(std::min<int64_t>((max_mn + 255) / 256, 64));
+  // blocks per layer: enough for ~16 blocks per SM over the whole table (a bucket of a few large layers gets more
+  // blocks per layer than the full 82-layer table)
+  const int64_t cap = std::max<int64_t>(64, (148 * 16) / ndesc);
+  const int bx = int(std::min<int64_t>((max_mn + 255) / 256, cap));
   wgrad_unpack_batched_kernel<<<dim3(bx, ndesc), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const WgradUnpackDesc*>(descs_dev), accumulate);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
