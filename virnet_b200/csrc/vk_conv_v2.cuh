@@ -418,6 +418,12 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  // Programmatic dependent launch: the prologue above ran while the previous kernel of the stream was finishing (the only
+  // global data it read is the bias vector, a parameter last written by the optimizer kernel, which is never launched
+  // programmatically); from here on the kernel reads activations the previous kernel produced and overwrites buffers it
+  // may still read, so wait for its completion first.  The next kernel may start its own prologue from now on.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== A producer =====================

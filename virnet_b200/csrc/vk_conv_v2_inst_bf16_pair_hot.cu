@@ -25,10 +25,8 @@ int launch_hot(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& e
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(v2_threads(true)), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr, cfg.numAttrs = fill_launch_attrs(attr, true);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, em, prm);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return e != cudaSuccess ? int(e) : int(cudaGetLastError());

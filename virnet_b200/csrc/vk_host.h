@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
 
 namespace vk {
 
@@ -17,5 +18,28 @@ extern std::atomic<uint64_t> g_launch_count;
 int make_tensor_map(CUtensorMap* out, int dtype, int rank, const void* ptr, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estrides,
                     int swizzle_bytes);
+
+// Launch attributes of the persistent tcgen05 kernels: CTA-pair clusters and programmatic dependent launch (PDL).
+// With PDL the CTAs of kernel N+1 become resident as the CTAs of kernel N retire and run their prologue (barrier init,
+// TMEM allocation, descriptor prefetch) under N's tail; every such kernel executes griddepcontrol.wait before it touches
+// global memory, which blocks until N has completed and flushed.  VK_NO_PDL=1 restores plain stream order.
+inline bool pdl_enabled() {
+  static const bool on = std::getenv("VK_NO_PDL") == nullptr;
+  return on;
+}
+inline unsigned fill_launch_attrs(cudaLaunchAttribute* attr, bool cluster2) {
+  unsigned n = 0;
+  if (cluster2) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 2, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  return n;
+}
 
 }  // namespace vk

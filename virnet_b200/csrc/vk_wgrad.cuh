@@ -190,6 +190,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();     // programmatic dependent launch: see conv_v2_kernel
+  pdl_wait();
 
   if (warp == 0 || warp >= 6) {
     // ===================== TMA producers (boxes of a stage spread over 4 warps) =====================

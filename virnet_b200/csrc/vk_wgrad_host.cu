@@ -28,9 +28,13 @@ int launch_wgrad_k(const CUtensorMap& ta, const CUtensorMap& tb, const WgradPara
     if (e != cudaSuccess) return int(e);
     cur = smem_bytes;
   }
-  kern<<<grid, kWgradThreads, smem_bytes, st>>>(ta, tb, prm);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = dim3(kWgradThreads), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr, cfg.numAttrs = fill_launch_attrs(attr, false);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, prm);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return int(cudaGetLastError());
+  return e != cudaSuccess ? int(e) : int(cudaGetLastError());
 }
 // bf16 with the M operand transposed into tensor memory by the epilogue warps (vk_wgrad.cuh, kTS)
 int launch_wgrad_ts(const CUtensorMap& ta, const CUtensorMap& tb, const WgradParams& prm, dim3 grid, int smem_bytes,
