@@ -128,6 +128,28 @@ assert abs(la[0].item() - lb[0].item()) <= 2e-2 * abs(la[0].item()) and (d > 1e-
 del tr_a, tr_b, net_a, net_b
 torch.cuda.empty_cache()
 
+# ---- 3b. deterministic mode at world > 1: run-to-run bit-identical, eager == graph, all ranks identical ----
+def det_run(mode, steps=4):
+    net = make("bf16", [32, 64, 96], 2)
+    tr = DenoiseTrainer(net, lr=1e-3, deterministic=True)
+    for it in range(steps):
+        (tr.step if mode == "eager" else tr.step_graph)(x, gt, sg, lr=1e-3 * (1 + it))
+    torch.cuda.synchronize()
+    return tr.engine.flat_params.clone(), tr.losses.clone()
+
+
+p1, l1 = det_run("eager")
+p2, l2 = det_run("eager")
+p3, l3 = det_run("graph")
+gathered = [torch.empty_like(p1) for _ in range(world)]
+dist.all_gather(gathered, p1)
+say(check="deterministic_world>1", run_to_run_equal=bool(torch.equal(p1, p2) and torch.equal(l1, l2)),
+    graph_equals_eager=bool(torch.equal(p1, p3)), max_abs_graph_vs_eager=(p1 - p3).abs().max().item(),
+    ranks_identical=bool(all(torch.equal(gathered[0], g) for g in gathered)))
+assert torch.equal(p1, p2) and torch.equal(l1, l2)
+del p1, p2, p3
+torch.cuda.empty_cache()
+
 # ---- 4. timings, full-size network ----
 for b in (32, 2):
     batch = bench.synth_batch(b, rank, dev)

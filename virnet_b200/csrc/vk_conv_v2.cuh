@@ -422,12 +422,15 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // global data it read is the bias vector, a parameter last written by the optimizer kernel, which is never launched
   // programmatically); from here on the kernel reads activations the previous kernel produced and overwrites buffers it
   // may still read, so wait for its completion first.  The next kernel may start its own prologue from now on.
+  // Only the roles that touch such data wait: the A producer and the epilogue warps.  The B producers stream the packed
+  // weights (written by vk_pack_weights, a plainly serialised kernel, long before) and start under the previous
+  // kernel's tail; the MMA issuer touches no global memory.
   pdl_launch_dependents();
-  pdl_wait();
 
   if (warp == 0) {
     // ===================== A producer =====================
     if (elect_one()) {
+      pdl_wait();
       int sa = 0;
       uint32_t ph = 0;
       long long w_empty = 0;
@@ -618,6 +621,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (prof && leader) tslot[1] = w_fa, tslot[2] = w_fb, tslot[3] = w_te, tslot[4] = clock64() - t_start;
   } else {
     // ===================== epilogue (warps 4 .. 4 + 4 * kGroups - 1) =====================
+    pdl_wait();
     const int ew = warp - 4;
     const int q4 = warp & 3;                   // TMEM lane quarter of this warp
     const int half = ew >> 2;
