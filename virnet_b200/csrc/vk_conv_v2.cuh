@@ -422,9 +422,10 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // global data it read is the bias vector, a parameter last written by the optimizer kernel, which is never launched
   // programmatically); from here on the kernel reads activations the previous kernel produced and overwrites buffers it
   // may still read, so wait for its completion first.  The next kernel may start its own prologue from now on.
-  // Only the roles that touch such data wait: the A producer and the epilogue warps.  The B producers stream the packed
-  // weights (written by vk_pack_weights, a plainly serialised kernel, long before) and start under the previous
-  // kernel's tail; the MMA issuer touches no global memory.
+  // Every role that touches global memory waits (A producer, B producers, epilogue warps); the MMA issuer touches none.
+  // (Letting the weight producers run ahead of the wait is safe only when a plainly serialised kernel separates
+  // vk_pack_weights from the first convolution, as in the engine; it bought 1 % at 2 patches per GPU and nothing
+  // elsewhere, so a C-ABI caller is not asked to guarantee that.)
   pdl_launch_dependents();
 
   if (warp == 0) {
@@ -483,6 +484,7 @@ conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== B producers (B items round-robin over 3 warps) =====================
     const int pw = warp - 1;
     if (elect_one()) {
+      pdl_wait();
       int sb = 0, turn = 0;
       uint32_t ph = 0;
       long long w_empty = 0;

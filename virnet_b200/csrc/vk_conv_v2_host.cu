@@ -233,7 +233,7 @@ int conv_v2_impl(const vk_conv_args* a, void* stream, int phase) {
 
   // ---- CTA pairs (cta_group::2): M = 256 per MMA, each CTA stages half of the weight rows ----
   // force_impl: 0/2 automatic, 3 single CTAs, 4 pairs
-  bool pair = a->force_impl == 4 || (a->force_impl != 3 && n_cta % 32 == 0 && n_cta >= 64);
+  bool pair = a->force_impl == 4 || (a->force_impl != 3 && n_cta % 32 == 0 && n_cta >= 32);
   if (n_cta % 32) pair = false;                 // each half must be a multiple of 16 rows (N % 16, swizzle atoms)
   const int b_rows = pair ? n_cta / 2 : n_cta;  // weight rows staged per CTA
   const int epi_groups = v2_epi_groups(pair);

@@ -40,6 +40,13 @@ def _pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
+def _wrows(c: int) -> int:
+    """Rows of a packed weight operand (GEMM N).  Layers with at most 16 output rows (tail, SNet end, head dgrad) are
+    padded to 32: a CTA pair then issues M=256 MMAs with 16 rows from each CTA — half as many MMAs per tile, and an N=16
+    MMA costs the same ~44 clocks of issue time as an N=32 one."""
+    return 32 if c <= 16 else _pad16(c)
+
+
 class _Layer:
     """One Conv2d / ConvTranspose2d: parameters plus their packed GEMM operands."""
 
@@ -231,11 +238,11 @@ class DenoiseEngine:
                 ly.wd = torch.empty(4, _pad16(ly.cin), cp(ly.cout), device=dev, dtype=tdt)
                 add(w, ly.wd, ly.cin, ly.cout, 4, _pad16(ly.cin), cp(ly.cout), 4, 3)
             else:
-                ly.wf = torch.empty(ly.taps, _pad16(ly.cout), cp(ly.cin), device=dev, dtype=tdt)
-                add(w, ly.wf, ly.cout, ly.cin, ly.taps, _pad16(ly.cout), cp(ly.cin), ly.taps, 0)
+                ly.wf = torch.empty(ly.taps, _wrows(ly.cout), cp(ly.cin), device=dev, dtype=tdt)
+                add(w, ly.wf, ly.cout, ly.cin, ly.taps, _wrows(ly.cout), cp(ly.cin), ly.taps, 0)
                 if ly.need_dgrad:
-                    ly.wd = torch.empty(ly.taps, _pad16(ly.cin), cp(ly.cout), device=dev, dtype=tdt)
-                    add(w, ly.wd, ly.cout, ly.cin, ly.taps, _pad16(ly.cin), cp(ly.cout), ly.taps,
+                    ly.wd = torch.empty(ly.taps, _wrows(ly.cin), cp(ly.cout), device=dev, dtype=tdt)
+                    add(w, ly.wd, ly.cout, ly.cin, ly.taps, _wrows(ly.cin), cp(ly.cout), ly.taps,
                         4 if ly.kind == "conv_s2" else 1)
             ws_total += w.numel()
         arr = (_l.vk_pack_desc * len(descs))(*descs)
