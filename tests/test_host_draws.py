@@ -56,3 +56,17 @@ def test_data_side_dropins_refuse_cpu_tensors():
         SimulateTrainGPU(32).synthesize(torch.zeros(2, 32, 32, 3, dtype=torch.uint8))
     with pytest.raises(RuntimeError):
         GeneralTrainGPU(4).degrade(torch.rand(1, 3, 48, 48))
+
+
+def test_adam_bias_corrections_match_the_kernel_formula():
+    """trainer._bias_corrections feeds the CUDA-graph path (vk_adam_clip_step_dev) with exactly what vk_adam_clip_step
+    computes for the eager path: double arithmetic on the betas rounded to fp32, results rounded to fp32."""
+    import numpy as np
+    from virnet_b200.trainer import _bias_corrections
+    for betas in ((0.9, 0.999), (0.5, 0.9), (0.95, 0.98)):
+        for step in (1, 2, 10, 1000, 123456):
+            b1, b2 = (float(np.float32(b)) for b in betas)
+            want = (1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5)
+            got = _bias_corrections(betas, step)
+            assert np.float32(got[0]) == np.float32(want[0]) and np.float32(got[1]) == np.float32(want[1])
+            assert 0.0 < got[0] <= 1.0 and 0.0 < got[1] <= 1.0
