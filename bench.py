@@ -93,12 +93,6 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        return self.summarise(t0, t1)
-
-    def summarise(self, t0, t1):
-        """Median SM clock and the throttle reasons seen between the wall-clock times t0 and t1."""
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], None, set()
         for ts, line in self.samples:
             f = [x.strip() for x in line.split(",")]
@@ -470,33 +464,21 @@ def _run_ours(args):
             e2e_last[0] = float(loss_host[(i - 1) & 1][0])
         e2e_i[0] = i + 1
 
-    # settle the power / clock state before anything is timed: the step is power-capped (sw_power_cap), and the first
-    # few hundred milliseconds after start-up run at different clocks than the steady state both timed regions should see
-    prewarm = max(0, 40 - args.warmup)
-    for _ in range(prewarm):
+    for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)          # nvidia-smi runs through BOTH timed regions (same conditions for both)
+    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.2)
-    for _ in range(args.warmup):
-        step_resident()
     l0 = lib.launch_count()
     t0 = time.time()
     ms = timed(step_resident, args.steps)
     t1 = time.time()
     launches = lib.launch_count() - l0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
     for _ in range(2):
         step_e2e()
-    t2 = time.time()
     ms_e2e = timed(step_e2e, args.steps)
-    t3 = time.time()
-    clocks_e2e = None
-    if rank == 0:
-        clocks = sampler.stop(t0, t1)
-        clocks_e2e = sampler.summarise(t2, t3)
-    else:
-        clocks = None
     torch.cuda.synchronize()
     final_loss = float(loss_host[(e2e_i[0] - 1) & 1][0])
 
@@ -581,10 +563,9 @@ def _run_ours(args):
                                    "n_feat=[96,192,288] n_resblocks=3 dep_S=5, 128x128x3 patches (configs[2])",
                        "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}",
                        "l2": "working set per step (activations >1 GB) exceeds the 126 MB L2; no flush needed",
-                       "train_gflop_per_patch": TRAIN_GFLOP_PER_PATCH, "final_loss": final_loss,
-                       "prewarm_steps": prewarm},
+                       "train_gflop_per_patch": TRAIN_GFLOP_PER_PATCH, "final_loss": final_loss},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
-                    "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e},
+                    "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "vk_conv_igemm launches (conv_v2_kernel + conv_igemm_kernel; fprop+dgrad), serialised",

@@ -26,7 +26,7 @@ int launch_hot(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Maps& e
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(v2_threads(true)), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
   cudaLaunchAttribute attr[2];
-  cfg.attrs = attr, cfg.numAttrs = fill_launch_attrs(attr, true);
+  cfg.attrs = attr, cfg.numAttrs = fill_launch_attrs(attr, true, prm.n_jobs <= 4LL * grid);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, em, prm);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return e != cudaSuccess ? int(e) : int(cudaGetLastError());

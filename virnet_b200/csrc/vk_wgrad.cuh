@@ -67,6 +67,7 @@ struct WgradParams {
   float* dbias_partials;
   long long slice_elems;
   int prefetch_dist;            // K tiles of L2 prefetch lookahead (0 = off)
+  int bias_mma;                 // tuning aid (VK_WGRAD_BIAS_MMA=1): bias gradient by the ones-MMA also in bf16
   int debug_skip_epi;           // tuning aid (VK_WGRAD_SKIP_EPI=1): leave the accumulators in TMEM, measure the mainloop alone
 };
 
@@ -162,10 +163,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   // K tiles of this CTA: blockIdx.x, blockIdx.x + ksplit, ...
   const int my_tiles = (prm.n_tiles - int(blockIdx.x) + prm.ksplit - 1) / prm.ksplit;
 
+  // bf16 (non-TS): the bias gradient (column sums of the M operand) is taken by the four otherwise idle epilogue warps
+  // straight from the staged tile instead of an extra N=16 MMA per K step against a tile of ones — an N=16 MMA costs the
+  // same ~44 clocks of issue time as a wide one, 8 % of the issue time of a 96-channel layer.  Those warps are further
+  // consumers of the stage: the "stage free" barrier then expects five arrivals (MMA commit + one per warp).
+  constexpr bool kBiasLds = !kTS && !kTF32;
+  const bool bias_lds = kBiasLds && bias_en && !prm.bias_mma;
   if (threadIdx.x == 0) {
     for (int s = 0; s < prm.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], bias_lds ? 5 : 1);
     }
     mbar_init(&tmem_full_bar, 1);
     for (int i = 0; i < 2; ++i) mbar_init(&a_ready[i], 4), mbar_init(&a_free[i], 1);
@@ -303,7 +310,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
           }
           if constexpr (kTS) umma_commit(&a_free[it & 1]);
-          if (!kTS && bias_en && (it % prm.n_groups) == group) {
+          if (!kTS && (!kBiasLds || prm.bias_mma) && bias_en && (it % prm.n_groups) == group) {
             uint32_t ad = a_lo;
             uint32_t acc = bias_accum;
             bias_accum = 1;
@@ -367,6 +374,67 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (++s == prm.stages) s = 0, ph ^= 1;
       }
     }
+    // ---- bias gradient from the staged M tiles (bf16): the four epilogue warps, a quarter of the pixel rows each ----
+    float bsum[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+    if (kBiasLds && bias_lds) {
+      // lane l owns logical 16-byte chunk (l & 7) = 8 channels of every 128-byte pixel row; this warp walks the rows
+      // (l >> 3) + 4 (warp - 2) + 16 i.  SW128: the chunk sits at physical position chunk ^ (bits [7:9] of the row address)
+      const uint32_t chunk = uint32_t(lane & 7);
+      const int r0 = (lane >> 3) + 4 * (warp - 2);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        if ((it % prm.n_groups) == group) {
+          const uint32_t a_s = smem_u32(smem + s * stage_bytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t blk = a_s + uint32_t(j) * uint32_t(a_block_bytes);
+#pragma unroll 4
+            for (int r = r0; r < kRows; r += 16) {
+              const uint32_t row_addr = blk + uint32_t(r) * 128u;
+              const uint32_t addr = row_addr + ((chunk ^ ((row_addr >> 7) & 7u)) << 4);
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+              float* b = bsum + 8 * j;
+              b[0] += __uint_as_float(w0 << 16), b[1] += __uint_as_float(w0 & 0xFFFF0000u);
+              b[2] += __uint_as_float(w1 << 16), b[3] += __uint_as_float(w1 & 0xFFFF0000u);
+              b[4] += __uint_as_float(w2 << 16), b[5] += __uint_as_float(w2 & 0xFFFF0000u);
+              b[6] += __uint_as_float(w3 << 16), b[7] += __uint_as_float(w3 & 0xFFFF0000u);
+            }
+          }
+        }
+        // the sums above consumed every loaded register, so no load of this warp is still in flight when the stage is
+        // handed back to the TMA producers (generic-proxy read -> async-proxy write, see vk_conv_v2.cuh)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (++s == prm.stages) s = 0, ph ^= 1;
+      }
+      // rows were dealt to the four 8-lane groups of each warp and to the four warps: add them up in a fixed order
+      // (the 2 KB `ones` tile is unused in this variant and serves as the exchange buffer) — lanes 0..7 of warp 2 end
+      // with the totals
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = bsum[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        bsum[i] = v;
+      }
+      float* xch = reinterpret_cast<float*>(ones);             // [4 warps][8 lanes][16]
+      if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xch[((warp - 2) * 8 + lane) * 16 + i] = bsum[i];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          bsum[i] = ((xch[(0 * 8 + lane) * 16 + i] + xch[(1 * 8 + lane) * 16 + i]) + xch[(2 * 8 + lane) * 16 + i]) +
+                    xch[(3 * 8 + lane) * 16 + i];
+      }
+    }
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after_sync();
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
@@ -419,6 +487,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           const int c = m0 + q4 * 32 + (i >> 1) * 16 + (i & 1) * 8 + (lane >> 2);
           if ((lane & 3) == 0 && c < prm.m_valid && my_tiles > 0) red_add(prm.dbias + c, v);
         }
+      }
+    } else if (kBiasLds && bias_lds) {
+      // lanes 0..7 of warp 2 hold the column sums of channels m0 + 64 j + 8 (lane & 7) + i; a group that saw no bias
+      // tile holds zeros (deterministic mode: still stored, every slot has exactly one writer)
+      if (warp == 2 && lane < 8 && !prm.debug_skip_epi) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = m0 + 64 * j + 8 * lane + i;
+            if (c < prm.m_valid) {
+              if (det)
+                prm.dbias_partials[(static_cast<long long>(blockIdx.x) * prm.n_groups + group) * prm.m_valid + c] = bsum[8 * j + i];
+              else if (group < my_tiles)
+                red_add(prm.dbias + c, bsum[8 * j + i]);
+            }
+          }
       }
     } else if (bias_en && det) {
       // one slot per (K slice, tap group); a group that saw no bias tile (fewer K tiles than groups) stores zero

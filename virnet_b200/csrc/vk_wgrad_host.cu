@@ -31,7 +31,7 @@ int launch_wgrad_k(const CUtensorMap& ta, const CUtensorMap& tb, const WgradPara
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid, cfg.blockDim = dim3(kWgradThreads), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
   cudaLaunchAttribute attr[2];
-  cfg.attrs = attr, cfg.numAttrs = fill_launch_attrs(attr, false);
+  cfg.attrs = attr, cfg.numAttrs = fill_launch_attrs(attr, false, prm.n_tiles <= 48LL * prm.ksplit);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, prm);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return e != cudaSuccess ? int(e) : int(cudaGetLastError());
@@ -90,6 +90,8 @@ int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* sl
   {
     static const int skip = getenv("VK_WGRAD_SKIP_EPI") != nullptr;
     prm.debug_skip_epi = skip;
+    static const int bias_mma = getenv("VK_WGRAD_BIAS_MMA") != nullptr;
+    prm.bias_mma = bias_mma;
     static const int pf = getenv("VK_WGRAD_PREFETCH") ? atoi(getenv("VK_WGRAD_PREFETCH")) : 0;   // measured: slower
     prm.prefetch_dist = pf;
   }
