@@ -124,6 +124,13 @@ typedef struct vk_wgrad_args {
   int32_t max_slices;
   float* partials;
   float* dbias_partials;
+  /* swapped != 0 (3x3 stride-1 conv whose OUTPUT has few channels: tail, last SNet layer): the caller passes the
+   * operands the other way round — a = X (m_valid = Cin), b = dY (n_valid = Cout <= 16) — so that the narrow tensor is
+   * the N operand (one 16-column MMA atom instead of a 128-row tile that is 97 % padding).  The kernel then labels the
+   * taps mirrored (shifting dY by +t equals shifting X by -t) and writes dw transposed, i.e. still as
+   * [taps][Cout][Cin]; dbias must be NULL (the column sums of `a` are not the bias gradient here). */
+  int32_t swapped;
+  int32_t pad_;
 } vk_wgrad_args;
 
 /* Weight (and bias) gradient: autograd of F.conv2d / F.conv_transpose2d w.r.t.

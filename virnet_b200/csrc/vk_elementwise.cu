@@ -338,22 +338,33 @@ channel_sum_vec_kernel(const DT* __restrict__ x, long long npix, int ld, int C, 
   float s[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) s[i] = 0.f;
-  if (pl < lanes)
-    for (long long p = blockIdx.x * static_cast<long long>(lanes) + pl; p < npix; p += static_cast<long long>(gridDim.x) * lanes) {
-      const uint4 r = *reinterpret_cast<const uint4*>(x + p * ld + cg * V);
-      if constexpr (sizeof(DT) == 2) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  auto acc = [&](const uint4& r) {
+    if constexpr (sizeof(DT) == 2) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h[i]);
-          s[2 * i] += f.x, s[2 * i + 1] += f.y;
-        }
-      } else {
-        const float* f = reinterpret_cast<const float*>(&r);
-#pragma unroll
-        for (int i = 0; i < V; ++i) s[i] += f[i];
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        s[2 * i] += f.x, s[2 * i + 1] += f.y;
       }
+    } else {
+      const float* f = reinterpret_cast<const float*>(&r);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += f[i];
     }
+  };
+  if (pl < lanes) {
+    // four independent 16-byte loads in flight per thread (narrow tensors are latency-bound otherwise)
+    const long long step = static_cast<long long>(gridDim.x) * lanes;
+    long long p = blockIdx.x * static_cast<long long>(lanes) + pl;
+    for (; p + 3 * step < npix; p += 4 * step) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(x + p * ld + cg * V);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(x + (p + step) * ld + cg * V);
+      const uint4 r2 = *reinterpret_cast<const uint4*>(x + (p + 2 * step) * ld + cg * V);
+      const uint4 r3 = *reinterpret_cast<const uint4*>(x + (p + 3 * step) * ld + cg * V);
+      acc(r0), acc(r1), acc(r2), acc(r3);
+    }
+    for (; p < npix; p += step) acc(*reinterpret_cast<const uint4*>(x + p * ld + cg * V));
+  }
   if (pl < lanes) {
 #pragma unroll
     for (int i = 0; i < V; ++i) cs_sm[pl * ld + cg * V + i] = s[i];

@@ -49,7 +49,7 @@ struct WgradParams {
   int n_loads, n_taps;          // per tap group
   int n_groups;                 // tap groups (blockIdx.z = group)
   WgradLoad loads[3][3];        // [group][load]
-  WgradTap taps[3][5];          // [group][tap]
+  WgradTap taps[3][9];          // [group][tap] (9: the merged-tap layout has one group with all nine taps)
   int b_kstep_rows;             // N-operand pixel rows between consecutive K steps (tile width, or slab width for halo slabs)
   int shared_tap;               // >= 0: tap slot computed by group g only on K tiles with (tile ^ g) even (split between 2 groups)
   int n_cta;                    // GEMM N per CTA (multiple of 16)
@@ -67,6 +67,14 @@ struct WgradParams {
   float* dbias_partials;
   long long slice_elems;
   int prefetch_dist;            // K tiles of L2 prefetch lookahead (0 = off)
+  // merged taps (3x3 stride 1, N operand of at most 16 channels = 32-byte pixel rows, bf16): the N-operand slabs are staged
+  // with 32-byte rows (SWIZZLE_32B) and ONE MMA per K step covers three vertical taps — its three 16-column N atoms are
+  // the same slab read tw pixel rows apart (LBO = tw * 32 bytes).  The three horizontal shifts are three small slabs of
+  // the same stage, so ONE CTA per K slice computes all nine taps and the wide M operand is fetched from L2 once instead
+  // of three times (these layers move 100 MB for ~0 FLOPs: the three tap-group CTAs re-reading it was their cost).
+  int swapped;                  // operands passed the other way round: write dw transposed ([tap][n][m]), see vk_wgrad_args
+  int merge_taps;
+  int b_row_bytes;              // bytes per pixel row of an N-operand buffer (128, or 32 with merge_taps)
   int bias_mma;                 // tuning aid (VK_WGRAD_BIAS_MMA=1): bias gradient by the ones-MMA also in bf16
   int debug_skip_epi;           // tuning aid (VK_WGRAD_SKIP_EPI=1): leave the accumulators in TMEM, measure the mainloop alone
 };
@@ -154,7 +162,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const bool bias_en = (prm.dbias != nullptr) && n_block == 0;
 
   const int a_block_bytes = prm.k_rows * 128;
-  const int b_block_bytes = prm.box_rows * 128;
+  const int b_block_bytes = prm.box_rows * prm.b_row_bytes;
   const int a_bytes = prm.n_a_blocks * a_block_bytes;
   const int b_bytes = prm.n_b_blocks * b_block_bytes;
   const int stage_bytes = a_bytes + prm.n_loads * b_bytes;
@@ -260,7 +268,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const uint32_t idesc_bias = make_idesc(DTraits<DT>::kFmt, 128, 16, 1, 1);
       const uint64_t desc_hi = make_smem_desc(0, 0, kSBO, kLayout) & 0xFFFFFFFF00000000ull;
       const uint32_t a_lbo = ((uint32_t(a_block_bytes) >> 4) & 0x3FFFu) << 16;
-      const uint32_t b_lbo = ((uint32_t(b_block_bytes) >> 4) & 0x3FFFu) << 16;
+      const bool merged = prm.merge_taps != 0;
+      // merged taps: MN-major SWIZZLE_32B atoms (16 channels x 8 pixel rows of 32 bytes), N atoms one tile row apart
+      const uint64_t desc_hi_b = merged ? (make_smem_desc(0, 0, 256u, 6u) & 0xFFFFFFFF00000000ull) : desc_hi;
+      const uint32_t idesc_merged = make_idesc(DTraits<DT>::kFmt, 128, 48, 1, 1);
+      const uint32_t b_lbo = merged ? (((uint32_t(prm.b_kstep_rows) * 32u) >> 4) & 0x3FFFu) << 16
+                                    : ((uint32_t(b_block_bytes) >> 4) & 0x3FFFu) << 16;
       const uint32_t ones_lo = ((smem_u32(ones) & 0x3FFFFu) >> 4) | (64u << 16);   // LBO 1024 B
       const uint32_t smem16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
       const uint32_t stage16 = uint32_t(stage_bytes) >> 4, a16 = uint32_t(a_bytes) >> 4;
@@ -273,7 +286,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         tap_off[tp] = (uint32_t(prm.taps[group][tp].load * b_bytes + prm.taps[group][tp].rowoff * 128) >> 4);
       // B advances by one tile row of the (possibly wider) N-operand buffer per K step; A tiles are dense
       // (b_kstep_rows differs from the tile width only for bf16 halo slabs of 16-pixel-wide tiles: one K step = one slab row)
-      const uint32_t b_adv16 = prm.b_kstep_rows == (1 << prm.tw_log2) ? kAdv16 : (uint32_t(prm.b_kstep_rows) * 128u) >> 4;
+      const uint32_t b_adv16 = merged ? (uint32_t(kRowsPerMma) * 32u) >> 4
+                               : prm.b_kstep_rows == (1 << prm.tw_log2) ? kAdv16 : (uint32_t(prm.b_kstep_rows) * 128u) >> 4;
       const int shared_tap = prm.shared_tap;
       uint32_t shared_accum = 0;
       const uint32_t acc_stride = prm.acc_stride;
@@ -289,9 +303,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         tc_fence_after_sync();
         const uint32_t a_lo = (smem16 + uint32_t(s) * stage16) | a_lbo;
         const uint32_t b_lo = (smem16 + uint32_t(s) * stage16 + a16) | b_lbo;
+        if (leader && merged) {
+          if constexpr (!kTS) {
+            // load l = horizontal shift l - 1: its three vertical taps land in accumulator columns [48 l, 48 l + 48)
+            for (int l = 0; l < prm.n_loads; ++l) {
+              const uint32_t bd = b_lo + uint32_t(l) * (uint32_t(b_bytes) >> 4);
+#pragma unroll
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_ss<kTF32>(tmem_base + uint32_t(l) * 48u, desc_hi | (a_lo + kk * kAdv16), desc_hi_b | (bd + kk * b_adv16),
+                               idesc_merged, kk == 0 ? accum : 1u);
+            }
+          }
+        }
         if (leader) {
 #pragma unroll
           for (int tp = 0; tp < 5; ++tp) {
+            if (merged) break;
             const bool is_shared = tp == shared_tap;
             if (tp < n_taps && (!is_shared || (((it ^ group) & 1) == 0))) {
               uint32_t ad = a_lo, bd = b_lo + tap_off[tp];
@@ -454,6 +481,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         tmem_ld16(lane_addr + tp * prm.acc_stride + jc, rr);
         tmem_ld_wait();
         const int n = n0 + jc;
+        if (prm.swapped) {
+          // transposed store: element (tap, n, m); consecutive lanes (m) are consecutive addresses
+          if (m_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n + i < prm.n_valid) {
+                float* q = out_base + (static_cast<long long>(tap) * prm.n_valid + (n + i)) * prm.m_valid + m;
+                if (det) *q = __uint_as_float(rr[i]);
+                else red_add(q, __uint_as_float(rr[i]));
+              }
+          }
+        } else
         if (m_ok && n < prm.n_valid) {
           if (vec_ok && n + 16 <= prm.n_valid) {
 #pragma unroll

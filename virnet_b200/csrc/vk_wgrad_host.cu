@@ -87,6 +87,8 @@ int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* sl
   prm.dbias = a->dbias;
   prm.partials = a->partials;
   prm.dbias_partials = a->dbias_partials;
+  prm.swapped = a->swapped != 0;
+  if (prm.swapped && (a->kind != VK_CONV3X3_S1 || a->dbias != nullptr)) return VK_E_BADARG;
   {
     static const int skip = getenv("VK_WGRAD_SKIP_EPI") != nullptr;
     prm.debug_skip_epi = skip;
@@ -109,7 +111,7 @@ int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* sl
     case VK_CONV3X3_S1:
       slab = true;
       prm.b_stride = 1, prm.n_groups = 3, prm.n_loads = 1, prm.n_taps = 3, prm.total_taps = 9;
-      if (!slab3 && a->dtype == VK_BF16 && !det) slab9 = true, prm.n_groups = 2, prm.n_taps = 5, prm.shared_tap = 4;
+      if (!slab3 && a->dtype == VK_BF16 && !det && !a->swapped) slab9 = true, prm.n_groups = 2, prm.n_taps = 5, prm.shared_tap = 4;
       break;
     case VK_CONV3X3_S2:
       prm.b_stride = 2, prm.n_groups = 3, prm.n_loads = 3, prm.n_taps = 3, prm.total_taps = 9;
@@ -151,6 +153,17 @@ int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* sl
   if (prm.tmem_cols > 512) return VK_E_UNSUPPORTED;
   prm.n_a_blocks = 128 / block_elems;
   prm.n_b_blocks = (n_cta + block_elems - 1) / block_elems;
+  // merged vertical taps for narrow N operands (head, first SNet layer): see WgradParams::merge_taps
+  static const bool no_merge = getenv("VK_WGRAD_NO_MERGE") != nullptr;
+  const bool merge = a->kind == VK_CONV3X3_S1 && a->dtype == VK_BF16 && !slab9 && !ts && !no_merge && n_cta == 16 &&
+                     a->ldb == 16 && parts == 1;
+  prm.merge_taps = merge ? 1 : 0;
+  prm.b_row_bytes = merge ? 32 : 128;
+  if (merge) {
+    prm.n_groups = 1, prm.n_loads = 3, prm.n_taps = 9;    // one CTA per K slice: three small slabs, nine taps
+    prm.acc_stride = 16;                                  // tap (r, s) = 16-column atom 3 s + r
+    prm.tmem_cols = next_pow2_cols(9 * 16 + 32);
+  }
   const int m_blocks = (a->m_valid + 127) / 128;
 
   // ---- K tile and stages under the smem budget ----
@@ -165,7 +178,7 @@ int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* sl
       if ((cand[i][1] == 7 || cand[i][1] == 6) && !slab9) continue;
       if (k_rows * esize < 32 * 8 / 8 * 8) { /* at least one UMMA K step */ }
       const int box_rows = slab9 ? (cand[i][1] + 2) * (cand[i][0] + 2) : slab ? (cand[i][1] + 2) * cand[i][0] : k_rows;
-      const int stage = prm.n_a_blocks * k_rows * 128 + prm.n_loads * prm.n_b_blocks * box_rows * 128;
+      const int stage = prm.n_a_blocks * k_rows * 128 + prm.n_loads * prm.n_b_blocks * box_rows * prm.b_row_bytes;
       int st = std::min(8, kWgradSmemBudget / stage);
       if (a->force_stages) st = std::min(st, a->force_stages);
       if (slab9 && cand[i][0] != 16) continue;           // a K step (16 pixels) must be one contiguous slab row
@@ -188,11 +201,19 @@ int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* sl
         prm.taps[g][i].load = 0, prm.taps[g][i].rowoff = (tap / 3) * (tw + 2) + (tap % 3), prm.taps[g][i].tap = tap;
       }
     }
+  } else if (slab && merge) {
+    for (int l = 0; l < 3; ++l) {
+      prm.loads[0][l].dx = l - 1, prm.loads[0][l].dy = -1;
+      for (int r = 0; r < 3; ++r) {
+        WgradTap& t = prm.taps[0][l * 3 + r];
+        t.load = l, t.rowoff = r * tw, t.tap = a->swapped ? 8 - (r * 3 + l) : r * 3 + l;
+      }
+    }
   } else if (slab) {
     for (int s = 0; s < 3; ++s) {
       prm.loads[s][0].dx = s - 1, prm.loads[s][0].dy = -1;
       for (int r = 0; r < 3; ++r)
-        prm.taps[s][r].load = 0, prm.taps[s][r].rowoff = r * tw, prm.taps[s][r].tap = r * 3 + s;
+        prm.taps[s][r].load = 0, prm.taps[s][r].rowoff = r * tw, prm.taps[s][r].tap = a->swapped ? 8 - (r * 3 + s) : r * 3 + s;
     }
   }
   prm.tiles_x = (a->gw + tw - 1) / tw;
@@ -236,13 +257,13 @@ int wgrad_impl(const vk_wgrad_args* a, void* stream, bool plan_only, int32_t* sl
     const uint32_t s = prm.b_stride;
     const uint32_t box_h = slab ? th + 2 : th;
     const uint32_t box_w = slab9 ? tw + 2 : tw;
-    const uint32_t box[4] = {uint32_t(block_elems), box_w * s, box_h * s, 1u};
+    const uint32_t box[4] = {uint32_t(merge ? 16 : block_elems), box_w * s, box_h * s, 1u};
     const uint32_t es[4] = {1u, s, s, 1u};
-    int r = make_tensor_map(&tb, a->dtype, 4, a->b, dims, strides, box, es, sw_code);
+    int r = make_tensor_map(&tb, a->dtype, 4, a->b, dims, strides, box, es, merge ? 32 : sw_code);
     if (r) return r;
   }
 
-  const int stage_bytes = prm.n_a_blocks * prm.k_rows * 128 + prm.n_loads * prm.n_b_blocks * prm.box_rows * 128;
+  const int stage_bytes = prm.n_a_blocks * prm.k_rows * 128 + prm.n_loads * prm.n_b_blocks * prm.box_rows * prm.b_row_bytes;
   const int smem_bytes = stages * stage_bytes + 2048 + 1024;
   dim3 grid(ksplit, m_blocks * parts, prm.n_groups);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -268,6 +268,7 @@ class DenoiseEngine:
         for ly in self.layers:
             ly.det = None
         self._csum_ws = ops.channel_sum_ws(max(max(ly.cout, ly.cin) for ly in self.layers), dev)
+        self._csum_ws2 = ops.channel_sum_ws(16, dev)       # the side stream's own scratch (narrow-output bias sums)
 
     def mark_params_dirty(self):
         self._packed_version = None
@@ -482,12 +483,20 @@ class DenoiseEngine:
         if ly.bias is not None and ly.kind != "convT":
             dbias = self.grad_view(ly.bias)
         kw = {}
+        # narrow-OUTPUT 3x3 layers (tail, last SNet layer): pass the operands the other way round so that the narrow dY is
+        # the N operand (vk_wgrad_args.swapped); the bias gradient is then a plain channel sum of dY
+        swap_bias = None
+        if (kind == VK_CONV3X3_S1 and self.dtype == VK_BF16 and ly.cout <= 16 < ly.cin and a.shape[-1] == 16
+                and os.environ.get("VIRNET_B200_NO_WGRAD_SWAP") is None):
+            swap_bias, dbias = dbias, None
+            a, b, m_valid, n_valid = b, a, n_valid, m_valid
+            kw["swapped"] = True
         if self.deterministic:
             key = (tuple(a.shape), tuple(b.shape), kind)
             ent = ly.det
             if ent is None or ent["key"] != key:
                 slices, bias_slots = ops.conv_wgrad_plan(a, b, dtype=self.dtype, kind=kind, m_valid=m_valid,
-                                                         n_valid=n_valid, dbias=dbias)
+                                                         n_valid=n_valid, dbias=dbias, swapped=kw.get("swapped", False))
                 dev = self.flat_params.device
                 ent = ly.det = {"key": key, "slices": slices, "bias_slots": bias_slots,
                                 "partials": torch.empty((slices,) + tuple(ly.ws.shape), device=dev, dtype=torch.float32),
@@ -495,10 +504,12 @@ class DenoiseEngine:
                                                                                 dtype=torch.float32)}
                 self._det_tables = {}
             self._det_ran[id(ly)] = ly
-            kw = dict(partials=ent["partials"], dbias_partials=ent["dbias"])
+            kw.update(partials=ent["partials"], dbias_partials=ent["dbias"])
         ws = self._wg_stream
         if ws is None:
             ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias, **kw)
+            if swap_bias is not None:
+                ops.channel_sum(b, n_valid, swap_bias, dtype=self.dtype, ws=self._csum_ws)
             return
         # weight gradients are leaves of the backward graph: run them on a side stream so their CTAs fill the SMs
         # the persistent dgrad kernels leave idle in their last (partial) round
@@ -508,6 +519,8 @@ class DenoiseEngine:
         ws.wait_event(ev)
         with torch.cuda.stream(ws):
             ops.conv_wgrad(a, b, ly.ws, dtype=self.dtype, kind=kind, m_valid=m_valid, n_valid=n_valid, dbias=dbias, **kw)
+            if swap_bias is not None:
+                ops.channel_sum(b, n_valid, swap_bias, dtype=self.dtype, ws=self._csum_ws2)
 
     def _bucket_done(self, first_layer: _Layer):
         """Every layer from `first_layer` (forward order) to the end of the previous bucket has had its weight-gradient

@@ -56,6 +56,7 @@ class vk_wgrad_args(C.Structure):
         ("dw", C.c_void_p), ("dbias", C.c_void_p),
         ("force_ksplit", C.c_int32), ("force_k_rows", C.c_int32), ("force_stages", C.c_int32),
         ("max_slices", C.c_int32), ("partials", C.c_void_p), ("dbias_partials", C.c_void_p),
+        ("swapped", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

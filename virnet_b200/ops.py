@@ -176,9 +176,11 @@ def conv_igemm(x, w_packed, *, dtype, kind, cout, bias=None, ldo=0, epi=VK_EPI_S
 # ---------------------------------------------------------------------------
 # vk_conv_wgrad
 # ---------------------------------------------------------------------------
-def _wgrad_args(a, b, dw, dtype, kind, m_valid, n_valid, dbias, tune):
+def _wgrad_args(a, b, dw, dtype, kind, m_valid, n_valid, dbias, tune, swapped=False):
     g = _l.vk_wgrad_args()
     g.dtype, g.kind = dtype, kind
+    g.swapped = int(bool(swapped))
+    assert not (swapped and dbias is not None), "swapped operands: the kernel cannot produce the bias gradient"
     g.a, g.n, g.gh, g.gw, g.lda, g.m_valid = _ptr(a), a.shape[0], a.shape[1], a.shape[2], a.shape[3], m_valid
     g.b, g.bh, g.bw, g.ldb, g.n_valid = _ptr(b), b.shape[1], b.shape[2], b.shape[3], n_valid
     g.dw, g.dbias = _ptr(dw), _ptr(dbias)
@@ -192,23 +194,25 @@ def _wgrad_args(a, b, dw, dtype, kind, m_valid, n_valid, dbias, tune):
 WGRAD_MAX_SLICES = 148      # a split-K wave never has more K slices than SMs
 
 
-def conv_wgrad_plan(a, b, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None, max_slices=WGRAD_MAX_SLICES):
+def conv_wgrad_plan(a, b, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None, max_slices=WGRAD_MAX_SLICES,
+                    swapped=False):
     """(K slices, bias slots) vk_conv_wgrad will write in the deterministic layout for these operands."""
-    g = _wgrad_args(a, b, None, dtype, kind, m_valid, n_valid, dbias, tune)
+    g = _wgrad_args(a, b, None, dtype, kind, m_valid, n_valid, dbias, tune, swapped)
     g.max_slices = max_slices
     sl, bs = C.c_int32(0), C.c_int32(0)
     _l.check(_l.load().vk_conv_wgrad_plan(C.byref(g), C.byref(sl), C.byref(bs)), "vk_conv_wgrad_plan")
     return sl.value, bs.value
 
 
-def conv_wgrad(a, b, dw, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None, partials=None, dbias_partials=None):
+def conv_wgrad(a, b, dw, *, dtype, kind, m_valid, n_valid, dbias=None, tune=None, partials=None, dbias_partials=None,
+               swapped=False):
     """a: M operand NHWC (conv: dY; convT: X); b: N operand NHWC (conv: X; convT: dY_up).
     dw: fp32 [taps, m_valid, n_valid] workspace, accumulated into with red.add — or, deterministic form, `partials`
     fp32 [slices, taps, m_valid, n_valid] (+ `dbias_partials` [bias slots, m_valid]) written with plain stores, one slab
     per K slice (sizes from conv_wgrad_plan); wgrad_unpack_batched sums the slabs in order."""
     assert a.is_contiguous() and b.is_contiguous() and dw.is_contiguous() and dw.dtype == torch.float32
     assert a.dtype == TORCH_DTYPE[dtype] and b.dtype == TORCH_DTYPE[dtype]
-    g = _wgrad_args(a, b, dw, dtype, kind, m_valid, n_valid, dbias, tune)
+    g = _wgrad_args(a, b, dw, dtype, kind, m_valid, n_valid, dbias, tune, swapped)
     if partials is not None:
         assert partials.dtype == torch.float32 and partials.is_contiguous() and partials.shape[1:] == dw.shape
         assert dbias is None or (dbias_partials is not None and dbias_partials.dtype == torch.float32)
