@@ -190,6 +190,12 @@ int vk_sft_mlp(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask, con
  * of g * x and g (accumulated: zero them first).  g, x, resid, gx: NHWC `dtype` [n][npix][ld]. */
 int vk_sft_bwd(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx, float* dmul,
                float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, void* stream);
+/* Deterministic form (bit-reproducible training, no atomics): every block stores its partial sums into `ws`
+ * (at least vk_sft_bwd_det_ws_floats(n, npix, c) floats), a second launch adds them in block order. */
+int64_t vk_sft_bwd_det_ws_floats(int32_t n, int32_t npix, int32_t c);
+int vk_sft_bwd_det(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx,
+                   float* dmul, float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, float* ws,
+                   int64_t ws_floats, void* stream);
 
 /* AttLayer MLP backward: parameter gradients are ACCUMULATED into gw1..gba (same shapes as the parameters),
  * d_extra [n][e] += dL/d(raw conditioning values). */
@@ -211,6 +217,10 @@ int vk_sft_mlp_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, c
                        uint32_t sqrt_mask, float alpha, void* stream);
 int vk_sft_mlp_bwd_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra, int32_t n,
                            int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra, void* stream);
+/* Deterministic form: one block per layer walks the samples in order (parameter gradients), one block per sample walks
+ * the layers in order (d_extra); same result up to the summation order, bit-identical run to run. */
+int vk_sft_mlp_bwd_batched_det(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra, int32_t n,
+                               int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra, void* stream);
 uint32_t vk_sizeof_sft_desc(void);
 
 /* ---- SFT modulation with SPATIALLY VARYING conditioning maps (csrc/vk_sft_spatial.cu) ----
@@ -279,6 +289,12 @@ int vk_pack_input_mixed(int32_t dtype, const float* img, int32_t n, int32_t c, i
 int vk_ca_layer_bwd(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1, const float* w2,
                     const float* b2, void* df, float* gw1, float* gb1, float* gw2, float* gb2, int32_t n, int32_t npix,
                     int32_t c, int32_t r, int32_t ld, float alpha, void* stream);
+/* Deterministic form: per-sample parameter-gradient slots in `ws` (at least n * (2 r c + r + c) floats), added in
+ * sample order by a second launch. */
+int vk_ca_layer_bwd_det(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1, const float* w2,
+                        const float* b2, void* df, float* gw1, float* gb1, float* gw2, float* gb2, int32_t n,
+                        int32_t npix, int32_t c, int32_t r, int32_t ld, float alpha, float* ws, int64_t ws_floats,
+                        void* stream);
 
 /* Backward of vk_gap_head: gx NHWC `dtype` [n][hw][ld] = gout[n][c] * head'(outv[n][c]) / hw (0 for c >= C). */
 int vk_gap_head_bwd(int32_t dtype, const float* gout, const float* outv, int32_t n, int32_t c, int32_t hw,
@@ -287,6 +303,10 @@ int vk_gap_head_bwd(int32_t dtype, const float* gout, const float* outv, int32_t
 /* Weight gradient of vk_knet_head, ACCUMULATED into gw [cout][c][9][9]; g NHWC `dtype` [n][oh][ow][ld]. */
 int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c, int32_t h,
                        int32_t wd, int32_t cout, int32_t ld, void* stream);
+/* Deterministic form: per-sample slots in `ws` (at least n * cout * c * 81 floats), added in sample order by a
+ * second launch (no atomics). */
+int vk_knet_head_wgrad_det(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c, int32_t h,
+                           int32_t wd, int32_t cout, int32_t ld, float* ws, int64_t ws_floats, void* stream);
 
 /* F.interpolate(x, scale_factor=sf, mode="nearest") on NCHW fp32 (networks/VIRNet.py:83). */
 int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,

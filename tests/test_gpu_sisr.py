@@ -215,3 +215,65 @@ def test_sisr_cuda_graph_step_matches_eager_step():
     for _ in range(20):
         last = tr_b.step_graph(*batch)[0].item()
     assert last < first
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# deterministic mode of the super-resolution step
+# ------------------------------------------------------------------------------------------------------------------
+def _run_sisr_det(mode, steps, n_feat, n_res, dep_K, precision, n, h, w, sf=4):
+    from virnet_b200.loss.ELBO_simple import sisr_draws
+    from virnet_b200.trainer import SISRTrainer
+    net, _ = make_sr(precision, n_feat=n_feat, n_res=n_res, dep_K=dep_K)
+    net.train()
+    tr = SISRTrainer(net, sf, lr=1e-4, deterministic=True)
+    batch = [t.cuda() for t in _sisr_batch(n, h, w, sf)]
+    torch.manual_seed(11)
+    hist = []
+    for it in range(steps):
+        draws = sisr_draws(batch[2], batch[0], 50.0)
+        fn = tr.step_graph if mode == "graph" else tr.step
+        terms = fn(*batch, lr=1e-4 * (1 + it), draws=draws)
+        hist.append(torch.cat([terms.clone(), tr.grad_norms.clone()]))
+    torch.cuda.synchronize()
+    return torch.stack(hist).cpu(), torch.cat([p.detach().flatten() for p in net.parameters()]).cpu()
+
+
+@pytest.mark.parametrize("n_feat,n_res,dep_K,precision,n,h,w", [((32, 64, 96), 1, 2, "tf32", 3, 16, 20),
+                                                                ((96, 160, 224), 2, 8, "bf16", 4, 48, 48)])
+def test_deterministic_sisr_training_is_bit_reproducible(n_feat, n_res, dep_K, precision, n, h, w):
+    """SISRTrainer(deterministic=True): ordered split-K slabs for the convolutions, the fixed-order forms of the small
+    per-sample kernels (SFT backward, AttLayer MLPs, CALayer, KNet head) and the atomic-free SISR loss make every loss
+    term, gradient norm and parameter bit-identical from run to run, eager or CUDA-graph replayed.  The second case is
+    the shipped x4 width (96/160/224, 8 KNet blocks) on 192x192 HR patches: 9 pixel chunks per sample in vk_sft_bwd_det."""
+    h1, p1 = _run_sisr_det("eager", 3, n_feat, n_res, dep_K, precision, n, h, w)
+    h2, p2 = _run_sisr_det("eager", 3, n_feat, n_res, dep_K, precision, n, h, w)
+    h3, p3 = _run_sisr_det("graph", 3, n_feat, n_res, dep_K, precision, n, h, w)
+    assert torch.isfinite(p1).all() and torch.isfinite(h1).all()
+    assert torch.equal(h1, h2) and torch.equal(p1, p2), "eager runs differ"
+    assert torch.equal(h1, h3) and torch.equal(p1, p3), "graph replay differs from the eager step"
+
+
+def test_deterministic_sisr_gradients_match_the_atomic_path():
+    """The fixed-order forms compute the same gradients as the atomic ones (to fp32 summation-order noise): every
+    parameter of SNet / KNet / RNet and the loss terms, one step at lr = 0 on the same draws."""
+    from virnet_b200.loss.ELBO_simple import sisr_draws
+    from virnet_b200.trainer import SISRTrainer
+    sf, n, h, w = 4, 3, 16, 20
+    batch = [t.cuda() for t in _sisr_batch(n, h, w, sf)]
+    torch.manual_seed(21)
+    draws = sisr_draws(batch[2], batch[0], 50.0)
+    out = []
+    for det in (False, True):
+        net, _ = make_sr("tf32", n_feat=(32, 64, 96), n_res=2, dep_K=3)
+        net.train()
+        tr = SISRTrainer(net, sf, deterministic=det)
+        terms = tr.step(*batch, lr=0.0, draws=draws).clone()
+        eng = tr.engine
+        offs = eng.flat_offsets + [eng.flat_total]
+        grads = {name: eng.flat_grads[offs[i]:offs[i + 1]].clone() for i, (name, _) in enumerate(net.named_parameters())}
+        out.append((terms, grads, tr.grad_norms.clone()))
+    (ta, ga, na), (tb, gb, nb) = out
+    torch.testing.assert_close(ta, tb, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(na, nb, rtol=1e-4, atol=1e-6)
+    for k in ga:
+        assert rel(gb[k], ga[k]) < 1e-4, (k, rel(gb[k], ga[k]))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Times the SISR training step (BASELINE.json configs[4]: train_SISR x4, 64x64 -> 256x256 patches, the
 shipped sisr_x4.json network) on one GPU and prints a per-family breakdown of one step.  Tuning aid.
-usage: sisr_train_bench.py [batch] [precision] [lr_size]"""
+usage: sisr_train_bench.py [batch] [precision] [lr_size] [--graph] [--det]   (--det: SISRTrainer(deterministic=True))"""
 import json
 import sys
 from collections import defaultdict
@@ -30,7 +30,8 @@ im_lr = torch.nn.functional.avg_pool2d(im_hr, sf) + 0.01 * torch.randn(B, 3, lr_
 kinfo_gt = torch.stack([0.5 + 3 * torch.rand(B, device=dev, generator=g), 0.5 + 3 * torch.rand(B, device=dev, generator=g),
                         torch.rand(B, device=dev, generator=g) - 0.5], dim=1)
 nlevel = torch.full((B, 1, 1, 1), (2.55 / 255) ** 2, device=dev)
-tr = SISRTrainer(net, sf)
+DET = "--det" in sys.argv
+tr = SISRTrainer(net, sf, deterministic=DET)
 for _ in range(3):
     tr.step(im_hr, im_lr, kinfo_gt, nlevel)
 torch.cuda.synchronize()
@@ -42,7 +43,8 @@ for _ in range(iters):
 e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / iters
-print(json.dumps(dict(workload=f"train_SISR x{sf} {lr_sz}->{lr_sz * sf} b={B} {prec}", ms_per_step=round(ms, 3),
+print(json.dumps(dict(workload=f"train_SISR x{sf} {lr_sz}->{lr_sz * sf} b={B} {prec}" + (" deterministic" if DET else ""),
+                      ms_per_step=round(ms, 3),
                       patches_per_s=round(B / ms * 1e3, 1), loss=terms[0].item())))
 if "--graph" in sys.argv:
     for _ in range(3):

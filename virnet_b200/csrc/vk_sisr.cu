@@ -267,7 +267,7 @@ template <typename DT>
 __global__ void __launch_bounds__(256)
 sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* __restrict__ mul,
                const DT* __restrict__ resid, DT* __restrict__ gx, float* __restrict__ dmul, float* __restrict__ dadd,
-               int npix, int C, int ld, int pix_per_block) {
+               int npix, int C, int ld, int pix_per_block, float* __restrict__ slots) {
   constexpr int V = SftVec<DT>::kN;
   extern __shared__ float sm[];            // [lanes][ld] x 2
   const int n = blockIdx.y;
@@ -313,8 +313,47 @@ sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* 
   for (int c = threadIdx.x; c < C; c += 256) {
     float tm = 0.f, ta = 0.f;
     for (int l = 0; l < lanes; ++l) tm += pm[l * ld + c], ta += pa[l * ld + c];
-    atomicAdd(dmul + n * C + c, tm);
-    atomicAdd(dadd + n * C + c, ta);
+    if (slots != nullptr) {
+      // deterministic form: slots [pixel chunk][mul | add][n][C], added in chunk order by slot_sum_kernel
+      const long long NC = static_cast<long long>(gridDim.y) * C;
+      slots[(blockIdx.x * 2ll + 0) * NC + n * C + c] = tm;
+      slots[(blockIdx.x * 2ll + 1) * NC + n * C + c] = ta;
+    } else {
+      atomicAdd(dmul + n * C + c, tm);
+      atomicAdd(dadd + n * C + c, ta);
+    }
+  }
+}
+
+// Ordered reduction of per-block / per-sample partial sums (the deterministic forms of the kernels in this file):
+//   seg.out[i] += sum_{s < nslots} ws[s * stride + seg.off + i],  s ascending;  blockIdx.y = segment.
+struct SlotSegs {
+  float* out[4];
+  int off[4];
+  int count[4];
+};
+__global__ void __launch_bounds__(256) slot_sum_kernel(const float* __restrict__ ws, int nslots, long long stride, SlotSegs segs) {
+  // block = 8 warps x 32 consecutive elements: warp w adds slots w, w + 8, ... in that order (coalesced rows), then the
+  // eight warp sums are added in warp order — a fixed summation tree
+  __shared__ float part[8][32];
+  const int k = blockIdx.y, w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  float* out = segs.out[k];
+  const float* src = ws + segs.off[k];
+  const int count = segs.count[k];
+  for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {
+    const int i = base + l;
+    float a = 0.f;
+    if (i < count)
+      for (int sl = w; sl < nslots; sl += 8) a += src[sl * stride + i];
+    part[w][l] = a;
+    __syncthreads();
+    if (w == 0 && i < count) {
+      float t = part[0][l];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) t += part[j][l];
+      out[i] += t;
+    }
+    __syncthreads();
   }
 }
 
@@ -329,7 +368,8 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
                                    const float* __restrict__ dmul, const float* __restrict__ dadd, float* __restrict__ gw1,
                                    float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2,
                                    float* __restrict__ gwm, float* __restrict__ gbm, float* __restrict__ gwa,
-                                   float* __restrict__ gba, float* __restrict__ d_extra) {
+                                   float* __restrict__ gba, float* __restrict__ d_extra, bool do_params = true,
+                                   bool do_extra = true) {
   extern __shared__ float sm[];   // e[E] f1p[C1] f1[C1] f2p[C2] f2[C2] gmp[C] gad[C] gf2[C2] gf1[C1]
   float* e = sm;
   float* f1p = e + E;
@@ -365,8 +405,10 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
       const float mu = 1.f / (1.f + expf(-a));
       const float g1 = dmul[n * C + c] * mu * (1.f - mu), g2 = dadd[n * C + c];
       gmp[c] = g1, gad[c] = g2;
-      atomicAdd(gbm + c, g1), atomicAdd(gba + c, g2);
-      for (int k = 0; k < C2; ++k) atomicAdd(gwm + c * C2 + k, g1 * f2[k]), atomicAdd(gwa + c * C2 + k, g2 * f2[k]);
+      if (do_params) {
+        atomicAdd(gbm + c, g1), atomicAdd(gba + c, g2);
+        for (int k = 0; k < C2; ++k) atomicAdd(gwm + c * C2 + k, g1 * f2[k]), atomicAdd(gwa + c * C2 + k, g2 * f2[k]);
+      }
     }
     __syncthreads();
     for (int k = t; k < C2; k += T) {
@@ -374,8 +416,10 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
       for (int c = 0; c < C; ++c) a = fmaf(wm[c * C2 + k], gmp[c], fmaf(wa[c * C2 + k], gad[c], a));
       a *= f2p[k] > 0.f ? 1.f : alpha;
       gf2[k] = a;
-      atomicAdd(gb2 + k, a);
-      for (int j = 0; j < C1; ++j) atomicAdd(gw2 + k * C1 + j, a * f1[j]);
+      if (do_params) {
+        atomicAdd(gb2 + k, a);
+        for (int j = 0; j < C1; ++j) atomicAdd(gw2 + k * C1 + j, a * f1[j]);
+      }
     }
     __syncthreads();
     for (int j = t; j < C1; j += T) {
@@ -383,11 +427,13 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
       for (int k = 0; k < C2; ++k) a = fmaf(w2[k * C1 + j], gf2[k], a);
       a *= f1p[j] > 0.f ? 1.f : alpha;
       gf1[j] = a;
-      atomicAdd(gb1 + j, a);
-      for (int i = 0; i < E; ++i) atomicAdd(gw1 + j * E + i, a * e[i]);
+      if (do_params) {
+        atomicAdd(gb1 + j, a);
+        for (int i = 0; i < E; ++i) atomicAdd(gw1 + j * E + i, a * e[i]);
+      }
     }
     __syncthreads();
-    if (t < E) {
+    if (do_extra && t < E) {
       float a = 0.f;
       for (int j = 0; j < C1; ++j) a = fmaf(w1[j * E + t], gf1[j], a);
       if (sqrt_mask & (1u << t)) a *= 0.5f / fmaxf(e[t], 1e-20f);
@@ -416,6 +462,25 @@ __global__ void sft_mlp_bwd_batched_kernel(const SftDesc* __restrict__ descs, co
                    d.dmul, d.dadd, d.gw1, d.gb1, d.gw2, d.gb2, d.gwm, d.gbm, d.gwa, d.gba, d_extra);
 }
 
+// Deterministic form: every address is accumulated by ONE thread of ONE block in a fixed order (atomics issued by one
+// thread to one address are performed in program order).  Blocks [0, n_layers): block l walks the samples in order and
+// accumulates the parameter gradients of layer l.  Blocks [n_layers, n_layers + N): block n walks the layers in order
+// and accumulates d_extra[n][:].  The forward of the small MLP is recomputed by both.
+__global__ void sft_mlp_bwd_batched_det_kernel(const SftDesc* __restrict__ descs, int n_layers,
+                                               const float* __restrict__ extra, int N, int E, unsigned sqrt_mask,
+                                               float alpha, float* __restrict__ d_extra) {
+  const bool params = int(blockIdx.x) < n_layers;
+  const int fixed = params ? int(blockIdx.x) : int(blockIdx.x) - n_layers;
+  const int steps = params ? N : n_layers;
+  for (int it = 0; it < steps; ++it) {
+    const SftDesc d = descs[params ? fixed : it];
+    sft_mlp_bwd_body(params ? it : fixed, extra, E, sqrt_mask, d.w1, d.b1, d.c1, d.w2, d.b2, d.c2, d.wm, d.bm, d.wa, d.ba,
+                     d.c, alpha, d.dmul, d.dadd, d.gw1, d.gb1, d.gw2, d.gb2, d.gwm, d.gbm, d.gwa, d.gba, d_extra, params,
+                     !params);
+    __syncthreads();
+  }
+}
+
 // CALayer + skip backward (autograd of out = f * s(mean f) + skip), one CTA per sample:
 //   d_f = g * s + dy / npix,  the skip gradient is g itself;  parameter gradients by atomicAdd over samples.
 template <typename DT>
@@ -423,9 +488,20 @@ __global__ void ca_layer_bwd_kernel(const DT* __restrict__ g, const DT* __restri
                                     const float* __restrict__ b1, const float* __restrict__ w2,
                                     const float* __restrict__ b2, DT* __restrict__ df, float* __restrict__ gw1,
                                     float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2, int npix,
-                                    int C, int R, int ld, float alpha) {
+                                    int C, int R, int ld, float alpha, float* __restrict__ slots) {
   extern __shared__ float sm[];   // part_y[L][C] part_d[L][C] y[C] ds[C] s[C] gsp[C] dy[C] zp[R] z[R] gzp[R]
   const int n = blockIdx.x;
+  // deterministic form: sample n stores its parameter gradients into its own slot [w1 | b1 | w2 | b2] (plain stores),
+  // slot_sum_kernel adds the slots in sample order
+  const bool plain = slots != nullptr;
+  if (plain) {
+    float* sl = slots + static_cast<long long>(n) * (2 * R * C + R + C);
+    gw1 = sl, gb1 = gw1 + R * C, gw2 = gb1 + R, gb2 = gw2 + C * R;
+  }
+  auto accum = [plain](float* p, float v) {
+    if (plain) *p = v;
+    else atomicAdd(p, v);
+  };
   const long long base = static_cast<long long>(n) * npix * ld;
   const int lanes = blockDim.x / C;
   const int c = threadIdx.x % C, pl = threadIdx.x / C;
@@ -467,8 +543,8 @@ __global__ void ca_layer_bwd_kernel(const DT* __restrict__ g, const DT* __restri
     s[threadIdx.x] = sv;
     const float gs = ds[threadIdx.x] * sv * (1.f - sv);
     gsp[threadIdx.x] = gs;
-    atomicAdd(gb2 + threadIdx.x, gs);
-    for (int k = 0; k < R; ++k) atomicAdd(gw2 + threadIdx.x * R + k, gs * z[k]);
+    accum(gb2 + threadIdx.x, gs);
+    for (int k = 0; k < R; ++k) accum(gw2 + threadIdx.x * R + k, gs * z[k]);
   }
   __syncthreads();
   if (threadIdx.x < R) {
@@ -476,8 +552,8 @@ __global__ void ca_layer_bwd_kernel(const DT* __restrict__ g, const DT* __restri
     for (int cc = 0; cc < C; ++cc) a = fmaf(w2[cc * R + threadIdx.x], gsp[cc], a);
     a *= zp[threadIdx.x] > 0.f ? 1.f : alpha;
     gzp[threadIdx.x] = a;
-    atomicAdd(gb1 + threadIdx.x, a);
-    for (int cc = 0; cc < C; ++cc) atomicAdd(gw1 + threadIdx.x * C + cc, a * y[cc]);
+    accum(gb1 + threadIdx.x, a);
+    for (int cc = 0; cc < C; ++cc) accum(gw1 + threadIdx.x * C + cc, a * y[cc]);
   }
   __syncthreads();
   if (threadIdx.x < C) {
@@ -516,16 +592,18 @@ __global__ void gap_head_bwd_kernel(const float* __restrict__ gout, const float*
   }
 }
 
-// Weight gradient of the KNet head (9x9, stride 4, pad 4): one thread per (weight element, sample), atomicAdd over samples.
+// Weight gradient of the KNet head (9x9, stride 4, pad 4): one thread per (weight element, sample), atomicAdd over samples;
+// deterministic form: the thread stores its sum into the sample's slot, slot_sum_kernel adds the slots in sample order.
 template <typename DT>
 __global__ void knet_head_wgrad_kernel(const float* __restrict__ x, const DT* __restrict__ g, float* __restrict__ gw,
-                                       int N, int C, int H, int W, int OH, int OW, int cout, int ld) {
+                                       int N, int C, int H, int W, int OH, int OW, int cout, int ld,
+                                       float* __restrict__ slots) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cout * C * 81) return;
   const int s = i % 9, r = (i / 9) % 9, c = (i / 81) % C, co = i / (81 * C);
   float acc = 0.f;
+  const int n = blockIdx.y;
   {
-    const int n = blockIdx.y;
     for (int oy = 0; oy < OH; ++oy) {
       const int iy = oy * 4 - 4 + r;
       if (iy < 0 || iy >= H) continue;
@@ -537,7 +615,8 @@ __global__ void knet_head_wgrad_kernel(const float* __restrict__ x, const DT* __
       }
     }
   }
-  atomicAdd(gw + i, acc);
+  if (slots != nullptr) slots[static_cast<long long>(n) * (cout * C * 81) + i] = acc;
+  else atomicAdd(gw + i, acc);
 }
 
 }  // namespace vk
@@ -624,6 +703,16 @@ extern "C" int vk_sft_mlp_bwd_batched(const void* descs_dev, int32_t n_layers, i
   VK_LAUNCHED();
 }
 
+extern "C" int vk_sft_mlp_bwd_batched_det(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra,
+                                          int32_t n, int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra,
+                                          void* stream) {
+  if (!descs_dev || !extra || !d_extra || n_layers <= 0 || n <= 0 || e <= 0 || e > 32 || max_c <= 0) return VK_E_BADARG;
+  const size_t smem = size_t(e + 5 * max_c) * sizeof(float);
+  sft_mlp_bwd_batched_det_kernel<<<n_layers + n, 128, smem, VK_ST(stream)>>>(reinterpret_cast<const SftDesc*>(descs_dev),
+                                                                            n_layers, extra, n, e, sqrt_mask, alpha, d_extra);
+  VK_LAUNCHED();
+}
+
 extern "C" uint32_t vk_sizeof_sft_desc(void) { return uint32_t(sizeof(SftDesc)); }
 
 extern "C" int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_t c, int32_t h, int32_t w, int32_t sf,
@@ -635,27 +724,66 @@ extern "C" int vk_upsample_nearest(const float* x, float* out, int32_t n, int32_
   VK_LAUNCHED();
 }
 
-extern "C" int vk_sft_bwd(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx,
-                          float* dmul, float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, void* stream) {
+namespace {
+constexpr int kSftBwdPixPerBlock = 512;
+
+// out[k][i] += the `nslots` partials of segment k, in slot order (second launch of the deterministic forms)
+int launch_slot_sum(const float* ws, int nslots, long long stride, const SlotSegs& segs, int nseg, cudaStream_t st) {
+  int most = 0;
+  for (int k = 0; k < nseg; ++k) most = std::max(most, segs.count[k]);
+  slot_sum_kernel<<<dim3((most + 31) / 32, nseg), 256, 0, st>>>(ws, nslots, stride, segs);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+int sft_bwd_launch(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx,
+                   float* dmul, float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, bool det, float* ws,
+                   int64_t ws_floats, void* stream) {
   if (!g || !x || !mul || !gx || !dmul || !dadd || n <= 0 || npix <= 0 || c <= 0 || c > ld) return VK_E_BADARG;
   const int vec = dtype == VK_BF16 ? 8 : 4;
   if (ld % vec != 0 || ld / vec > 256) return VK_E_BADARG;
-  const int ppb = 512;
+  const int ppb = kSftBwdPixPerBlock;
   const size_t smem = size_t(2) * (256 / (ld / vec)) * ld * sizeof(float);
   if (smem > 48 * 1024) return VK_E_BADARG;
   dim3 grid((npix + ppb - 1) / ppb, n);
+  const long long nc = static_cast<long long>(n) * c;
+  if (det && (!ws || ws_floats < static_cast<long long>(grid.x) * 2 * nc)) return VK_E_BADARG;
+  float* slots = det ? ws : nullptr;
   if (dtype == VK_BF16)
     sft_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, VK_ST(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), mul,
-        reinterpret_cast<const __nv_bfloat16*>(resid), reinterpret_cast<__nv_bfloat16*>(gx), dmul, dadd, npix, c, ld, ppb);
+        reinterpret_cast<const __nv_bfloat16*>(resid), reinterpret_cast<__nv_bfloat16*>(gx), dmul, dadd, npix, c, ld, ppb,
+        slots);
   else if (dtype == VK_TF32)
     sft_bwd_kernel<float><<<grid, 256, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(g),
                                                            reinterpret_cast<const float*>(x), mul,
                                                            reinterpret_cast<const float*>(resid),
-                                                           reinterpret_cast<float*>(gx), dmul, dadd, npix, c, ld, ppb);
+                                                           reinterpret_cast<float*>(gx), dmul, dadd, npix, c, ld, ppb, slots);
   else
     return VK_E_BADARG;
-  VK_LAUNCHED();
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (!det) return int(cudaGetLastError());
+  SlotSegs segs{};
+  segs.out[0] = dmul, segs.off[0] = 0, segs.count[0] = int(nc);
+  segs.out[1] = dadd, segs.off[1] = int(nc), segs.count[1] = int(nc);
+  return launch_slot_sum(ws, int(grid.x), 2 * nc, segs, 2, VK_ST(stream));
+}
+}  // namespace
+
+extern "C" int vk_sft_bwd(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx,
+                          float* dmul, float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, void* stream) {
+  return sft_bwd_launch(dtype, g, x, mul, resid, gx, dmul, dadd, n, npix, c, ld, false, nullptr, 0, stream);
+}
+
+extern "C" int64_t vk_sft_bwd_det_ws_floats(int32_t n, int32_t npix, int32_t c) {
+  if (n <= 0 || npix <= 0 || c <= 0) return -1;
+  return static_cast<int64_t>((npix + kSftBwdPixPerBlock - 1) / kSftBwdPixPerBlock) * 2 * n * c;
+}
+
+extern "C" int vk_sft_bwd_det(int32_t dtype, const void* g, const void* x, const float* mul, const void* resid, void* gx,
+                              float* dmul, float* dadd, int32_t n, int32_t npix, int32_t c, int32_t ld, float* ws,
+                              int64_t ws_floats, void* stream) {
+  return sft_bwd_launch(dtype, g, x, mul, resid, gx, dmul, dadd, n, npix, c, ld, true, ws, ws_floats, stream);
 }
 
 extern "C" int vk_sft_mlp_bwd(const float* extra, int32_t n, int32_t e, uint32_t sqrt_mask, const float* w1,
@@ -673,26 +801,54 @@ extern "C" int vk_sft_mlp_bwd(const float* extra, int32_t n, int32_t e, uint32_t
   VK_LAUNCHED();
 }
 
-extern "C" int vk_ca_layer_bwd(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1,
-                               const float* w2, const float* b2, void* df, float* gw1, float* gb1, float* gw2,
-                               float* gb2, int32_t n, int32_t npix, int32_t c, int32_t r, int32_t ld, float alpha,
-                               void* stream) {
+namespace {
+int ca_layer_bwd_launch(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1, const float* w2,
+                        const float* b2, void* df, float* gw1, float* gb1, float* gw2, float* gb2, int32_t n, int32_t npix,
+                        int32_t c, int32_t r, int32_t ld, float alpha, bool det, float* ws, int64_t ws_floats,
+                        void* stream) {
   if (!g || !f || !w1 || !b1 || !w2 || !b2 || !df || !gw1 || !gb1 || !gw2 || !gb2) return VK_E_BADARG;
   if (n <= 0 || npix <= 0 || c <= 0 || r <= 0 || c > ld || c > 256) return VK_E_BADARG;
+  const int slot = 2 * r * c + r + c;
+  if (det && (!ws || ws_floats < static_cast<int64_t>(n) * slot)) return VK_E_BADARG;
+  float* slots = det ? ws : nullptr;
   const int threads = std::max(c, 256 / c * c);
   const size_t smem = (size_t(2 * (threads / c)) * c + 5 * c + 3 * r) * sizeof(float);
   if (dtype == VK_BF16)
     ca_layer_bwd_kernel<__nv_bfloat16><<<n, threads, smem, VK_ST(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(f), w1, b1, w2, b2,
-        reinterpret_cast<__nv_bfloat16*>(df), gw1, gb1, gw2, gb2, npix, c, r, ld, alpha);
+        reinterpret_cast<__nv_bfloat16*>(df), gw1, gb1, gw2, gb2, npix, c, r, ld, alpha, slots);
   else if (dtype == VK_TF32)
     ca_layer_bwd_kernel<float><<<n, threads, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(g),
                                                                   reinterpret_cast<const float*>(f), w1, b1, w2, b2,
                                                                   reinterpret_cast<float*>(df), gw1, gb1, gw2, gb2,
-                                                                  npix, c, r, ld, alpha);
+                                                                  npix, c, r, ld, alpha, slots);
   else
     return VK_E_BADARG;
-  VK_LAUNCHED();
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (!det) return int(cudaGetLastError());
+  SlotSegs segs{};                     // slot layout of ca_layer_bwd_kernel: [w1 | b1 | w2 | b2]
+  segs.out[0] = gw1, segs.off[0] = 0, segs.count[0] = r * c;
+  segs.out[1] = gb1, segs.off[1] = r * c, segs.count[1] = r;
+  segs.out[2] = gw2, segs.off[2] = r * c + r, segs.count[2] = c * r;
+  segs.out[3] = gb2, segs.off[3] = 2 * r * c + r, segs.count[3] = c;
+  return launch_slot_sum(ws, n, slot, segs, 4, VK_ST(stream));
+}
+}  // namespace
+
+extern "C" int vk_ca_layer_bwd(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1,
+                               const float* w2, const float* b2, void* df, float* gw1, float* gb1, float* gw2,
+                               float* gb2, int32_t n, int32_t npix, int32_t c, int32_t r, int32_t ld, float alpha,
+                               void* stream) {
+  return ca_layer_bwd_launch(dtype, g, f, w1, b1, w2, b2, df, gw1, gb1, gw2, gb2, n, npix, c, r, ld, alpha, false, nullptr,
+                             0, stream);
+}
+
+extern "C" int vk_ca_layer_bwd_det(int32_t dtype, const void* g, const void* f, const float* w1, const float* b1,
+                                   const float* w2, const float* b2, void* df, float* gw1, float* gb1, float* gw2,
+                                   float* gb2, int32_t n, int32_t npix, int32_t c, int32_t r, int32_t ld, float alpha,
+                                   float* ws, int64_t ws_floats, void* stream) {
+  return ca_layer_bwd_launch(dtype, g, f, w1, b1, w2, b2, df, gw1, gb1, gw2, gb2, n, npix, c, r, ld, alpha, true, ws,
+                             ws_floats, stream);
 }
 
 extern "C" int vk_gap_head_bwd(int32_t dtype, const float* gout, const float* outv, int32_t n, int32_t c, int32_t hw,
@@ -713,18 +869,38 @@ extern "C" int vk_gap_head_bwd(int32_t dtype, const float* gout, const float* ou
   VK_LAUNCHED();
 }
 
-extern "C" int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c,
-                                  int32_t h, int32_t wd, int32_t cout, int32_t ld, void* stream) {
+namespace {
+int knet_head_wgrad_launch(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c, int32_t h,
+                           int32_t wd, int32_t cout, int32_t ld, bool det, float* ws, int64_t ws_floats, void* stream) {
   if (!x || !g || !gw || n <= 0 || c <= 0 || h <= 0 || wd <= 0 || cout <= 0 || cout > ld) return VK_E_BADARG;
   const int oh = (h - 1) / 4 + 1, ow = (wd - 1) / 4 + 1;
   const int total = cout * c * 81;
+  if (det && (!ws || ws_floats < static_cast<int64_t>(n) * total)) return VK_E_BADARG;
+  float* slots = det ? ws : nullptr;
+  const dim3 grid((total + 127) / 128, n);
   if (dtype == VK_BF16)
-    knet_head_wgrad_kernel<__nv_bfloat16><<<dim3((total + 127) / 128, n), 128, 0, VK_ST(stream)>>>(
-        x, reinterpret_cast<const __nv_bfloat16*>(g), gw, n, c, h, wd, oh, ow, cout, ld);
+    knet_head_wgrad_kernel<__nv_bfloat16><<<grid, 128, 0, VK_ST(stream)>>>(
+        x, reinterpret_cast<const __nv_bfloat16*>(g), gw, n, c, h, wd, oh, ow, cout, ld, slots);
   else if (dtype == VK_TF32)
-    knet_head_wgrad_kernel<float><<<dim3((total + 127) / 128, n), 128, 0, VK_ST(stream)>>>(x, reinterpret_cast<const float*>(g),
-                                                                                gw, n, c, h, wd, oh, ow, cout, ld);
+    knet_head_wgrad_kernel<float><<<grid, 128, 0, VK_ST(stream)>>>(x, reinterpret_cast<const float*>(g), gw, n, c, h, wd, oh,
+                                                                 ow, cout, ld, slots);
   else
     return VK_E_BADARG;
-  VK_LAUNCHED();
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (!det) return int(cudaGetLastError());
+  SlotSegs segs{};
+  segs.out[0] = gw, segs.off[0] = 0, segs.count[0] = total;
+  return launch_slot_sum(ws, n, total, segs, 1, VK_ST(stream));
+}
+}  // namespace
+
+extern "C" int vk_knet_head_wgrad(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c,
+                                  int32_t h, int32_t wd, int32_t cout, int32_t ld, void* stream) {
+  return knet_head_wgrad_launch(dtype, x, g, gw, n, c, h, wd, cout, ld, false, nullptr, 0, stream);
+}
+
+extern "C" int vk_knet_head_wgrad_det(int32_t dtype, const float* x, const void* g, float* gw, int32_t n, int32_t c,
+                                      int32_t h, int32_t wd, int32_t cout, int32_t ld, float* ws, int64_t ws_floats,
+                                      void* stream) {
+  return knet_head_wgrad_launch(dtype, x, g, gw, n, c, h, wd, cout, ld, true, ws, ws_floats, stream);
 }

@@ -228,9 +228,11 @@ sisr_plane_gemm_kernel(const float* __restrict__ A, long long a_plane, int a_rs,
   }
 }
 
+// Every reduction of this loss goes through per-block slots that a later step adds in a fixed order: no atomics, so the
+// terms and all gradients are bit-identical run to run.
 // ---- 5: likelihood residual (ELBO_simple.py:58): O -> gO in place, per-sample sum of squares ----
 __global__ void sisr_residual_kernel(float* __restrict__ O, const float* __restrict__ x, const float* __restrict__ sigma_est,
-                                     float alpha0, int per_sample, float inv_count, double* __restrict__ ssq) {
+                                     float alpha0, int per_sample, float inv_count, double* __restrict__ ssq_part) {
   __shared__ double red[32];
   const int n = blockIdx.y;
   const float coef = (alpha0 - 1.f) / (sigma_est[n] * alpha0) * inv_count;
@@ -247,14 +249,14 @@ __global__ void sisr_residual_kernel(float* __restrict__ O, const float* __restr
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < int(blockDim.x >> 5); ++i) t += red[i];
-    atomicAdd(ssq + n, t);
+    ssq_part[n * gridDim.x + blockIdx.x] = t;            // one slot per block, summed in block order by step 11
   }
 }
 
 // ---- 9: d_mu = Gaussian-KL gradient + reflect-fold of the padded blur gradient; sum (mu - hr)^2 ----
 __global__ void sisr_mu_grad_kernel(const float* __restrict__ mu, const float* __restrict__ hr,
                                     const float* __restrict__ gpad, float* __restrict__ d_mu, int H, int W, int pad,
-                                    float kl_coef, long long total, double* __restrict__ sq_acc) {
+                                    float kl_coef, long long total, double* __restrict__ sq_part) {
   __shared__ double red[32];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   double s = 0.0;
@@ -284,14 +286,15 @@ __global__ void sisr_mu_grad_kernel(const float* __restrict__ mu, const float* _
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < int(blockDim.x >> 5); ++i) t += red[i];
-    atomicAdd(sq_acc, t);
+    sq_part[blockIdx.x] = t;
   }
 }
 
-// ---- 10: gradient w.r.t. the blur kernel: gk[n][i][j] += sum over a 32x32 tile of gB * zz_pad(y+i, x+j) ----
+// ---- 10: gradient w.r.t. the blur kernel, one partial per (plane, 32x32 tile):
+//          gk_part[n][slot][i][j] = sum over the tile of gB * zz_pad(y+i, x+j),  slot = (channel, tile row, tile column) ----
 __global__ void __launch_bounds__(256)
 sisr_kernel_wgrad_kernel(const float* __restrict__ mu, const float* __restrict__ noise, float nscale,
-                         const float* __restrict__ gB, float* __restrict__ gk, int C, int H, int W, int K) {
+                         const float* __restrict__ gB, float* __restrict__ gk_part, int C, int H, int W, int K) {
   extern __shared__ float sm[];
   const int TW = kBlurTile + K - 1, TP = TW + 1;
   float* tile = sm;                          // [TW][TP] zz with halo
@@ -316,6 +319,8 @@ sisr_kernel_wgrad_kernel(const float* __restrict__ mu, const float* __restrict__
   // a thread accumulates two horizontally adjacent taps (i, 2jj) and (i, 2jj + 1): they read the same staged row
   // shifted by one, so a step is 2 shared loads (one broadcast gradient, one value) for 2 FMAs
   const int KK = K * K, KH = (K + 1) / 2;
+  const int tiles_per_plane = gridDim.x * gridDim.y;
+  float* gk = gk_part + (static_cast<long long>(p) * tiles_per_plane + blockIdx.y * gridDim.x + blockIdx.x) * KK;   // p = n * C + channel
   for (int w = threadIdx.x; w < K * KH; w += 256) {
     const int i = w / KH, j = (w - i * KH) * 2;
     float acc0 = 0.f, acc1 = 0.f;
@@ -331,21 +336,33 @@ sisr_kernel_wgrad_kernel(const float* __restrict__ mu, const float* __restrict__
         t0 = t1;
       }
     }
-    atomicAdd(gk + n * KK + i * K + j, acc0);
-    if (j + 1 < K) atomicAdd(gk + n * KK + i * K + j + 1, acc1);
+    gk[i * K + j] = acc0;
+    if (j + 1 < K) gk[i * K + j + 1] = acc1;
+  }
+}
+
+// ---- 10b: gk[n][t] = sum of the `slots` partials of sample n, in slot order ----
+__global__ void sisr_kernel_wgrad_reduce_kernel(const float* __restrict__ gk_part, float* __restrict__ gk, int slots, int KK) {
+  const int n = blockIdx.x;
+  const float* src = gk_part + static_cast<long long>(n) * slots * KK;
+  for (int t = threadIdx.x; t < KK; t += blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < slots; ++s) a += src[static_cast<long long>(s) * KK + t];
+    gk[n * KK + t] = a;
   }
 }
 
 // ---- 11: backward of kernel synthesis + all per-sample scalar terms ----
-// acc (fp64): [0] sum_n lh_n, [1] sum (mu-hr)^2 (written by mu_grad), [2] sum_n kl_snet_n, [3..5] sum_n kl_k{0,1,2}_n
+// per (fp64) [n][5]: lh_n, kl_snet_n, kl_k{0,1,2}_n — summed over n in order by step 12
 __global__ void sisr_kernel_bwd_kernel(const float* __restrict__ kernel, const float* __restrict__ gk,
                                        const float* __restrict__ aux, const float* __restrict__ kinfo,
                                        const float* __restrict__ kinfo_gt, const float* __restrict__ gamma_draw,
                                        const float* __restrict__ sigma_est, const float* __restrict__ prior_mean,
-                                       const float* __restrict__ prior_logmean, const double* __restrict__ ssq, int N,
+                                       const float* __restrict__ prior_logmean, const double* __restrict__ ssq_part,
+                                       int ssq_slots, int N,
                                        int K, float center, float kappa0, float r2, float pk0, float pk1, float alpha0,
                                        float digamma_am1, float lr_per_sample, float* __restrict__ d_kinfo,
-                                       float* __restrict__ d_sigma, double* __restrict__ acc) {
+                                       float* __restrict__ d_sigma, double* __restrict__ per) {
   __shared__ float red[4][32];
   const int n = blockIdx.x, KK = K * K;
   const float* kp = kernel + n * KK;
@@ -392,22 +409,39 @@ __global__ void sisr_kernel_bwd_kernel(const float* __restrict__ kernel, const f
   d_kinfo[n * 3 + 0] = g_v1 * kappa0 / gamma_draw[n * 2 + 0] + kscale * (kappa0 - 1.f) * (1.f / k0 - t0 / (k0 * k0));
   d_kinfo[n * 3 + 1] = g_v2 * kappa0 / gamma_draw[n * 2 + 1] + kscale * (kappa0 - 1.f) * (1.f / k1 - t1 / (k1 * k1));
   d_kinfo[n * 3 + 2] = g_rho + kscale * pk0 * (k2 - t2) / r2;
-  atomicAdd(acc + 3, double((kappa0 - 1.f) * ((t0 / k0 - 1.f) + (logf(kappa0 * k0) - logf(kappa0 * t0)))));
-  atomicAdd(acc + 4, double((kappa0 - 1.f) * ((t1 / k1 - 1.f) + (logf(kappa0 * k1) - logf(kappa0 * t1)))));
-  atomicAdd(acc + 5, double((k2 - t2) * (k2 - t2)));
+  per[n * 5 + 2] = double((kappa0 - 1.f) * ((t0 / k0 - 1.f) + (logf(kappa0 * k0) - logf(kappa0 * t0))));
+  per[n * 5 + 3] = double((kappa0 - 1.f) * ((t1 / k1 - 1.f) + (logf(kappa0 * k1) - logf(kappa0 * t1))));
+  per[n * 5 + 4] = double((k2 - t2) * (k2 - t2));
   // noise variance: likelihood + inverse-Gamma KL (ELBO_simple.py:113-115, :58)
   const float beta = sigma_est[n] * alpha0, am1 = alpha0 - 1.f;
   const float b0m = prior_mean[n] * alpha0, lb0m = logf(alpha0) + prior_logmean[n];
-  const float msq = float(ssq[n] / double(lr_per_sample));
-  atomicAdd(acc + 0, double(0.9189385332046727f + 0.5f * (logf(beta) - digamma_am1) + 0.5f * am1 / beta * msq));
-  atomicAdd(acc + 2, double(am1 * ((b0m / beta - 1.f) + (logf(beta) - lb0m))));
+  double ssq = 0.0;
+  for (int i = 0; i < ssq_slots; ++i) ssq += ssq_part[n * ssq_slots + i];
+  const float msq = float(ssq / double(lr_per_sample));
+  per[n * 5 + 0] = double(0.9189385332046727f + 0.5f * (logf(beta) - digamma_am1) + 0.5f * am1 / beta * msq);
+  per[n * 5 + 1] = double(am1 * ((b0m / beta - 1.f) + (logf(beta) - lb0m)));
   const float dbeta = 0.5f / beta - 0.5f * am1 * msq / (beta * beta) + am1 * (1.f / beta - b0m / (beta * beta));
   d_sigma[n] = alpha0 * dbeta * invN;
 }
 
 // ---- 12: terms = [loss, lh, kl_rnet, kl_snet, kl_knet, kl_knet0, kl_knet1, kl_knet2] ----
-__global__ void sisr_finalize_kernel(const double* __restrict__ acc, int N, double hr_count, float eps2, float r2,
-                                     float pk0, float pk1, float* __restrict__ terms) {
+// one block of 256 threads: thread t adds the (mu - hr)^2 partials t, t + 256, ... in order, then thread 0 adds the 256
+// sums and the per-sample scalars in index order
+__global__ void sisr_finalize_kernel(const double* __restrict__ per, const double* __restrict__ sq_part, int sq_slots,
+                                     int N, double hr_count, float eps2, float r2, float pk0, float pk1,
+                                     float* __restrict__ terms) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < sq_slots; i += 256) s += sq_part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < 256; ++i) acc[1] += red[i];
+  for (int n = 0; n < N; ++n) {
+    acc[0] += per[n * 5 + 0], acc[2] += per[n * 5 + 1];
+    acc[3] += per[n * 5 + 2], acc[4] += per[n * 5 + 3], acc[5] += per[n * 5 + 4];
+  }
   const double lh = acc[0] / N, kl_r = 0.5 * acc[1] / (double(eps2) * hr_count), kl_s = acc[2] / N;
   const double k0 = acc[3] / N, k1 = acc[4] / N, k2 = 0.5 * acc[5] / (double(r2) * N) * pk0;
   const double kl_k = (k0 + k1 + k2) / 3.0 * pk1;
@@ -431,9 +465,12 @@ __global__ void sisr_add_noise_kernel(const float* __restrict__ blur, const floa
 using namespace vk;
 
 namespace {
+constexpr int kResidualBlocks = 64;          // blocks per sample of step 5 (slots of the per-sample sum of squares)
+constexpr int kMuGradBlocks = 148 * 16;      // blocks of step 9 (slots of sum (mu - hr)^2)
 struct SisrWs {
-  size_t b, t, o, gpad, gk, aux, acc, total;
+  size_t b, t, o, gpad, gk, gk_part, aux, acc, total;
 };
+int blur_tiles(long long v) { return int((v + kBlurTile - 1) / kBlurTile); }
 SisrWs sisr_ws_layout(long long n, long long c, long long H, long long W, long long h, long long w, long long k) {
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   SisrWs L{};
@@ -443,8 +480,10 @@ SisrWs sisr_ws_layout(long long n, long long c, long long H, long long W, long l
   L.o = o, o += al(size_t(n * c * h * w) * 4);                       // O, then gO in place
   L.gpad = o, o += al(size_t(n * c * (H + k - 1) * (W + k - 1)) * 4);
   L.gk = o, o += al(size_t(n * k * k) * 4);
+  L.gk_part = o, o += al(size_t(n * c * blur_tiles(H) * blur_tiles(W) * k * k) * 4);   // step 10's per-tile partials
   L.aux = o, o += al(size_t(n * 8) * 4);
-  L.acc = o, o += al(size_t(n + 8) * 8);                             // [0..7] scalar sums, [8..8+n) per-sample ssq
+  // fp64: per-sample scalars [n][5], step 5's slots [n][kResidualBlocks], step 9's slots [kMuGradBlocks]
+  L.acc = o, o += al(size_t(n * 5 + n * kResidualBlocks + kMuGradBlocks) * 8);
   L.total = o;
   return L;
 }
@@ -475,13 +514,13 @@ extern "C" int vk_elbo_sisr(const vk_elbo_sisr_args* a, void* stream_) {
   float* Of = reinterpret_cast<float*>(base + L.o);
   float* gpad = reinterpret_cast<float*>(base + L.gpad);
   float* gk = reinterpret_cast<float*>(base + L.gk);
+  float* gk_part = reinterpret_cast<float*>(base + L.gk_part);
   float* aux = reinterpret_cast<float*>(base + L.aux);
-  double* acc = reinterpret_cast<double*>(base + L.acc);
-  double* ssq = acc + 8;
+  double* per = reinterpret_cast<double*>(base + L.acc);
+  double* ssq_part = per + size_t(N) * 5;
+  double* sq_part = ssq_part + size_t(N) * kResidualBlocks;
   const int P = N * C, KK = K * K, pad = K / 2;
   const float nscale = sqrtf(a->eps2);
-  cudaMemsetAsync(acc, 0, size_t(N + 8) * 8, st);
-  cudaMemsetAsync(gk, 0, size_t(N) * KK * 4, st);
   int launches = 0;
 
   sisr_kernel_fwd_kernel<<<N, 256, 0, st>>>(a->kinfo_est, a->gamma_draw, a->rho_draw, a->kappa0, a->r2, K, a->center,
@@ -513,8 +552,9 @@ extern "C" int vk_elbo_sisr(const vk_elbo_sisr_args* a, void* stream_) {
   gemm(a->rh, 0, H, 1, Tf, (long long)H * w, w, 1, Of, (long long)h * w, h, w, H);
   // 5: residual / likelihood gradient w.r.t. the degraded image
   const int per_sample = C * h * w;
-  sisr_residual_kernel<<<dim3(std::min((per_sample + 255) / 256, 64), N), 256, 0, st>>>(
-      Of, a->im_lr, a->sigma_est, a->alpha0, per_sample, 1.f / (float(N) * float(per_sample)), ssq);
+  const int res_blocks = std::min((per_sample + 255) / 256, kResidualBlocks);
+  sisr_residual_kernel<<<dim3(res_blocks, N), 256, 0, st>>>(Of, a->im_lr, a->sigma_est, a->alpha0, per_sample,
+                                                            1.f / (float(N) * float(per_sample)), ssq_part);
   ++launches;
   // 6: T[p] (H x w) = Rh^T (H x h) * gO[p]    7: gB[p] (H x W) = T[p] (H x w) * Rw (w x W)
   gemm(a->rh, 0, 1, H, Of, (long long)h * w, w, 1, Tf, (long long)H * w, H, w, h);
@@ -527,18 +567,21 @@ extern "C" int vk_elbo_sisr(const vk_elbo_sisr_args* a, void* stream_) {
   // 9: d_mu
   const long long total = (long long)P * H * W;
   const double hr_count = double(total);
-  sisr_mu_grad_kernel<<<int(std::min<long long>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
-      a->mu, a->im_hr, gpad, a->d_mu, H, W, pad, float(1.0 / (double(a->eps2) * hr_count)), total, acc + 1);
+  const int mu_blocks = int(std::min<long long>((total + 255) / 256, kMuGradBlocks));
+  sisr_mu_grad_kernel<<<mu_blocks, 256, 0, st>>>(a->mu, a->im_hr, gpad, a->d_mu, H, W, pad,
+                                                 float(1.0 / (double(a->eps2) * hr_count)), total, sq_part);
   ++launches;
   // 10: gradient w.r.t. the blur kernel
-  sisr_kernel_wgrad_kernel<<<dim3(tiles(W), tiles(H), P), 256, wg_smem, st>>>(a->mu, a->z_draw, nscale, Bf, gk, C, H, W, K);
-  ++launches;
+  sisr_kernel_wgrad_kernel<<<dim3(tiles(W), tiles(H), P), 256, wg_smem, st>>>(a->mu, a->z_draw, nscale, Bf, gk_part, C, H, W,
+                                                                             K);
+  sisr_kernel_wgrad_reduce_kernel<<<N, 256, 0, st>>>(gk_part, gk, C * tiles(W) * tiles(H), KK);
+  launches += 2;
   // 11, 12
   sisr_kernel_bwd_kernel<<<N, 256, 0, st>>>(a->kernel, gk, aux, a->kinfo_est, a->kinfo_gt, a->gamma_draw, a->sigma_est,
-                                            a->prior_mean, a->prior_logmean, ssq, N, K, a->center, a->kappa0, a->r2,
-                                            a->pk0, a->pk1, a->alpha0, a->digamma_am1, float(per_sample), a->d_kinfo,
-                                            a->d_sigma, acc);
-  sisr_finalize_kernel<<<1, 1, 0, st>>>(acc, N, hr_count, a->eps2, a->r2, a->pk0, a->pk1, a->terms);
+                                            a->prior_mean, a->prior_logmean, ssq_part, res_blocks, N, K, a->center,
+                                            a->kappa0, a->r2, a->pk0, a->pk1, a->alpha0, a->digamma_am1, float(per_sample),
+                                            a->d_kinfo, a->d_sigma, per);
+  sisr_finalize_kernel<<<1, 256, 0, st>>>(per, sq_part, mu_blocks, N, hr_count, a->eps2, a->r2, a->pk0, a->pk1, a->terms);
   launches += 2;
   g_launch_count.fetch_add(launches, std::memory_order_relaxed);
   return int(cudaGetLastError());

@@ -969,13 +969,27 @@ class DenoiseEngine:
         G2 = self._buf(f"g.sr.{tag}.G2", (N, hh, ww, c))
         self._dgrad(gX, c2, VK_CONV3X3_S1, c, ldo=c, mask=S[tag + ".b"], out1=G2, alpha=0.2)
         gF1 = self._buf(f"g.sr.{tag}.F1", (N, hh, ww, c))
-        ops.sft_bwd(G2, S[tag + ".f1"], m2, gF1, dm[(ii, b, "sft2")], dd[(ii, b, "sft2")], dtype=self.dtype, c=c)
+        det_ws = self._det_scratch(ops.sft_bwd_det_ws_floats(N, hh * ww, c)) if self.deterministic else None
+        ops.sft_bwd(G2, S[tag + ".f1"], m2, gF1, dm[(ii, b, "sft2")], dd[(ii, b, "sft2")], dtype=self.dtype, c=c,
+                    det_ws=det_ws)
         self._wgrad(c1, gF1, S[tag + ".a"], VK_CONV3X3_S1)
         G1 = self._buf(f"g.sr.{tag}.G1", (N, hh, ww, c))
         self._dgrad(gF1, c1, VK_CONV3X3_S1, c, ldo=c, mask=S[tag + ".a"], out1=G1, alpha=0.2)
         gXp = self._buf(f"g.sr.{tag}.X", (N, hh, ww, c))
-        ops.sft_bwd(G1, S[tag + ".x"], m1, gXp, dm[(ii, b, "sft1")], dd[(ii, b, "sft1")], dtype=self.dtype, c=c, resid=gX)
+        ops.sft_bwd(G1, S[tag + ".x"], m1, gXp, dm[(ii, b, "sft1")], dd[(ii, b, "sft1")], dtype=self.dtype, c=c, resid=gX,
+                    det_ws=det_ws)
         return gXp
+
+    def _det_scratch(self, floats: int):
+        """fp32 scratch of the deterministic forms of the small per-sample kernels (slots of partial sums that a second
+        launch adds in a fixed order); grown on demand, kept for the life of the engine (CUDA graphs capture its address),
+        used on the main stream only."""
+        buf = getattr(self, "_det_ws_buf", None)
+        if buf is None or buf.numel() < floats:
+            if buf is not None:
+                self._det_ws_old = getattr(self, "_det_ws_old", []) + [buf]      # a captured graph may still point at it
+            buf = self._det_ws_buf = torch.empty(max(floats, 1 << 16), device=self.flat_params.device, dtype=torch.float32)
+        return buf
 
     def _sft_block_bwd_spatial(self, ii, b, c1, c2, gX, shape, src, d_cst, d_map):
         """Backward of one AttResBlock whose AttLayers run per pixel (vk_sft_apply_bwd + four 1x1 weight-gradient GEMMs
@@ -1061,7 +1075,7 @@ class DenoiseEngine:
         self._wgrad(self.head, gX, S["r0"], VK_CONV3X3_S1)
         if sft_const:
             # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values, every AttLayer in one launch
-            ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, extra, d_cst, sqrt_mask=sqrt_mask)
+            ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, extra, d_cst, sqrt_mask=sqrt_mask, det=self.deterministic)
         if self.head_extra:
             cin0 = C + self.head_extra
             gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))
@@ -1072,7 +1086,11 @@ class DenoiseEngine:
                 E = n_cst
                 kc = self.kc
                 hsum = torch.zeros(N, cin0, device=dev, dtype=f32)
-                ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
+                if self.deterministic:                    # per sample through the atomic-free, block-ordered form
+                    for n in range(N):
+                        ops.channel_sum(gR0[n], cin0, hsum[n], dtype=dt, ws=self._csum_ws)
+                else:
+                    ops.channel_sum_batched(gR0, cin0, hsum, dtype=dt)
                 # the head saw [kinfo, sqrt(sigma)] as constant planes: chain the sqrt for the variance channels
                 hext = hsum[:, C:C + E].clone()
                 if E > kc:
@@ -1172,7 +1190,11 @@ class DenoiseEngine:
         for b in reversed(range(len(self.k_blocks))):
             c1, c2, ca = self.k_blocks[b]
             dF = self._buf(f"g.sr.k{b}.df", (N, kh, kw, cp(nfk)))
-            ops.ca_layer_bwd(gH, S[f"k{b}.f"], ca, dF, self.grad_view, dtype=dt, c=nfk)
+            ca_ws = None
+            if self.deterministic:
+                r = ca.body[0].weight.shape[0]
+                ca_ws = self._det_scratch(N * (2 * r * nfk + r + nfk))
+            ops.ca_layer_bwd(gH, S[f"k{b}.f"], ca, dF, self.grad_view, dtype=dt, c=nfk, det_ws=ca_ws)
             self._wgrad(c2, dF, S[f"k{b}.a"], VK_CONV3X3_S1)
             gA = self._buf(f"g.sr.k{b}.ga", (N, kh, kw, cp(nfk)))
             self._dgrad(dF, c2, VK_CONV3X3_S1, nfk, ldo=cp(nfk), mask=S[f"k{b}.a"], out1=gA, alpha=0.2)
@@ -1180,7 +1202,8 @@ class DenoiseEngine:
             gHn = self._buf(f"g.sr.k{b}.gh", (N, kh, kw, cp(nfk)))
             self._dgrad(gA, c1, VK_CONV3X3_S1, nfk, ldo=cp(nfk), resid=gH, out1=gHn)
             gH = gHn
-        ops.knet_head_wgrad(S["x"], gH, self.grad_view(knet.head.weight), dtype=dt)
+        ops.knet_head_wgrad(S["x"], gH, self.grad_view(knet.head.weight), dtype=dt,
+                            det_ws=self._det_scratch(N * knet.head.weight.numel()) if self.deterministic else None)
         # ---- SNet: per-pixel map head, or the global-average head ----
         if spatial:
             self._snet_backward_map(S, gs_map, N, h, w, "sr.")

@@ -145,18 +145,26 @@ _SIGNATURES = {
                              C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "vk_sft_bwd": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p]),
+    "vk_sft_bwd_det_ws_floats": (C.c_int64, [C.c_int32] * 3),
+    "vk_sft_bwd_det": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p, C.c_int64, C.c_void_p]),
     "vk_sft_mlp_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_float] + [C.c_void_p] * 12),
     "vk_ca_layer_bwd": (C.c_int, [C.c_int32] + [C.c_void_p] * 11 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
+    "vk_ca_layer_bwd_det": (C.c_int, [C.c_int32] + [C.c_void_p] * 11 + [C.c_int32] * 5 + [C.c_float, C.c_void_p, C.c_int64,
+                                                                                              C.c_void_p]),
     "vk_gap_head_bwd": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
                                   C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "vk_knet_head_wgrad": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    "vk_knet_head_wgrad_det": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 +
+                               [C.c_void_p, C.c_int64, C.c_void_p]),
     "vk_upsample_nearest": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
     "vk_sft_mlp_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
                                      C.c_float, C.c_void_p]),
     "vk_sft_mlp_bwd_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
                                          C.c_float, C.c_void_p, C.c_void_p]),
+    "vk_sft_mlp_bwd_batched_det": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                             C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]),
     "vk_sizeof_sft_desc": (C.c_uint32, []),
     "vk_sft_apply": (C.c_int, [C.POINTER(vk_sft_apply_args), C.c_void_p]),
     "vk_sizeof_sft_apply_args": (C.c_uint32, []),

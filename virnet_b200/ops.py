@@ -415,13 +415,29 @@ def upsample_nearest_nchw(x, out, sf):
 # ---------------------------------------------------------------------------
 # backward of the super-resolution network's small layers
 # ---------------------------------------------------------------------------
-def sft_bwd(g, x, mul, gx, dmul, dadd, *, dtype, c, resid=None):
-    """gx = g * mul (+ resid); dmul/dadd [n, c] += sums over pixels of g * x and g.  NHWC tensors [n, h, w, ld]."""
+def sft_bwd_det_ws_floats(n, npix, c):
+    """Floats of scratch the deterministic form of sft_bwd needs for [n, npix, *] tensors with c channels."""
+    need = _l.load().vk_sft_bwd_det_ws_floats(n, npix, c)
+    if need < 0:
+        raise _l.VkError("vk_sft_bwd_det_ws_floats: bad shape")
+    return need
+
+
+def sft_bwd(g, x, mul, gx, dmul, dadd, *, dtype, c, resid=None, det_ws=None):
+    """gx = g * mul (+ resid); dmul/dadd [n, c] += sums over pixels of g * x and g.  NHWC tensors [n, h, w, ld].
+    det_ws (fp32 scratch of at least sft_bwd_det_ws_floats(...) elements): the bit-reproducible form without atomics."""
     n, ld = g.shape[0], g.shape[-1]
     npix = g.shape[1] * g.shape[2]
     for t in (g, x, gx) + ((resid,) if resid is not None else ()):
         assert t.is_contiguous() and t.shape == g.shape
     assert mul.shape == (n, c) and dmul.shape == (n, c) and dadd.shape == (n, c)
+    if det_ws is not None:
+        assert det_ws.dtype == torch.float32 and det_ws.is_cuda and det_ws.is_contiguous()
+        with _Prof("sft_bwd"):
+            _l.check(_l.load().vk_sft_bwd_det(dtype, _ptr(g), _ptr(x), _ptr(mul), _ptr(resid), _ptr(gx), _ptr(dmul),
+                                              _ptr(dadd), n, npix, c, ld, _ptr(det_ws), det_ws.numel(), _stream()),
+                     "vk_sft_bwd_det")
+        return
     with _Prof("sft_bwd"):
         _l.check(_l.load().vk_sft_bwd(dtype, _ptr(g), _ptr(x), _ptr(mul), _ptr(resid), _ptr(gx), _ptr(dmul), _ptr(dadd), n,
                                       npix, c, ld, _stream()), "vk_sft_bwd")
@@ -441,11 +457,20 @@ def sft_mlp_bwd(extra, att, dmul, dadd, grads, d_extra, *, sqrt_mask=0, alpha=0.
             "vk_sft_mlp_bwd")
 
 
-def ca_layer_bwd(g, f, ca, df, grads, *, dtype, c, alpha=0.2):
-    """ca: CALayer container (body[0], body[2] 1x1 convs); df = g * s + dy / npix; parameter grads accumulated."""
+def ca_layer_bwd(g, f, ca, df, grads, *, dtype, c, alpha=0.2, det_ws=None):
+    """ca: CALayer container (body[0], body[2] 1x1 convs); df = g * s + dy / npix; parameter grads accumulated.
+    det_ws (fp32 scratch, at least n * (2 r c + r + c) elements): the bit-reproducible form without atomics."""
     n, ld = g.shape[0], g.shape[-1]
     npix = g.shape[1] * g.shape[2]
     w1, b1, w2, b2 = ca.body[0].weight, ca.body[0].bias, ca.body[2].weight, ca.body[2].bias
+    if det_ws is not None:
+        assert det_ws.dtype == torch.float32 and det_ws.is_cuda and det_ws.is_contiguous()
+        with _Prof("ca_layer_bwd"):
+            _l.check(_l.load().vk_ca_layer_bwd_det(dtype, _ptr(g), _ptr(f), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(df),
+                                                   _ptr(grads(w1)), _ptr(grads(b1)), _ptr(grads(w2)), _ptr(grads(b2)), n,
+                                                   npix, c, w1.shape[0], ld, alpha, _ptr(det_ws), det_ws.numel(),
+                                                   _stream()), "vk_ca_layer_bwd_det")
+        return
     with _Prof("ca_layer_bwd"):
         _l.check(_l.load().vk_ca_layer_bwd(dtype, _ptr(g), _ptr(f), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(df),
                                            _ptr(grads(w1)), _ptr(grads(b1)), _ptr(grads(w2)), _ptr(grads(b2)), n, npix, c,
@@ -462,11 +487,19 @@ def gap_head_bwd(gout, outv, gx, *, dtype, c, exp_mask=0, tanh_mask=0, lo=0.0, h
                                            ld, _stream()), "vk_gap_head_bwd")
 
 
-def knet_head_wgrad(x, g, gw, *, dtype):
+def knet_head_wgrad(x, g, gw, *, dtype, det_ws=None):
+    """gw [cout, c, 9, 9] += weight gradient of the KNet head.  det_ws (fp32 scratch, at least n * gw.numel() elements):
+    per-sample slots added in sample order instead of atomics."""
     n, c, h, wd = x.shape
     with _Prof("knet_head_wgrad"):
-        _l.check(_l.load().vk_knet_head_wgrad(dtype, _ptr(x), _ptr(g), _ptr(gw), n, c, h, wd, gw.shape[0], g.shape[-1],
-                                              _stream()), "vk_knet_head_wgrad")
+        if det_ws is not None:
+            assert det_ws.dtype == torch.float32 and det_ws.is_cuda and det_ws.is_contiguous()
+            _l.check(_l.load().vk_knet_head_wgrad_det(dtype, _ptr(x), _ptr(g), _ptr(gw), n, c, h, wd, gw.shape[0],
+                                                      g.shape[-1], _ptr(det_ws), det_ws.numel(), _stream()),
+                     "vk_knet_head_wgrad_det")
+        else:
+            _l.check(_l.load().vk_knet_head_wgrad(dtype, _ptr(x), _ptr(g), _ptr(gw), n, c, h, wd, gw.shape[0], g.shape[-1],
+                                                  _stream()), "vk_knet_head_wgrad")
 
 
 # ---------------------------------------------------------------------------
@@ -575,11 +608,13 @@ def sft_mlp_batched(descs_dev, n_layers, max_c, extra, *, sqrt_mask=0, alpha=0.2
                                               _stream()), "vk_sft_mlp_batched")
 
 
-def sft_mlp_bwd_batched(descs_dev, n_layers, max_c, extra, d_extra, *, sqrt_mask=0, alpha=0.2):
+def sft_mlp_bwd_batched(descs_dev, n_layers, max_c, extra, d_extra, *, sqrt_mask=0, alpha=0.2, det=False):
+    """det=True: fixed accumulation order over samples (parameter gradients) and layers (d_extra), no racing atomics."""
     n, e = extra.shape
+    fn = _l.load().vk_sft_mlp_bwd_batched_det if det else _l.load().vk_sft_mlp_bwd_batched
     with _Prof("sft_mlp_bwd"):
-        _l.check(_l.load().vk_sft_mlp_bwd_batched(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask, alpha,
-                                                  _ptr(d_extra), _stream()), "vk_sft_mlp_bwd_batched")
+        _l.check(fn(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask, alpha, _ptr(d_extra), _stream()),
+                 "vk_sft_mlp_bwd_batched_det" if det else "vk_sft_mlp_bwd_batched")
 
 
 def sisr_degrade(im_hr, kernels, rh, rw, noise, std):

@@ -321,9 +321,15 @@ class SISRTrainer:
 
     def __init__(self, net, sf, lr=1e-4, clip_grad_R=5e2, clip_grad_S=1e2, clip_grad_K=5e2, var_window=9, kappa0=50.0,
                  r2=1e-4, eps2=1e-5, k_size=21, penalty_K=(0.02, 2), kernel_shift=False, downsampler="Bicubic",
-                 betas=(0.9, 0.999), adam_eps=1e-8, process_group=None):
+                 betas=(0.9, 0.999), adam_eps=1e-8, process_group=None, deterministic=None):
+        """deterministic=True: bit-reproducible training for per-sample-constant conditioning (the shipped configurations) —
+        split-K weight gradients in ordered slabs (engine.deterministic) and the fixed-order forms of the small per-sample
+        kernels (vk_sft_bwd_det, vk_sft_mlp_bwd_batched_det, vk_ca_layer_bwd_det, vk_knet_head_wgrad_det); the loss
+        (vk_elbo_sisr) never uses atomics.  Per-pixel conditioning maps (noise_avg=False) still scatter with atomics."""
         self.net, self.sf = net, int(sf)
         self.engine = eng = net.engine()
+        if deterministic is not None:
+            eng.deterministic = bool(deterministic)
         eng._ensure_flat()
         dev = eng.flat_params.device
         self.lr, self.betas, self.adam_eps = lr, betas, adam_eps
