@@ -354,9 +354,15 @@ def extra_configs(args, dev, local_rank, peaks):
         tr = SISRTrainer(net, sf)
         ms = _gpu_timed(lambda: tr.step(im_hr, im_lr, kinfo_gt, nlevel), args.steps, args.warmup)
         v = B / ms * 1e3
-        return {"workload": "configs[4] train_SISR.py step x4, 64x64 -> 256x256 patches, batch 16 (fwd SNet+KNet+SFT RNet, "
-                            "elbo_sisr, bwd, clip x3, Adam)", "value": v, "unit": "patches/s", "ms_per_step": ms, "dtype": "bf16",
-                "roofline_frac_whole_step": v * SISR_TRAIN_GFLOP / 1e3 / peak_bf16, "peak": peak_bf16}
+        res = {"workload": "configs[4] train_SISR.py step x4, 64x64 -> 256x256 patches, batch 16 (fwd SNet+KNet+SFT RNet, "
+                           "elbo_sisr, bwd, clip x3, Adam)", "value": v, "unit": "patches/s", "ms_per_step": ms, "dtype": "bf16",
+               "roofline_frac_whole_step": v * SISR_TRAIN_GFLOP / 1e3 / peak_bf16, "peak": peak_bf16}
+        # the same step bit-reproducible (ordered split-K slabs + the fixed-order forms of the per-sample kernels)
+        del tr
+        tr_det = SISRTrainer(sr_net("bf16").train(), sf, deterministic=True)
+        ms_det = _gpu_timed(lambda: tr_det.step(im_hr, im_lr, kinfo_gt, nlevel), args.steps, args.warmup)
+        res["deterministic"] = {"value": B / ms_det * 1e3, "ms_per_step": ms_det}
+        return res
     add("train_sisr_x4_b16", train_sr)
     return out
 

@@ -6,6 +6,7 @@
 // sample, everything staged through shared memory / registers, no atomics.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/virnet_b200.h"
 #include "vk_common.cuh"
@@ -235,7 +236,9 @@ template <>
 struct SftVec<__nv_bfloat16> {
   static constexpr int kN = 8;
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
-    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    unpack(*reinterpret_cast<const uint4*>(p), v);
+  }
+  static __device__ __forceinline__ void unpack(const uint4& r, float* v) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -255,16 +258,20 @@ template <>
 struct SftVec<float> {
   static constexpr int kN = 4;
   static __device__ __forceinline__ void load(const float* p, float* v) {
-    const float4 r = *reinterpret_cast<const float4*>(p);
-    v[0] = r.x, v[1] = r.y, v[2] = r.z, v[3] = r.w;
+    unpack(*reinterpret_cast<const uint4*>(p), v);
+  }
+  static __device__ __forceinline__ void unpack(const uint4& r, float* v) {
+    v[0] = __uint_as_float(r.x), v[1] = __uint_as_float(r.y), v[2] = __uint_as_float(r.z), v[3] = __uint_as_float(r.w);
   }
   static __device__ __forceinline__ void store(float* p, const float* v) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
 };
 
-template <typename DT>
-__global__ void __launch_bounds__(256)
+// U = pixels a thread has in flight per loop step (all their 16-byte loads are issued before the first use): the kernel
+// is bound by bytes in flight per SM (registers cap the resident threads), not by arithmetic.
+template <typename DT, int U>
+__global__ void __launch_bounds__(256, U == 1 ? 4 : 3)
 sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* __restrict__ mul,
                const DT* __restrict__ resid, DT* __restrict__ gx, float* __restrict__ dmul, float* __restrict__ dadd,
                int npix, int C, int ld, int pix_per_block, float* __restrict__ slots) {
@@ -282,27 +289,48 @@ sft_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ x, const float* 
     m[i] = c < C ? mul[n * C + c] : 0.f;
     sm_[i] = sa_[i] = 0.f;
   }
-  if (pl < lanes)
-    for (int p = p0 + pl; p < p1; p += lanes) {
-      const long long i0 = base + static_cast<long long>(p) * ld + cg * V;
-      float gv[V], xv[V], o[V];
-      SftVec<DT>::load(g + i0, gv);
-      SftVec<DT>::load(x + i0, xv);
-      if (resid != nullptr) {
-        SftVec<DT>::load(resid + i0, o);
+  const bool has_resid = resid != nullptr;
+  auto ldv = [](const DT* p) { return *reinterpret_cast<const uint4*>(p); };
+  auto one = [&](long long i0, const uint4& gr, const uint4& xr, const uint4& rr) {
+    float gv[V], xv[V], o[V];
+    SftVec<DT>::unpack(gr, gv);
+    SftVec<DT>::unpack(xr, xv);
+    if (has_resid) {
+      SftVec<DT>::unpack(rr, o);
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = fmaf(gv[i], m[i], o[i]);
-      } else {
+      for (int i = 0; i < V; ++i) o[i] = fmaf(gv[i], m[i], o[i]);
+    } else {
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = gv[i] * m[i];
-      }
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        sm_[i] = fmaf(gv[i], xv[i], sm_[i]);
-        sa_[i] += gv[i];
-      }
-      SftVec<DT>::store(gx + i0, o);
+      for (int i = 0; i < V; ++i) o[i] = gv[i] * m[i];
     }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sm_[i] = fmaf(gv[i], xv[i], sm_[i]);
+      sa_[i] += gv[i];
+    }
+    SftVec<DT>::store(gx + i0, o);
+  };
+  if (pl < lanes) {
+    int p = p0 + pl;
+    if constexpr (U == 2) {
+      for (; p + lanes < p1; p += 2 * lanes) {
+        const long long i0 = base + static_cast<long long>(p) * ld + cg * V;
+        const long long i1 = i0 + static_cast<long long>(lanes) * ld;
+        const uint4 g0 = ldv(g + i0), x0 = ldv(x + i0), g1 = ldv(g + i1), x1 = ldv(x + i1);
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        if (has_resid) r0 = ldv(resid + i0), r1 = ldv(resid + i1);
+        one(i0, g0, x0, r0);
+        one(i1, g1, x1, r1);
+      }
+    }
+    for (; p < p1; p += lanes) {
+      const long long i0 = base + static_cast<long long>(p) * ld + cg * V;
+      const uint4 g0 = ldv(g + i0), x0 = ldv(x + i0);
+      uint4 r0 = make_uint4(0, 0, 0, 0);
+      if (has_resid) r0 = ldv(resid + i0);
+      one(i0, g0, x0, r0);
+    }
+  }
   float* pm = sm;
   float* pa = sm + lanes * ld;
   if (pl < lanes) {
@@ -749,16 +777,25 @@ int sft_bwd_launch(int32_t dtype, const void* g, const void* x, const float* mul
   const long long nc = static_cast<long long>(n) * c;
   if (det && (!ws || ws_floats < static_cast<long long>(grid.x) * 2 * nc)) return VK_E_BADARG;
   float* slots = det ? ws : nullptr;
+  // pixels in flight per thread: 2 for bf16, 1 for fp32 storage (measured, profiles/r02_sft_bwd_unroll.txt);
+  // VK_SFT_BWD_UNROLL=1|2 overrides (tuning knob)
+  static const int forced = [] {
+    const char* e = std::getenv("VK_SFT_BWD_UNROLL");
+    return e && (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;
+  }();
+  const int unroll = forced ? forced : (dtype == VK_BF16 ? 2 : 1);
+  auto launch = [&](auto tag, auto u) {
+    using DT = decltype(tag);
+    sft_bwd_kernel<DT, decltype(u)::value><<<grid, 256, smem, VK_ST(stream)>>>(
+        reinterpret_cast<const DT*>(g), reinterpret_cast<const DT*>(x), mul, reinterpret_cast<const DT*>(resid),
+        reinterpret_cast<DT*>(gx), dmul, dadd, npix, c, ld, ppb, slots);
+  };
+  using U1 = std::integral_constant<int, 1>;
+  using U2 = std::integral_constant<int, 2>;
   if (dtype == VK_BF16)
-    sft_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, VK_ST(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(x), mul,
-        reinterpret_cast<const __nv_bfloat16*>(resid), reinterpret_cast<__nv_bfloat16*>(gx), dmul, dadd, npix, c, ld, ppb,
-        slots);
+    unroll == 1 ? launch(__nv_bfloat16{}, U1{}) : launch(__nv_bfloat16{}, U2{});
   else if (dtype == VK_TF32)
-    sft_bwd_kernel<float><<<grid, 256, smem, VK_ST(stream)>>>(reinterpret_cast<const float*>(g),
-                                                           reinterpret_cast<const float*>(x), mul,
-                                                           reinterpret_cast<const float*>(resid),
-                                                           reinterpret_cast<float*>(gx), dmul, dadd, npix, c, ld, ppb, slots);
+    unroll == 1 ? launch(float{}, U1{}) : launch(float{}, U2{});
   else
     return VK_E_BADARG;
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
