@@ -29,35 +29,57 @@ __device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) {
 
 // ---------------------------------------------------------------------------
 // KNet head: Conv2d(c -> cout, k = 9, stride 4, pad 4, no bias), NCHW fp32 in, NHWC DT out.
-// One thread per (output pixel, output channel); the 9x9xc window is read through L1 (every
-// input pixel is shared by ~5 windows and all `cout` threads of a pixel).
+// One thread per (output pixel, output channel), a block = 256 / ld pixels x ld channels.  Per input channel the
+// 81 x cout filter slice is staged TRANSPOSED in shared memory ([tap][co]: the lanes of a warp read consecutive words;
+// straight from the OIHW tensor they would touch 32 cache lines per load), the input pixel is a warp-wide broadcast
+// through L1 (every input pixel is shared by ~5 windows and all `cout` threads of a pixel).
 // ---------------------------------------------------------------------------
 template <typename DT>
-__global__ void knet_head_kernel(const float* __restrict__ x, const float* __restrict__ w, DT* __restrict__ out, int N,
-                                 int C, int H, int W, int OH, int OW, int cout, int ld) {
-  const long long total = static_cast<long long>(N) * OH * OW * ld;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int co = int(i % ld);
-    const long long pix = i / ld;
-    const int ox = int(pix % OW), oy = int((pix / OW) % OH), n = int(pix / (static_cast<long long>(OW) * OH));
-    float acc = 0.f;
-    if (co < cout) {
-      for (int c = 0; c < C; ++c) {
+__global__ void __launch_bounds__(256)
+knet_head_kernel(const float* __restrict__ x, const float* __restrict__ w, DT* __restrict__ out, int N, int C, int H,
+                 int W, int OH, int OW, int cout, int ld) {
+  constexpr int G = 4;                   // pixel groups per staged filter slice
+  extern __shared__ float ws[];          // [81][ld]
+  const int ppb = 256 / ld;              // pixels per group (host guarantees ld <= 256)
+  const int co = threadIdx.x % ld, pl = threadIdx.x / ld;
+  const long long npix = static_cast<long long>(N) * OH * OW;
+  for (long long p0 = static_cast<long long>(blockIdx.x) * ppb * G; p0 < npix;
+       p0 += static_cast<long long>(gridDim.x) * ppb * G) {
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      __syncthreads();                   // the previous slice has been consumed
+#pragma unroll 5
+      for (int i = threadIdx.x; i < 81 * ld; i += 256) {
+        const int t = i % 81, k = i / 81;            // consecutive threads read consecutive taps of one filter
+        ws[t * ld + k] = k < cout ? __ldg(w + (static_cast<long long>(k) * C + c) * 81 + t) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const long long pix = p0 + g * ppb + pl;
+        if (pl >= ppb || pix >= npix) continue;
+        const int ox = int(pix % OW), oy = int((pix / OW) % OH), n = int(pix / (static_cast<long long>(OW) * OH));
         const float* xp = x + (static_cast<long long>(n) * C + c) * H * W;
-        const float* wp = w + (static_cast<long long>(co) * C + c) * 81;
+        float a = acc[g];
         for (int r = 0; r < 9; ++r) {
           const int iy = oy * 4 - 4 + r;
           if (iy < 0 || iy >= H) continue;
           for (int s = 0; s < 9; ++s) {
             const int ix = ox * 4 - 4 + s;
             if (ix < 0 || ix >= W) continue;
-            acc = fmaf(__ldg(xp + iy * W + ix), __ldg(wp + r * 9 + s), acc);
+            a = fmaf(__ldg(xp + iy * W + ix), ws[(r * 9 + s) * ld + co], a);
           }
         }
+        acc[g] = a;
       }
     }
-    st_f<DT>(out + i, acc);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const long long pix = p0 + g * ppb + pl;
+      if (pl < ppb && pix < npix) st_f<DT>(out + pix * ld + co, acc[g]);
+    }
   }
 }
 
@@ -66,7 +88,7 @@ __global__ void knet_head_kernel(const float* __restrict__ x, const float* __res
 //   y = mean_pix f;  z = LReLU(W1 y + b1);  s = sigmoid(W2 z + b2);  out = f * s + skip
 // ---------------------------------------------------------------------------
 template <typename DT>
-__global__ void ca_layer_kernel(const DT* __restrict__ f, const DT* __restrict__ skip, const float* __restrict__ w1,
+__global__ void __launch_bounds__(1024) ca_layer_kernel(const DT* __restrict__ f, const DT* __restrict__ skip, const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ w2,
                                 const float* __restrict__ b2, DT* __restrict__ out, int npix, int C, int R, int ld,
                                 float alpha) {
@@ -512,7 +534,7 @@ __global__ void sft_mlp_bwd_batched_det_kernel(const SftDesc* __restrict__ descs
 // CALayer + skip backward (autograd of out = f * s(mean f) + skip), one CTA per sample:
 //   d_f = g * s + dy / npix,  the skip gradient is g itself;  parameter gradients by atomicAdd over samples.
 template <typename DT>
-__global__ void ca_layer_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ f, const float* __restrict__ w1,
+__global__ void __launch_bounds__(1024) ca_layer_bwd_kernel(const DT* __restrict__ g, const DT* __restrict__ f, const float* __restrict__ w1,
                                     const float* __restrict__ b1, const float* __restrict__ w2,
                                     const float* __restrict__ b2, DT* __restrict__ df, float* __restrict__ gw1,
                                     float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2, int npix,
@@ -651,6 +673,13 @@ __global__ void knet_head_wgrad_kernel(const float* __restrict__ x, const DT* __
 
 using namespace vk;
 
+// CALayer kernels run one CTA per sample: the SM has nothing else to do, so use up to 1024 threads (a multiple of the
+// channel count) as soon as every pixel lane has a few pixels to sum
+static int ca_threads(int npix, int c) {
+  const int cap = static_cast<long long>(npix) * c >= 8192 ? 1024 : 256;
+  return std::max(c, cap / c * c);
+}
+
 #define VK_ST(s) reinterpret_cast<cudaStream_t>(s)
 #define VK_LAUNCHED()                                        \
   g_launch_count.fetch_add(1, std::memory_order_relaxed);    \
@@ -660,14 +689,17 @@ extern "C" int vk_knet_head(int32_t dtype, const float* x, const float* w, void*
                             int32_t wd, int32_t cout, int32_t ld, void* stream) {
   if (!x || !w || !out || n <= 0 || c <= 0 || h <= 0 || wd <= 0 || cout <= 0 || cout > ld) return VK_E_BADARG;
   const int oh = (h - 1) / 4 + 1, ow = (wd - 1) / 4 + 1;
-  const long long total = static_cast<long long>(n) * oh * ow * ld;
-  const int grid = int(std::min<long long>((total + 255) / 256, 148 * 8));
+  const size_t smem = size_t(81) * ld * sizeof(float);               // one input channel's filter slice, transposed
+  if (ld > 256 || smem > 48 * 1024) return VK_E_BADARG;
+  const long long per_block = static_cast<long long>(256 / ld) * 4;  // pixels per block step (4 groups per staged slice)
+  const long long npix = static_cast<long long>(n) * oh * ow;
+  const int grid = int(std::min<long long>((npix + per_block - 1) / per_block, 148 * 8));
   if (dtype == VK_BF16)
-    knet_head_kernel<__nv_bfloat16><<<grid, 256, 0, VK_ST(stream)>>>(x, w, reinterpret_cast<__nv_bfloat16*>(out), n, c,
-                                                                    h, wd, oh, ow, cout, ld);
+    knet_head_kernel<__nv_bfloat16><<<grid, 256, smem, VK_ST(stream)>>>(x, w, reinterpret_cast<__nv_bfloat16*>(out), n, c,
+                                                                       h, wd, oh, ow, cout, ld);
   else if (dtype == VK_TF32)
-    knet_head_kernel<float><<<grid, 256, 0, VK_ST(stream)>>>(x, w, reinterpret_cast<float*>(out), n, c, h, wd, oh, ow,
-                                                            cout, ld);
+    knet_head_kernel<float><<<grid, 256, smem, VK_ST(stream)>>>(x, w, reinterpret_cast<float*>(out), n, c, h, wd, oh, ow,
+                                                               cout, ld);
   else
     return VK_E_BADARG;
   VK_LAUNCHED();
@@ -678,7 +710,7 @@ extern "C" int vk_ca_layer(int32_t dtype, const void* f, const void* skip, const
                            int32_t ld, float alpha, void* stream) {
   if (!f || !skip || !w1 || !b1 || !w2 || !b2 || !out || n <= 0 || npix <= 0 || c <= 0 || r <= 0 || c > ld || c > 256)
     return VK_E_BADARG;
-  const int threads = std::max(c, 256 / c * c);
+  const int threads = ca_threads(npix, c);
   const size_t smem = (size_t(threads / c) * c + 2 * c + r) * sizeof(float);
   if (dtype == VK_BF16)
     ca_layer_kernel<__nv_bfloat16><<<n, threads, smem, VK_ST(stream)>>>(
@@ -848,7 +880,7 @@ int ca_layer_bwd_launch(int32_t dtype, const void* g, const void* f, const float
   const int slot = 2 * r * c + r + c;
   if (det && (!ws || ws_floats < static_cast<int64_t>(n) * slot)) return VK_E_BADARG;
   float* slots = det ? ws : nullptr;
-  const int threads = std::max(c, 256 / c * c);
+  const int threads = ca_threads(npix, c);
   const size_t smem = (size_t(2 * (threads / c)) * c + 5 * c + 3 * r) * sizeof(float);
   if (dtype == VK_BF16)
     ca_layer_bwd_kernel<__nv_bfloat16><<<n, threads, smem, VK_ST(stream)>>>(
