@@ -217,10 +217,13 @@ int vk_sft_mlp_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, c
                        uint32_t sqrt_mask, float alpha, void* stream);
 int vk_sft_mlp_bwd_batched(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra, int32_t n,
                            int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra, void* stream);
-/* Deterministic form: one block per layer walks the samples in order (parameter gradients), one block per sample walks
- * the layers in order (d_extra); same result up to the summation order, bit-identical run to run. */
+/* Deterministic form: block (sample, layer) stores its gradients into private slots of `ws`, a second launch adds the
+ * sample slots in sample order (parameter gradients) and the layer slots in layer order (d_extra).
+ * params_per_sample = sum over the layers of c1*e + c1 + c2*c1 + c2 + 2*(c*c2 + c);
+ * ws_floats >= n * params_per_sample + n_layers * n * e. */
 int vk_sft_mlp_bwd_batched_det(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra, int32_t n,
-                               int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra, void* stream);
+                               int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra, int64_t params_per_sample,
+                               float* ws, int64_t ws_floats, void* stream);
 uint32_t vk_sizeof_sft_desc(void);
 
 /* ---- SFT modulation with SPATIALLY VARYING conditioning maps (csrc/vk_sft_spatial.cu) ----

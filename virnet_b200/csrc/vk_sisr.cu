@@ -418,8 +418,12 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
                                    const float* __restrict__ dmul, const float* __restrict__ dadd, float* __restrict__ gw1,
                                    float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2,
                                    float* __restrict__ gwm, float* __restrict__ gbm, float* __restrict__ gwa,
-                                   float* __restrict__ gba, float* __restrict__ d_extra, bool do_params = true,
-                                   bool do_extra = true) {
+                                   float* __restrict__ gba, float* __restrict__ d_extra, bool plain = false) {
+  // plain: every gradient pointer addresses a private slot of this (layer, sample): plain stores instead of atomics
+  auto accum = [plain](float* p, float v) {
+    if (plain) *p = v;
+    else atomicAdd(p, v);
+  };
   extern __shared__ float sm[];   // e[E] f1p[C1] f1[C1] f2p[C2] f2[C2] gmp[C] gad[C] gf2[C2] gf1[C1]
   float* e = sm;
   float* f1p = e + E;
@@ -455,10 +459,8 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
       const float mu = 1.f / (1.f + expf(-a));
       const float g1 = dmul[n * C + c] * mu * (1.f - mu), g2 = dadd[n * C + c];
       gmp[c] = g1, gad[c] = g2;
-      if (do_params) {
-        atomicAdd(gbm + c, g1), atomicAdd(gba + c, g2);
-        for (int k = 0; k < C2; ++k) atomicAdd(gwm + c * C2 + k, g1 * f2[k]), atomicAdd(gwa + c * C2 + k, g2 * f2[k]);
-      }
+      accum(gbm + c, g1), accum(gba + c, g2);
+      for (int k = 0; k < C2; ++k) accum(gwm + c * C2 + k, g1 * f2[k]), accum(gwa + c * C2 + k, g2 * f2[k]);
     }
     __syncthreads();
     for (int k = t; k < C2; k += T) {
@@ -466,10 +468,8 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
       for (int c = 0; c < C; ++c) a = fmaf(wm[c * C2 + k], gmp[c], fmaf(wa[c * C2 + k], gad[c], a));
       a *= f2p[k] > 0.f ? 1.f : alpha;
       gf2[k] = a;
-      if (do_params) {
-        atomicAdd(gb2 + k, a);
-        for (int j = 0; j < C1; ++j) atomicAdd(gw2 + k * C1 + j, a * f1[j]);
-      }
+      accum(gb2 + k, a);
+      for (int j = 0; j < C1; ++j) accum(gw2 + k * C1 + j, a * f1[j]);
     }
     __syncthreads();
     for (int j = t; j < C1; j += T) {
@@ -477,17 +477,15 @@ __device__ __forceinline__ void sft_mlp_bwd_body(int n, const float* __restrict_
       for (int k = 0; k < C2; ++k) a = fmaf(w2[k * C1 + j], gf2[k], a);
       a *= f1p[j] > 0.f ? 1.f : alpha;
       gf1[j] = a;
-      if (do_params) {
-        atomicAdd(gb1 + j, a);
-        for (int i = 0; i < E; ++i) atomicAdd(gw1 + j * E + i, a * e[i]);
-      }
+      accum(gb1 + j, a);
+      for (int i = 0; i < E; ++i) accum(gw1 + j * E + i, a * e[i]);
     }
     __syncthreads();
-    if (do_extra && t < E) {
+    if (t < E) {
       float a = 0.f;
       for (int j = 0; j < C1; ++j) a = fmaf(w1[j * E + t], gf1[j], a);
       if (sqrt_mask & (1u << t)) a *= 0.5f / fmaxf(e[t], 1e-20f);
-      atomicAdd(d_extra + n * E + t, a);
+      accum(d_extra + n * E + t, a);
     }
   }
 }
@@ -512,21 +510,81 @@ __global__ void sft_mlp_bwd_batched_kernel(const SftDesc* __restrict__ descs, co
                    d.dmul, d.dadd, d.gw1, d.gb1, d.gw2, d.gb2, d.gwm, d.gbm, d.gwa, d.gba, d_extra);
 }
 
-// Deterministic form: every address is accumulated by ONE thread of ONE block in a fixed order (atomics issued by one
-// thread to one address are performed in program order).  Blocks [0, n_layers): block l walks the samples in order and
-// accumulates the parameter gradients of layer l.  Blocks [n_layers, n_layers + N): block n walks the layers in order
-// and accumulates d_extra[n][:].  The forward of the small MLP is recomputed by both.
-__global__ void sft_mlp_bwd_batched_det_kernel(const SftDesc* __restrict__ descs, int n_layers,
-                                               const float* __restrict__ extra, int N, int E, unsigned sqrt_mask,
-                                               float alpha, float* __restrict__ d_extra) {
-  const bool params = int(blockIdx.x) < n_layers;
-  const int fixed = params ? int(blockIdx.x) : int(blockIdx.x) - n_layers;
-  const int steps = params ? N : n_layers;
-  for (int it = 0; it < steps; ++it) {
-    const SftDesc d = descs[params ? fixed : it];
-    sft_mlp_bwd_body(params ? it : fixed, extra, E, sqrt_mask, d.w1, d.b1, d.c1, d.w2, d.b2, d.c2, d.wm, d.bm, d.wa, d.ba,
-                     d.c, alpha, d.dmul, d.dadd, d.gw1, d.gb1, d.gw2, d.gb2, d.gwm, d.gbm, d.gwa, d.gba, d_extra, params,
-                     !params);
+// Deterministic form: block (sample n, layer l) stores its parameter gradients into its own slot
+//   ws[n * P + off_l + (w1 | b1 | w2 | b2 | wm | bm | wa | ba)],  P = parameters of all layers, off_l = those before l,
+// and its conditioning gradient into ws[N * P + (l * N + n) * E + e]; sft_mlp_slot_reduce_kernel then adds the sample
+// slots in sample order into the parameter gradients and the layer slots in layer order into d_extra.
+__device__ __forceinline__ long long sft_layer_params(const SftDesc& d, int E) {
+  return static_cast<long long>(d.c1) * E + d.c1 + static_cast<long long>(d.c2) * d.c1 + d.c2 +
+         2 * (static_cast<long long>(d.c) * d.c2 + d.c);
+}
+
+__global__ void sft_mlp_bwd_batched_slots_kernel(const SftDesc* __restrict__ descs, const float* __restrict__ extra, int N,
+                                                 int E, unsigned sqrt_mask, float alpha, float* __restrict__ ws,
+                                                 long long P) {
+  const int n = blockIdx.x, l = blockIdx.y;
+  long long off = 0;
+  for (int j = 0; j < l; ++j) off += sft_layer_params(descs[j], E);
+  const SftDesc d = descs[l];
+  float* gw1 = ws + n * P + off;
+  float* gb1 = gw1 + d.c1 * E;
+  float* gw2 = gb1 + d.c1;
+  float* gb2 = gw2 + d.c2 * d.c1;
+  float* gwm = gb2 + d.c2;
+  float* gbm = gwm + d.c * d.c2;
+  float* gwa = gbm + d.c;
+  float* gba = gwa + d.c * d.c2;
+  float* dslot = ws + static_cast<long long>(N) * P + static_cast<long long>(l) * N * E;
+  sft_mlp_bwd_body(n, extra, E, sqrt_mask, d.w1, d.b1, d.c1, d.w2, d.b2, d.c2, d.wm, d.bm, d.wa, d.ba, d.c, alpha, d.dmul,
+                   d.dadd, gw1, gb1, gw2, gb2, gwm, gbm, gwa, gba, dslot, true);
+}
+
+// blockIdx.y < n_layers: the parameter gradients of that layer; blockIdx.y == n_layers: d_extra.  Block = 8 warps x 32
+// consecutive elements; warp w adds slots w, w + 8, ... in order, the warp sums are then added in warp order.
+__global__ void __launch_bounds__(256)
+sft_mlp_slot_reduce_kernel(const SftDesc* __restrict__ descs, int n_layers, int N, int E, const float* __restrict__ ws,
+                           long long P, float* __restrict__ d_extra) {
+  __shared__ float part[8][32];
+  const int l = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_extra = l == n_layers;
+  long long off = 0, count = static_cast<long long>(N) * E, stride = count;
+  const float* src = ws + static_cast<long long>(N) * P;
+  int nslots = n_layers;
+  SftDesc d{};
+  if (!is_extra) {
+    for (int j = 0; j < l; ++j) off += sft_layer_params(descs[j], E);
+    d = descs[l];
+    count = sft_layer_params(d, E), stride = P, src = ws + off, nslots = N;
+  }
+  for (long long base = blockIdx.x * 32ll; base < count; base += gridDim.x * 32ll) {
+    const long long i = base + lane;
+    float a = 0.f;
+    if (i < count)
+      for (int sl = w; sl < nslots; sl += 8) a += src[sl * stride + i];
+    part[w][lane] = a;
+    __syncthreads();
+    if (w == 0 && i < count) {
+      float t = part[0][lane];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) t += part[j][lane];
+      float* out = d_extra;
+      long long k = i;
+      if (!is_extra) {
+        // segment of the slot layout w1 | b1 | w2 | b2 | wm | bm | wa | ba
+        const long long s1 = static_cast<long long>(d.c1) * E, s2 = s1 + d.c1, s3 = s2 + static_cast<long long>(d.c2) * d.c1,
+                        s4 = s3 + d.c2, s5 = s4 + static_cast<long long>(d.c) * d.c2, s6 = s5 + d.c,
+                        s7 = s6 + static_cast<long long>(d.c) * d.c2;
+        if (i < s1) out = d.gw1;
+        else if (i < s2) out = d.gb1, k = i - s1;
+        else if (i < s3) out = d.gw2, k = i - s2;
+        else if (i < s4) out = d.gb2, k = i - s3;
+        else if (i < s5) out = d.gwm, k = i - s4;
+        else if (i < s6) out = d.gbm, k = i - s5;
+        else if (i < s7) out = d.gwa, k = i - s6;
+        else out = d.gba, k = i - s7;
+      }
+      out[k] += t;
+    }
     __syncthreads();
   }
 }
@@ -765,12 +823,20 @@ extern "C" int vk_sft_mlp_bwd_batched(const void* descs_dev, int32_t n_layers, i
 
 extern "C" int vk_sft_mlp_bwd_batched_det(const void* descs_dev, int32_t n_layers, int32_t max_c, const float* extra,
                                           int32_t n, int32_t e, uint32_t sqrt_mask, float alpha, float* d_extra,
-                                          void* stream) {
-  if (!descs_dev || !extra || !d_extra || n_layers <= 0 || n <= 0 || e <= 0 || e > 32 || max_c <= 0) return VK_E_BADARG;
+                                          int64_t params_per_sample, float* ws, int64_t ws_floats, void* stream) {
+  if (!descs_dev || !extra || !d_extra || !ws || n_layers <= 0 || n <= 0 || e <= 0 || e > 32 || max_c <= 0 ||
+      params_per_sample <= 0)
+    return VK_E_BADARG;
+  if (ws_floats < static_cast<int64_t>(n) * params_per_sample + static_cast<int64_t>(n_layers) * n * e) return VK_E_BADARG;
   const size_t smem = size_t(e + 5 * max_c) * sizeof(float);
-  sft_mlp_bwd_batched_det_kernel<<<n_layers + n, 128, smem, VK_ST(stream)>>>(reinterpret_cast<const SftDesc*>(descs_dev),
-                                                                            n_layers, extra, n, e, sqrt_mask, alpha, d_extra);
-  VK_LAUNCHED();
+  const SftDesc* descs = reinterpret_cast<const SftDesc*>(descs_dev);
+  sft_mlp_bwd_batched_slots_kernel<<<dim3(n, n_layers), 128, smem, VK_ST(stream)>>>(descs, extra, n, e, sqrt_mask, alpha, ws,
+                                                                                  params_per_sample);
+  // the largest layer has fewer than 3 max_c^2 / 4 parameters: 64 blocks of 32 elements per grid step are plenty
+  sft_mlp_slot_reduce_kernel<<<dim3(64, n_layers + 1), 256, 0, VK_ST(stream)>>>(descs, n_layers, n, e, ws, params_per_sample,
+                                                                              d_extra);
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  return int(cudaGetLastError());
 }
 
 extern "C" uint32_t vk_sizeof_sft_desc(void) { return uint32_t(sizeof(SftDesc)); }

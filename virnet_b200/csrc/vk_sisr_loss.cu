@@ -341,14 +341,23 @@ sisr_kernel_wgrad_kernel(const float* __restrict__ mu, const float* __restrict__
   }
 }
 
-// ---- 10b: gk[n][t] = sum of the `slots` partials of sample n, in slot order ----
-__global__ void sisr_kernel_wgrad_reduce_kernel(const float* __restrict__ gk_part, float* __restrict__ gk, int slots, int KK) {
-  const int n = blockIdx.x;
+// ---- 10b: gk[n][t] = sum of the `slots` partials of sample n in a fixed order: block = 8 warps x 32 consecutive t,
+//           warp w adds slots w, w + 8, ... (coalesced rows), the eight warp sums are then added in warp order ----
+__global__ void __launch_bounds__(256)
+sisr_kernel_wgrad_reduce_kernel(const float* __restrict__ gk_part, float* __restrict__ gk, int slots, int KK) {
+  __shared__ float part[8][32];
+  const int n = blockIdx.y, w = threadIdx.x >> 5, t = blockIdx.x * 32 + (threadIdx.x & 31);
   const float* src = gk_part + static_cast<long long>(n) * slots * KK;
-  for (int t = threadIdx.x; t < KK; t += blockDim.x) {
-    float a = 0.f;
-    for (int s = 0; s < slots; ++s) a += src[static_cast<long long>(s) * KK + t];
-    gk[n * KK + t] = a;
+  float a = 0.f;
+  if (t < KK)
+    for (int s = w; s < slots; s += 8) a += src[static_cast<long long>(s) * KK + t];
+  part[w][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (w == 0 && t < KK) {
+    float v = part[0][threadIdx.x];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) v += part[j][threadIdx.x];
+    gk[n * KK + t] = v;
   }
 }
 
@@ -574,7 +583,7 @@ extern "C" int vk_elbo_sisr(const vk_elbo_sisr_args* a, void* stream_) {
   // 10: gradient w.r.t. the blur kernel
   sisr_kernel_wgrad_kernel<<<dim3(tiles(W), tiles(H), P), 256, wg_smem, st>>>(a->mu, a->z_draw, nscale, Bf, gk_part, C, H, W,
                                                                              K);
-  sisr_kernel_wgrad_reduce_kernel<<<N, 256, 0, st>>>(gk_part, gk, C * tiles(W) * tiles(H), KK);
+  sisr_kernel_wgrad_reduce_kernel<<<dim3((KK + 31) / 32, N), 256, 0, st>>>(gk_part, gk, C * tiles(W) * tiles(H), KK);
   launches += 2;
   // 11, 12
   sisr_kernel_bwd_kernel<<<N, 256, 0, st>>>(a->kernel, gk, aux, a->kinfo_est, a->kinfo_gt, a->gamma_draw, a->sigma_est,

@@ -735,7 +735,8 @@ class DenoiseEngine:
             descs.append(d)
         arr = (_l.vk_sft_desc * len(descs))(*descs)
         table = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev)
-        out = (sft, table, len(descs), max(nfeat), dmd, grads, vals)
+        n_params = sum(p_.numel() for _, _, _, att in layers for p_ in att.parameters())
+        out = (sft, table, len(descs), max(nfeat), dmd, grads, vals, n_params)
         self._tables[key] = out
         return out[:4]
 
@@ -1075,7 +1076,13 @@ class DenoiseEngine:
         self._wgrad(self.head, gX, S["r0"], VK_CONV3X3_S1)
         if sft_const:
             # SFT MLPs: (dmul, dadd) -> their 1x1 convs and the conditioning values, every AttLayer in one launch
-            ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, extra, d_cst, sqrt_mask=sqrt_mask, det=self.deterministic)
+            if self.deterministic:
+                n_params = tables[7]
+                ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, extra, d_cst, sqrt_mask=sqrt_mask,
+                                        det_ws=self._det_scratch(N * n_params + sft_n * N * extra.shape[1]),
+                                        params_per_sample=n_params)
+            else:
+                ops.sft_mlp_bwd_batched(sft_descs, sft_n, sft_maxc, extra, d_cst, sqrt_mask=sqrt_mask)
         if self.head_extra:
             cin0 = C + self.head_extra
             gR0 = self._buf("g.sr.r0", (N, Hp, Wp, cp(cin0)))

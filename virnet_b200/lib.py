@@ -164,7 +164,8 @@ _SIGNATURES = {
     "vk_sft_mlp_bwd_batched": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
                                          C.c_float, C.c_void_p, C.c_void_p]),
     "vk_sft_mlp_bwd_batched_det": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
-                                             C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]),
+                                             C.c_uint32, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                             C.c_void_p]),
     "vk_sizeof_sft_desc": (C.c_uint32, []),
     "vk_sft_apply": (C.c_int, [C.POINTER(vk_sft_apply_args), C.c_void_p]),
     "vk_sizeof_sft_apply_args": (C.c_uint32, []),

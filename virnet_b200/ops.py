@@ -608,13 +608,20 @@ def sft_mlp_batched(descs_dev, n_layers, max_c, extra, *, sqrt_mask=0, alpha=0.2
                                               _stream()), "vk_sft_mlp_batched")
 
 
-def sft_mlp_bwd_batched(descs_dev, n_layers, max_c, extra, d_extra, *, sqrt_mask=0, alpha=0.2, det=False):
-    """det=True: fixed accumulation order over samples (parameter gradients) and layers (d_extra), no racing atomics."""
+def sft_mlp_bwd_batched(descs_dev, n_layers, max_c, extra, d_extra, *, sqrt_mask=0, alpha=0.2, det_ws=None,
+                        params_per_sample=0):
+    """det_ws (fp32 scratch, at least n * params_per_sample + n_layers * n * e elements; params_per_sample = parameters of
+    all the AttLayers): per-(sample, layer) slots added in a fixed order instead of racing atomics."""
     n, e = extra.shape
-    fn = _l.load().vk_sft_mlp_bwd_batched_det if det else _l.load().vk_sft_mlp_bwd_batched
     with _Prof("sft_mlp_bwd"):
-        _l.check(fn(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask, alpha, _ptr(d_extra), _stream()),
-                 "vk_sft_mlp_bwd_batched_det" if det else "vk_sft_mlp_bwd_batched")
+        if det_ws is not None:
+            assert det_ws.dtype == torch.float32 and det_ws.is_cuda and det_ws.is_contiguous() and params_per_sample > 0
+            _l.check(_l.load().vk_sft_mlp_bwd_batched_det(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask,
+                                                          alpha, _ptr(d_extra), params_per_sample, _ptr(det_ws),
+                                                          det_ws.numel(), _stream()), "vk_sft_mlp_bwd_batched_det")
+        else:
+            _l.check(_l.load().vk_sft_mlp_bwd_batched(_ptr(descs_dev), n_layers, max_c, _ptr(extra), n, e, sqrt_mask, alpha,
+                                                      _ptr(d_extra), _stream()), "vk_sft_mlp_bwd_batched")
 
 
 def sisr_degrade(im_hr, kernels, rh, rw, noise, std):
