@@ -594,25 +594,51 @@ struct WgradUnpackDesc {
   int nslices, pad;         // > 1: ws holds nslices split-K partial slabs, summed here in slice order (deterministic)
   long long slice_stride;   // elements between consecutive slabs
 };
-__global__ void wgrad_unpack_batched_kernel(const WgradUnpackDesc* __restrict__ descs, int accumulate) {
+// A block transposes 256 consecutive (m, n) elements x taps through shared memory: the workspace rows are read
+// coalesced (consecutive elements of one tap), the parameter layout is written as one contiguous run of 256 * taps floats
+// (written straight from the per-tap loop it is a 36-byte-stride scatter that costs nine partial-sector passes).
+__global__ void __launch_bounds__(256)
+wgrad_unpack_batched_kernel(const WgradUnpackDesc* __restrict__ descs, int accumulate) {
+  constexpr int kMaxTaps = 9;
+  __shared__ float tile[kMaxTaps][257];
   const WgradUnpackDesc d = descs[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.mn; i += gridDim.x * blockDim.x) {
-    for (int t = 0; t < d.taps; ++t) {
-      const float* src = d.ws + static_cast<long long>(t) * d.mn + i;
-      float v = src[0];
-      if (d.nslices > 1) {
-        // fixed summation order 0, 1, 2, ...; four independent loads in flight per step
-        int s = 1;
-        for (; s + 4 <= d.nslices; s += 4) {
-          const float x0 = src[(s + 0) * d.slice_stride], x1 = src[(s + 1) * d.slice_stride];
-          const float x2 = src[(s + 2) * d.slice_stride], x3 = src[(s + 3) * d.slice_stride];
-          v = (((v + x0) + x1) + x2) + x3;
-        }
-        for (; s < d.nslices; ++s) v += src[s * d.slice_stride];
+  auto value = [&](int t, int i) {
+    const float* src = d.ws + static_cast<long long>(t) * d.mn + i;
+    float v = src[0];
+    if (d.nslices > 1) {
+      // fixed summation order 0, 1, 2, ...; four independent loads in flight per step
+      int s = 1;
+      for (; s + 4 <= d.nslices; s += 4) {
+        const float x0 = src[(s + 0) * d.slice_stride], x1 = src[(s + 1) * d.slice_stride];
+        const float x2 = src[(s + 2) * d.slice_stride], x3 = src[(s + 3) * d.slice_stride];
+        v = (((v + x0) + x1) + x2) + x3;
       }
-      float* o = d.out + static_cast<long long>(i) * d.taps + t;
-      *o = accumulate ? *o + v : v;
+      for (; s < d.nslices; ++s) v += src[s * d.slice_stride];
     }
+    return v;
+  };
+  if (d.taps > kMaxTaps) {                       // not used by this network: plain per-element form
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.mn; i += gridDim.x * blockDim.x)
+      for (int t = 0; t < d.taps; ++t) {
+        float* o = d.out + static_cast<long long>(i) * d.taps + t;
+        const float v = value(t, i);
+        *o = accumulate ? *o + v : v;
+      }
+    return;
+  }
+  for (int i0 = blockIdx.x * 256; i0 < d.mn; i0 += gridDim.x * 256) {
+    const int i = i0 + threadIdx.x;
+    if (i < d.mn)
+      for (int t = 0; t < d.taps; ++t) tile[t][threadIdx.x] = value(t, i);
+    __syncthreads();
+    const int cnt = min(256, d.mn - i0) * d.taps;
+    float* o = d.out + static_cast<long long>(i0) * d.taps;
+    for (int j = threadIdx.x; j < cnt; j += 256) {
+      const int ii = j / d.taps, t = j - ii * d.taps;
+      const float v = tile[t][ii];
+      o[j] = accumulate ? o[j] + v : v;
+    }
+    __syncthreads();
   }
 }
 
