@@ -81,3 +81,46 @@ def test_header_is_valid_c99_and_struct_layouts_match_ctypes(tmp_path):
         assert int(out[name]) == ctypes.sizeof(ct), name
         for field, _ in ct._fields_:
             assert int(out[f"{name}.{field}"]) == getattr(ct, field).offset, f"{name}.{field}"
+
+
+def declared_prototypes():
+    """{name: [parameter declarations]} of every function prototype in the header."""
+    text = (ROOT / "include" / "virnet_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"^\s*(?:const\s+)?(?:int|int64_t|uint32_t|uint64_t|char\s*\*|const char\s*\*)\s+\**(vk_\w+)\s*\(([^;{]*?)\)\s*;",
+                         text, flags=re.M | re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return out
+
+
+def test_ctypes_signatures_follow_the_header():
+    """Every prototype of include/virnet_b200.h must have a ctypes signature in virnet_b200/lib.py with the same number
+    of parameters and the same parameter classes (pointer / 32-bit / 64-bit integer / float / double): a prototype that
+    changes without its binding would pass garbage to the kernels."""
+    from virnet_b200 import lib
+
+    def cls_of_decl(decl):
+        if "*" in decl:
+            return "ptr"
+        ty = decl.rsplit(" ", 1)[0].replace("const", "").strip()
+        return {"int32_t": "i32", "uint32_t": "i32", "int": "i32", "int64_t": "i64", "uint64_t": "i64", "float": "f32",
+                "double": "f64"}[ty]
+
+    def cls_of_ctype(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_int32: "i32", ctypes.c_uint32: "i32", ctypes.c_int: "i32", ctypes.c_int64: "i64",
+                ctypes.c_uint64: "i64", ctypes.c_float: "f32", ctypes.c_double: "f64"}[t]
+
+    protos = declared_prototypes()
+    assert len(protos) >= 40, len(protos)
+    missing = sorted(set(protos) - set(lib._SIGNATURES))
+    assert not missing, f"header functions without a ctypes signature: {missing}"
+    for name, params in protos.items():
+        _, args = lib._SIGNATURES[name]
+        assert len(args) == len(params), (name, len(args), len(params))
+        got = [cls_of_ctype(t) for t in args]
+        want = [cls_of_decl(p) for p in params]
+        assert got == want, (name, got, want)
