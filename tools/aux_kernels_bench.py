@@ -94,6 +94,6 @@ rh = downsample_matrix(H, sf, "bicubic", dev)
 t = timeit(lambda: ops.elbo_sisr(mu, hr, lr, sig, kin, kin, sig, sig.log(), gam, rho, z, rh, rh, k_size=21, center=10.0,
                                  alpha0=40.5, digamma_am1=3.6788, kappa0=50.0, r2=1e-4, eps2=1e-5, pk0=0.02, pk1=2.0))
 fma = N * 3 * (H * H * 441 * 2 + (H + 20) * (H + 20) * 441)
-print(json.dumps(dict(kernel="vk_elbo_sisr (12 launches)", us=round(t * 1e6, 1), blur_GFMA=round(fma / 1e9, 2),
+print(json.dumps(dict(kernel="vk_elbo_sisr (13 launches)", us=round(t * 1e6, 1), blur_GFMA=round(fma / 1e9, 2),
                       achieved_TFMAps=round(fma / t / 1e12, 2),
                       note="b=16 x4 64->256: CUDA-core bound (three 21x21 blur passes); HBM traffic ~0.3 GB")), flush=True)
