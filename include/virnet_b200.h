@@ -370,6 +370,8 @@ int vk_synth_denoise(const uint8_t* patches, const double* params, const int32_t
  * gamma_draw [n][2] ~ Gamma(kappa0-1, 1), rho_draw [n] ~ N(0,1), z_draw like mu ~ N(0,1).
  * prior_mean / prior_logmean [n]: per-sample mean of sigma_prior and of log(sigma_prior) (equal to
  * sigma_prior and its log for the N x 1 x 1 x 1 Gaussian-noise prior of train_SISR.py:202).
+ * Every reduction goes through per-block slots of the workspace that are added in a fixed order (no atomics):
+ * the terms and all gradients are bit-identical from run to run.
  * terms[8] = loss, lh, kl_rnet, kl_snet, kl_knet, kl_knet0, kl_knet1, kl_knet2 (the reference's return order);
  * kernel [n][k_size*k_size] is the re-sampled blur kernel (last entry of the reference's detail list). */
 typedef struct vk_elbo_sisr_args {
